@@ -1,0 +1,965 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY.  Not part of the product.
+//
+// CPU restatement of the reference's `Predictor::predict` path
+// (daac-tools/vaporetto @ 1d215b8, crate vaporetto 0.6.5).  Only `tests/`,
+// `__graft_entry__.smoke()` and bench.py's cpu_baseline / `--impl reference`
+// legs may load this library; the product (`vaporetto_b200/`) never does.
+//
+// Parity status: PINNED.  The reference itself (Rust) cannot be compiled in
+// this image (no cargo/rustc; daachorse/bincode are un-vendored crates), so
+// this restatement is pinned against every known-answer test the reference
+// holds for the path (tests/test_oracle_golden.py) and
+// against the reference's binary fixtures committed under tests/golden/.
+//
+// Third-party arithmetic restated from its published behaviour:
+//  * daachorse 1.x (vaporetto/Cargo.toml:17) `find_overlapping_no_suffix_iter`:
+//    at every text position report only the longest pattern ending there;
+//    `find_overlapping_iter`: all patterns ending there.  Implemented here as a
+//    classic goto/failure Aho-Corasick automaton (no double array: layout does
+//    not affect results).
+//  * bincode 2.0.1 `config::standard()` (vaporetto/Cargo.toml:16): varint
+//    integers, zigzag for signed, length-prefixed Vec/String.
+//
+// Each function cites the reference file:line it follows
+// (paths relative to /root/reference/vaporetto/src).
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <utility>
+#include <vector>
+
+namespace ora {
+
+using std::string;
+using std::vector;
+
+static thread_local string g_err;
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const string& m) : std::runtime_error(m), code(c) {}
+};
+enum { OK = 0, INVALID_MODEL = 1, INVALID_ARGUMENT = 2, DECODE_ERROR = 3 };
+
+// ---------------------------------------------------------------------------
+// bincode standard-config decoder (bincode 2.0.1 varint spec).
+// ---------------------------------------------------------------------------
+struct Reader {
+    const uint8_t* p;
+    size_t n, pos = 0;
+    uint8_t u8() {
+        if (pos >= n) throw Error(DECODE_ERROR, "unexpected end of model data");
+        return p[pos++];
+    }
+    uint64_t fixed(int bytes) {
+        uint64_t v = 0;
+        for (int i = 0; i < bytes; ++i) v |= uint64_t(u8()) << (8 * i);
+        return v;
+    }
+    uint64_t varint() {
+        uint8_t b = u8();
+        if (b < 251) return b;
+        if (b == 251) return fixed(2);
+        if (b == 252) return fixed(4);
+        if (b == 253) return fixed(8);
+        throw Error(DECODE_ERROR, "unsupported varint width");
+    }
+    int64_t zigzag() {
+        uint64_t u = varint();
+        return int64_t(u >> 1) ^ -int64_t(u & 1);
+    }
+    size_t len() {
+        uint64_t l = varint();
+        if (l > n - pos + 8 && l > (1ull << 40)) throw Error(DECODE_ERROR, "length too large");
+        return size_t(l);
+    }
+    string bytes() {
+        size_t l = len();
+        if (l > n - pos) throw Error(DECODE_ERROR, "unexpected end of model data");
+        string s(reinterpret_cast<const char*>(p + pos), l);
+        pos += l;
+        return s;
+    }
+    vector<int32_t> vec_i32() {
+        size_t l = len();
+        if (l > n - pos) throw Error(DECODE_ERROR, "unexpected end of model data");
+        vector<int32_t> v(l);
+        for (auto& x : v) x = int32_t(zigzag());
+        return v;
+    }
+};
+
+static bool valid_utf8(const string& s) {
+    size_t i = 0, n = s.size();
+    auto b = [&](size_t k) { return uint8_t(s[k]); };
+    while (i < n) {
+        uint8_t c = b(i);
+        if (c < 0x80) { i += 1; continue; }
+        int need; uint32_t cp;
+        if (c >= 0xC2 && c <= 0xDF) { need = 1; cp = c & 0x1F; }
+        else if (c >= 0xE0 && c <= 0xEF) { need = 2; cp = c & 0x0F; }
+        else if (c >= 0xF0 && c <= 0xF4) { need = 3; cp = c & 0x07; }
+        else return false;
+        if (i + size_t(need) >= n) return false;
+        for (int k = 1; k <= need; ++k) {
+            if ((b(i + k) & 0xC0) != 0x80) return false;
+            cp = (cp << 6) | (b(i + k) & 0x3F);
+        }
+        if (need == 2 && (cp < 0x800 || (cp >= 0xD800 && cp <= 0xDFFF))) return false;
+        if (need == 3 && (cp < 0x10000 || cp > 0x10FFFF)) return false;
+        i += need + 1;
+    }
+    return true;
+}
+
+// ---------------------------------------------------------------------------
+// Model data (model.rs:41-47,61-70; ngram_model.rs:6-27; dict_model.rs:18-22)
+// ---------------------------------------------------------------------------
+struct NgramData { string ngram; vector<int32_t> weights; };
+struct TagWeight { uint8_t rel_position; vector<int32_t> weights; };
+struct TagNgramData { string ngram; vector<TagWeight> weights; };
+struct WordWeightRecord { string word; vector<int32_t> weights; string comment; };
+struct TagModel {
+    string token;
+    vector<vector<string>> tags;
+    vector<TagNgramData> char_ngram_model, type_ngram_model;
+    vector<int32_t> bias;
+};
+struct Model {
+    vector<NgramData> char_ngram_model, type_ngram_model;
+    vector<WordWeightRecord> dict_model;
+    int32_t bias = 0;
+    uint8_t char_window_size = 0, type_window_size = 0;
+    vector<TagModel> tag_models;
+};
+
+static const char MODEL_MAGIC[] = "VaporettoTokenizer 0.5.0\n";  // model.rs:15
+
+static vector<NgramData> read_ngrams(Reader& r, bool is_str) {
+    size_t l = r.len();
+    vector<NgramData> v;
+    for (size_t i = 0; i < l; ++i) {
+        NgramData d;
+        d.ngram = r.bytes();
+        if (is_str && !valid_utf8(d.ngram)) throw Error(DECODE_ERROR, "invalid UTF-8 in model string");
+        d.weights = r.vec_i32();
+        v.push_back(std::move(d));
+    }
+    return v;
+}
+static vector<TagNgramData> read_tag_ngrams(Reader& r, bool is_str) {
+    size_t l = r.len();
+    vector<TagNgramData> v;
+    for (size_t i = 0; i < l; ++i) {
+        TagNgramData d;
+        d.ngram = r.bytes();
+        if (is_str && !valid_utf8(d.ngram)) throw Error(DECODE_ERROR, "invalid UTF-8 in model string");
+        size_t m = r.len();
+        for (size_t j = 0; j < m; ++j) {
+            TagWeight w;
+            w.rel_position = r.u8();
+            w.weights = r.vec_i32();
+            d.weights.push_back(std::move(w));
+        }
+        v.push_back(std::move(d));
+    }
+    return v;
+}
+
+// Model::read_slice (model.rs:127-134)
+static Model model_read(const uint8_t* data, size_t n, size_t* consumed) {
+    const size_t ml = sizeof(MODEL_MAGIC) - 1;
+    if (n < ml || memcmp(data, MODEL_MAGIC, ml) != 0) throw Error(INVALID_MODEL, "model version mismatch");
+    Reader r{data + ml, n - ml};
+    Model m;
+    m.char_ngram_model = read_ngrams(r, true);
+    m.type_ngram_model = read_ngrams(r, false);
+    size_t nd = r.len();
+    for (size_t i = 0; i < nd; ++i) {
+        WordWeightRecord w;
+        w.word = r.bytes();
+        if (!valid_utf8(w.word)) throw Error(DECODE_ERROR, "invalid UTF-8 in model string");
+        w.weights = r.vec_i32();
+        w.comment = r.bytes();
+        m.dict_model.push_back(std::move(w));
+    }
+    m.bias = int32_t(r.zigzag());
+    m.char_window_size = r.u8();
+    m.type_window_size = r.u8();
+    size_t nt = r.len();
+    for (size_t i = 0; i < nt; ++i) {
+        TagModel t;
+        t.token = r.bytes();
+        size_t ns = r.len();
+        for (size_t j = 0; j < ns; ++j) {
+            size_t nc = r.len();
+            vector<string> c;
+            for (size_t k = 0; k < nc; ++k) c.push_back(r.bytes());
+            t.tags.push_back(std::move(c));
+        }
+        t.char_ngram_model = read_tag_ngrams(r, true);
+        t.type_ngram_model = read_tag_ngrams(r, false);
+        t.bias = r.vec_i32();
+        m.tag_models.push_back(std::move(t));
+    }
+    if (consumed) *consumed = ml + r.pos;
+    return m;
+}
+
+// ---------------------------------------------------------------------------
+// PositionalWeight (predictor.rs:138-165) and the tag variant (:217-262)
+// ---------------------------------------------------------------------------
+static inline int32_t wadd(int32_t a, int32_t b) { return int32_t(uint32_t(a) + uint32_t(b)); }
+
+struct PW {
+    int offset = 0;  // i16 in the reference
+    vector<int32_t> weight;
+    // AddAssign (predictor.rs:149-165)
+    void add(const PW& o) {
+        int new_offset = std::min(offset, o.offset);
+        size_t shift = size_t(offset - new_offset);
+        size_t oshift = size_t(o.offset - new_offset);
+        size_t new_size = std::max(shift + weight.size(), oshift + o.weight.size());
+        weight.resize(new_size, 0);
+        std::rotate(weight.begin(), weight.end() - (new_size ? shift % new_size : 0), weight.end());
+        for (size_t i = 0; i < o.weight.size() && oshift + i < weight.size(); ++i)
+            weight[oshift + i] = wadd(weight[oshift + i], o.weight[i]);
+        offset = new_offset;
+    }
+};
+
+struct PWTag {
+    std::optional<PW> weight;
+    std::map<std::pair<size_t, uint8_t>, vector<int32_t>> tag_info;
+    // AddAssign (predictor.rs:242-262)
+    void add(const PWTag& o) {
+        if (weight) {
+            if (o.weight) weight->add(*o.weight);
+        } else {
+            weight = o.weight;
+        }
+        for (auto& kv : o.tag_info) {
+            auto it = tag_info.find(kv.first);
+            if (it == tag_info.end()) {
+                tag_info[kv.first] = kv.second;
+            } else {
+                auto& w = it->second;
+                for (size_t i = 0; i < w.size() && i < kv.second.size(); ++i) w[i] = wadd(w[i], kv.second[i]);
+            }
+        }
+    }
+};
+
+// start offsets of the proper suffixes of `s` that begin on a symbol boundary
+static vector<size_t> suffix_starts(const string& s, bool utf8) {
+    vector<size_t> v;
+    for (size_t j = 1; j < s.size(); ++j)
+        if (!utf8 || (uint8_t(s[j]) & 0xC0) != 0x80) v.push_back(j);
+    return v;
+}
+
+// CharWeightMerger / TypeWeightMerger (char_scorer.rs:29-79, type_scorer.rs:38-88)
+template <class W>
+struct Merger {
+    struct Cell { W w; bool done = false; };
+    std::map<string, Cell> map;  // BTreeMap: byte-lexicographic order
+    bool utf8;
+    explicit Merger(bool u) : utf8(u) {}
+    void add(const string& ngram, const W& w) {
+        auto it = map.find(ngram);
+        if (it != map.end()) it->second.w.add(w);
+        else map.emplace(ngram, Cell{w, false});
+    }
+    vector<std::pair<string, W>> merge() {
+        vector<Cell*> stack;
+        for (auto& kv : map) {
+            if (kv.second.done) continue;
+            stack.push_back(&kv.second);
+            for (size_t j : suffix_starts(kv.first, utf8)) {
+                auto it = map.find(kv.first.substr(j));
+                if (it != map.end()) {
+                    stack.push_back(&it->second);
+                    if (it->second.done) break;
+                }
+            }
+            Cell* from = stack.back();
+            stack.pop_back();
+            from->done = true;
+            while (!stack.empty()) {
+                Cell* to = stack.back();
+                stack.pop_back();
+                to->done = true;
+                to->w.add(from->w);
+                from = to;
+            }
+        }
+        vector<std::pair<string, W>> out;
+        for (auto& kv : map) out.emplace_back(kv.first, std::move(kv.second.w));
+        return out;
+    }
+};
+
+// ---------------------------------------------------------------------------
+// Aho-Corasick over bytes (semantics of daachorse; see header).
+// ---------------------------------------------------------------------------
+struct AC {
+    struct Node {
+        vector<std::pair<uint8_t, int>> ch;  // sorted by byte
+        int fail = 0;
+        int out = -1;       // longest pattern ending at this state (own, else via suffix)
+        int own = -1;       // pattern ending exactly here
+        int out_link = -1;  // next shorter pattern-bearing suffix state
+    };
+    vector<Node> nodes;
+    vector<int> root_next;  // 256 direct transitions from the root
+    void build(const vector<string>& pats) {
+        nodes.assign(1, Node());
+        for (size_t i = 0; i < pats.size(); ++i) {
+            if (pats[i].empty()) throw Error(INVALID_MODEL, "failed to build the automaton");
+            int s = 0;
+            for (unsigned char c : pats[i]) {
+                int nx = -1;
+                for (auto& e : nodes[s].ch) if (e.first == c) { nx = e.second; break; }
+                if (nx < 0) {
+                    nx = int(nodes.size());
+                    nodes.push_back(Node());
+                    nodes[s].ch.emplace_back(c, nx);
+                }
+                s = nx;
+            }
+            if (nodes[s].own >= 0) throw Error(INVALID_MODEL, "failed to build the automaton");  // duplicate
+            nodes[s].own = int(i);
+        }
+        for (auto& nd : nodes) std::sort(nd.ch.begin(), nd.ch.end());
+        vector<int> q;
+        for (auto& e : nodes[0].ch) { nodes[e.second].fail = 0; q.push_back(e.second); }
+        for (size_t h = 0; h < q.size(); ++h) {
+            int s = q[h];
+            Node& ns = nodes[s];
+            int f = ns.fail;
+            ns.out = ns.own >= 0 ? ns.own : nodes[f].out;
+            ns.out_link = nodes[f].own >= 0 ? f : nodes[f].out_link;
+            for (auto& e : ns.ch) {
+                int t = ns.fail;
+                int nx;
+                while ((nx = child(t, e.first)) < 0 && t != 0) t = nodes[t].fail;
+                nodes[e.second].fail = nx < 0 ? 0 : nx;
+                q.push_back(e.second);
+            }
+        }
+        root_next.assign(256, 0);
+        for (auto& e : nodes[0].ch) root_next[e.first] = e.second;
+    }
+    int child(int s, uint8_t c) const {
+        const auto& ch = nodes[s].ch;
+        if (ch.size() <= 8) {
+            for (auto& e : ch) if (e.first == c) return e.second;
+            return -1;
+        }
+        auto it = std::lower_bound(ch.begin(), ch.end(), std::make_pair(c, -1));
+        return (it != ch.end() && it->first == c) ? it->second : -1;
+    }
+    inline int step(int s, uint8_t c) const {
+        for (;;) {
+            if (s == 0) return root_next[c];
+            int nx = child(s, c);
+            if (nx >= 0) return nx;
+            s = nodes[s].fail;
+        }
+    }
+};
+
+// CharacterType::get_type (sentence.rs:50-67)
+static inline uint8_t get_type(uint32_t c) {
+    if ((c >= 0x30 && c <= 0x39) || (c >= 0xFF10 && c <= 0xFF19)) return 1;
+    if ((c >= 0x41 && c <= 0x5A) || (c >= 0x61 && c <= 0x7A) || (c >= 0xFF21 && c <= 0xFF3A) ||
+        (c >= 0xFF41 && c <= 0xFF5A)) return 2;
+    if (c >= 0x3040 && c <= 0x3096) return 3;
+    if ((c >= 0x30A0 && c <= 0x30FA) || (c >= 0x30FC && c <= 0x30FF) || (c >= 0xFF66 && c <= 0xFF9F)) return 4;
+    if ((c >= 0x3400 && c <= 0x4DBF) || (c >= 0x4E00 && c <= 0x9FFF) || (c >= 0xF900 && c <= 0xFAFF) ||
+        (c >= 0x20000 && c <= 0x2A6DF) || (c >= 0x2A700 && c <= 0x2B73F) || (c >= 0x2B740 && c <= 0x2B81F) ||
+        (c >= 0x2B820 && c <= 0x2CEAF) || (c >= 0x2F800 && c <= 0x2FA1F)) return 5;
+    return 6;
+}
+
+// Sentence state touched by predict (sentence.rs:85-101)
+struct Sentence {
+    string text;
+    vector<uint8_t> char_types;
+    vector<uint8_t> boundaries;
+    vector<int32_t> boundary_scores;  // padded strip
+    size_t score_padding = 0;
+    vector<uint32_t> char_pma_states, type_pma_states;
+    vector<uint32_t> str_to_char_pos, char_to_str_pos;
+    size_t len() const { return char_types.size(); }
+    // Sentence::parse_raw (sentence.rs:160-196); text must be valid UTF-8
+    void parse_raw(const char* s, size_t nbytes) {
+        text.assign(s, nbytes);
+        char_types.clear(); boundaries.clear(); str_to_char_pos.clear(); char_to_str_pos.clear();
+        boundary_scores.clear(); char_pma_states.clear(); type_pma_states.clear(); score_padding = 0;
+        if (!valid_utf8(text)) throw Error(INVALID_ARGUMENT, "InvalidArgumentError: text: must be valid UTF-8");
+        char_to_str_pos.push_back(0);
+        size_t pos = 0;
+        while (pos < nbytes) {
+            uint8_t b = uint8_t(s[pos]);
+            uint32_t cp; int l;
+            if (b < 0x80) { cp = b; l = 1; }
+            else if (b < 0xE0) { cp = b & 0x1F; l = 2; }
+            else if (b < 0xF0) { cp = b & 0x0F; l = 3; }
+            else { cp = b & 0x07; l = 4; }
+            for (int k = 1; k < l; ++k) cp = (cp << 6) | (uint8_t(s[pos + k]) & 0x3F);
+            if (cp == 0) throw Error(INVALID_ARGUMENT, "InvalidArgumentError: text: must not contain NULL");
+            char_types.push_back(get_type(cp));
+            pos += l;
+            char_to_str_pos.push_back(uint32_t(pos));
+        }
+        if (char_types.empty())
+            throw Error(INVALID_ARGUMENT, "InvalidArgumentError: text: must contain at least one character");
+        str_to_char_pos.assign(pos + 1, 0);
+        for (size_t i = 0; i < char_to_str_pos.size(); ++i) str_to_char_pos[char_to_str_pos[i]] = uint32_t(i);
+        boundaries.assign(char_types.size() - 1, 2);  // Unknown
+    }
+};
+
+// PositionalWeight<WeightVector>::add_score (predictor.rs:176-213).  The Fixed
+// branch is the Variable branch on a zero-padded vector, so one ragged add with
+// clipping at both ends of the strip covers both (the Fixed branch never clips
+// for models the reference accepts; it would panic otherwise).
+static inline void add_score(const PW& w, long end, vector<int32_t>& ys) {
+    long pos = end + w.offset;
+    long n = long(ys.size());
+    for (long k = 0; k < long(w.weight.size()); ++k) {
+        long p = pos + k;
+        if (p < 0) continue;
+        if (p >= n) break;
+        ys[p] = wadd(ys[p], w.weight[k]);
+    }
+}
+
+struct TagTable {  // tag_weight[token_id][rel_position] : pattern id -> weights
+    vector<vector<std::unordered_map<uint32_t, vector<int32_t>>>> t;
+};
+
+// WeightVector::add_scores (predictor.rs:81-107): zip truncates; Fixed pads to 8.
+static inline void add_tag_vec(const vector<int32_t>& w, vector<int32_t>& ys) {
+    for (size_t i = 0; i < w.size() && i < ys.size(); ++i) ys[i] = wadd(ys[i], w[i]);
+}
+
+// One automaton-backed scorer: CharScorerBoundary / CharScorerBoundaryTag /
+// TypeScorerBoundary / TypeScorerBoundaryTag
+// (char_scorer/boundary_scorer.rs:56-113, char_scorer/boundary_tag_scorer.rs:62-174,
+//  type_scorer/boundary_scorer.rs:45-80, type_scorer/boundary_tag_scorer.rs:51-143)
+struct PmaScorer {
+    AC pma;
+    vector<std::optional<PW>> weights;
+    TagTable tag_weight;
+    bool tag_variant = false;
+    bool is_char = true;
+
+    void build(const vector<NgramData>& ngrams, const vector<WordWeightRecord>& dict, uint8_t window,
+               const vector<const vector<TagNgramData>*>& tag_ngrams, bool is_char_) {
+        is_char = is_char_;
+        tag_variant = !tag_ngrams.empty();
+        Merger<PWTag> merger(is_char);
+        for (auto& d : ngrams) {
+            PWTag w; w.weight = PW{-int(window), d.weights};
+            merger.add(d.ngram, w);
+        }
+        for (auto& d : dict) {
+            size_t word_len = 0;
+            for (unsigned char c : d.word) if ((c & 0xC0) != 0x80) ++word_len;
+            if (word_len > 32767)
+                throw Error(INVALID_MODEL, "words must be shorter than or equal to 32767 characters");
+            PWTag w; w.weight = PW{-int(word_len), d.weights};
+            merger.add(d.word, w);
+        }
+        tag_weight.t.assign(tag_ngrams.size(),
+                            vector<std::unordered_map<uint32_t, vector<int32_t>>>(size_t(window) + 1));
+        for (size_t i = 0; i < tag_ngrams.size(); ++i)
+            for (auto& d : *tag_ngrams[i])
+                for (auto& w : d.weights) {
+                    PWTag pw; pw.tag_info[{i, w.rel_position}] = w.weights;
+                    merger.add(d.ngram, pw);
+                }
+        vector<string> pats;
+        auto merged = merger.merge();
+        for (size_t i = 0; i < merged.size(); ++i) {
+            pats.push_back(merged[i].first);
+            weights.push_back(merged[i].second.weight);
+            for (auto& kv : merged[i].second.tag_info) {
+                if (kv.first.second >= tag_weight.t[kv.first.first].size())
+                    throw Error(INVALID_MODEL, "tag rel_position exceeds the window size");  // ref: index panic
+                tag_weight.t[kv.first.first][kv.first.second][uint32_t(i)] = kv.second;
+            }
+        }
+        pma.build(pats);
+    }
+
+    // add_scores: walk, longest match per end position (boundary_scorer.rs:93-113 etc.)
+    void add_scores(Sentence& s) const {
+        vector<uint32_t>* states = nullptr;
+        if (tag_variant) {
+            states = is_char ? &s.char_pma_states : &s.type_pma_states;
+            states->assign(s.len(), 0xFFFFFFFFu);
+        }
+        int st = 0;
+        if (is_char) {
+            const size_t nb = s.text.size();
+            for (size_t i = 0; i < nb; ++i) {
+                st = pma.step(st, uint8_t(s.text[i]));
+                int p = pma.nodes[st].out;
+                if (p < 0) continue;
+                size_t end = s.str_to_char_pos[i + 1];
+                if (weights[p]) add_score(*weights[p], long(end + s.score_padding) - 1, s.boundary_scores);
+                if (states) (*states)[end - 1] = uint32_t(p);
+            }
+        } else {
+            for (size_t i = 0; i < s.char_types.size(); ++i) {
+                st = pma.step(st, s.char_types[i]);
+                int p = pma.nodes[st].out;
+                if (p < 0) continue;
+                size_t end = i + 1;
+                if (weights[p]) add_score(*weights[p], long(end + s.score_padding) - 1, s.boundary_scores);
+                if (states) (*states)[end - 1] = uint32_t(p);
+            }
+        }
+    }
+
+    // add_tag_scores (boundary_tag_scorer.rs:154-174 / :123-143)
+    void add_tag_scores(uint32_t token_id, size_t pos, const vector<uint32_t>& states,
+                        vector<int32_t>& scores) const {
+        const auto& tw = tag_weight.t[token_id];
+        for (size_t r = 0; r < tw.size() && pos + r < states.size(); ++r) {
+            auto it = tw[r].find(states[pos + r]);
+            if (it != tw[r].end()) add_tag_vec(it->second, scores);
+        }
+    }
+};
+
+// TypeScorerBoundaryCache (type_scorer/boundary_scorer_cache.rs:22-110)
+struct TypeCache {
+    vector<int32_t> scores;
+    uint8_t window = 0;
+    size_t mask = 0;
+    void build(const vector<NgramData>& model, uint8_t w) {
+        {   // DoubleArrayAhoCorasick::new rejects empty and duplicate patterns
+            std::map<string, int> seen;
+            for (auto& d : model) {
+                if (d.ngram.empty() || seen.count(d.ngram))
+                    throw Error(INVALID_MODEL, "invalid character type n-grams");
+                seen[d.ngram] = 1;
+            }
+        }
+        window = w;
+        size_t seq = size_t(w) * 2;
+        size_t all = size_t(1) << (3 * seq);
+        mask = all - 1;
+        scores.assign(all, 0);
+        vector<uint8_t> s(seq);
+        for (size_t id = 0; id < all; ++id) {
+            size_t x = id; bool ok = true;
+            for (size_t k = seq; k-- > 0;) { s[k] = uint8_t(x & 7); if (s[k] == 7) { ok = false; break; } x >>= 3; }
+            if (!ok) continue;
+            int32_t y = 0;
+            // find_overlapping_iter: every occurrence of every n-gram
+            for (auto& d : model) {
+                size_t L = d.ngram.size();
+                for (size_t end = L; end <= seq; ++end) {
+                    if (memcmp(d.ngram.data(), s.data() + end - L, L) != 0) continue;
+                    size_t idx = seq - end;
+                    if (idx < d.weights.size()) y = wadd(y, d.weights[idx]);
+                }
+            }
+            scores[id] = y;
+        }
+    }
+    void add_scores(Sentence& s) const {
+        s.type_pma_states.clear();
+        size_t seqid = 0;
+        for (size_t i = 0; i < window; ++i)
+            seqid = ((seqid << 3) | (i < s.char_types.size() ? s.char_types[i] : 0)) & mask;
+        for (size_t i = 0; i < s.boundaries.size(); ++i) {
+            size_t j = i + window;
+            seqid = ((seqid << 3) | (j < s.char_types.size() ? s.char_types[j] : 0)) & mask;
+            int32_t& y = s.boundary_scores[s.score_padding + i];
+            y = wadd(y, scores[seqid]);
+        }
+    }
+};
+
+struct TagPredictor {  // predictor.rs:264-304
+    vector<vector<string>> tags;
+    vector<int32_t> bias;  // WeightVector::from: zero-padded to >= 8 (predictor.rs:118-135)
+};
+
+struct Predictor {
+    std::unique_ptr<PmaScorer> char_scorer, type_pma;
+    std::unique_ptr<TypeCache> type_cache;
+    int32_t bias = 0;
+    bool predict_tags = false;
+    std::unordered_map<string, std::pair<uint32_t, TagPredictor>> tag_predictor;
+    size_t n_tags = 0;
+
+    // Predictor::new (predictor.rs:450-508), CharScorer::new (char_scorer.rs:92-124),
+    // TypeScorer::new (type_scorer.rs:104-143)
+    Predictor(const Model& m, bool ptags) : bias(m.bias), predict_tags(ptags) {
+        vector<const vector<TagNgramData>*> tag_char, tag_type;
+        if (ptags) {
+            for (size_t i = 0; i < m.tag_models.size(); ++i) {
+                auto& t = m.tag_models[i];
+                n_tags = std::max(n_tags, t.tags.size());
+                TagPredictor tp{t.tags, t.bias};
+                if (tp.bias.size() < 8) tp.bias.resize(8, 0);
+                tag_predictor[t.token] = {uint32_t(i), std::move(tp)};
+                tag_char.push_back(&t.char_ngram_model);
+                tag_type.push_back(&t.type_ngram_model);
+            }
+        }
+        if (!((m.char_ngram_model.empty() && m.dict_model.empty()) || m.char_window_size == 0)) {
+            char_scorer.reset(new PmaScorer());
+            char_scorer->build(m.char_ngram_model, m.dict_model, m.char_window_size, tag_char, true);
+        }
+        if (!(m.type_ngram_model.empty() || m.type_window_size == 0)) {
+            if (tag_type.empty() && m.type_window_size <= 3) {
+                type_cache.reset(new TypeCache());
+                type_cache->build(m.type_ngram_model, m.type_window_size);
+            } else {
+                type_pma.reset(new PmaScorer());
+                type_pma->build(m.type_ngram_model, {}, m.type_window_size, tag_type, false);
+            }
+        }
+    }
+
+    // Predictor::predict (predictor.rs:518-543)
+    void predict(Sentence& s) const {
+        s.score_padding = 7;
+        s.boundary_scores.assign(s.score_padding * 2 + s.len() - 1, bias);
+        if (char_scorer) char_scorer->add_scores(s);
+        if (type_cache) type_cache->add_scores(s);
+        if (type_pma) type_pma->add_scores(s);
+        for (size_t i = 0; i < s.boundaries.size(); ++i)
+            s.boundaries[i] = s.boundary_scores[s.score_padding + i] > 0 ? 1 : 0;
+    }
+
+    // TagPredictor::predict (predictor.rs:286-304): tag index per slot, -1 = None
+    static void pick(const TagPredictor& tp, const vector<int32_t>& scores, int32_t* out, size_t n_out) {
+        size_t offset = 0;
+        for (size_t k = 0; k < tp.tags.size() && k < n_out; ++k) {
+            size_t nc = tp.tags[k].size();
+            if (nc >= 2) {
+                size_t idx = 0; int32_t mx = INT32_MIN;
+                for (size_t i = 0; i < nc; ++i) {
+                    int32_t sc = scores.at(offset + i);
+                    if (sc > mx) { idx = i; mx = sc; }
+                }
+                out[k] = int32_t(idx);
+                offset += nc;
+            } else {
+                out[k] = nc == 1 ? 0 : -1;
+            }
+        }
+    }
+
+    // Predictor::predict_tags (predictor.rs:546-637).  Output per char position i,
+    // slot k: tag_token[i] = token id owning the tags (or -1), tag_idx[i*n_tags+k] =
+    // candidate index (or -1).
+    void fill_tags(const Sentence& s, vector<int32_t>& tag_token, vector<int32_t>& tag_idx,
+                   vector<vector<int32_t>>* raw_scores) const {
+        if (!predict_tags) throw Error(INVALID_ARGUMENT, "this predictor is created with predict_tags = false");
+        tag_token.assign(s.len(), -1);
+        tag_idx.assign(s.len() * n_tags, -1);
+        if (raw_scores) raw_scores->assign(s.len(), {});
+        if (n_tags == 0) return;
+        auto run = [&](size_t start, size_t i) {  // token = chars [start, i], last char index i
+            string tok = s.text.substr(s.char_to_str_pos[start], s.char_to_str_pos[i + 1] - s.char_to_str_pos[start]);
+            auto it = tag_predictor.find(tok);
+            if (it == tag_predictor.end()) return;
+            const TagPredictor& tp = it->second.second;
+            vector<int32_t> scores(tp.bias.size(), 0);
+            add_tag_vec(tp.bias, scores);
+            if (char_scorer) char_scorer->add_tag_scores(it->second.first, i, s.char_pma_states, scores);
+            if (type_pma) type_pma->add_tag_scores(it->second.first, i, s.type_pma_states, scores);
+            pick(tp, scores, &tag_idx[i * n_tags], n_tags);
+            tag_token[i] = int32_t(it->second.first);
+            if (raw_scores) (*raw_scores)[i] = scores;
+        };
+        bool have = true; size_t start = 0;
+        for (size_t i = 0; i < s.boundaries.size(); ++i) {
+            uint8_t b = s.boundaries[i];
+            if (b == 2) { have = false; }
+            else if (b == 1) {
+                if (have) run(start, i);
+                have = true; start = i + 1;
+            }
+        }
+        if (have) run(start, s.len() - 1);
+    }
+};
+
+// Sentence::write_tokenized_text (sentence.rs:850-886) + TokenIterator (:1273-1299)
+static string write_tokenized(const Predictor& p, const Sentence& s, const vector<int32_t>* tag_token,
+                              const vector<int32_t>* tag_idx) {
+    string buf;
+    auto esc = [&](const string& t) {
+        for (char c : t) { if (c == ' ' || c == '\\' || c == '/') buf.push_back('\\'); buf.push_back(c); }
+    };
+    vector<string> tok_names(p.tag_predictor.size());
+    vector<const TagPredictor*> tps(p.tag_predictor.size(), nullptr);
+    for (auto& kv : p.tag_predictor) tps[kv.second.first] = &kv.second.second;
+    size_t start = 0, n = s.len();
+    bool skip = false;
+    auto emit = [&](size_t st, size_t en) {  // chars [st, en)
+        if (!buf.empty()) buf.push_back(' ');
+        esc(s.text.substr(s.char_to_str_pos[st], s.char_to_str_pos[en] - s.char_to_str_pos[st]));
+        if (tag_token && p.n_tags) {
+            size_t i = en - 1;
+            int last = -1;
+            for (size_t k = 0; k < p.n_tags; ++k) if ((*tag_idx)[i * p.n_tags + k] >= 0) last = int(k);
+            for (int k = 0; k <= last; ++k) {
+                buf.push_back('/');
+                int ci = (*tag_idx)[i * p.n_tags + size_t(k)];
+                if (ci >= 0) esc(tps[size_t((*tag_token)[i])]->tags[size_t(k)][size_t(ci)]);
+            }
+        }
+    };
+    for (size_t i = 0; i + 1 < n; ++i) {
+        uint8_t b = s.boundaries[i];
+        if (b == 1) {
+            if (!skip) emit(start, i + 1);
+            skip = false; start = i + 1;
+        } else if (b == 2) skip = true;
+    }
+    if (!skip) emit(start, n);
+    return buf;
+}
+
+}  // namespace ora
+
+// ---------------------------------------------------------------------------
+// C interface for tests / bench (ctypes)
+// ---------------------------------------------------------------------------
+using namespace ora;
+
+#define ORA_TRY try {
+#define ORA_CATCH(ret)                                   \
+    } catch (const Error& e) { g_err = e.what(); return ret(e.code); } \
+      catch (const std::exception& e) { g_err = e.what(); return ret(99); }
+static inline int idret(int c) { return c; }
+
+extern "C" {
+
+const char* ora_last_error() { return g_err.c_str(); }
+
+int ora_model_read(const uint8_t* data, size_t n, void** out, size_t* consumed) {
+    ORA_TRY
+    *out = new Model(model_read(data, n, consumed));
+    return 0;
+    ORA_CATCH(idret)
+}
+void ora_model_free(void* m) { delete static_cast<Model*>(m); }
+
+int ora_predictor_new(const void* model, int predict_tags, void** out) {
+    ORA_TRY
+    *out = new Predictor(*static_cast<const Model*>(model), predict_tags != 0);
+    return 0;
+    ORA_CATCH(idret)
+}
+void ora_predictor_free(void* p) { delete static_cast<Predictor*>(p); }
+int ora_predictor_n_tags(const void* p) { return int(static_cast<const Predictor*>(p)->n_tags); }
+
+// 0: cache table, 1: automaton, -1: none
+int ora_type_variant(const void* p) {
+    auto* pr = static_cast<const Predictor*>(p);
+    return pr->type_cache ? 0 : (pr->type_pma ? 1 : -1);
+}
+
+// merged pattern table of the char (which=0) or type (which=1) automaton scorer, for
+// the merger known-answer tests: writes "<pattern bytes>\t<offset>\t<w0,w1,..>\n" lines.
+long ora_dump_patterns(const void* p, int which, char* buf, size_t cap) {
+    auto* pr = static_cast<const Predictor*>(p);
+    const PmaScorer* sc = which == 0 ? pr->char_scorer.get() : pr->type_pma.get();
+    if (!sc) return 0;
+    string out;
+    // recover pattern strings by walking the trie
+    vector<string> pats(sc->weights.size());
+    struct Rec { static void go(const AC& ac, int s, string& cur, vector<string>& pats) {
+        if (ac.nodes[s].own >= 0) pats[size_t(ac.nodes[s].own)] = cur;
+        for (auto& e : ac.nodes[s].ch) { cur.push_back(char(e.first)); go(ac, e.second, cur, pats); cur.pop_back(); }
+    } };
+    string cur; Rec::go(sc->pma, 0, cur, pats);
+    for (size_t i = 0; i < pats.size(); ++i) {
+        out += pats[i]; out += '\t';
+        if (sc->weights[i]) {
+            out += std::to_string(sc->weights[i]->offset); out += '\t';
+            for (size_t k = 0; k < sc->weights[i]->weight.size(); ++k) {
+                if (k) out += ',';
+                out += std::to_string(sc->weights[i]->weight[k]);
+            }
+        } else out += "none\t";
+        out += '\n';
+    }
+    if (out.size() + 1 > cap) return -long(out.size() + 1);
+    memcpy(buf, out.c_str(), out.size() + 1);
+    return long(out.size());
+}
+
+// predict one sentence.  Returns n_chars (>=1) or -(error code).
+// scores/boundaries: n_chars-1 entries; states: n_chars entries (nullable).
+long ora_predict(const void* p, const char* utf8, size_t nbytes, int32_t* scores, uint8_t* boundaries,
+                 uint32_t* char_states, uint32_t* type_states) {
+    auto neg = [](int c) { return -long(c); };
+    ORA_TRY
+    auto* pr = static_cast<const Predictor*>(p);
+    Sentence s;
+    s.parse_raw(utf8, nbytes);
+    pr->predict(s);
+    size_t nb = s.boundaries.size();
+    for (size_t i = 0; i < nb; ++i) {
+        if (scores) scores[i] = s.boundary_scores[s.score_padding + i];
+        if (boundaries) boundaries[i] = s.boundaries[i];
+    }
+    if (char_states) for (size_t i = 0; i < s.len(); ++i)
+        char_states[i] = i < s.char_pma_states.size() ? s.char_pma_states[i] : 0xFFFFFFFFu;
+    if (type_states) for (size_t i = 0; i < s.len(); ++i)
+        type_states[i] = i < s.type_pma_states.size() ? s.type_pma_states[i] : 0xFFFFFFFFu;
+    return long(s.len());
+    ORA_CATCH(neg)
+}
+
+// char types of a sentence (Sentence::char_types). Returns n_chars or -(code).
+long ora_char_types(const char* utf8, size_t nbytes, uint8_t* out) {
+    auto neg = [](int c) { return -long(c); };
+    ORA_TRY
+    Sentence s; s.parse_raw(utf8, nbytes);
+    memcpy(out, s.char_types.data(), s.len());
+    return long(s.len());
+    ORA_CATCH(neg)
+}
+
+// predict + (optional) fill_tags + write_tokenized_text.  `boundaries_in` (nullable)
+// overrides the predicted boundaries before tag filling (post-filter hook).
+long ora_tokenize(const void* p, const char* utf8, size_t nbytes, int fill_tags, char* buf, size_t cap) {
+    auto neg = [](int c) { return -long(c); };
+    ORA_TRY
+    auto* pr = static_cast<const Predictor*>(p);
+    Sentence s; s.parse_raw(utf8, nbytes);
+    pr->predict(s);
+    vector<int32_t> tt, ti;
+    if (fill_tags) pr->fill_tags(s, tt, ti, nullptr);
+    string out = write_tokenized(*pr, s, fill_tags ? &tt : nullptr, fill_tags ? &ti : nullptr);
+    if (out.size() + 1 > cap) return -long(1000000 + out.size() + 1);
+    memcpy(buf, out.c_str(), out.size() + 1);
+    return long(out.size());
+    ORA_CATCH(neg)
+}
+
+// predict + fill_tags: tag_token[n_chars], tag_idx[n_chars*n_tags]. Returns n_chars.
+long ora_predict_tags(const void* p, const char* utf8, size_t nbytes, int32_t* tag_token, int32_t* tag_idx) {
+    auto neg = [](int c) { return -long(c); };
+    ORA_TRY
+    auto* pr = static_cast<const Predictor*>(p);
+    Sentence s; s.parse_raw(utf8, nbytes);
+    pr->predict(s);
+    vector<int32_t> tt, ti;
+    pr->fill_tags(s, tt, ti, nullptr);
+    memcpy(tag_token, tt.data(), tt.size() * 4);
+    if (!ti.empty()) memcpy(tag_idx, ti.data(), ti.size() * 4);
+    return long(s.len());
+    ORA_CATCH(neg)
+}
+
+// raw add_tag_scores of one scorer (which: 0 char, 1 type) after predict, for the
+// known-answer tests char_scorer.rs:405-525 / type_scorer.rs:367-473.
+int ora_add_tag_scores(const void* p, int which, const char* utf8, size_t nbytes, uint32_t token_id, size_t pos,
+                       int32_t* scores, size_t n_scores) {
+    ORA_TRY
+    auto* pr = static_cast<const Predictor*>(p);
+    Sentence s; s.parse_raw(utf8, nbytes);
+    pr->predict(s);
+    vector<int32_t> sc(scores, scores + n_scores);
+    const PmaScorer* scr = which == 0 ? pr->char_scorer.get() : pr->type_pma.get();
+    if (!scr || !scr->tag_variant) throw Error(INVALID_ARGUMENT, "unsupported");
+    scr->add_tag_scores(token_id, pos, which == 0 ? s.char_pma_states : s.type_pma_states, sc);
+    memcpy(scores, sc.data(), n_scores * 4);
+    return 0;
+    ORA_CATCH(idret)
+}
+
+// Batch predict over a concatenated buffer, `nthreads` host threads, sentences sharded
+// contiguously (CPU baseline procedure; mirrors the loop at
+// predict/src/main.rs:152-181 minus I/O).  bound_offsets[n+1] must be precomputed
+// (chars_i - 1 prefix sums) unless scores==NULL and boundaries==NULL.
+// status[i] (nullable) = 0 ok / error code.
+int ora_predict_batch(const void* p, const char* utf8, const uint64_t* byte_offsets, size_t n_sent,
+                      const uint64_t* bound_offsets, int32_t* scores, uint8_t* boundaries, int32_t* status,
+                      int nthreads) {
+    ORA_TRY
+    auto* pr = static_cast<const Predictor*>(p);
+    if (nthreads < 1) nthreads = 1;
+    auto work = [&](size_t lo, size_t hi) {
+        Sentence s;
+        for (size_t i = lo; i < hi; ++i) {
+            try {
+                s.parse_raw(utf8 + byte_offsets[i], size_t(byte_offsets[i + 1] - byte_offsets[i]));
+                pr->predict(s);
+                if (bound_offsets) {
+                    size_t o = size_t(bound_offsets[i]);
+                    for (size_t k = 0; k < s.boundaries.size(); ++k) {
+                        if (scores) scores[o + k] = s.boundary_scores[s.score_padding + k];
+                        if (boundaries) boundaries[o + k] = s.boundaries[k];
+                    }
+                }
+                if (status) status[i] = 0;
+            } catch (const Error& e) {
+                if (status) status[i] = e.code;
+            }
+        }
+    };
+    if (nthreads == 1) { work(0, n_sent); return 0; }
+    vector<std::thread> th;
+    // shard by bytes
+    uint64_t total = byte_offsets[n_sent] - byte_offsets[0];
+    size_t lo = 0;
+    for (int t = 0; t < nthreads; ++t) {
+        uint64_t target = byte_offsets[0] + total * uint64_t(t + 1) / uint64_t(nthreads);
+        size_t hi = t + 1 == nthreads ? n_sent
+                                      : size_t(std::lower_bound(byte_offsets, byte_offsets + n_sent + 1, target) - byte_offsets);
+        if (hi < lo) hi = lo;
+        if (hi > n_sent) hi = n_sent;
+        th.emplace_back(work, lo, hi);
+        lo = hi;
+    }
+    for (auto& t : th) t.join();
+    return 0;
+    ORA_CATCH(idret)
+}
+
+// PositionalWeight += (predictor.rs:149-165) exposed for the known-answer tests :678-747.
+// y (len ny, capacity cap) += x; returns new length, *off_y updated.
+long ora_pw_add(int* off_y, int32_t* y, size_t ny, size_t cap, int off_x, const int32_t* x, size_t nx) {
+    PW a{*off_y, vector<int32_t>(y, y + ny)}, b{off_x, vector<int32_t>(x, x + nx)};
+    a.add(b);
+    if (a.weight.size() > cap) return -1;
+    memcpy(y, a.weight.data(), a.weight.size() * 4);
+    *off_y = a.offset;
+    return long(a.weight.size());
+}
+
+// chars per sentence (so callers can size outputs). Returns 0 or error code.
+int ora_count_chars(const char* utf8, const uint64_t* byte_offsets, size_t n_sent, uint64_t* n_chars) {
+    for (size_t i = 0; i < n_sent; ++i) {
+        uint64_t c = 0;
+        for (uint64_t b = byte_offsets[i]; b < byte_offsets[i + 1]; ++b) c += (uint8_t(utf8[b]) & 0xC0) != 0x80;
+        n_chars[i] = c;
+    }
+    return 0;
+}
+
+}  // extern "C"
