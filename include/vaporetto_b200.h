@@ -1,0 +1,182 @@
+/* vaporetto_b200 — C ABI of the B200-native `Predictor::predict` path.
+ *
+ * The reference (daac-tools/vaporetto, crate `vaporetto` 0.6.5) has no FFI layer: its surface is the
+ * Rust API `Model` / `Predictor` / `Sentence` (vaporetto/src/lib.rs:82-91).  Every entry point below
+ * names the Rust item it stands in for (paths relative to the reference's vaporetto/src/).  A Rust shim
+ * that keeps the crate API and forwards to these symbols is sketched in INTEGRATION.md.
+ *
+ * Conventions
+ *  - every function returns a vpt_status (0 = ok); the message of the last failure on the calling thread
+ *    is available from vpt_last_error() (mirrors `VaporettoError`'s Display, errors.rs:41-56).
+ *  - no panics/aborts cross the ABI; CUDA failures are reported as VPT_CUDA_ERROR.
+ *  - a predictor is immutable after creation and may be shared by many host threads
+ *    (`Predictor: Send + Sync`, shared as Arc<Predictor> in vaporetto_tantivy/src/lib.rs:62-67);
+ *    each call uses its own CUDA stream and staging buffers.
+ *  - there is no CPU fallback: without a usable CUDA device every compute entry point fails.
+ */
+#ifndef VAPORETTO_B200_H
+#define VAPORETTO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+typedef enum vpt_status {
+    VPT_OK = 0,
+    VPT_INVALID_MODEL = 1,    /* VaporettoError::InvalidModel    (errors.rs:16) */
+    VPT_INVALID_ARGUMENT = 2, /* VaporettoError::InvalidArgument (errors.rs:19) */
+    VPT_INVALID_SENTENCE = 3, /* VaporettoError::InvalidSentence (errors.rs:22) */
+    VPT_DECODE_ERROR = 4,     /* VaporettoError::DecodeError     (errors.rs:34) */
+    VPT_IO_ERROR = 5,         /* VaporettoError::IOError         (errors.rs:28) */
+    VPT_CUDA_ERROR = 16,
+    VPT_UNSUPPORTED = 17,
+    VPT_INTERNAL = 18
+} vpt_status;
+
+/* per-sentence status written by the batch entry points (what `Sentence::from_raw` / `update_raw`
+ * would have rejected, sentence.rs:174-189, plus malformed UTF-8 which a Rust &str cannot hold) */
+enum {
+    VPT_SENT_OK = 0,
+    VPT_SENT_EMPTY = 1,        /* "text: must contain at least one character" */
+    VPT_SENT_NUL = 2,          /* "text: must not contain NULL" */
+    VPT_SENT_BAD_UTF8 = 3
+};
+
+#define VPT_NO_PATTERN 0xFFFFFFFFu /* u32::MAX in char_pma_states / type_pma_states (boundary_tag_scorer.rs:122-123) */
+
+typedef struct vpt_model vpt_model;
+typedef struct vpt_predictor vpt_predictor;
+
+/* Message of the last error raised on this thread ("" if none). */
+const char* vpt_last_error(void);
+
+/* ---- Model --------------------------------------------------------------------------------------- */
+
+/* `Model::read_slice(&[u8]) -> Result<(Model, &[u8])>` (model.rs:127-134) and `Model::read` (model.rs:142-153).
+ * `data` is the raw (already un-zstd'd) model image; `*consumed` (nullable) receives the bytes used. */
+int vpt_model_read(const uint8_t* data, size_t len, vpt_model** out, size_t* consumed);
+void vpt_model_free(vpt_model* model);
+
+/* ---- Predictor ----------------------------------------------------------------------------------- */
+
+/* `Predictor::new(model: Model, predict_tags: bool) -> Result<Predictor>` (predictor.rs:450-508).
+ * Consumes `model` (it is freed, success or failure), builds the merged weight rows and the flat device
+ * tables, and uploads them to CUDA device `device`. */
+int vpt_predictor_new(vpt_model* model, int predict_tags, int device, vpt_predictor** out);
+void vpt_predictor_free(vpt_predictor* predictor);
+
+typedef struct vpt_predictor_info {
+    int32_t device;
+    int32_t predict_tags;       /* created with predict_tags = true */
+    int32_t n_tags;             /* Sentence::n_tags after fill_tags (predictor.rs:553) */
+    int32_t char_scorer;        /* 0 none, 1 Boundary, 2 BoundaryTag       (char_scorer.rs:84-89) */
+    int32_t type_scorer;        /* 0 none, 1 Boundary, 2 BoundaryCache, 3 BoundaryTag (type_scorer.rs:92-101) */
+    int32_t fast_path;          /* 1: k_score_fast (all rows inline), 0: k_score_general */
+    int32_t bias;
+    int32_t char_window, type_window;
+    uint32_t n_char_patterns, n_type_patterns;
+    uint32_t n_char_nodes, n_type_nodes;
+    uint32_t max_char_pattern_len;
+    uint64_t blob_bytes;        /* size of the device-resident model */
+    int32_t kernel_launches_per_batch;
+} vpt_predictor_info;
+int vpt_predictor_get_info(const vpt_predictor* predictor, vpt_predictor_info* out);
+
+/* Flat device model: serialise on one rank, broadcast as bytes (NCCL), rebuild on the others.
+ * (Replaces `Predictor::serialize_to_vec` / `deserialize_from_slice_unchecked`, predictor.rs:640-664, whose
+ * daachorse-private layout is not reproducible; the blob format is this library's own.)
+ * Predictors made from a blob score boundaries; tag prediction needs vpt_predictor_new. */
+uint64_t vpt_predictor_blob_size(const vpt_predictor* predictor);
+int vpt_predictor_blob_export(const vpt_predictor* predictor, void* dst, uint64_t capacity);
+int vpt_predictor_from_blob(const void* blob, uint64_t len, int device, vpt_predictor** out);
+
+/* ---- predict ------------------------------------------------------------------------------------- */
+
+/* Batched `Predictor::predict(&self, &mut Sentence)` (predictor.rs:518-543) over HOST buffers.
+ *
+ * Sentence i is utf8[byte_offsets[i] .. byte_offsets[i+1]) (raw text, as given to `Sentence::from_raw`).
+ * With n_i = number of characters of sentence i, its boundaries occupy
+ *   scores_out / boundaries_out [ bound_offsets_out[i] .. bound_offsets_out[i] + max(n_i - 1, 0) )
+ * (`Sentence::boundary_scores()`, sentence.rs:1040-1046; `Sentence::boundaries()` as 0 = NotWordBoundary,
+ * 1 = WordBoundary, sentence.rs:70-82) and, when requested, its pattern states occupy
+ *   char_states_out / type_states_out [ char_offsets_out[i] .. + n_i )
+ * (`char_pma_states` / `type_pma_states`, sentence.rs:92-93; only meaningful for a predictor created with
+ * predict_tags = true on a model that has tag models).
+ * Rejected sentences (status_out[i] != 0) keep their slots, filled with zeros / VPT_NO_PATTERN.
+ *
+ * out_capacity / states_capacity are the element capacities of the output arrays; if too small the call
+ * fails with VPT_INVALID_ARGUMENT and the required sizes are in *n_boundaries_out / *n_chars_out.
+ * scores_out, char_states_out, type_states_out, char_offsets_out, status_out may be NULL.
+ * For full PCIe bandwidth pass page-locked (pinned) host buffers. */
+int vpt_predict_batch(const vpt_predictor* predictor, const uint8_t* utf8, const uint64_t* byte_offsets, size_t n_sent,
+                      int32_t* scores_out, uint8_t* boundaries_out, size_t out_capacity, uint64_t* bound_offsets_out,
+                      int32_t* status_out, uint32_t* char_states_out, uint32_t* type_states_out,
+                      size_t states_capacity, uint64_t* char_offsets_out, uint64_t* n_boundaries_out,
+                      uint64_t* n_chars_out);
+
+/* Same over DEVICE buffers, asynchronous on `cuda_stream` (a cudaStream_t; NULL = default stream).
+ * d_utf8 must be 16-byte aligned and its allocation readable up to the next multiple of 16 bytes.
+ * d_workspace: vpt_workspace_size(n_sent) bytes of scratch.  d_scores/d_boundaries must hold the batch's
+ * total boundary count (an upper bound is total_bytes - 1); d_bound_offsets [n_sent+1];
+ * d_status [n_sent]; d_char_states / d_type_states / d_char_offsets nullable. */
+uint64_t vpt_workspace_size(size_t n_sent);
+int vpt_predict_batch_dev(const vpt_predictor* predictor, const uint8_t* d_utf8, const uint64_t* d_byte_offsets,
+                          size_t n_sent, void* d_workspace, uint64_t workspace_bytes, int32_t* d_scores,
+                          uint8_t* d_boundaries, uint64_t* d_bound_offsets, int32_t* d_status,
+                          uint32_t* d_char_states, uint32_t* d_type_states, uint64_t* d_char_offsets,
+                          void* cuda_stream);
+
+/* Single-sentence `Predictor::predict` (batch of one).  Returns VPT_INVALID_ARGUMENT with the reference's
+ * message for an empty text or a text containing U+0000 (sentence.rs:174-189).  *n_chars_out receives n;
+ * scores_out/boundaries_out need n-1 entries (capacity in elements), states n entries (nullable). */
+int vpt_predict(const vpt_predictor* predictor, const uint8_t* utf8, size_t n_bytes, int32_t* scores_out,
+                uint8_t* boundaries_out, size_t out_capacity, uint32_t* char_states_out, uint32_t* type_states_out,
+                size_t states_capacity, uint64_t* n_chars_out);
+
+/* ---- tags (host side; `Sentence::fill_tags` -> `Predictor::predict_tags`, predictor.rs:546-637) ------ */
+
+/* For one sentence with final boundaries (0 not / 1 boundary / 2 unknown, sentence.rs:70-82) and the
+ * states produced by predict: for every character position i that ends a token known to the tag model,
+ * tag_token_out[i] = token id (else -1) and tag_cand_out[i*n_tags + k] = index of the chosen candidate of
+ * tag slot k (else -1).  tag_scores_out (nullable, n_chars * score_stride) receives the raw score vectors
+ * (`Predictor::store_tag_scores`, predictor.rs:512).  Fails with VPT_INVALID_ARGUMENT
+ * ("this predictor is created with predict_tags = false") where the reference panics (predictor.rs:547-551). */
+int vpt_fill_tags(const vpt_predictor* predictor, const uint8_t* utf8, size_t n_bytes, const uint8_t* boundaries,
+                  const uint32_t* char_states, const uint32_t* type_states, int32_t* tag_token_out,
+                  int32_t* tag_cand_out, int32_t* tag_scores_out, size_t score_stride);
+/* tag string of (token id, slot, candidate); NULL if out of range. Valid for the predictor's lifetime. */
+const char* vpt_tag_string(const vpt_predictor* predictor, uint32_t token_id, uint32_t slot, uint32_t cand);
+/* number of candidates of a slot (0 if out of range) and the score-vector length of a token */
+uint32_t vpt_tag_n_candidates(const vpt_predictor* predictor, uint32_t token_id, uint32_t slot);
+uint32_t vpt_tag_score_len(const vpt_predictor* predictor, uint32_t token_id);
+uint32_t vpt_tag_n_tokens(const vpt_predictor* predictor);
+
+/* ---- Sentence helpers (host side) ----------------------------------------------------------------- */
+
+/* `CharacterType::get_type` per character (sentence.rs:50-67) / `Sentence::char_types()` (sentence.rs:993).
+ * Returns the reference's InvalidArgument errors for empty text / NUL.  *n_chars_out receives n. */
+int vpt_char_types(const uint8_t* utf8, size_t n_bytes, uint8_t* types_out, size_t capacity, uint64_t* n_chars_out);
+
+/* `Sentence::write_tokenized_text` (sentence.rs:850-886): tokens joined by ' ', with '/tag' suffixes when
+ * tag_token/tag_cand are given (NULL otherwise), escaping ' ', '\\', '/'.  Tokens adjacent to an Unknown
+ * boundary are skipped.  Returns the byte length needed in *len_out; writes at most `capacity` bytes. */
+int vpt_write_tokenized_text(const vpt_predictor* predictor, const uint8_t* utf8, size_t n_bytes,
+                             const uint8_t* boundaries, const int32_t* tag_token, const int32_t* tag_cand,
+                             char* buf, size_t capacity, uint64_t* len_out);
+
+/* library build info, e.g. "vaporetto_b200 0.1.0 sm_100a" */
+const char* vpt_version(void);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* VAPORETTO_B200_H */

@@ -1,0 +1,136 @@
+// TEST INFRASTRUCTURE: interprets the flat model blob produced by the product's host builder
+// (vaporetto_b200/csrc/predictor_build.cpp) on the CPU, following the same probe sequence as the kernels
+// (kernels.cu: find_node / k_score_fast / k_score_general), so that table construction can be checked
+// against the oracle without a GPU.  Not part of the product; never linked into libvaporetto_b200.so.
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../vaporetto_b200/csrc/predictor_build.hpp"
+#include "../../vaporetto_b200/csrc/common.hpp"
+
+using namespace vpt;
+
+namespace {
+
+struct Tab {
+    const BlobTable* bt;
+    const uint8_t* base;
+    TableGeom geom() const { return TableGeom{bt->nslots, bt->nbuckets, bt->salt}; }
+    const uint16_t* seeds() const { return reinterpret_cast<const uint16_t*>(base + bt->seeds_off); }
+    const uint32_t* rec(uint32_t slot) const { return reinterpret_cast<const uint32_t*>(base + bt->rec_off + size_t(slot) * 32); }
+    const uint32_t* slot_node() const { return reinterpret_cast<const uint32_t*>(base + bt->node_off); }
+    const int32_t* pool() const { return reinterpret_cast<const int32_t*>(base + bt->pool_off); }
+    bool probe(uint64_t key, const uint32_t*& r, uint32_t& slot) const {
+        slot = table_slot(geom(), seeds(), key);
+        r = rec(slot);
+        uint64_t k = (uint64_t(r[1]) << 32) | r[0];
+        return (k & ~kExtFlag) == key;
+    }
+};
+
+uint8_t ctype(uint32_t c) {
+    if ((c >= 0x30 && c <= 0x39) || (c >= 0xFF10 && c <= 0xFF19)) return 1;
+    if ((c >= 0x41 && c <= 0x5A) || (c >= 0x61 && c <= 0x7A) || (c >= 0xFF21 && c <= 0xFF3A) || (c >= 0xFF41 && c <= 0xFF5A)) return 2;
+    if (c >= 0x3040 && c <= 0x3096) return 3;
+    if ((c >= 0x30A0 && c <= 0x30FA) || (c >= 0x30FC && c <= 0x30FF) || (c >= 0xFF66 && c <= 0xFF9F)) return 4;
+    if ((c >= 0x3400 && c <= 0x4DBF) || (c >= 0x4E00 && c <= 0x9FFF) || (c >= 0xF900 && c <= 0xFAFF) || (c >= 0x20000 && c <= 0x2A6DF) ||
+        (c >= 0x2A700 && c <= 0x2B73F) || (c >= 0x2B740 && c <= 0x2B81F) || (c >= 0x2B820 && c <= 0x2CEAF) || (c >= 0x2F800 && c <= 0x2FA1F)) return 5;
+    return 6;
+}
+
+bool find_node(const Tab& t, const std::vector<uint32_t>& sym, size_t g, const uint32_t*& rec, uint32_t& slot) {
+    uint32_t c3 = sym[g], c2 = g >= 1 ? sym[g - 1] : 0, c1 = g >= 2 ? sym[g - 2] : 0;
+    bool found = t.probe(shallow_key(c1, c2, c3), rec, slot);
+    bool depth3 = found && c1 != 0;
+    if (!found && c1 != 0) found = t.probe(shallow_key(0, c2, c3), rec, slot);
+    if (!found && c2 != 0) found = t.probe(shallow_key(0, 0, c3), rec, slot);
+    if (depth3 && (rec[1] >> 31) && g >= 3) {
+        size_t i = g - 2;
+        uint32_t node = t.slot_node()[slot];
+        while (i > 0) {
+            --i;
+            const uint32_t* nrec; uint32_t nslot;
+            if (!t.probe(deep_key(node, sym[i]), nrec, nslot)) break;
+            rec = nrec; slot = nslot;
+            if (!(rec[1] >> 31)) break;
+            node = t.slot_node()[slot];
+        }
+    }
+    return found;
+}
+
+}  // namespace
+
+extern "C" {
+
+// returns n_chars (>0) or -(status).  scores: n-1; states: n each (nullable).  info[0]=fast path flag.
+long emul_predict(const uint8_t* model, size_t model_len, int predict_tags, const uint8_t* utf8, size_t nbytes,
+                  int32_t* scores, uint32_t* cstates, uint32_t* tstates, int32_t* info) {
+    try {
+        size_t consumed = 0;
+        Model m = Model::read(model, model_len, &consumed);
+        HostPredictor hp = build_host_predictor(m, predict_tags != 0);
+        const uint8_t* base = hp.blob.data();
+        BlobHeader h;
+        memcpy(&h, base, sizeof h);
+        Tab ct{&h.ct, base}, tt{&h.tt, base};
+        std::vector<uint32_t> cps = utf8_to_codepoints(std::string(reinterpret_cast<const char*>(utf8), nbytes));
+        const size_t n = cps.size();
+        std::vector<uint32_t> tys(n);
+        for (size_t i = 0; i < n; ++i) tys[i] = ctype(cps[i]);
+        const long nout = long(n) - 1;
+        const bool fast = (!h.ct.present || h.ct.fast) && !h.tt.present && !h.emit_states;
+        if (info) { info[0] = fast; info[1] = h.char_variant; info[2] = h.type_variant; }
+        for (long i = 0; i < nout; ++i) {
+            int32_t v = h.bias;
+            if (h.type_cache_window) {
+                const int w = h.type_cache_window;
+                uint32_t idx = 0;
+                for (int k = 0; k < 2 * w; ++k) {
+                    long j = i - w + 1 + k;
+                    idx = (idx << 3) | ((j >= 0 && j < long(n)) ? tys[size_t(j)] : 0u);
+                }
+                v = wrapping_add(v, reinterpret_cast<const int32_t*>(base + h.type_cache_off)[idx]);
+            }
+            scores[i] = v;
+        }
+        for (size_t g = 0; g < n; ++g) {
+            if (cstates) cstates[g] = kNoPattern;
+            if (tstates) tstates[g] = kNoPattern;
+        }
+        for (int which = 0; which < 2; ++which) {
+            const Tab& t = which ? tt : ct;
+            if (!t.bt->present) continue;
+            const std::vector<uint32_t>& sym = which ? tys : cps;
+            for (size_t g = 0; g < n; ++g) {
+                const uint32_t* rec; uint32_t slot;
+                if (!find_node(t, sym, g, rec, slot)) continue;
+                if (t.bt->fast) {
+                    for (int j = 0; j < kInlineWidth; ++j) {
+                        long i = long(g) + t.bt->r0 + j;
+                        if (i >= 0 && i < nout) scores[i] = wrapping_add(scores[i], int32_t(rec[2 + j]));
+                    }
+                } else {
+                    if (h.emit_states) { if (which == 0 && cstates) cstates[g] = rec[2]; if (which == 1 && tstates) tstates[g] = rec[2]; }
+                    if (rec[3] != kNoPattern) {
+                        const int32_t off = int32_t(rec[4]);
+                        for (uint32_t k = 0; k < rec[5]; ++k) {
+                            long i = long(g) + off + long(k);
+                            if (i >= 0 && i < nout) scores[i] = wrapping_add(scores[i], t.pool()[rec[3] + k]);
+                        }
+                    }
+                }
+            }
+        }
+        return long(n);
+    } catch (const Error& e) {
+        set_last_error(e.what());
+        return -long(e.code);
+    }
+}
+
+const char* emul_last_error() { return last_error(); }
+
+}

@@ -1,0 +1,293 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle and the reference's
+known-answer vectors.  Bit-exact (integer work).  Run with `-m gpu` on a B200."""
+import os
+
+import numpy as np
+import pytest
+
+import vaporetto_b200 as vb
+from golden import reference_kat as kat
+from vpt_testlib import synth
+from vpt_testlib.bincode_model import encode_model
+from vpt_testlib.oracle import OraclePredictor
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def read(fn):
+    with open(os.path.join(GOLDEN, fn), "rb") as f:
+        return f.read()
+
+
+def make(model_bytes, tags=False):
+    return vb.Predictor(vb.Model.read(model_bytes), predict_tags=tags)
+
+
+# ---- the reference's own unit tests, through the mirrored API ------------------------------------------
+
+@pytest.mark.parametrize("name", sorted(kat.SCORE_CASES))
+def test_reference_score_vectors(name):
+    case = kat.SCORE_CASES[name]
+    p = make(encode_model(case["model"]))
+    s = vb.Sentence.from_raw(case["text"])
+    p.predict(s)
+    assert s.boundary_scores().tolist() == case["scores"]
+    want_b = case.get("boundaries", [1 if x > 0 else 0 for x in case["scores"]])
+    assert s.boundaries().tolist() == want_b
+
+
+@pytest.mark.parametrize("name", sorted(kat.TAG_SCORE_CASES))
+def test_reference_score_vectors_tag_variants(name):
+    case = kat.TAG_SCORE_CASES[name]
+    mb = encode_model(case["model"])
+    p = make(mb, tags=True)
+    s = vb.Sentence.from_raw(case["text"])
+    p.predict(s)
+    assert s.boundary_scores().tolist() == case["scores"]
+    o = OraclePredictor(mb, predict_tags=True)
+    _, _, ocs, ots = o.predict(case["text"], states=True)
+    if p.info["char_scorer"] == 2:
+        assert s._char_states.tolist() == ocs.tolist()
+    if p.info["type_scorer"] == 3:
+        assert s._type_states.tolist() == ots.tolist()
+
+
+def test_reference_predict_tags():
+    # predictor.rs:863-903 test_predict_tags
+    case = kat.PREDICT_BOUNDARIES
+    p = make(encode_model(case["model"]), tags=True)
+    s = vb.Sentence.from_raw(case["text"])
+    p.predict(s)
+    s.fill_tags()
+    assert s.boundary_scores().tolist() == case["scores"]
+    assert s.boundaries().tolist() == case["boundaries"]
+    assert s.n_tags() == 2
+    assert s.tags() == case["tags"]
+
+
+def test_fill_tags_unsupported():
+    # predictor.rs:974-987: panics in the reference; an InvalidArgument error here
+    p = make(encode_model(kat.PREDICTOR_TEST_MODEL), tags=False)
+    s = vb.Sentence.from_raw("この人は地球人だ")
+    p.predict(s)
+    with pytest.raises(vb.VaporettoError) as e:
+        s.fill_tags()
+    assert "predict_tags = false" in str(e.value)
+
+
+def test_model_bin_doctests():
+    # lib.rs:17-41, predictor.rs:388-429, sentence.rs:1121-1137
+    data = read("model.bin")
+    for tags in (False, True):
+        p = make(data, tags=tags)
+        for text, with_tags, want in kat.MODEL_BIN_TOKENIZE:
+            if with_tags and not tags:
+                continue
+            s = vb.Sentence.from_raw(text)
+            p.predict(s)
+            assert s.boundary_scores().tolist() == kat.MODEL_BIN_SCORES[text]
+            if with_tags:
+                s.fill_tags()
+            assert s.write_tokenized_text() == want
+
+
+def test_docs_tok_config1():
+    # BASELINE config 1: resources/docs.tok with resources/model.bin
+    p = make(read("model.bin"), tags=True)
+    for line in read("docs.tok").decode().splitlines():
+        raw = "".join(tok.split("/")[0] for tok in line.split(" "))
+        s = vb.Sentence.from_raw(raw)
+        p.predict(s)
+        s.fill_tags()
+        assert s.write_tokenized_text() == line
+
+
+def test_tantivy_fixture():
+    p = make(read("tantivy_model.bin"))
+    for text, want in kat.TANTIVY_TOKENIZE:
+        s = vb.Sentence.from_raw(text)
+        p.predict(s)
+        assert s.write_tokenized_text() == want
+        # byte offsets of tokens (vaporetto_tantivy/src/lib.rs:183-191)
+    s = vb.Sentence.from_raw("東京特許許可局")
+    p.predict(s)
+    toks = list(s.iter_tokens())
+    assert [(t.start(), t.end()) for t in toks] == [(0, 2), (2, 4), (4, 6), (6, 7)]
+
+
+# ---- batches against the oracle ----------------------------------------------------------------------
+
+def oracle_batch(o, text, offs):
+    return o.predict_batch(text, offs, nthreads=4)
+
+
+def check_batch(p, o, text, offs, want_states=False):
+    r = p.predict_batch(text, offs, want_states=want_states)
+    sc, bd, boff, st = oracle_batch(o, text, offs)
+    assert r.bound_offsets.tolist() == boff.tolist()
+    ok = st == 0
+    assert (r.status == 0).tolist() == ok.tolist()
+    assert np.array_equal(r.scores, sc)
+    assert np.array_equal(r.boundaries, bd)
+    return r
+
+
+def test_edge_cases():
+    data = read("model.bin")
+    p, o = make(data), OraclePredictor(data)
+    sents = ["まぁ社長は火星猫だ", "", "猫", "a\0b", "まぁ良いだろう", "𠀋𠀋火星🤌🏿", "x" * 700, "火" * 1000 + "星人" * 333, " "]
+    blob = b"".join(s.encode() for s in sents) + b"\xe3\x81" + b"ok" + b"\xff"
+    lens = [len(s.encode()) for s in sents] + [2, 2, 1]
+    offs = np.zeros(len(lens) + 1, np.uint64)
+    np.cumsum(lens, out=offs[1:])
+    text = np.frombuffer(blob, np.uint8)
+    r = p.predict_batch(text, offs)
+    assert r.status.tolist() == [0, 1, 0, 2, 0, 0, 0, 0, 0, 3, 0, 3]
+    for i, s in enumerate(sents):
+        if r.status[i] != 0:
+            continue
+        want, wb = o.predict(s)
+        assert r.sentence_scores(i).tolist() == want.tolist(), i
+        assert r.sentence_boundaries(i).tolist() == wb.tolist(), i
+    # rejected sentences keep zero-filled slots: "a\0b" has 3 chars -> 2 slots
+    assert r.sentence_scores(3).tolist() == [0, 0]
+    assert int(r.bound_offsets[2] - r.bound_offsets[1]) == 0
+    # single-sentence entry point reports the reference's errors
+    for bad, msg in (("", "at least one character"), ("a\0b", "NULL")):
+        with pytest.raises(vb.VaporettoError) as e:
+            vb.Sentence.from_raw(bad)
+        assert msg in str(e.value)
+
+
+def _random_model(rng, cw, tw, n_ng=40, n_dict=20, maxdict=9, tags=0):
+    alpha = "あいうえおアイウ人火星地球猫社長aB1。、"
+    def word(lo, hi):
+        return "".join(rng.choice(list(alpha), size=rng.integers(lo, hi + 1)))
+    cng = {}
+    for _ in range(n_ng):
+        g = word(1, 3)
+        cng[g] = rng.integers(-32767, 32768, size=max(2 * cw - len(g) + 1, 0)).tolist()
+    dic = [(word(1, maxdict),) for _ in range(n_dict)]
+    dic = [(w, rng.integers(-32767, 32768, size=len(w) + 1).tolist(), "") for (w,) in dic]
+    tng = {}
+    for _ in range(30):
+        g = bytes(rng.integers(1, 7, size=rng.integers(1, 4)).tolist())
+        tng[g] = rng.integers(-32767, 32768, size=max(2 * tw - len(g) + 1, 0)).tolist()
+    tms = []
+    for t in range(tags):
+        cn = [(word(1, 3), [(int(rng.integers(0, cw + 1)), rng.integers(-99, 99, size=2).tolist())]) for _ in range(5)]
+        tn = [(bytes(rng.integers(1, 7, size=rng.integers(1, 4)).tolist()),
+               [(int(rng.integers(0, tw + 1)), rng.integers(-99, 99, size=2).tolist())]) for _ in range(3)]
+        tms.append(dict(token=word(1, 2), tags=[["x", "y"]], char_ngrams=cn, type_ngrams=tn, bias=[1, 2]))
+    return dict(char_ngrams=list(cng.items()), type_ngrams=list(tng.items()), dict=dic,
+                bias=int(rng.integers(-1000, 1000)), char_window=cw, type_window=tw, tag_models=tms), alpha
+
+
+@pytest.mark.parametrize("cw,tw,maxdict,tags", [(3, 3, 3, 0), (3, 3, 9, 0), (2, 2, 2, 0), (4, 4, 6, 0), (5, 1, 12, 0),
+                                                (3, 3, 5, 3), (3, 0, 4, 0), (0, 3, 1, 0), (1, 5, 3, 2)])
+def test_random_models_vs_oracle(cw, tw, maxdict, tags):
+    rng = np.random.default_rng(1000 * cw + 100 * tw + maxdict + tags)
+    model, alpha = _random_model(rng, cw, tw, maxdict=maxdict, tags=tags)
+    mb = encode_model(model)
+    p, o = make(mb, tags=tags > 0), OraclePredictor(mb, predict_tags=tags > 0)
+    sents = ["".join(rng.choice(list(alpha), size=rng.integers(1, 90))) for _ in range(700)]
+    sents += ["".join(rng.choice(list(alpha), size=n)) for n in (1, 2, 31, 32, 33, 63, 64, 65, 96, 97, 300, 1025)]
+    lens = [len(s.encode()) for s in sents]
+    offs = np.zeros(len(lens) + 1, np.uint64)
+    np.cumsum(lens, out=offs[1:])
+    text = np.frombuffer("".join(sents).encode(), np.uint8)
+    r = check_batch(p, o, text, offs, want_states=tags > 0)
+    if tags:
+        for i in (0, 5, len(sents) - 1):
+            _, _, ocs, ots = o.predict(sents[i], states=True)
+            c0 = int(r.char_offsets[i])
+            if p.info["char_scorer"] == 2:
+                assert r.char_states[c0:c0 + len(ocs)].tolist() == ocs.tolist()
+            if p.info["type_scorer"] == 3:
+                assert r.type_states[c0:c0 + len(ots)].tolist() == ots.tolist()
+
+
+@pytest.fixture(scope="module")
+def synth_model():
+    return synth.gen_model_bccwj_shaped(n_patterns=30000, sample_sentences=60000)
+
+
+def test_synthetic_config2_shape(synth_model):
+    # bccwj-suw-shaped (reduced pattern count so the CPU oracle builds in seconds): fast path, bit-exact
+    p, o = make(synth_model), OraclePredictor(synth_model)
+    assert p.info["fast_path"] == 1 and p.info["type_scorer"] == 2
+    text, offs, _ = synth.gen_text(30000, 40)
+    check_batch(p, o, text, offs)
+    text, offs, _ = synth.gen_text(8000, ragged=True)
+    check_batch(p, o, text, offs)
+
+
+def test_synthetic_config4_shape():
+    # KyTea-shaped: + dictionary with words up to 16 chars (Variable-length rows, general kernel)
+    mb = synth.gen_model_bccwj_shaped(n_patterns=20000, sample_sentences=40000, dict_words=20000)
+    p, o = make(mb), OraclePredictor(mb)
+    assert p.info["fast_path"] == 0 and p.info["max_char_pattern_len"] > 8
+    text, offs, _ = synth.gen_text(10000, 40)
+    check_batch(p, o, text, offs)
+    text, offs, _ = synth.gen_text(3000, ragged=True)
+    check_batch(p, o, text, offs)
+
+
+def test_blob_roundtrip_and_device_api(synth_model):
+    import ctypes as C
+    import torch
+    p = make(synth_model)
+    blob = p.export_blob()
+    q = vb.Predictor.from_blob(blob)
+    text, offs, _ = synth.gen_text(5000, 40)
+    a = p.predict_batch(text, offs)
+    b = q.predict_batch(text, offs)
+    assert np.array_equal(a.scores, b.scores) and np.array_equal(a.boundaries, b.boundaries)
+    # device-pointer entry point
+    dev = torch.device("cuda:0")
+    n = len(offs) - 1
+    d_text = torch.zeros(len(text) + 64, dtype=torch.uint8, device=dev)
+    d_text[: len(text)] = torch.from_numpy(text.copy()).to(dev)
+    d_off = torch.from_numpy(offs.astype(np.int64)).to(dev)
+    ws = torch.empty(vb.lib().vpt_workspace_size(n), dtype=torch.uint8, device=dev)
+    d_scores = torch.empty(len(text), dtype=torch.int32, device=dev)
+    d_bounds = torch.empty(len(text), dtype=torch.uint8, device=dev)
+    d_boff = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    d_status = torch.empty(n, dtype=torch.int32, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    rc = vb.lib().vpt_predict_batch_dev(q._h, d_text.data_ptr(), d_off.data_ptr(), n, ws.data_ptr(), ws.numel(),
+                                        d_scores.data_ptr(), d_bounds.data_ptr(), d_boff.data_ptr(),
+                                        d_status.data_ptr(), None, None, None, C.c_void_p(st))
+    assert rc == 0, vb.lib().vpt_last_error()
+    torch.cuda.synchronize()
+    nb = int(d_boff[-1].item())
+    assert nb == a.n_boundaries
+    assert np.array_equal(d_scores[:nb].cpu().numpy(), a.scores)
+    assert np.array_equal(d_bounds[:nb].cpu().numpy(), a.boundaries)
+    assert int(d_status.abs().sum().item()) == 0
+
+
+def test_full_size_properties():
+    """BASELINE config-2 size (1M x 40 chars) is checked through size-independent properties:
+    (1) a batch equals the concatenation of its halves (sentences are independent);
+    (2) scoring is invariant to the sentence's position in the batch (permutation);
+    (3) the sample scored by the oracle matches bit-exactly."""
+    mb = synth.gen_model_bccwj_shaped(n_patterns=30000, sample_sentences=60000)
+    p, o = make(mb), OraclePredictor(mb)
+    n = 1_000_000
+    text, offs, _ = synth.gen_text(n, 40)
+    full = p.predict_batch(text, offs)
+    assert full.n_boundaries == n * 39 and int(full.status.sum()) == 0
+    h = n // 2
+    a = p.predict_batch(text, offs[: h + 1])
+    b = p.predict_batch(text, offs[h:])
+    assert np.array_equal(np.concatenate([a.scores, b.scores]), full.scores)
+    assert np.array_equal(np.concatenate([a.boundaries, b.boundaries]), full.boundaries)
+    assert np.array_equal(full.boundaries, (full.scores > 0).astype(np.uint8))
+    # checksum of a strided sample against the oracle
+    idx = np.arange(0, n, 997)
+    for i in idx[:300]:
+        s = bytes(text[int(offs[i]):int(offs[i + 1])]).decode()
+        assert full.sentence_scores(i).tolist() == o.predict(s)[0].tolist()

@@ -1,0 +1,141 @@
+"""CPU checks of the product's host-side builder (merged rows, reversed-suffix node table, perfect hash,
+flat blob) by interpreting the blob with the kernels' probe sequence (tests/native/host_emul.cpp) and
+comparing with the oracle.  No GPU, no product compute path involved."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+from hypothesis import given, settings, strategies as st
+
+from golden import reference_kat as kat
+from vpt_testlib.bincode_model import encode_model
+from vpt_testlib.oracle import OraclePredictor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+GOLDEN = os.path.join(HERE, "golden")
+CSRC = os.path.join(ROOT, "vaporetto_b200", "csrc")
+
+
+@pytest.fixture(scope="module")
+def emul():
+    so = os.path.join(HERE, "native", "libhost_emul.so")
+    srcs = [os.path.join(HERE, "native", "host_emul.cpp")] + [os.path.join(CSRC, f) for f in
+                                                             ("predictor_build.cpp", "builder.cpp", "model.cpp")]
+    deps = srcs + [os.path.join(CSRC, f) for f in ("builder.hpp", "keys.hpp", "predictor_build.hpp", "common.hpp")]
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so] + srcs)
+    L = C.CDLL(so)
+    L.emul_predict.restype = C.c_long
+    L.emul_predict.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_char_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                               C.c_void_p, C.c_void_p]
+    L.emul_last_error.restype = C.c_char_p
+    return L
+
+
+def run(L, model_bytes, text, tags=False):
+    b = text.encode()
+    sc = np.zeros(len(b) + 1, np.int32)
+    cs = np.zeros(len(b) + 1, np.uint32)
+    ts = np.zeros(len(b) + 1, np.uint32)
+    info = np.zeros(4, np.int32)
+    n = L.emul_predict(model_bytes, len(model_bytes), int(tags), b, len(b), sc.ctypes.data, cs.ctypes.data,
+                       ts.ctypes.data, info.ctypes.data)
+    assert n > 0, L.emul_last_error()
+    return sc[: n - 1].tolist(), cs[:n].tolist(), ts[:n].tolist(), info.tolist()
+
+
+@pytest.mark.parametrize("name", sorted(kat.SCORE_CASES))
+def test_tables_on_reference_vectors(emul, name):
+    case = kat.SCORE_CASES[name]
+    sc, _, _, info = run(emul, encode_model(case["model"]), case["text"])
+    assert sc == case["scores"]
+
+
+@pytest.mark.parametrize("name", sorted(kat.TAG_SCORE_CASES))
+def test_tables_on_reference_vectors_tags(emul, name):
+    case = kat.TAG_SCORE_CASES[name]
+    mb = encode_model(case["model"])
+    sc, cs, ts, info = run(emul, mb, case["text"], tags=True)
+    assert sc == case["scores"]
+    o = OraclePredictor(mb, predict_tags=True)
+    _, _, ocs, ots = o.predict(case["text"], states=True)
+    assert cs == ocs.tolist()
+    assert ts == ots.tolist()
+    assert info[0] == 0
+
+
+def test_fast_path_selected(emul):
+    # n-gram-only W=3 models and short dictionary words fit the 6-wide inline rows
+    _, _, _, info = run(emul, encode_model(kat.PREDICTOR_TEST_MODEL), "この人は地球人だ")
+    assert info[0] == 1
+    _, _, _, info = run(emul, encode_model(kat.CHAR_ADD_SCORES_3["model"]), "我らは全世界の国民")
+    assert info[0] == 0  # 5-char dictionary word: rows wider than the inline window
+    _, _, _, info = run(emul, encode_model(kat.TYPE_ADD_SCORES["model"]), "我らは全世界の国民")
+    assert info[0] == 0 and info[2] == 1  # type window 4: automaton variant
+
+
+def test_fixture_models(emul):
+    for fn, texts in (("model.bin", list(kat.MODEL_BIN_SCORES)), ("tantivy_model.bin", [t for t, _ in kat.TANTIVY_TOKENIZE])):
+        with open(os.path.join(GOLDEN, fn), "rb") as f:
+            mb = f.read()
+        for tags in (False, True):
+            o = OraclePredictor(mb, predict_tags=tags)
+            for text in texts:
+                sc, cs, ts, _ = run(emul, mb, text, tags=tags)
+                osc, _, ocs, ots = o.predict(text, states=True)
+                assert sc == osc.tolist()
+                if tags:
+                    assert cs == ocs.tolist() and ts == ots.tolist()
+
+
+ALPHA = "あいうアイ人火星地球aB1。"
+chars = st.sampled_from(list(ALPHA))
+w = st.integers(-40000, 40000)
+
+
+@st.composite
+def models(draw):
+    cw = draw(st.integers(0, 5))
+    tw = draw(st.integers(0, 5))
+    cng = {}
+    for _ in range(draw(st.integers(0, 8))):
+        g = "".join(draw(st.lists(chars, min_size=1, max_size=5)))
+        full = max(2 * cw - len(g) + 1, 0)
+        cng[g] = draw(st.lists(w, min_size=0, max_size=full + 1))
+    dic = []
+    for _ in range(draw(st.integers(0, 6))):
+        g = "".join(draw(st.lists(chars, min_size=1, max_size=9)))
+        dic.append((g, draw(st.lists(w, min_size=0, max_size=len(g) + 2)), ""))
+    tng = {}
+    for _ in range(draw(st.integers(0, 6))):
+        g = bytes(draw(st.lists(st.integers(1, 6), min_size=1, max_size=5)))
+        full = max(2 * tw - len(g) + 1, 0)
+        tng[g] = draw(st.lists(w, min_size=0, max_size=full + 1))
+    tms = []
+    for t in range(draw(st.integers(0, 2))):
+        cn = [("".join(draw(st.lists(chars, min_size=1, max_size=4))),
+               [(draw(st.integers(0, cw)), draw(st.lists(w, min_size=1, max_size=3)))]) for _ in range(draw(st.integers(0, 3)))]
+        tn = [(bytes(draw(st.lists(st.integers(1, 6), min_size=1, max_size=4))),
+               [(draw(st.integers(0, tw)), draw(st.lists(w, min_size=1, max_size=3)))]) for _ in range(draw(st.integers(0, 3)))]
+        tms.append(dict(token="tok%d" % t, tags=[["x", "y"]], char_ngrams=cn, type_ngrams=tn, bias=[1, 2]))
+    return dict(char_ngrams=list(cng.items()), type_ngrams=list(tng.items()), dict=dic,
+                bias=draw(st.sampled_from([0, 5, -7, 2**31 - 1])), char_window=cw, type_window=tw, tag_models=tms)
+
+
+@settings(max_examples=300, deadline=None)
+@given(models(), st.lists(chars, min_size=1, max_size=24), st.booleans())
+def test_tables_equal_oracle(emul, model, text, tags):
+    text = "".join(text)
+    mb = encode_model(model)
+    o = OraclePredictor(mb, predict_tags=tags)
+    osc, _, ocs, ots = o.predict(text, states=True)
+    sc, cs, ts, info = run(emul, mb, text, tags=tags)
+    assert sc == osc.tolist()
+    if tags and model["tag_models"]:
+        if o.type_variant == 1:
+            assert ts == ots.tolist()
+        if model["char_window"] and (model["char_ngrams"] or model["dict"]):
+            assert cs == ocs.tolist()

@@ -1,0 +1,392 @@
+"""vaporetto_b200 — Python mirror of the reference's `Model` / `Predictor` / `Sentence` API
+(vaporetto/src/lib.rs:82-91) over the C ABI of libvaporetto_b200.so (include/vaporetto_b200.h).
+
+The compute path is the CUDA library; there is no CPU fallback.  Importing this package works without a GPU
+(so the ABI can be inspected), creating a `Predictor` does not.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+__all__ = ["Model", "Predictor", "Sentence", "VaporettoError", "CharacterBoundary", "CharacterType", "lib", "build",
+           "BatchResult"]
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_PKG, "libvaporetto_b200.so")
+
+
+def build(force: bool = False) -> str:
+    """Compile the CUDA extension in-tree with nvcc for sm_100a (see csrc/Makefile)."""
+    import subprocess
+    csrc = os.path.join(_PKG, "csrc")
+    if force and os.path.exists(_SO):
+        os.remove(_SO)
+    subprocess.check_call(["make", "-C", csrc, "-s"])
+    return _SO
+
+
+class VaporettoError(Exception):
+    """Mirror of `VaporettoError` (vaporetto/src/errors.rs:15-38)."""
+
+    KIND = {1: "InvalidModel", 2: "InvalidArgument", 3: "InvalidSentence", 4: "DecodeError", 5: "IOError",
+            16: "CudaError", 17: "Unsupported", 18: "Internal"}
+
+    def __init__(self, code: int, msg: str):
+        super().__init__(msg)
+        self.code = code
+        self.kind = self.KIND.get(code, "Unknown")
+
+
+class CharacterBoundary:  # sentence.rs:70-82
+    NotWordBoundary = 0
+    WordBoundary = 1
+    Unknown = 2
+
+
+class CharacterType:  # sentence.rs:9-29
+    Digit, Roman, Hiragana, Katakana, Kanji, Other = 1, 2, 3, 4, 5, 6
+
+
+class _Info(C.Structure):
+    _fields_ = [("device", C.c_int32), ("predict_tags", C.c_int32), ("n_tags", C.c_int32), ("char_scorer", C.c_int32),
+                ("type_scorer", C.c_int32), ("fast_path", C.c_int32), ("bias", C.c_int32), ("char_window", C.c_int32),
+                ("type_window", C.c_int32), ("n_char_patterns", C.c_uint32), ("n_type_patterns", C.c_uint32),
+                ("n_char_nodes", C.c_uint32), ("n_type_nodes", C.c_uint32), ("max_char_pattern_len", C.c_uint32),
+                ("blob_bytes", C.c_uint64), ("kernel_launches_per_batch", C.c_int32)]
+
+
+# every symbol include/vaporetto_b200.h declares: (name, restype, argtypes)
+_P = C.c_void_p
+ABI = [
+    ("vpt_last_error", C.c_char_p, []),
+    ("vpt_version", C.c_char_p, []),
+    ("vpt_model_read", C.c_int, [C.c_char_p, C.c_size_t, C.POINTER(_P), C.POINTER(C.c_size_t)]),
+    ("vpt_model_free", None, [_P]),
+    ("vpt_predictor_new", C.c_int, [_P, C.c_int, C.c_int, C.POINTER(_P)]),
+    ("vpt_predictor_free", None, [_P]),
+    ("vpt_predictor_get_info", C.c_int, [_P, C.POINTER(_Info)]),
+    ("vpt_predictor_blob_size", C.c_uint64, [_P]),
+    ("vpt_predictor_blob_export", C.c_int, [_P, _P, C.c_uint64]),
+    ("vpt_predictor_from_blob", C.c_int, [_P, C.c_uint64, C.c_int, C.POINTER(_P)]),
+    ("vpt_predict_batch", C.c_int, [_P, _P, _P, C.c_size_t, _P, _P, C.c_size_t, _P, _P, _P, _P, C.c_size_t, _P,
+                                    C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    ("vpt_workspace_size", C.c_uint64, [C.c_size_t]),
+    ("vpt_predict_batch_dev", C.c_int, [_P, _P, _P, C.c_size_t, _P, C.c_uint64, _P, _P, _P, _P, _P, _P, _P, _P]),
+    ("vpt_predict", C.c_int, [_P, C.c_char_p, C.c_size_t, _P, _P, C.c_size_t, _P, _P, C.c_size_t, C.POINTER(C.c_uint64)]),
+    ("vpt_fill_tags", C.c_int, [_P, C.c_char_p, C.c_size_t, _P, _P, _P, _P, _P, _P, C.c_size_t]),
+    ("vpt_tag_string", C.c_char_p, [_P, C.c_uint32, C.c_uint32, C.c_uint32]),
+    ("vpt_tag_n_candidates", C.c_uint32, [_P, C.c_uint32, C.c_uint32]),
+    ("vpt_tag_score_len", C.c_uint32, [_P, C.c_uint32]),
+    ("vpt_tag_n_tokens", C.c_uint32, [_P]),
+    ("vpt_char_types", C.c_int, [C.c_char_p, C.c_size_t, _P, C.c_size_t, C.POINTER(C.c_uint64)]),
+    ("vpt_write_tokenized_text", C.c_int, [_P, C.c_char_p, C.c_size_t, _P, _P, _P, _P, C.c_size_t,
+                                           C.POINTER(C.c_uint64)]),
+]
+
+_lib = None
+
+
+def lib():
+    """Loads libvaporetto_b200.so; fails loudly if the extension has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            raise ImportError(f"{_SO} is missing: the CUDA extension must be built first "
+                              f"(python -c 'import __graft_entry__ as g; g.build()'); there is no CPU fallback")
+        L = C.CDLL(_SO)
+        for name, res, args in ABI:
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise VaporettoError(rc, lib().vpt_last_error().decode("utf-8", "replace"))
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data
+
+
+class Model:
+    """`vaporetto::Model` (model.rs:58-168): an on-disk model image."""
+
+    def __init__(self, handle, consumed: int):
+        self._h = handle
+        self.consumed = consumed
+
+    @classmethod
+    def read(cls, src) -> "Model":
+        """`Model::read` (model.rs:142-153): file-like object or bytes with the raw (un-zstd'd) model."""
+        data = src if isinstance(src, (bytes, bytearray, memoryview)) else src.read()
+        return cls.read_slice(bytes(data))[0]
+
+    @classmethod
+    def read_slice(cls, data: bytes):
+        """`Model::read_slice` (model.rs:127-134): returns (model, remaining bytes)."""
+        h = _P()
+        used = C.c_size_t()
+        _check(lib().vpt_model_read(data, len(data), C.byref(h), C.byref(used)))
+        return cls(h, used.value), data[used.value:]
+
+    def _take(self):
+        h, self._h = self._h, None
+        if h is None:
+            raise VaporettoError(2, "InvalidArgumentError: model: already consumed by Predictor::new")
+        return h
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().vpt_model_free(self._h)
+            self._h = None
+
+
+class BatchResult:
+    """Outputs of a batched predict: flat arrays + per-sentence offsets."""
+
+    def __init__(self, scores, boundaries, bound_offsets, status, char_states=None, type_states=None,
+                 char_offsets=None):
+        self.scores = scores
+        self.boundaries = boundaries
+        self.bound_offsets = bound_offsets
+        self.status = status
+        self.char_states = char_states
+        self.type_states = type_states
+        self.char_offsets = char_offsets
+
+    def sentence_scores(self, i: int) -> np.ndarray:
+        return self.scores[int(self.bound_offsets[i]):int(self.bound_offsets[i + 1])]
+
+    def sentence_boundaries(self, i: int) -> np.ndarray:
+        return self.boundaries[int(self.bound_offsets[i]):int(self.bound_offsets[i + 1])]
+
+
+class Predictor:
+    """`vaporetto::Predictor` (predictor.rs:434-665) resident on one CUDA device."""
+
+    def __init__(self, model: Model, predict_tags: bool = False, device: int = 0):
+        """`Predictor::new(model, predict_tags)` — consumes `model` (predictor.rs:450)."""
+        h = _P()
+        _check(lib().vpt_predictor_new(model._take(), int(predict_tags), device, C.byref(h)))
+        self._h = h
+        self._load_info()
+
+    @classmethod
+    def from_blob(cls, blob, device: int = 0) -> "Predictor":
+        self = cls.__new__(cls)
+        b = np.ascontiguousarray(np.frombuffer(blob, dtype=np.uint8))
+        h = _P()
+        _check(lib().vpt_predictor_from_blob(b.ctypes.data, b.size, device, C.byref(h)))
+        self._h = h
+        self._load_info()
+        return self
+
+    def _load_info(self):
+        info = _Info()
+        _check(lib().vpt_predictor_get_info(self._h, C.byref(info)))
+        self.info = {k: getattr(info, k) for k, _ in _Info._fields_}
+        self.n_tags = info.n_tags
+        self.predict_tags = bool(info.predict_tags)
+
+    def export_blob(self) -> np.ndarray:
+        n = lib().vpt_predictor_blob_size(self._h)
+        out = np.empty(n, np.uint8)
+        _check(lib().vpt_predictor_blob_export(self._h, out.ctypes.data, n))
+        return out
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().vpt_predictor_free(self._h)
+            self._h = None
+
+    # -- predict ------------------------------------------------------------------------------------
+    def predict(self, sentence: "Sentence") -> None:
+        """`Predictor::predict(&self, &mut Sentence)` (predictor.rs:518-543)."""
+        b = sentence._bytes
+        n = sentence._n
+        scores = np.zeros(max(n - 1, 1), np.int32)
+        bounds = np.zeros(max(n - 1, 1), np.uint8)
+        want = self.info["char_scorer"] == 2 or self.info["type_scorer"] == 3
+        cs = np.full(n, 0xFFFFFFFF, np.uint32) if want else None
+        ts = np.full(n, 0xFFFFFFFF, np.uint32) if want else None
+        nch = C.c_uint64()
+        _check(lib().vpt_predict(self._h, b, len(b), scores.ctypes.data, bounds.ctypes.data, max(n - 1, 1), _ptr(cs),
+                                 _ptr(ts), n, C.byref(nch)))
+        assert nch.value == n
+        sentence._scores = scores[: n - 1]
+        sentence._boundaries = bounds[: n - 1].copy()
+        sentence._char_states = cs
+        sentence._type_states = ts
+        sentence._predictor = self
+        sentence._tags = None
+
+    def predict_batch(self, text, offsets, want_scores: bool = True, want_states: bool = False,
+                      out: Optional[BatchResult] = None) -> BatchResult:
+        """Batched predict over host buffers (vpt_predict_batch).  text: uint8 array / bytes,
+        offsets: uint64 [n+1].  Outputs are sized from the text length unless `out` supplies buffers."""
+        t = np.frombuffer(text, np.uint8) if isinstance(text, (bytes, bytearray)) else np.ascontiguousarray(text, np.uint8)
+        off = np.ascontiguousarray(offsets, np.uint64)
+        n = off.size - 1
+        nbytes = int(off[-1] - off[0]) if n > 0 else 0
+        if out is None:
+            cap = max(nbytes, 1)
+            out = BatchResult(np.empty(cap, np.int32) if want_scores else None, np.empty(cap, np.uint8),
+                              np.empty(n + 1, np.uint64), np.empty(max(n, 1), np.int32),
+                              np.empty(cap, np.uint32) if want_states else None,
+                              np.empty(cap, np.uint32) if want_states else None,
+                              np.empty(n + 1, np.uint64))
+        nb = C.c_uint64()
+        nc = C.c_uint64()
+        _check(lib().vpt_predict_batch(self._h, t.ctypes.data, off.ctypes.data, n, _ptr(out.scores),
+                                       out.boundaries.ctypes.data, out.boundaries.size, out.bound_offsets.ctypes.data,
+                                       _ptr(out.status), _ptr(out.char_states), _ptr(out.type_states),
+                                       0 if out.char_states is None else out.char_states.size,
+                                       _ptr(out.char_offsets), C.byref(nb), C.byref(nc)))
+        res = BatchResult(None if out.scores is None else out.scores[: nb.value], out.boundaries[: nb.value],
+                          out.bound_offsets, out.status[:n],
+                          None if out.char_states is None else out.char_states[: nc.value],
+                          None if out.type_states is None else out.type_states[: nc.value], out.char_offsets)
+        res.n_boundaries = nb.value
+        res.n_chars = nc.value
+        return res
+
+
+class Token:
+    """`vaporetto::Token` (sentence.rs:1195-1258)."""
+
+    def __init__(self, sentence: "Sentence", start: int, end: int):
+        self._s, self._start, self._end = sentence, start, end
+
+    def surface(self) -> str:
+        p = self._s._pos
+        return self._s._bytes[p[self._start]:p[self._end]].decode("utf-8")
+
+    def start(self) -> int:
+        return self._start
+
+    def end(self) -> int:
+        return self._end
+
+    def tags(self) -> List[Optional[str]]:
+        k = self._s.n_tags()
+        return self._s.tags()[(self._end - 1) * k:self._end * k]
+
+
+class Sentence:
+    """`vaporetto::Sentence` (sentence.rs:85-1193), raw-text subset used around `predict`."""
+
+    def __init__(self, text: str):
+        self._set(text)
+
+    @classmethod
+    def from_raw(cls, text: str) -> "Sentence":
+        """`Sentence::from_raw` (sentence.rs:217-247)."""
+        return cls(text)
+
+    def update_raw(self, text: str) -> None:
+        """`Sentence::update_raw` (sentence.rs:264-283); on error the sentence becomes " "."""
+        try:
+            self._set(text)
+        except VaporettoError:
+            self._set(" ")
+            raise
+
+    def _set(self, text: str):
+        b = text.encode("utf-8") if isinstance(text, str) else bytes(text)
+        types = np.zeros(max(len(b), 1), np.uint8)
+        n = C.c_uint64()
+        _check(lib().vpt_char_types(b, len(b), types.ctypes.data, types.size, C.byref(n)))
+        self._bytes = b
+        self._n = n.value
+        self._types = types[: self._n].copy()
+        starts = [i for i, c in enumerate(b) if (c & 0xC0) != 0x80]
+        self._pos = starts + [len(b)]
+        self._boundaries = np.full(self._n - 1, CharacterBoundary.Unknown, np.uint8)
+        self._scores = np.zeros(0, np.int32)
+        self._char_states = None
+        self._type_states = None
+        self._predictor = None
+        self._tags = None
+        self._tag_token = None
+        self._tag_cand = None
+
+    def as_raw_text(self) -> str:
+        return self._bytes.decode("utf-8")
+
+    def char_types(self) -> np.ndarray:
+        return self._types
+
+    def boundaries(self) -> np.ndarray:
+        return self._boundaries
+
+    def boundaries_mut(self) -> np.ndarray:
+        return self._boundaries
+
+    def boundary_scores(self) -> np.ndarray:
+        """`Sentence::boundary_scores` (sentence.rs:1040-1046)."""
+        return self._scores
+
+    def n_tags(self) -> int:
+        return 0 if self._tags is None else self._predictor.n_tags
+
+    def fill_tags(self) -> None:
+        """`Sentence::fill_tags` (sentence.rs:1144-1148) -> `Predictor::predict_tags` (predictor.rs:546-637)."""
+        p = self._predictor
+        if p is None:
+            return
+        k = p.n_tags
+        tt = np.full(self._n, -1, np.int32)
+        tc = np.full(max(self._n * k, 1), -1, np.int32)
+        _check(lib().vpt_fill_tags(p._h, self._bytes, len(self._bytes), self._boundaries.ctypes.data,
+                                   _ptr(self._char_states), _ptr(self._type_states), tt.ctypes.data, tc.ctypes.data,
+                                   None, 0))
+        self._tag_token, self._tag_cand = tt, tc
+        tags: List[Optional[str]] = []
+        for i in range(self._n):
+            for s in range(k):
+                c = tc[i * k + s]
+                if tt[i] < 0 or c < 0:
+                    tags.append(None)
+                else:
+                    tags.append(lib().vpt_tag_string(p._h, int(tt[i]), s, int(c)).decode("utf-8"))
+        self._tags = tags
+
+    def tags(self) -> List[Optional[str]]:
+        return [] if self._tags is None else self._tags
+
+    def iter_tokens(self):
+        """`Sentence::iter_tokens` (sentence.rs:819; TokenIterator :1273-1299)."""
+        start, skip = 0, False
+        for i, b in enumerate(self._boundaries):
+            if b == CharacterBoundary.WordBoundary:
+                if not skip:
+                    yield Token(self, start, i + 1)
+                skip = False
+                start = i + 1
+            elif b == CharacterBoundary.Unknown:
+                skip = True
+        if not skip:
+            yield Token(self, start, self._n)
+
+    def write_tokenized_text(self) -> str:
+        """`Sentence::write_tokenized_text` (sentence.rs:850-886)."""
+        p = self._predictor
+        cap = 8 * len(self._bytes) + 64
+        if self._tags is not None:
+            cap += 64 * self._n * max(p.n_tags, 1)
+        buf = C.create_string_buffer(cap)
+        ln = C.c_uint64()
+        have = self._tags is not None
+        _check(lib().vpt_write_tokenized_text(p._h if p else None, self._bytes, len(self._bytes),
+                                              self._boundaries.ctypes.data,
+                                              self._tag_token.ctypes.data if have else None,
+                                              self._tag_cand.ctypes.data if have else None, buf, cap, C.byref(ln)))
+        assert ln.value < cap
+        return buf.raw[: ln.value].decode("utf-8")

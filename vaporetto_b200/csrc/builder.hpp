@@ -1,0 +1,73 @@
+// Builds the flat, device-resident form of a predictor from a Model.
+//
+// What the reference does at `Predictor::new` (vaporetto/src/predictor.rs:450-508):
+//   * CharScorer::new (char_scorer.rs:92-124) / TypeScorer::new (type_scorer.rs:104-143) select the
+//     scorer variants, merge weights per pattern string and suffix-sum them
+//     (CharWeightMerger, char_scorer.rs:29-79) and build a daachorse automaton.
+// What this build does instead (B200-first):
+//   * the same merged weight rows, but no automaton.  Matching is position-parallel on the GPU:
+//     for the text ending at a character the kernel looks up the longest suffix that is a suffix of
+//     some pattern in a *perfect-hash table of reversed-pattern trie nodes*; every node record carries
+//     the merged weight row of the longest pattern that is a suffix of the node string, so one probe
+//     yields what `find_overlapping_no_suffix_iter` + `weights[id]` yield in the reference.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "keys.hpp"
+#include "model.hpp"
+
+namespace vpt {
+
+
+// One merged weight row: adds w[k] to boundary (last_char_index + off + k).
+struct Row {
+    bool present = false;
+    int off = 0;
+    std::vector<int32_t> w;
+};
+
+// Per-pattern tag weights, suffix-merged like the boundary rows
+// (PositionalWeightWithTag, predictor.rs:217-262): (token_id, rel_position) -> weights.
+using TagInfo = std::vector<std::pair<std::pair<uint32_t, uint8_t>, std::vector<int32_t>>>;
+
+struct PatternSet {
+    bool utf8 = true;                          // char patterns (code points) or type patterns (bytes)
+    std::vector<std::string> raw;              // pattern bytes, sorted byte-lexicographically; index = pattern id
+    std::vector<std::vector<uint32_t>> syms;   // the same patterns as symbol sequences
+    std::vector<Row> rows;                     // merged boundary rows (zero-trimmed)
+    std::vector<TagInfo> tags;                 // merged tag weights per pattern (tag variant only)
+    bool tag_variant = false;
+    size_t max_len = 0;                        // longest pattern in symbols
+};
+
+struct NodeTable {
+    bool present = false;
+    bool fast = false;          // records are FastRecord (all rows fit the inline window)
+    int r0 = 0;                 // inline window start (fast) — relative position of w[0]
+    TableGeom geom;
+    uint32_t n_nodes = 0;
+    uint32_t max_depth = 0;
+    std::vector<uint8_t> records;       // nslots * 32 bytes
+    std::vector<uint16_t> seeds;        // nbuckets
+    std::vector<uint32_t> slot_node;    // nslots: node id of the record in the slot (deep keys)
+    std::vector<uint32_t> slot_pid;     // nslots: best pattern id (tag states); fast tables only
+    std::vector<int32_t> pool;          // general rows
+    int rel_min = 0, rel_max = 0;       // union extent of all rows: [rel_min, rel_max)
+};
+
+// Builds merged pattern rows.  `dict` may be null (type scorer).
+PatternSet build_patterns(const std::vector<NgramEntry>& ngrams, const std::vector<DictEntry>* dict, uint8_t window,
+                          const std::vector<const std::vector<TagNgramEntry>*>& tag_ngrams, bool utf8);
+
+// Reversed-pattern trie -> perfect-hash table.  `force_general` disables the inline format.
+NodeTable build_node_table(const PatternSet& ps, bool force_general);
+
+// Type score table of TypeScorerBoundaryCache::new (type_scorer/boundary_scorer_cache.rs:22-56).
+std::vector<int32_t> build_type_cache(const std::vector<NgramEntry>& type_ngrams, uint8_t window);
+
+uint32_t table_slot(const TableGeom& g, const uint16_t* seeds, uint64_t key);
+
+}  // namespace vpt

@@ -1,0 +1,608 @@
+// C ABI (include/vaporetto_b200.h) — host side of the predictor: model parsing, table build, upload,
+// batch staging, tag prediction and the Sentence helpers.  Compiled with nvcc (needs cuda_runtime.h).
+#include "../../include/vaporetto_b200.h"
+
+#include <algorithm>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "builder.hpp"
+#include "common.hpp"
+#include "device_model.hpp"
+#include "model.hpp"
+#include "predictor_build.hpp"
+
+using namespace vpt;
+
+struct vpt_model {
+    Model m;
+};
+
+namespace {
+
+void cuda_check(cudaError_t e, const char* what) {
+    if (e != cudaSuccess)
+        throw Error(kCudaError, std::string("CUDA error in ") + what + ": " + cudaGetErrorString(e));
+}
+
+// Per-call scratch: a stream plus grow-only device buffers.
+struct Scratch {
+    cudaStream_t stream = nullptr;
+    void* d_text = nullptr; size_t text_cap = 0;
+    void* d_off = nullptr; size_t off_cap = 0;
+    void* d_ws = nullptr; size_t ws_cap = 0;
+    void* d_status = nullptr; size_t status_cap = 0;
+    void* d_boff = nullptr; size_t boff_cap = 0;
+    void* d_coff = nullptr; size_t coff_cap = 0;
+    void* d_scores = nullptr; size_t scores_cap = 0;
+    void* d_bounds = nullptr; size_t bounds_cap = 0;
+    void* d_cst = nullptr; size_t cst_cap = 0;
+    void* d_tst = nullptr; size_t tst_cap = 0;
+    uint64_t* h_totals = nullptr;  // pinned, 2 x u64
+    ~Scratch() {
+        for (void* p : {d_text, d_off, d_ws, d_status, d_boff, d_coff, d_scores, d_bounds, d_cst, d_tst})
+            if (p) cudaFree(p);
+        if (h_totals) cudaFreeHost(h_totals);
+        if (stream) cudaStreamDestroy(stream);
+    }
+    static void ensure(void*& p, size_t& cap, size_t need) {
+        if (need <= cap) return;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = align_up(need + need / 8 + 256, 256);
+        cuda_check(cudaMalloc(&p, want), "cudaMalloc(scratch)");
+        cap = want;
+    }
+};
+
+}  // namespace
+
+struct vpt_predictor : HostPredictor {
+    int device = 0;
+    bool from_blob = false;
+    void* d_blob = nullptr;
+    DevModel dm;
+    // scratch pool
+    mutable std::mutex mu;
+    mutable std::vector<std::unique_ptr<Scratch>> pool;
+
+    ~vpt_predictor() {
+        if (d_blob) {
+            cudaSetDevice(device);
+            pool.clear();
+            cudaFree(d_blob);
+        }
+    }
+};
+
+namespace {
+
+int fail(const Error& e) {
+    set_last_error(e.what());
+    return e.code;
+}
+int fail(const std::exception& e) {
+    set_last_error(std::string("internal error: ") + e.what());
+    return kInternal;
+}
+
+#define VPT_API_BEGIN try {
+#define VPT_API_END \
+    } catch (const Error& e) { return fail(e); } \
+      catch (const std::exception& e) { return fail(e); }
+
+DevTable dev_table(const BlobTable& bt, const uint8_t* base) {
+    DevTable d;
+    d.present = bt.present;
+    if (!bt.present) return d;
+    d.fast = bt.fast;
+    d.r0 = bt.r0;
+    d.max_depth = bt.max_depth;
+    d.nslots = bt.nslots;
+    d.nbuckets = bt.nbuckets;
+    d.salt = bt.salt;
+    d.records = base + bt.rec_off;
+    d.seeds = reinterpret_cast<const uint16_t*>(base + bt.seeds_off);
+    d.slot_node = reinterpret_cast<const uint32_t*>(base + bt.node_off);
+    d.slot_pid = reinterpret_cast<const uint32_t*>(base + bt.pid_off);
+    d.pool = reinterpret_cast<const int32_t*>(base + bt.pool_off);
+    return d;
+}
+
+void upload(vpt_predictor& p) {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        throw Error(kCudaError, std::string("no usable CUDA device (vaporetto_b200 has no CPU fallback): ") +
+                                    cudaGetErrorString(e));
+    if (p.device < 0 || p.device >= ndev) throw Error(kInvalidArgument, "InvalidArgumentError: device: out of range");
+    cuda_check(cudaSetDevice(p.device), "cudaSetDevice");
+    cuda_check(cudaMalloc(&p.d_blob, align_up(p.blob.size(), 256)), "cudaMalloc(model)");
+    cuda_check(cudaMemcpy(p.d_blob, p.blob.data(), p.blob.size(), cudaMemcpyHostToDevice), "cudaMemcpy(model)");
+    const uint8_t* base = static_cast<const uint8_t*>(p.d_blob);
+    const BlobHeader& h = p.hdr;
+    p.dm = DevModel();
+    p.dm.ct = dev_table(h.ct, base);
+    p.dm.tt = dev_table(h.tt, base);
+    p.dm.type_cache_window = h.type_cache_window;
+    p.dm.type_cache = h.type_cache_window ? reinterpret_cast<const int32_t*>(base + h.type_cache_off) : nullptr;
+    p.dm.bias = h.bias;
+    p.dm.char_window = h.char_window;
+    p.dm.type_window = h.type_window;
+    p.dm.emit_states = h.emit_states;
+}
+
+struct ScratchLease {
+    const vpt_predictor& p;
+    std::unique_ptr<Scratch> s;
+    explicit ScratchLease(const vpt_predictor& pr) : p(pr) {
+        {
+            std::lock_guard<std::mutex> g(p.mu);
+            if (!p.pool.empty()) { s = std::move(p.pool.back()); p.pool.pop_back(); }
+        }
+        if (!s) {
+            s.reset(new Scratch());
+            cuda_check(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking), "cudaStreamCreate");
+            cuda_check(cudaMallocHost(reinterpret_cast<void**>(&s->h_totals), 16), "cudaMallocHost");
+        }
+    }
+    ~ScratchLease() {
+        std::lock_guard<std::mutex> g(p.mu);
+        p.pool.push_back(std::move(s));
+    }
+};
+
+struct WorkspaceLayout {
+    size_t n_chars, local_bound, local_char, group_bound, group_char, total;
+};
+WorkspaceLayout workspace_layout(size_t n) {
+    WorkspaceLayout l;
+    const size_t ng = (n + kGroup - 1) / kGroup;
+    size_t o = 0;
+    l.n_chars = o; o = align_up(o + 4 * n, 256);
+    l.local_bound = o; o = align_up(o + 4 * n, 256);
+    l.local_char = o; o = align_up(o + 4 * n, 256);
+    l.group_bound = o; o = align_up(o + 8 * (ng + 1), 256);
+    l.group_char = o; o = align_up(o + 8 * (ng + 1), 256);
+    l.total = o + 256;
+    return l;
+}
+
+void bind_workspace(BatchArgs& a, void* ws, size_t n) {
+    const WorkspaceLayout l = workspace_layout(n);
+    uint8_t* b = static_cast<uint8_t*>(ws);
+    a.n_chars = reinterpret_cast<uint32_t*>(b + l.n_chars);
+    a.local_bound = reinterpret_cast<uint32_t*>(b + l.local_bound);
+    a.local_char = reinterpret_cast<uint32_t*>(b + l.local_char);
+    a.group_bound = reinterpret_cast<uint64_t*>(b + l.group_bound);
+    a.group_char = reinterpret_cast<uint64_t*>(b + l.group_char);
+}
+
+// ---- host-side text helpers ------------------------------------------------------------------------
+
+// Sentence::parse_raw checks (reference sentence.rs:160-196)
+void check_raw_text(const uint8_t* s, size_t n) {
+    if (!is_valid_utf8(s, n)) throw Error(kInvalidArgument, "InvalidArgumentError: text: must be valid UTF-8");
+    if (memchr(s, 0, n) != nullptr) throw Error(kInvalidArgument, "InvalidArgumentError: text: must not contain NULL");
+    if (n == 0) throw Error(kInvalidArgument, "InvalidArgumentError: text: must contain at least one character");
+}
+
+// CharacterType::get_type (reference sentence.rs:50-67)
+uint8_t host_char_type(uint32_t c) {
+    struct R { uint32_t lo, hi; uint8_t t; };
+    static const R ranges[] = {
+        {0x30, 0x39, 1}, {0xFF10, 0xFF19, 1},
+        {0x41, 0x5A, 2}, {0x61, 0x7A, 2}, {0xFF21, 0xFF3A, 2}, {0xFF41, 0xFF5A, 2},
+        {0x3040, 0x3096, 3},
+        {0x30A0, 0x30FA, 4}, {0x30FC, 0x30FF, 4}, {0xFF66, 0xFF9F, 4},
+        {0x3400, 0x4DBF, 5}, {0x4E00, 0x9FFF, 5}, {0xF900, 0xFAFF, 5}, {0x20000, 0x2A6DF, 5},
+        {0x2A700, 0x2B73F, 5}, {0x2B740, 0x2B81F, 5}, {0x2B820, 0x2CEAF, 5}, {0x2F800, 0x2FA1F, 5},
+    };
+    for (const R& r : ranges) if (c >= r.lo && c <= r.hi) return r.t;
+    return 6;
+}
+
+// byte offset of every character start, plus the end (char_to_str_pos, sentence.rs:100)
+std::vector<uint32_t> char_starts(const uint8_t* s, size_t n) {
+    std::vector<uint32_t> v;
+    for (size_t i = 0; i < n; ++i) if ((s[i] & 0xC0) != 0x80) v.push_back(uint32_t(i));
+    v.push_back(uint32_t(n));
+    return v;
+}
+
+void add_truncated(const std::vector<int32_t>& w, std::vector<int32_t>& ys) {  // WeightVector::add_scores
+    const size_t n = std::min(w.size(), ys.size());
+    for (size_t i = 0; i < n; ++i) ys[i] = wrapping_add(ys[i], w[i]);
+}
+
+void add_tag_scores(const TagWeightMap& tw, uint32_t token, size_t pos, const uint32_t* states, size_t n,
+                    std::vector<int32_t>& scores) {  // boundary_tag_scorer.rs:154-174
+    const auto& per_rel = tw[token];
+    for (size_t r = 0; r < per_rel.size() && pos + r < n; ++r) {
+        auto it = per_rel[r].find(states[pos + r]);
+        if (it != per_rel[r].end()) add_truncated(it->second, scores);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* vpt_last_error(void) { return last_error(); }
+const char* vpt_version(void) { return "vaporetto_b200 0.1.0 sm_100a"; }
+
+int vpt_model_read(const uint8_t* data, size_t len, vpt_model** out, size_t* consumed) {
+    VPT_API_BEGIN
+    if (!out) throw Error(kInvalidArgument, "InvalidArgumentError: out: must not be NULL");
+    *out = nullptr;
+    std::unique_ptr<vpt_model> m(new vpt_model());
+    m->m = Model::read(data, len, consumed);
+    *out = m.release();
+    return kOk;
+    VPT_API_END
+}
+
+void vpt_model_free(vpt_model* model) { delete model; }
+
+int vpt_predictor_new(vpt_model* model, int predict_tags, int device, vpt_predictor** out) {
+    std::unique_ptr<vpt_model> owned(model);  // consumed like Predictor::new(model, ..)
+    VPT_API_BEGIN
+    if (!out || !model) throw Error(kInvalidArgument, "InvalidArgumentError: model/out: must not be NULL");
+    *out = nullptr;
+    std::unique_ptr<vpt_predictor> p(new vpt_predictor());
+    static_cast<HostPredictor&>(*p) = build_host_predictor(owned->m, predict_tags != 0);
+    p->device = device;
+    upload(*p);
+    *out = p.release();
+    return kOk;
+    VPT_API_END
+}
+
+void vpt_predictor_free(vpt_predictor* predictor) { delete predictor; }
+
+int vpt_predictor_get_info(const vpt_predictor* p, vpt_predictor_info* o) {
+    VPT_API_BEGIN
+    if (!p || !o) throw Error(kInvalidArgument, "InvalidArgumentError: predictor/out: must not be NULL");
+    memset(o, 0, sizeof *o);
+    o->device = p->device;
+    o->predict_tags = p->predict_tags;
+    o->n_tags = int32_t(p->n_tags);
+    o->char_scorer = p->hdr.char_variant;
+    o->type_scorer = p->hdr.type_variant;
+    o->fast_path = (!p->dm.ct.present || p->dm.ct.fast) && !p->dm.tt.present && !p->dm.emit_states;
+    o->bias = p->hdr.bias;
+    o->char_window = p->hdr.char_window;
+    o->type_window = p->hdr.type_window;
+    o->n_char_patterns = p->hdr.ct.n_patterns;
+    o->n_type_patterns = p->hdr.tt.n_patterns;
+    o->n_char_nodes = p->hdr.ct.n_nodes;
+    o->n_type_nodes = p->hdr.tt.n_nodes;
+    o->max_char_pattern_len = uint32_t(p->hdr.max_char_pattern_len);
+    o->blob_bytes = p->blob.size();
+    o->kernel_launches_per_batch = launches_per_batch(p->dm);
+    return kOk;
+    VPT_API_END
+}
+
+uint64_t vpt_predictor_blob_size(const vpt_predictor* p) { return p ? p->blob.size() : 0; }
+
+int vpt_predictor_blob_export(const vpt_predictor* p, void* dst, uint64_t capacity) {
+    VPT_API_BEGIN
+    if (!p || !dst) throw Error(kInvalidArgument, "InvalidArgumentError: predictor/dst: must not be NULL");
+    if (capacity < p->blob.size()) throw Error(kInvalidArgument, "InvalidArgumentError: capacity: too small");
+    memcpy(dst, p->blob.data(), p->blob.size());
+    return kOk;
+    VPT_API_END
+}
+
+int vpt_predictor_from_blob(const void* blob, uint64_t len, int device, vpt_predictor** out) {
+    VPT_API_BEGIN
+    if (!blob || !out) throw Error(kInvalidArgument, "InvalidArgumentError: blob/out: must not be NULL");
+    *out = nullptr;
+    BlobHeader h;
+    if (len < sizeof h) throw Error(kInvalidModel, "InvalidModelError: blob too short");
+    memcpy(&h, blob, sizeof h);
+    if (memcmp(h.magic, kBlobMagic, 8) != 0 || h.total_bytes != len)
+        throw Error(kInvalidModel, "InvalidModelError: not a vaporetto_b200 model blob");
+    std::unique_ptr<vpt_predictor> p(new vpt_predictor());
+    p->device = device;
+    p->from_blob = true;
+    p->hdr = h;
+    p->blob.assign(static_cast<const uint8_t*>(blob), static_cast<const uint8_t*>(blob) + len);
+    upload(*p);
+    *out = p.release();
+    return kOk;
+    VPT_API_END
+}
+
+uint64_t vpt_workspace_size(size_t n_sent) { return workspace_layout(n_sent).total; }
+
+int vpt_predict_batch_dev(const vpt_predictor* p, const uint8_t* d_utf8, const uint64_t* d_byte_offsets, size_t n_sent,
+                          void* d_workspace, uint64_t workspace_bytes, int32_t* d_scores, uint8_t* d_boundaries,
+                          uint64_t* d_bound_offsets, int32_t* d_status, uint32_t* d_char_states,
+                          uint32_t* d_type_states, uint64_t* d_char_offsets, void* cuda_stream) {
+    VPT_API_BEGIN
+    if (!p) throw Error(kInvalidArgument, "InvalidArgumentError: predictor: must not be NULL");
+    if (n_sent == 0) return kOk;
+    if (!d_utf8 || !d_byte_offsets || !d_workspace || !d_scores || !d_boundaries || !d_bound_offsets || !d_status)
+        throw Error(kInvalidArgument, "InvalidArgumentError: device buffers: must not be NULL");
+    if (workspace_bytes < workspace_layout(n_sent).total)
+        throw Error(kInvalidArgument, "InvalidArgumentError: workspace: too small");
+    if (reinterpret_cast<uintptr_t>(d_utf8) & 15)
+        throw Error(kInvalidArgument, "InvalidArgumentError: d_utf8: must be 16-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    BatchArgs a;
+    a.text = d_utf8;
+    a.offsets = d_byte_offsets;
+    a.n_sent = n_sent;
+    bind_workspace(a, d_workspace, n_sent);
+    a.status = d_status;
+    a.scores = d_scores;
+    a.boundaries = d_boundaries;
+    a.bound_offsets = d_bound_offsets;
+    a.char_offsets = d_char_offsets;
+    a.char_states = d_char_states;
+    a.type_states = d_type_states;
+    cuda_check(launch_count(a, st), "launch(count)");
+    cuda_check(launch_score(p->dm, a, st), "launch(score)");
+    return kOk;
+    VPT_API_END
+}
+
+int vpt_predict_batch(const vpt_predictor* p, const uint8_t* utf8, const uint64_t* byte_offsets, size_t n_sent,
+                      int32_t* scores_out, uint8_t* boundaries_out, size_t out_capacity, uint64_t* bound_offsets_out,
+                      int32_t* status_out, uint32_t* char_states_out, uint32_t* type_states_out,
+                      size_t states_capacity, uint64_t* char_offsets_out, uint64_t* n_boundaries_out,
+                      uint64_t* n_chars_out) {
+    VPT_API_BEGIN
+    if (!p) throw Error(kInvalidArgument, "InvalidArgumentError: predictor: must not be NULL");
+    if (n_boundaries_out) *n_boundaries_out = 0;
+    if (n_chars_out) *n_chars_out = 0;
+    if (!byte_offsets || !bound_offsets_out)
+        throw Error(kInvalidArgument, "InvalidArgumentError: byte_offsets/bound_offsets_out: must not be NULL");
+    if (n_sent == 0) { bound_offsets_out[0] = 0; if (char_offsets_out) char_offsets_out[0] = 0; return kOk; }
+    const uint64_t base = byte_offsets[0], end = byte_offsets[n_sent];
+    if (end < base) throw Error(kInvalidArgument, "InvalidArgumentError: byte_offsets: must be non-decreasing");
+    const size_t nbytes = size_t(end - base);
+    if (nbytes && !utf8) throw Error(kInvalidArgument, "InvalidArgumentError: utf8: must not be NULL");
+    cuda_check(cudaSetDevice(p->device), "cudaSetDevice");
+    ScratchLease lease(*p);
+    Scratch& s = *lease.s;
+    cudaStream_t st = s.stream;
+    const WorkspaceLayout wl = workspace_layout(n_sent);
+    // the text is staged starting at a 16-byte aligned device address keeping base's low bits
+    const size_t shift = size_t(base & 15);
+    Scratch::ensure(s.d_text, s.text_cap, shift + nbytes + 64);
+    Scratch::ensure(s.d_off, s.off_cap, 8 * (n_sent + 1));
+    Scratch::ensure(s.d_ws, s.ws_cap, wl.total);
+    Scratch::ensure(s.d_status, s.status_cap, 4 * n_sent);
+    Scratch::ensure(s.d_boff, s.boff_cap, 8 * (n_sent + 1));
+    Scratch::ensure(s.d_coff, s.coff_cap, 8 * (n_sent + 1));
+    if (nbytes)
+        cuda_check(cudaMemcpyAsync(static_cast<uint8_t*>(s.d_text) + shift, utf8 + base, nbytes, cudaMemcpyHostToDevice, st),
+                   "H2D(text)");
+    cuda_check(cudaMemcpyAsync(s.d_off, byte_offsets, 8 * (n_sent + 1), cudaMemcpyHostToDevice, st), "H2D(offsets)");
+    BatchArgs a;
+    // offsets are absolute in the caller's buffer: bias the text pointer so that text[offset] is right
+    a.text = static_cast<const uint8_t*>(s.d_text) + shift - base;
+    a.offsets = static_cast<const uint64_t*>(s.d_off);
+    a.n_sent = n_sent;
+    bind_workspace(a, s.d_ws, n_sent);
+    a.status = static_cast<int32_t*>(s.d_status);
+    a.bound_offsets = static_cast<uint64_t*>(s.d_boff);
+    a.char_offsets = static_cast<uint64_t*>(s.d_coff);
+    cuda_check(launch_count(a, st), "launch(count)");
+    const size_t ng = (n_sent + kGroup - 1) / kGroup;
+    cuda_check(cudaMemcpyAsync(&s.h_totals[0], a.group_bound + ng, 8, cudaMemcpyDeviceToHost, st), "D2H(total)");
+    cuda_check(cudaMemcpyAsync(&s.h_totals[1], a.group_char + ng, 8, cudaMemcpyDeviceToHost, st), "D2H(total)");
+    cuda_check(cudaStreamSynchronize(st), "sync(count)");
+    const uint64_t nb = s.h_totals[0], nc = s.h_totals[1];
+    if (n_boundaries_out) *n_boundaries_out = nb;
+    if (n_chars_out) *n_chars_out = nc;
+    if (nb > out_capacity || (nb && !boundaries_out))
+        throw Error(kInvalidArgument, "InvalidArgumentError: out_capacity: too small for the batch");
+    const bool want_states = char_states_out || type_states_out;
+    if (want_states && nc > states_capacity)
+        throw Error(kInvalidArgument, "InvalidArgumentError: states_capacity: too small for the batch");
+    Scratch::ensure(s.d_scores, s.scores_cap, 4 * nb + 4);
+    Scratch::ensure(s.d_bounds, s.bounds_cap, nb + 4);
+    a.scores = static_cast<int32_t*>(s.d_scores);
+    a.boundaries = static_cast<uint8_t*>(s.d_bounds);
+    if (char_states_out) { Scratch::ensure(s.d_cst, s.cst_cap, 4 * nc + 4); a.char_states = static_cast<uint32_t*>(s.d_cst); }
+    if (type_states_out) { Scratch::ensure(s.d_tst, s.tst_cap, 4 * nc + 4); a.type_states = static_cast<uint32_t*>(s.d_tst); }
+    cuda_check(launch_score(p->dm, a, st), "launch(score)");
+    if (nb) {
+        if (scores_out) cuda_check(cudaMemcpyAsync(scores_out, s.d_scores, 4 * nb, cudaMemcpyDeviceToHost, st), "D2H(scores)");
+        cuda_check(cudaMemcpyAsync(boundaries_out, s.d_bounds, nb, cudaMemcpyDeviceToHost, st), "D2H(boundaries)");
+    }
+    cuda_check(cudaMemcpyAsync(bound_offsets_out, s.d_boff, 8 * (n_sent + 1), cudaMemcpyDeviceToHost, st), "D2H(offsets)");
+    if (char_offsets_out)
+        cuda_check(cudaMemcpyAsync(char_offsets_out, s.d_coff, 8 * (n_sent + 1), cudaMemcpyDeviceToHost, st), "D2H(offsets)");
+    if (status_out) cuda_check(cudaMemcpyAsync(status_out, s.d_status, 4 * n_sent, cudaMemcpyDeviceToHost, st), "D2H(status)");
+    if (nc && char_states_out) cuda_check(cudaMemcpyAsync(char_states_out, s.d_cst, 4 * nc, cudaMemcpyDeviceToHost, st), "D2H(states)");
+    if (nc && type_states_out) cuda_check(cudaMemcpyAsync(type_states_out, s.d_tst, 4 * nc, cudaMemcpyDeviceToHost, st), "D2H(states)");
+    cuda_check(cudaStreamSynchronize(st), "sync(score)");
+    return kOk;
+    VPT_API_END
+}
+
+int vpt_predict(const vpt_predictor* p, const uint8_t* utf8, size_t n_bytes, int32_t* scores_out, uint8_t* boundaries_out,
+                size_t out_capacity, uint32_t* char_states_out, uint32_t* type_states_out, size_t states_capacity,
+                uint64_t* n_chars_out) {
+    VPT_API_BEGIN
+    if (!p) throw Error(kInvalidArgument, "InvalidArgumentError: predictor: must not be NULL");
+    if (n_bytes && !utf8) throw Error(kInvalidArgument, "InvalidArgumentError: utf8: must not be NULL");
+    check_raw_text(utf8, n_bytes);
+    const uint64_t offs[2] = {0, n_bytes};
+    uint64_t boff[2], nb = 0, nc = 0;
+    int32_t status = 0;
+    uint8_t dummy = 0;
+    int rc = vpt_predict_batch(p, utf8, offs, 1, scores_out, boundaries_out ? boundaries_out : &dummy, out_capacity, boff,
+                               &status, char_states_out, type_states_out, states_capacity, nullptr, &nb, &nc);
+    if (n_chars_out) *n_chars_out = nc;
+    if (rc != kOk) return rc;
+    if (status != 0) throw Error(kInternal, "internal error: device validation disagrees with host validation");
+    return kOk;
+    VPT_API_END
+}
+
+int vpt_char_types(const uint8_t* utf8, size_t n_bytes, uint8_t* types_out, size_t capacity, uint64_t* n_chars_out) {
+    VPT_API_BEGIN
+    if (n_bytes && !utf8) throw Error(kInvalidArgument, "InvalidArgumentError: utf8: must not be NULL");
+    check_raw_text(utf8, n_bytes);
+    std::vector<uint32_t> cps = utf8_to_codepoints(std::string(reinterpret_cast<const char*>(utf8), n_bytes));
+    if (n_chars_out) *n_chars_out = cps.size();
+    if (cps.size() > capacity) throw Error(kInvalidArgument, "InvalidArgumentError: capacity: too small");
+    for (size_t i = 0; i < cps.size(); ++i) types_out[i] = host_char_type(cps[i]);
+    return kOk;
+    VPT_API_END
+}
+
+uint32_t vpt_tag_n_tokens(const vpt_predictor* p) { return p ? uint32_t(p->tag_preds.size()) : 0; }
+
+const char* vpt_tag_string(const vpt_predictor* p, uint32_t token_id, uint32_t slot, uint32_t cand) {
+    if (!p || token_id >= p->tag_preds.size()) return nullptr;
+    const auto& t = p->tag_preds[token_id].tags;
+    if (slot >= t.size() || cand >= t[slot].size()) return nullptr;
+    return t[slot][cand].c_str();
+}
+
+uint32_t vpt_tag_n_candidates(const vpt_predictor* p, uint32_t token_id, uint32_t slot) {
+    if (!p || token_id >= p->tag_preds.size()) return 0;
+    const auto& t = p->tag_preds[token_id].tags;
+    return slot < t.size() ? uint32_t(t[slot].size()) : 0;
+}
+
+uint32_t vpt_tag_score_len(const vpt_predictor* p, uint32_t token_id) {
+    if (!p || token_id >= p->tag_preds.size()) return 0;
+    return uint32_t(p->tag_preds[token_id].bias.size());
+}
+
+int vpt_fill_tags(const vpt_predictor* p, const uint8_t* utf8, size_t n_bytes, const uint8_t* boundaries,
+                  const uint32_t* char_states, const uint32_t* type_states, int32_t* tag_token_out,
+                  int32_t* tag_cand_out, int32_t* tag_scores_out, size_t score_stride) {
+    VPT_API_BEGIN
+    if (!p) throw Error(kInvalidArgument, "InvalidArgumentError: predictor: must not be NULL");
+    if (!p->predict_tags || p->from_blob)
+        throw Error(kInvalidArgument, "InvalidArgumentError: this predictor is created with predict_tags = false");
+    check_raw_text(utf8, n_bytes);
+    const std::vector<uint32_t> pos = char_starts(utf8, n_bytes);
+    const size_t n = pos.size() - 1;
+    const size_t nt = p->n_tags;
+    for (size_t i = 0; i < n; ++i) tag_token_out[i] = -1;
+    for (size_t i = 0; i < n * nt; ++i) tag_cand_out[i] = -1;
+    if (nt == 0) return kOk;  // predictor.rs:553-555
+    if ((p->char_tags && !char_states) || (p->type_tags && !type_states))
+        throw Error(kInvalidArgument, "InvalidArgumentError: states: required for tag prediction");
+    std::vector<int32_t> scores;
+    auto run = [&](size_t start, size_t last) {  // token = chars [start, last]
+        std::string tok(reinterpret_cast<const char*>(utf8) + pos[start], pos[last + 1] - pos[start]);
+        auto it = p->token_ids.find(tok);
+        if (it == p->token_ids.end()) return;
+        const uint32_t tid = it->second;
+        const TagPredictorHost& tp = p->tag_preds[tid];
+        scores.assign(tp.bias.size(), 0);
+        add_truncated(tp.bias, scores);
+        if (p->char_tags) add_tag_scores(p->char_tag_weight, tid, last, char_states, n, scores);
+        if (p->type_tags) add_tag_scores(p->type_tag_weight, tid, last, type_states, n, scores);
+        // TagPredictor::predict (predictor.rs:286-304): first strict maximum per slot with >= 2 candidates
+        size_t off = 0;
+        for (size_t k = 0; k < tp.tags.size() && k < nt; ++k) {
+            const size_t ncand = tp.tags[k].size();
+            if (ncand >= 2) {
+                if (off + ncand > scores.size())
+                    throw Error(kInvalidModel, "InvalidModelError: tag bias is shorter than the number of candidates");
+                size_t best = 0;
+                int32_t mx = INT32_MIN;
+                for (size_t c = 0; c < ncand; ++c)
+                    if (scores[off + c] > mx) { best = c; mx = scores[off + c]; }
+                tag_cand_out[last * nt + k] = int32_t(best);
+                off += ncand;
+            } else {
+                tag_cand_out[last * nt + k] = ncand == 1 ? 0 : -1;
+            }
+        }
+        tag_token_out[last] = int32_t(tid);
+        if (tag_scores_out) {
+            const size_t m = std::min(score_stride, scores.size());
+            memcpy(tag_scores_out + last * score_stride, scores.data(), m * 4);
+        }
+    };
+    bool have = true;
+    size_t start = 0;
+    for (size_t i = 0; i + 1 < n; ++i) {
+        const uint8_t b = boundaries[i];
+        if (b == 2) have = false;
+        else if (b == 1) {
+            if (have) run(start, i);
+            have = true;
+            start = i + 1;
+        }
+    }
+    if (have) run(start, n - 1);
+    return kOk;
+    VPT_API_END
+}
+
+int vpt_write_tokenized_text(const vpt_predictor* p, const uint8_t* utf8, size_t n_bytes, const uint8_t* boundaries,
+                             const int32_t* tag_token, const int32_t* tag_cand, char* buf, size_t capacity,
+                             uint64_t* len_out) {
+    VPT_API_BEGIN
+    check_raw_text(utf8, n_bytes);
+    const std::vector<uint32_t> pos = char_starts(utf8, n_bytes);
+    const size_t n = pos.size() - 1;
+    const size_t nt = (p && tag_token && tag_cand) ? p->n_tags : 0;
+    std::string out;
+    auto put = [&](const char* s, size_t l) {
+        for (size_t i = 0; i < l; ++i) {
+            if (s[i] == ' ' || s[i] == '\\' || s[i] == '/') out.push_back('\\');
+            out.push_back(s[i]);
+        }
+    };
+    auto emit = [&](size_t st, size_t en) {  // chars [st, en)
+        if (!out.empty()) out.push_back(' ');
+        put(reinterpret_cast<const char*>(utf8) + pos[st], pos[en] - pos[st]);
+        if (nt) {
+            const size_t i = en - 1;
+            int last = -1;
+            for (size_t k = 0; k < nt; ++k) if (tag_cand[i * nt + k] >= 0) last = int(k);
+            for (int k = 0; k <= last; ++k) {
+                out.push_back('/');
+                const int32_t c = tag_cand[i * nt + size_t(k)];
+                if (c >= 0) {
+                    const char* t = vpt_tag_string(p, uint32_t(tag_token[i]), uint32_t(k), uint32_t(c));
+                    if (t) put(t, strlen(t));
+                }
+            }
+        }
+    };
+    // TokenIterator (sentence.rs:1273-1299): tokens adjacent to Unknown boundaries are skipped
+    size_t start = 0;
+    bool skip = false;
+    for (size_t i = 0; i + 1 < n; ++i) {
+        const uint8_t b = boundaries[i];
+        if (b == 1) {
+            if (!skip) emit(start, i + 1);
+            skip = false;
+            start = i + 1;
+        } else if (b == 2) skip = true;
+    }
+    if (!skip) emit(start, n);
+    if (len_out) *len_out = out.size();
+    if (buf && capacity) {
+        const size_t m = std::min(capacity - 1, out.size());
+        memcpy(buf, out.data(), m);
+        buf[m] = 0;
+    }
+    return kOk;
+    VPT_API_END
+}
+
+}  // extern "C"

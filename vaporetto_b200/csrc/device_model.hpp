@@ -1,0 +1,65 @@
+// Device-side view of a predictor (pointers into the flat model blob in HBM) and the launch API
+// between the C ABI (capi.cpp) and the kernels (kernels.cu).
+#pragma once
+#include <cstdint>
+
+#include <cuda_runtime.h>
+
+namespace vpt {
+
+struct DevTable {
+    const void* records = nullptr;     // nslots x 32 B (FastRecord or GeneralRecord)
+    const uint16_t* seeds = nullptr;   // nbuckets
+    const uint32_t* slot_node = nullptr;
+    const uint32_t* slot_pid = nullptr;
+    const int32_t* pool = nullptr;     // general rows
+    uint64_t salt = 0;
+    uint32_t nslots = 0;
+    uint32_t nbuckets = 0;
+    int32_t r0 = 0;
+    uint32_t max_depth = 0;
+    int32_t present = 0;
+    int32_t fast = 0;
+};
+
+struct DevModel {
+    DevTable ct;                         // char + dictionary patterns
+    DevTable tt;                         // type patterns (automaton variant only)
+    const int32_t* type_cache = nullptr; // 8^(2W) table (cache variant only)
+    int32_t type_cache_window = 0;       // 0 = no cache table
+    int32_t bias = 0;
+    int32_t char_window = 0;
+    int32_t type_window = 0;
+    int32_t emit_states = 0;             // tag variant: pattern-id states are meaningful
+};
+
+// Per-batch device buffers (all device pointers).
+struct BatchArgs {
+    const uint8_t* text = nullptr;        // concatenated UTF-8, 16-byte aligned, readable up to a multiple of 16
+    const uint64_t* offsets = nullptr;    // [n_sent + 1] byte offsets into text
+    uint64_t n_sent = 0;
+    // scratch written by the count pass
+    uint32_t* n_chars = nullptr;          // [n_sent]
+    int32_t* status = nullptr;            // [n_sent] 0 ok, 1 empty, 2 NUL, 3 invalid UTF-8
+    uint32_t* local_bound = nullptr;      // [n_sent] boundary offset inside its 64-sentence group
+    uint32_t* local_char = nullptr;       // [n_sent] char offset inside its group
+    uint64_t* group_bound = nullptr;      // [n_groups + 1]
+    uint64_t* group_char = nullptr;       // [n_groups + 1]
+    // outputs
+    int32_t* scores = nullptr;            // [sum(max(chars_i - 1, 0))]
+    uint8_t* boundaries = nullptr;        // same length
+    uint64_t* bound_offsets = nullptr;    // [n_sent + 1]
+    uint64_t* char_offsets = nullptr;     // [n_sent + 1] (nullable)
+    uint32_t* char_states = nullptr;      // [sum(chars_i)] (nullable)
+    uint32_t* type_states = nullptr;      // [sum(chars_i)] (nullable)
+};
+
+constexpr int kGroup = 64;  // sentences per count-pass block
+
+// Launch helpers; all asynchronous on `stream`.  Return cudaError_t of the launch.
+cudaError_t launch_count(const BatchArgs& a, cudaStream_t stream);
+cudaError_t launch_score(const DevModel& m, const BatchArgs& a, cudaStream_t stream);
+// number of kernel launches issued by launch_count + launch_score for this model
+int launches_per_batch(const DevModel& m);
+
+}  // namespace vpt

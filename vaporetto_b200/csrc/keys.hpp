@@ -1,0 +1,47 @@
+// Record formats, key encoding and hash geometry shared by the host table builder and the kernels.
+#pragma once
+#include <cstdint>
+
+#include "common.hpp"
+
+namespace vpt {
+
+constexpr uint32_t kNoPattern = 0xFFFFFFFFu;
+constexpr int kInlineWidth = 6;  // weights stored inside a 32-byte fast record
+
+// Hash-table geometry shared by host builder and device kernels.
+struct TableGeom {
+    uint32_t nslots = 0;
+    uint32_t nbuckets = 0;
+    uint64_t salt = 0;
+};
+
+// 32-byte records.  `key` bit 63 = node has longer extensions (a deeper node exists).
+struct alignas(32) FastRecord {
+    uint64_t key;
+    int32_t w[kInlineWidth];  // boundary weights for relative positions R0 .. R0+5
+};
+struct alignas(32) GeneralRecord {
+    uint64_t key;
+    uint32_t pid;      // longest pattern that is a suffix of the node string, or kNoPattern
+    uint32_t row_ptr;  // index of the row's first weight in the pool, or kNoPattern
+    int32_t off;       // row offset (relative to the matched end char)
+    uint32_t len;      // row length
+    uint32_t node_id;
+    uint32_t pad;
+};
+static_assert(sizeof(FastRecord) == 32 && sizeof(GeneralRecord) == 32, "record size");
+
+constexpr uint64_t kExtFlag = 1ull << 63;
+constexpr uint64_t kDeepMarker = 0x110000ull;  // first invalid code point: marks (parent node, symbol) keys
+
+// key of a node at depth <= 3: c3 is the last symbol of the suffix, c1 the first (0 if absent).
+VPT_HD uint64_t shallow_key(uint32_t c1, uint32_t c2, uint32_t c3) {
+    return (uint64_t(c1) << 42) | (uint64_t(c2) << 21) | uint64_t(c3);
+}
+// key of a node at depth >= 4: parent node id and the symbol preceding the parent's string.
+VPT_HD uint64_t deep_key(uint32_t parent_id, uint32_t sym) {
+    return ((kDeepMarker + (uint64_t(parent_id) >> 21)) << 42) | ((uint64_t(parent_id) & 0x1FFFFF) << 21) | uint64_t(sym);
+}
+
+}  // namespace vpt

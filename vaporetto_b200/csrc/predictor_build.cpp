@@ -1,0 +1,124 @@
+#include "predictor_build.hpp"
+
+#include <algorithm>
+#include <cstring>
+
+#include "common.hpp"
+
+namespace vpt {
+
+namespace {
+
+struct BlobWriter {
+    std::vector<uint8_t> buf;
+    uint64_t add(const void* p, size_t n) {
+        size_t off = align_up(buf.size(), 256);
+        buf.resize(off + n);
+        if (n) memcpy(buf.data() + off, p, n);
+        return off;
+    }
+};
+
+void write_table(BlobWriter& w, const NodeTable& t, size_t n_patterns, BlobTable& bt) {
+    memset(&bt, 0, sizeof bt);
+    bt.present = t.present;
+    if (!t.present) return;
+    bt.fast = t.fast;
+    bt.r0 = t.r0;
+    bt.max_depth = t.max_depth;
+    bt.nslots = t.geom.nslots;
+    bt.nbuckets = t.geom.nbuckets;
+    bt.salt = t.geom.salt;
+    bt.n_nodes = t.n_nodes;
+    bt.n_patterns = uint32_t(n_patterns);
+    bt.rec_off = w.add(t.records.data(), t.records.size());
+    bt.seeds_off = w.add(t.seeds.data(), t.seeds.size() * 2);
+    bt.node_off = w.add(t.slot_node.data(), t.slot_node.size() * 4);
+    bt.pid_off = w.add(t.slot_pid.data(), t.slot_pid.size() * 4);
+    bt.pool_off = w.add(t.pool.data(), t.pool.size() * 4);
+}
+
+
+TagWeightMap collect_tag_weights(const PatternSet& ps, size_t n_tokens, size_t window) {
+    TagWeightMap m(n_tokens, std::vector<std::unordered_map<uint32_t, std::vector<int32_t>>>(window + 1));
+    for (size_t pid = 0; pid < ps.tags.size(); ++pid)
+        for (const auto& kv : ps.tags[pid]) m[kv.first.first][kv.first.second][uint32_t(pid)] = kv.second;
+    return m;
+}
+
+}  // namespace
+
+// Predictor::new (reference predictor.rs:450-508)
+HostPredictor build_host_predictor(const Model& m, bool predict_tags) {
+    HostPredictor hp;
+    HostPredictor* p = &hp;
+    p->predict_tags = predict_tags;
+
+    std::vector<const std::vector<TagNgramEntry>*> tag_char, tag_type;
+    if (predict_tags) {
+        for (size_t i = 0; i < m.tag_models.size(); ++i) {
+            const auto& t = m.tag_models[i];
+            p->n_tags = std::max(p->n_tags, t.tags.size());
+            TagPredictorHost tp{t.tags, t.bias};
+            if (tp.bias.size() < 8) tp.bias.resize(8, 0);
+            p->token_ids[t.token] = uint32_t(i);  // "token does not duplicate in the model": last insert wins
+            p->tag_preds.push_back(std::move(tp));
+            tag_char.push_back(&t.char_ngrams);
+            tag_type.push_back(&t.type_ngrams);
+        }
+    }
+
+    // variant selection: CharScorer::new (char_scorer.rs:92-124), TypeScorer::new (type_scorer.rs:104-143)
+    const bool has_char = !((m.char_ngrams.empty() && m.dict.empty()) || m.char_window == 0);
+    const bool has_type = !(m.type_ngrams.empty() || m.type_window == 0);
+    const bool tags = !tag_char.empty();
+    int type_variant = 0;  // 0 none, 1 Boundary (automaton), 2 BoundaryCache, 3 BoundaryTag
+    if (has_type) type_variant = tags ? 3 : (m.type_window <= 3 ? 2 : 1);
+    const int char_variant = has_char ? (tags ? 2 : 1) : 0;
+
+    PatternSet cps, tps;
+    NodeTable ctab, ttab;
+    std::vector<int32_t> tcache;
+    const bool need_general = tags || type_variant == 1 || type_variant == 3;
+    if (has_char) {
+        cps = build_patterns(m.char_ngrams, &m.dict, m.char_window, tag_char, true);
+        ctab = build_node_table(cps, need_general);
+    }
+    if (type_variant == 2) tcache = build_type_cache(m.type_ngrams, m.type_window);
+    else if (type_variant != 0) {
+        tps = build_patterns(m.type_ngrams, nullptr, m.type_window, tag_type, false);
+        ttab = build_node_table(tps, true);
+    }
+    // a general-format type table forces the general kernel, which needs a general char table
+    if (has_char && ctab.fast && (ttab.present)) ctab = build_node_table(cps, true);
+
+    if (tags) {
+        if (has_char) { p->char_tag_weight = collect_tag_weights(cps, m.tag_models.size(), m.char_window); p->char_tags = true; }
+        if (type_variant == 3) { p->type_tag_weight = collect_tag_weights(tps, m.tag_models.size(), m.type_window); p->type_tags = true; }
+    }
+
+    BlobWriter w;
+    BlobHeader h{};
+    w.buf.resize(sizeof(BlobHeader));
+    memcpy(h.magic, kBlobMagic, 8);
+    h.bias = m.bias;
+    h.char_window = m.char_window;
+    h.type_window = m.type_window;
+    h.type_cache_window = type_variant == 2 ? m.type_window : 0;
+    h.emit_states = tags ? 1 : 0;
+    h.char_variant = char_variant;
+    h.type_variant = type_variant;
+    h.max_char_pattern_len = int32_t(cps.max_len);
+    write_table(w, ctab, cps.raw.size(), h.ct);
+    write_table(w, ttab, tps.raw.size(), h.tt);
+    if (type_variant == 2) h.type_cache_off = w.add(tcache.data(), tcache.size() * 4);
+    w.buf.resize(align_up(w.buf.size(), 256));
+    h.total_bytes = w.buf.size();
+    memcpy(w.buf.data(), &h, sizeof h);
+    p->hdr = h;
+    p->blob.swap(w.buf);
+    return hp;
+}
+
+
+}  // namespace vpt
