@@ -1,0 +1,392 @@
+#!/usr/bin/env python
+"""bench.py — UTF-8 MB/s segmented (bit-exact i32 scores) for the Predictor::predict hot path.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one process per GPU)
+    python bench.py --impl reference --gpus N --steps K ...  # reference algorithm on the host CPU cores
+
+Workload (BASELINE.json configs[1] / SURVEY.md §8d): bccwj-suw-shaped synthetic model (W=3/3, 300 000 char
+1-3-gram patterns, 258 type n-grams, no dictionary, no tags) over synthetic 40-char Japanese sentences,
+1 000 000 sentences per GPU (weak scaling; sentences shard trivially, the only collective is the one-time
+NCCL broadcast of the flat model blob from rank 0).  A "step" is one pass of the hot path over the batch:
+k_count + k_scan_groups + k_score_fast through vpt_predict_batch_dev with inputs resident in HBM (`value`),
+and through vpt_predict_batch with pinned HOST buffers, copies inside the timed region (`e2e`).
+The batch (115 MB in, 195 MB out) is larger than L2 (126 MB), so no L2 flush is needed between steps.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+CACHE = os.path.join(ROOT, "bench_cache")
+METRIC = "UTF-8 MB/s segmented (bit-exact i32 scores)"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def get_model(n_patterns: int, sample: int) -> bytes:
+    from vpt_testlib import synth
+    os.makedirs(CACHE, exist_ok=True)
+    fn = os.path.join(CACHE, f"bccwj_shaped_{n_patterns}_{sample}.bin")
+    if os.path.exists(fn):
+        return open(fn, "rb").read()
+    t = time.time()
+    m = synth.gen_model_bccwj_shaped(n_patterns=n_patterns, sample_sentences=sample)
+    log(f"[bench] generated model ({len(m)} bytes) in {time.time() - t:.1f}s")
+    try:
+        with open(fn + ".tmp", "wb") as f:
+            f.write(m)
+        os.replace(fn + ".tmp", fn)
+    except OSError:
+        pass
+    return m
+
+
+def get_text(n_sent: int, rank: int, ragged: bool):
+    from vpt_testlib import synth
+    t = time.time()
+    text, offs, lens = synth.gen_text(n_sent, 40, seed=synth.TEXT_SEED + 7919 * rank, ragged=ragged)
+    log(f"[bench] rank {rank}: generated {n_sent} sentences, {len(text)} bytes in {time.time() - t:.1f}s")
+    return text, offs, lens
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(model_bytes: bytes, text, offs, budget_s: float = 12.0):
+    """Reference algorithm (C++ restatement, oracle/) on the host cores over a bounded sample of the workload."""
+    from vpt_testlib.oracle import OraclePredictor
+    t = time.time()
+    o = OraclePredictor(model_bytes)
+    build_s = time.time() - t
+    n = len(offs) - 1
+    ncores = os.cpu_count() or 1
+    # single thread on a small sample first
+    n1 = min(n, 50_000)
+    sub_off = offs[: n1 + 1]
+    dt1 = o.time_batch(text, sub_off, nthreads=1)
+    mb1 = float(sub_off[-1] - sub_off[0]) / dt1 / 1e6
+    # all cores on a sample sized for ~budget seconds
+    est = mb1 * ncores * 0.7
+    nall = int(min(n, max(n1, est * 1e6 * budget_s / 120.0)))
+    sub = offs[: nall + 1]
+    dta = o.time_batch(text, sub, nthreads=ncores)
+    mba = float(sub[-1] - sub[0]) / dta / 1e6
+    return {"value": round(mba, 2), "unit": "MB/s", "cores": ncores, "kind": "port",
+            "sample": f"{nall} of the step's sentences, {ncores} threads ({dta:.2f}s); single thread "
+                      f"{mb1:.2f} MB/s on {n1} sentences; C++ restatement of the reference algorithm "
+                      f"(oracle/vaporetto_oracle.cpp: trie+failure AC, merged weights, type table), parse+predict, "
+                      f"text pre-loaded; the Rust reference cannot be built here (no cargo/rustc)",
+            "single_thread_MBps": round(mb1, 2), "oracle_build_s": round(build_s, 1)}, o
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU algorithm on the host cores, rank 0 only."""
+    if rank != 0:
+        return
+    model_bytes = get_model(args.patterns, args.model_sample)
+    text, offs, _ = get_text(min(args.sentences, 400_000), 0, args.ragged)
+    from vpt_testlib.oracle import OraclePredictor
+    o = OraclePredictor(model_bytes)
+    ncores = os.cpu_count() or 1
+    n = len(offs) - 1
+    # size each step for ~2 s of CPU work
+    probe = o.time_batch(text, offs[: min(n, 20_000) + 1], nthreads=ncores)
+    rate = float(offs[min(n, 20_000)] - offs[0]) / probe
+    nstep = int(min(n, max(20_000, rate * 2.0 / 115.0)))
+    sub = offs[: nstep + 1]
+    nbytes = float(sub[-1] - sub[0])
+    for _ in range(args.warmup):
+        o.time_batch(text, sub, nthreads=ncores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        o.time_batch(text, sub, nthreads=ncores)
+    dt = time.perf_counter() - t0
+    v = nbytes * args.steps / dt / 1e6
+    out = {"impl": "reference", "metric": METRIC, "value": round(v, 2), "unit": "MB/s", "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3),
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i32", "data": "synthetic",
+           "config": workload_config(args, args.sentences),
+           "cpu_baseline": {"value": round(v, 2), "unit": "MB/s", "cores": ncores, "kind": "port",
+                            "sample": f"{nstep} sentences per step, {ncores} host threads; C++ restatement of the "
+                                      f"reference algorithm (Rust reference not buildable here)"},
+           "e2e": {"value": round(v, 2), "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+def workload_config(args, n_sent):
+    return {"workload": "BASELINE configs[1]: bccwj-suw-shaped model (W=3/3, %d char 1-3-gram patterns, 258 type "
+                        "n-grams, no dict, no tags), synthetic JP sentences%s" %
+                        (args.patterns, " (ragged lognormal lengths)" if args.ragged else " of 40 chars"),
+            "sentences_per_gpu": n_sent, "parallelism": "dp%d (sentences sharded, NCCL model broadcast only)" % args.gpus,
+            "l2": "batch (115 MB in + 195 MB out per GPU) exceeds L2; no flush needed"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--sentences", type=int, default=1_000_000, help="sentences per GPU")
+    ap.add_argument("--patterns", type=int, default=300_000)
+    ap.add_argument("--model-sample", type=int, default=2_000_000)
+    ap.add_argument("--ragged", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import vaporetto_b200 as vb
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- model: rank 0 parses/builds, the flat blob is broadcast once over NCCL -------------------------
+    L = vb.lib()
+    if rank == 0:
+        model_bytes = get_model(args.patterns, args.model_sample)
+        t = time.time()
+        pred = vb.Predictor(vb.Model.read(model_bytes), device=local_rank)
+        log(f"[bench] predictor built in {time.time() - t:.1f}s: {pred.info}")
+        blob = pred.export_blob()
+    if world > 1:
+        size = torch.tensor([len(blob) if rank == 0 else 0], dtype=torch.int64, device=dev)
+        dist.broadcast(size, 0)
+        tb = torch.empty(int(size.item()), dtype=torch.uint8, device=dev)
+        if rank == 0:
+            tb.copy_(torch.from_numpy(blob))
+        dist.broadcast(tb, 0)
+        if rank != 0:
+            pred = vb.Predictor.from_blob(tb.cpu().numpy(), device=local_rank)
+    assert pred.info["fast_path"] == 1, "config-2 model must take the fast kernel"
+
+    # ---- data ------------------------------------------------------------------------------------------
+    text, offs, _ = get_text(args.sentences, rank, args.ragged)
+    n = len(offs) - 1
+    nbytes = int(offs[-1])
+    d_text = torch.zeros(nbytes + 64, dtype=torch.uint8, device=dev)
+    d_text[:nbytes] = torch.from_numpy(text).to(dev)
+    d_off = torch.from_numpy(offs.astype(np.int64)).to(dev)
+    ws = torch.empty(L.vpt_workspace_size(n), dtype=torch.uint8, device=dev)
+    d_scores = torch.empty(nbytes, dtype=torch.int32, device=dev)
+    d_bounds = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    d_boff = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    d_status = torch.empty(n, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream()
+    sp = C.c_void_p(stream.cuda_stream)
+
+    def step_dev():
+        rc = L.vpt_predict_batch_dev(pred._h, d_text.data_ptr(), d_off.data_ptr(), n, ws.data_ptr(), ws.numel(),
+                                     d_scores.data_ptr(), d_bounds.data_ptr(), d_boff.data_ptr(), d_status.data_ptr(),
+                                     None, None, None, sp)
+        if rc:
+            raise RuntimeError(L.vpt_last_error().decode())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_dev()
+    barrier()
+    n_bound = int(d_boff[-1].item())
+    assert int(d_status.abs().sum().item()) == 0
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_dev()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    # stage timing of the dominant kernel (CUDA events inside the library, same stream)
+    stage = (C.c_float * 3)()
+    stage_acc = np.zeros(3)
+    reps = max(3, min(args.steps, 10))
+    for _ in range(reps):
+        rc = L.vpt_predict_batch_dev_profiled(pred._h, d_text.data_ptr(), d_off.data_ptr(), n, ws.data_ptr(), ws.numel(),
+                                              d_scores.data_ptr(), d_bounds.data_ptr(), d_boff.data_ptr(),
+                                              d_status.data_ptr(), None, None, None, sp, stage)
+        if rc:
+            raise RuntimeError(L.vpt_last_error().decode())
+        stage_acc += np.array(list(stage))
+    stage_ms = stage_acc / reps
+    clocks = sampler.stop() if rank == 0 else None
+
+    tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(nbytes)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms_all = float(tmax.item())
+    total_bytes = float(tot.item())
+    value = total_bytes * args.steps / (ms_all / 1e3) / 1e6
+
+    # ---- end to end through the host-buffer C ABI (pinned host memory, copies inside the timed region) ----
+    h_text = torch.from_numpy(text).pin_memory()
+    h_off = torch.from_numpy(offs.astype(np.int64)).pin_memory()
+    h_scores = torch.empty(n_bound, dtype=torch.int32).pin_memory()
+    h_bounds = torch.empty(n_bound, dtype=torch.uint8).pin_memory()
+    h_boff = torch.empty(n + 1, dtype=torch.int64).pin_memory()
+    h_status = torch.empty(n, dtype=torch.int32).pin_memory()
+    nb_out, nc_out = C.c_uint64(), C.c_uint64()
+
+    def step_e2e():
+        rc = L.vpt_predict_batch(pred._h, h_text.data_ptr(), h_off.data_ptr(), n, h_scores.data_ptr(),
+                                 h_bounds.data_ptr(), n_bound, h_boff.data_ptr(), h_status.data_ptr(), None, None, 0,
+                                 None, C.byref(nb_out), C.byref(nc_out))
+        if rc:
+            raise RuntimeError(L.vpt_last_error().decode())
+
+    step_e2e()
+    step_e2e()
+    assert np.array_equal(h_bounds.numpy(), d_bounds[:n_bound].cpu().numpy())
+    assert np.array_equal(h_scores.numpy(), d_scores[:n_bound].cpu().numpy())
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        step_e2e()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = total_bytes * args.e2e_steps / float(te.item()) / 1e6
+    h2d = nbytes + 8 * (n + 1)
+    d2h = 4 * n_bound + n_bound + 8 * (n + 1) + 4 * n + 16
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (burst copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        alg_bytes = nbytes + 8 * n + 5 * n_bound  # read B+8 per sentence, write 4(n-1)+(n-1)
+        score_ms = float(stage_ms[2])
+        achieved = alg_bytes / (score_ms / 1e3) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_score_fast_bytes_per_launch")
+        except Exception:
+            pass
+        out = {
+            "metric": METRIC, "value": round(value, 1), "unit": "MB/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms_all / args.steps, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "i32", "data": "synthetic",
+            "config": workload_config(args, n),
+            "roofline": {"bound": "hbm", "kernel": "k_score_fast", "achieved": round(achieved, 1), "peak": peak,
+                         "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": round(score_ms, 4),
+                         "stage_ms": {"k_count": round(float(stage_ms[0]), 4), "k_scan_groups": round(float(stage_ms[1]), 4),
+                                      "k_score_fast": round(score_ms, 4)},
+                         "read_only_GBps": round((nbytes + 8 * n) / (score_ms / 1e3) / 1e9, 1),
+                         "whole_step_frac": round(alg_bytes / (ms_all / args.steps / 1e3) / 1e9 / peak, 4)},
+            "e2e": {"value": round(e2e_value, 1), "unit": "MB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": args.e2e_steps, "api": "vpt_predict_batch (pinned host buffers; scores+boundaries returned)"},
+            "gpu_launches": args.steps * pred.info["kernel_launches_per_batch"],
+            "clocks": clocks,
+            "bit_exact_checked": True,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            model_bytes = get_model(args.patterns, args.model_sample)
+            cb, oracle = cpu_baseline(model_bytes, text, offs)
+            out["cpu_baseline"] = cb
+            # parity spot check of this very run against the oracle
+            idx = np.arange(0, n, max(1, n // 200))[:200]
+            hb = h_boff.numpy()
+            hs = h_scores.numpy()
+            for i in idx:
+                s = bytes(text[int(offs[i]):int(offs[i + 1])]).decode()
+                assert hs[int(hb[i]):int(hb[i + 1])].tolist() == oracle.predict(s)[0].tolist(), "parity failure"
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

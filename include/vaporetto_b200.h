@@ -132,6 +132,16 @@ int vpt_predict_batch_dev(const vpt_predictor* predictor, const uint8_t* d_utf8,
                           uint32_t* d_char_states, uint32_t* d_type_states, uint64_t* d_char_offsets,
                           void* cuda_stream);
 
+/* vpt_predict_batch_dev with CUDA events recorded on `cuda_stream` around each stage; synchronises the stream
+ * and returns the device time of each stage in milliseconds: stage_ms[0] = k_count, [1] = k_scan_groups,
+ * [2] = k_score_*  (bench.py's roofline leg times the dominant kernel with this). */
+int vpt_predict_batch_dev_profiled(const vpt_predictor* predictor, const uint8_t* d_utf8,
+                                   const uint64_t* d_byte_offsets, size_t n_sent, void* d_workspace,
+                                   uint64_t workspace_bytes, int32_t* d_scores, uint8_t* d_boundaries,
+                                   uint64_t* d_bound_offsets, int32_t* d_status, uint32_t* d_char_states,
+                                   uint32_t* d_type_states, uint64_t* d_char_offsets, void* cuda_stream,
+                                   float* stage_ms);
+
 /* Single-sentence `Predictor::predict` (batch of one).  Returns VPT_INVALID_ARGUMENT with the reference's
  * message for an empty text or a text containing U+0000 (sentence.rs:174-189).  *n_chars_out receives n;
  * scores_out/boundaries_out need n-1 entries (capacity in elements), states n entries (nullable). */

@@ -18,7 +18,7 @@ struct Tab {
     const BlobTable* bt;
     const uint8_t* base;
     TableGeom geom() const { return TableGeom{bt->nslots, bt->nbuckets, bt->salt}; }
-    const uint16_t* seeds() const { return reinterpret_cast<const uint16_t*>(base + bt->seeds_off); }
+    const uint8_t* seeds() const { return base + bt->seeds_off; }
     const uint32_t* rec(uint32_t slot) const { return reinterpret_cast<const uint32_t*>(base + bt->rec_off + size_t(slot) * 32); }
     const uint32_t* slot_node() const { return reinterpret_cast<const uint32_t*>(base + bt->node_off); }
     const int32_t* pool() const { return reinterpret_cast<const int32_t*>(base + bt->pool_off); }
@@ -92,7 +92,13 @@ long emul_predict(const uint8_t* model, size_t model_len, int predict_tags, cons
                     long j = i - w + 1 + k;
                     idx = (idx << 3) | ((j >= 0 && j < long(n)) ? tys[size_t(j)] : 0u);
                 }
-                v = wrapping_add(v, reinterpret_cast<const int32_t*>(base + h.type_cache_off)[idx]);
+                const int32_t full = reinterpret_cast<const int32_t*>(base + h.type_cache_off)[idx];
+                if (h.type_a_off) {
+                    const int32_t sp = wrapping_add(reinterpret_cast<const int32_t*>(base + h.type_a_off)[idx >> 6],
+                                                    reinterpret_cast<const int32_t*>(base + h.type_b_off)[idx & 4095]);
+                    if (sp != full) throw Error(kInternal, "split type tables disagree with the full table");
+                }
+                v = wrapping_add(v, full);
             }
             scores[i] = v;
         }

@@ -161,6 +161,48 @@ def test_edge_cases():
         assert msg in str(e.value)
 
 
+def test_utf8_validation_matches_strict_decoder():
+    """status 3 <=> the bytes are not valid UTF-8 (Python's strict decoder = Rust's str validity rules:
+    no overlongs, no surrogates, <= U+10FFFF); 2 <=> valid but contains NUL; 1 <=> empty."""
+    p = make(read("model.bin"))
+    rng = np.random.default_rng(7)
+    pool = "aZ0 \x00é߿ࠀ਀퟿\ue000￿𐀀𠀋\U0010ffffあ漢カ".encode("utf-8", "surrogatepass")
+    special = [b"\xc0\x80", b"\xc1\xbf", b"\xe0\x80\x80", b"\xe0\x9f\xbf", b"\xe0\xa0\x80", b"\xed\x9f\xbf",
+               b"\xed\xa0\x80", b"\xed\xbf\xbf", b"\xf0\x80\x80\x80", b"\xf0\x8f\xbf\xbf", b"\xf0\x90\x80\x80",
+               b"\xf4\x8f\xbf\xbf", b"\xf4\x90\x80\x80", b"\xf5\x80\x80\x80", b"\xff", b"\xfe", b"\x80", b"\xbf",
+               b"\xe3\x81", b"\xe3", b"\xf0\x9f\xa4", b"\xc3", b"\xe3\x81\x82\x82", b"\xe3\x41\x81\x81", b"\xc3\xc3\xa9"]
+    sents = []
+    for _ in range(3000):
+        kind = rng.integers(0, 4)
+        if kind == 0:  # valid text
+            s = "".join(rng.choice(list("aZ0 é߿ࠀ퟿\ue000￿𐀀𠀋\U0010ffffあ漢カ"), size=rng.integers(0, 40))).encode()
+        elif kind == 1:  # valid with a mutation
+            b = bytearray("".join(rng.choice(list("aé߿ࠀ𐀀あ漢カ"), size=rng.integers(1, 30))).encode())
+            for _ in range(rng.integers(1, 3)):
+                b[rng.integers(0, len(b))] = int(rng.integers(0, 256))
+            s = bytes(b)
+        elif kind == 2:  # random bytes biased to the interesting ranges
+            s = bytes(rng.choice(list(pool) + [0x80, 0xBF, 0xC0, 0xC2, 0xE0, 0xED, 0xF0, 0xF4, 0xF5, 0xFF],
+                                 size=rng.integers(0, 24)).astype(np.uint8))
+        else:  # special sequences embedded in valid text, truncated at random
+            s = "あ漢".encode() + special[rng.integers(0, len(special))] + "カa".encode()
+            s = s[rng.integers(0, 4):len(s) - rng.integers(0, 4)]
+        sents.append(s)
+    sents += special + [b"", b"\x00", b"a\x00", "漢".encode() * 200 + b"\xe3\x81", b"\x81" + "あ".encode() * 50]
+    lens = [len(s) for s in sents]
+    offs = np.zeros(len(lens) + 1, np.uint64)
+    np.cumsum(lens, out=offs[1:])
+    text = np.frombuffer(b"".join(sents) + b"\0" * 8, np.uint8)
+    r = p.predict_batch(text[: int(offs[-1])] if False else text, offs)
+    for i, s in enumerate(sents):
+        try:
+            u = s.decode("utf-8")
+            want = 1 if len(u) == 0 else (2 if "\0" in u else 0)
+        except UnicodeDecodeError:
+            want = 3
+        assert int(r.status[i]) == want, (i, s, int(r.status[i]), want)
+
+
 def _random_model(rng, cw, tw, n_ng=40, n_dict=20, maxdict=9, tags=0):
     alpha = "あいうえおアイウ人火星地球猫社長aB1。、"
     def word(lo, hi):

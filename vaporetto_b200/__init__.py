@@ -76,6 +76,8 @@ ABI = [
                                     C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     ("vpt_workspace_size", C.c_uint64, [C.c_size_t]),
     ("vpt_predict_batch_dev", C.c_int, [_P, _P, _P, C.c_size_t, _P, C.c_uint64, _P, _P, _P, _P, _P, _P, _P, _P]),
+    ("vpt_predict_batch_dev_profiled", C.c_int, [_P, _P, _P, C.c_size_t, _P, C.c_uint64, _P, _P, _P, _P, _P, _P, _P, _P,
+                                                 _P]),
     ("vpt_predict", C.c_int, [_P, C.c_char_p, C.c_size_t, _P, _P, C.c_size_t, _P, _P, C.c_size_t, C.POINTER(C.c_uint64)]),
     ("vpt_fill_tags", C.c_int, [_P, C.c_char_p, C.c_size_t, _P, _P, _P, _P, _P, _P, C.c_size_t]),
     ("vpt_tag_string", C.c_char_p, [_P, C.c_uint32, C.c_uint32, C.c_uint32]),

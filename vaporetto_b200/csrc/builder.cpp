@@ -218,11 +218,45 @@ std::vector<int32_t> build_type_cache(const std::vector<NgramEntry>& type_ngrams
     return table;
 }
 
-uint32_t table_slot(const TableGeom& g, const uint16_t* seeds, uint64_t key) {
-    const uint64_t h = mix64(key + g.salt);
-    const uint32_t bucket = uint32_t((uint64_t(uint32_t(h >> 32)) * g.nbuckets) >> 32);
-    const uint64_t h2 = mix64(key ^ (uint64_t(seeds[bucket]) + 1) * 0x9E3779B97F4A7C15ULL);
-    return uint32_t((uint64_t(uint32_t(h2 >> 32)) * g.nslots) >> 32);
+bool build_type_split(const std::vector<NgramEntry>& type_ngrams, uint8_t window, std::vector<int32_t>& ta,
+                      std::vector<int32_t>& tb) {
+    if (window != 3) return false;
+    for (const auto& d : type_ngrams)
+        if (d.ngram.size() > 3) return false;
+    const size_t seq = 6, sub = 4;
+    ta.assign(size_t(1) << (3 * sub), 0);
+    tb.assign(size_t(1) << (3 * sub), 0);
+    for (const auto& d : type_ngrams) {
+        const size_t L = d.ngram.size();
+        bool ok = L > 0;
+        for (unsigned char c : d.ngram) ok = ok && c <= 6;
+        if (!ok) continue;
+        for (size_t end = L; end <= seq; ++end) {  // occurrence covers window positions [end-L, end)
+            const size_t widx = seq - end;
+            if (widx >= d.weights.size() || d.weights[widx] == 0) continue;
+            const int32_t wv = d.weights[widx];
+            const bool in_a = end <= sub;                  // entirely inside positions 0..3
+            const size_t shift = in_a ? 0 : 2;             // B covers positions 2..5
+            std::vector<int32_t>& tab = in_a ? ta : tb;
+            const size_t start = end - L - shift;          // position inside the 4-type sub-window
+            for (size_t id = 0; id < tab.size(); ++id) {
+                bool match = true, valid = true;
+                for (size_t p = 0; p < sub; ++p) {
+                    const uint32_t dgt = uint32_t(id >> (3 * (sub - 1 - p))) & 7u;
+                    if (dgt == 7) { valid = false; break; }
+                    if (p >= start && p < start + L && dgt != uint8_t(d.ngram[p - start])) { match = false; break; }
+                }
+                if (valid && match) tab[id] = wrapping_add(tab[id], wv);
+            }
+        }
+    }
+    return true;
+}
+
+uint32_t table_slot(const TableGeom& g, const uint8_t* seeds, uint64_t key) {
+    uint32_t ha, hb;
+    key_hashes(key, g.salt, ha, hb);
+    return slot_with_seed(ha, hb, seeds[bucket_of(ha, g.nbuckets)], g.nslots);
 }
 
 namespace {
@@ -237,15 +271,16 @@ struct TrieNode {
     uint32_t c1 = 0, c2 = 0, c3 = 0;  // shallow key symbols (depth <= 3)
 };
 
-// Hash-and-displace perfect hash: every bucket of keys gets a 16-bit seed such that all keys land in
+// Hash-and-displace perfect hash: every bucket of keys gets an 8-bit seed such that all keys land in
 // distinct free slots.  Buckets are placed largest first.
-bool place_keys(const std::vector<uint64_t>& keys, TableGeom& g, std::vector<uint16_t>& seeds,
+bool place_keys(const std::vector<uint64_t>& keys, TableGeom& g, std::vector<uint8_t>& seeds,
                 std::vector<uint32_t>& slot_of_key) {
     const size_t n = keys.size();
+    std::vector<uint32_t> ha(n), hb(n);
     std::vector<std::vector<uint32_t>> buckets(g.nbuckets);
     for (size_t i = 0; i < n; ++i) {
-        const uint64_t h = mix64(keys[i] + g.salt);
-        buckets[size_t((uint64_t(uint32_t(h >> 32)) * g.nbuckets) >> 32)].push_back(uint32_t(i));
+        key_hashes(keys[i], g.salt, ha[i], hb[i]);
+        buckets[bucket_of(ha[i], g.nbuckets)].push_back(uint32_t(i));
     }
     std::vector<uint32_t> order(g.nbuckets);
     std::iota(order.begin(), order.end(), 0u);
@@ -259,13 +294,11 @@ bool place_keys(const std::vector<uint64_t>& keys, TableGeom& g, std::vector<uin
         const auto& ks = buckets[b];
         if (ks.empty()) break;
         bool placed = false;
-        for (uint32_t seed = 0; seed < 65536 && !placed; ++seed) {
+        for (uint32_t seed = 0; seed < 256 && !placed; ++seed) {
             tmp.clear();
             bool ok = true;
-            const uint64_t sm = (uint64_t(seed) + 1) * 0x9E3779B97F4A7C15ULL;
             for (uint32_t ki : ks) {
-                const uint64_t h2 = mix64(keys[ki] ^ sm);
-                const uint32_t slot = uint32_t((uint64_t(uint32_t(h2 >> 32)) * g.nslots) >> 32);
+                const uint32_t slot = slot_with_seed(ha[ki], hb[ki], seed, g.nslots);
                 if (used[slot]) { ok = false; break; }
                 for (uint32_t s2 : tmp) if (s2 == slot) { ok = false; break; }
                 if (!ok) break;
@@ -273,7 +306,7 @@ bool place_keys(const std::vector<uint64_t>& keys, TableGeom& g, std::vector<uin
             }
             if (ok) {
                 for (size_t k = 0; k < ks.size(); ++k) { used[tmp[k]] = 1; slot_of_key[ks[k]] = tmp[k]; }
-                seeds[b] = uint16_t(seed);
+                seeds[b] = uint8_t(seed);
                 placed = true;
             }
         }
@@ -345,13 +378,16 @@ NodeTable build_node_table(const PatternSet& ps, bool force_general) {
     }
     std::vector<uint32_t> slot_of_key;
     bool ok = false;
-    double alpha = 0.6;
-    for (int attempt = 0; attempt < 8 && !ok; ++attempt) {
-        t.geom.nslots = uint32_t(std::max<double>(16.0, double(n) / alpha + 1.0));
-        t.geom.nbuckets = uint32_t(std::max<size_t>(1, (n + 7) / 8));
+    // load factor 0.6 and 8 keys per bucket on average: 256 seeds per bucket are enough in practice and
+    // keep the seed array at one byte per 8 nodes (it is staged in shared memory by the tile kernel);
+    // on failure retry with another salt and a sparser table, then with smaller buckets.
+    static const double kAlpha[] = {0.60, 0.50, 0.42, 0.35, 0.30, 0.30, 0.25, 0.25, 0.20, 0.15};
+    static const double kLambda[] = {8.0, 8.0, 8.0, 8.0, 8.0, 6.0, 6.0, 4.0, 4.0, 3.0};
+    for (int attempt = 0; attempt < 10 && !ok; ++attempt) {
+        t.geom.nslots = uint32_t(std::max<double>(16.0, double(n) / kAlpha[attempt] + 1.0));
+        t.geom.nbuckets = uint32_t(std::max<double>(1.0, double(n) / kLambda[attempt] + 1.0));
         t.geom.salt = 0x5bd1e9955bd1e995ULL * uint64_t(attempt + 1);
         ok = place_keys(keys, t.geom, t.seeds, slot_of_key);
-        alpha *= 0.85;
     }
     if (!ok) throw Error(kInternal, "internal error: perfect hash construction failed");
 

@@ -51,7 +51,7 @@ struct NodeTable {
     uint32_t n_nodes = 0;
     uint32_t max_depth = 0;
     std::vector<uint8_t> records;       // nslots * 32 bytes
-    std::vector<uint16_t> seeds;        // nbuckets
+    std::vector<uint8_t> seeds;         // nbuckets
     std::vector<uint32_t> slot_node;    // nslots: node id of the record in the slot (deep keys)
     std::vector<uint32_t> slot_pid;     // nslots: best pattern id (tag states); fast tables only
     std::vector<int32_t> pool;          // general rows
@@ -68,6 +68,12 @@ NodeTable build_node_table(const PatternSet& ps, bool force_general);
 // Type score table of TypeScorerBoundaryCache::new (type_scorer/boundary_scorer_cache.rs:22-56).
 std::vector<int32_t> build_type_cache(const std::vector<NgramEntry>& type_ngrams, uint8_t window);
 
-uint32_t table_slot(const TableGeom& g, const uint16_t* seeds, uint64_t key);
+// For window 3 and n-grams of at most 3 types the 8^6-entry table splits exactly into two 8^4-entry
+// tables: T[t0..t5] = A[t0..t3] + B[t2..t5] (A: occurrences inside positions 0..3, B: the others, which all
+// lie inside positions 2..5).  Returns false if the model does not qualify.  Both tables fit in shared memory.
+bool build_type_split(const std::vector<NgramEntry>& type_ngrams, uint8_t window, std::vector<int32_t>& a,
+                      std::vector<int32_t>& b);
+
+uint32_t table_slot(const TableGeom& g, const uint8_t* seeds, uint64_t key);
 
 }  // namespace vpt

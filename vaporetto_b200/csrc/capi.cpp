@@ -109,7 +109,7 @@ DevTable dev_table(const BlobTable& bt, const uint8_t* base) {
     d.nbuckets = bt.nbuckets;
     d.salt = bt.salt;
     d.records = base + bt.rec_off;
-    d.seeds = reinterpret_cast<const uint16_t*>(base + bt.seeds_off);
+    d.seeds = base + bt.seeds_off;
     d.slot_node = reinterpret_cast<const uint32_t*>(base + bt.node_off);
     d.slot_pid = reinterpret_cast<const uint32_t*>(base + bt.pid_off);
     d.pool = reinterpret_cast<const int32_t*>(base + bt.pool_off);
@@ -133,6 +133,8 @@ void upload(vpt_predictor& p) {
     p.dm.tt = dev_table(h.tt, base);
     p.dm.type_cache_window = h.type_cache_window;
     p.dm.type_cache = h.type_cache_window ? reinterpret_cast<const int32_t*>(base + h.type_cache_off) : nullptr;
+    p.dm.type_a = h.type_a_off ? reinterpret_cast<const int32_t*>(base + h.type_a_off) : nullptr;
+    p.dm.type_b = h.type_b_off ? reinterpret_cast<const int32_t*>(base + h.type_b_off) : nullptr;
     p.dm.bias = h.bias;
     p.dm.char_window = h.char_window;
     p.dm.type_window = h.type_window;
@@ -160,7 +162,7 @@ struct ScratchLease {
 };
 
 struct WorkspaceLayout {
-    size_t n_chars, local_bound, local_char, group_bound, group_char, total;
+    size_t n_chars, local_bound, local_char, group_bound, group_char, ticket, total;
 };
 WorkspaceLayout workspace_layout(size_t n) {
     WorkspaceLayout l;
@@ -171,6 +173,7 @@ WorkspaceLayout workspace_layout(size_t n) {
     l.local_char = o; o = align_up(o + 4 * n, 256);
     l.group_bound = o; o = align_up(o + 8 * (ng + 1), 256);
     l.group_char = o; o = align_up(o + 8 * (ng + 1), 256);
+    l.ticket = o; o += 256;
     l.total = o + 256;
     return l;
 }
@@ -183,6 +186,7 @@ void bind_workspace(BatchArgs& a, void* ws, size_t n) {
     a.local_char = reinterpret_cast<uint32_t*>(b + l.local_char);
     a.group_bound = reinterpret_cast<uint64_t*>(b + l.group_bound);
     a.group_char = reinterpret_cast<uint64_t*>(b + l.group_char);
+    a.ticket = reinterpret_cast<uint32_t*>(b + l.ticket);
 }
 
 // ---- host-side text helpers ------------------------------------------------------------------------
@@ -324,13 +328,13 @@ int vpt_predictor_from_blob(const void* blob, uint64_t len, int device, vpt_pred
 
 uint64_t vpt_workspace_size(size_t n_sent) { return workspace_layout(n_sent).total; }
 
-int vpt_predict_batch_dev(const vpt_predictor* p, const uint8_t* d_utf8, const uint64_t* d_byte_offsets, size_t n_sent,
+static void run_batch_dev(const vpt_predictor* p, const uint8_t* d_utf8, const uint64_t* d_byte_offsets, size_t n_sent,
                           void* d_workspace, uint64_t workspace_bytes, int32_t* d_scores, uint8_t* d_boundaries,
                           uint64_t* d_bound_offsets, int32_t* d_status, uint32_t* d_char_states,
-                          uint32_t* d_type_states, uint64_t* d_char_offsets, void* cuda_stream) {
-    VPT_API_BEGIN
+                          uint32_t* d_type_states, uint64_t* d_char_offsets, void* cuda_stream, float* stage_ms) {
     if (!p) throw Error(kInvalidArgument, "InvalidArgumentError: predictor: must not be NULL");
-    if (n_sent == 0) return kOk;
+    if (stage_ms) stage_ms[0] = stage_ms[1] = stage_ms[2] = 0.f;
+    if (n_sent == 0) return;
     if (!d_utf8 || !d_byte_offsets || !d_workspace || !d_scores || !d_boundaries || !d_bound_offsets || !d_status)
         throw Error(kInvalidArgument, "InvalidArgumentError: device buffers: must not be NULL");
     if (workspace_bytes < workspace_layout(n_sent).total)
@@ -350,11 +354,94 @@ int vpt_predict_batch_dev(const vpt_predictor* p, const uint8_t* d_utf8, const u
     a.char_offsets = d_char_offsets;
     a.char_states = d_char_states;
     a.type_states = d_type_states;
-    cuda_check(launch_count(a, st), "launch(count)");
+    if (!stage_ms) {
+        cuda_check(launch_count(a, st), "launch(count)");
+        cuda_check(launch_score(p->dm, a, st), "launch(score)");
+        return;
+    }
+    cudaEvent_t ev[4];
+    for (auto& e : ev) cuda_check(cudaEventCreate(&e), "cudaEventCreate");
+    cuda_check(cudaEventRecord(ev[0], st), "record");
+    cuda_check(launch_count_only(a, st), "launch(count)");
+    cuda_check(cudaEventRecord(ev[1], st), "record");
+    cuda_check(launch_scan_only(a, st), "launch(scan)");
+    cuda_check(cudaEventRecord(ev[2], st), "record");
     cuda_check(launch_score(p->dm, a, st), "launch(score)");
+    cuda_check(cudaEventRecord(ev[3], st), "record");
+    cuda_check(cudaStreamSynchronize(st), "sync(profiled)");
+    for (int i = 0; i < 3; ++i) cuda_check(cudaEventElapsedTime(&stage_ms[i], ev[i], ev[i + 1]), "elapsed");
+    for (auto& e : ev) cudaEventDestroy(e);
+}
+
+int vpt_predict_batch_dev(const vpt_predictor* p, const uint8_t* d_utf8, const uint64_t* d_byte_offsets, size_t n_sent,
+                          void* d_workspace, uint64_t workspace_bytes, int32_t* d_scores, uint8_t* d_boundaries,
+                          uint64_t* d_bound_offsets, int32_t* d_status, uint32_t* d_char_states,
+                          uint32_t* d_type_states, uint64_t* d_char_offsets, void* cuda_stream) {
+    VPT_API_BEGIN
+    run_batch_dev(p, d_utf8, d_byte_offsets, n_sent, d_workspace, workspace_bytes, d_scores, d_boundaries,
+                  d_bound_offsets, d_status, d_char_states, d_type_states, d_char_offsets, cuda_stream, nullptr);
     return kOk;
     VPT_API_END
 }
+
+int vpt_predict_batch_dev_profiled(const vpt_predictor* p, const uint8_t* d_utf8, const uint64_t* d_byte_offsets,
+                                   size_t n_sent, void* d_workspace, uint64_t workspace_bytes, int32_t* d_scores,
+                                   uint8_t* d_boundaries, uint64_t* d_bound_offsets, int32_t* d_status,
+                                   uint32_t* d_char_states, uint32_t* d_type_states, uint64_t* d_char_offsets,
+                                   void* cuda_stream, float* stage_ms) {
+    VPT_API_BEGIN
+    if (!stage_ms) throw Error(kInvalidArgument, "InvalidArgumentError: stage_ms: must not be NULL");
+    run_batch_dev(p, d_utf8, d_byte_offsets, n_sent, d_workspace, workspace_bytes, d_scores, d_boundaries,
+                  d_bound_offsets, d_status, d_char_states, d_type_states, d_char_offsets, cuda_stream, stage_ms);
+    return kOk;
+    VPT_API_END
+}
+
+namespace {
+
+constexpr size_t kChunkSentences = 65536;  // sentences per pipelined chunk of vpt_predict_batch
+
+struct ChunkState {
+    size_t s_lo = 0, n = 0;       // sentence range
+    uint64_t byte_lo = 0, nbytes = 0;
+    cudaEvent_t counted = nullptr;
+    BatchArgs a;
+};
+
+// stage 1 of a chunk: H2D of text + offsets, count + scan, totals to pinned host memory
+void chunk_count(Scratch& s, ChunkState& ch, const uint8_t* utf8, const uint64_t* byte_offsets) {
+    cudaStream_t st = s.stream;
+    const WorkspaceLayout wl = workspace_layout(ch.n);
+    const size_t shift = size_t(ch.byte_lo & 15);
+    Scratch::ensure(s.d_text, s.text_cap, shift + ch.nbytes + 64);
+    Scratch::ensure(s.d_off, s.off_cap, 8 * (ch.n + 1));
+    Scratch::ensure(s.d_ws, s.ws_cap, wl.total);
+    Scratch::ensure(s.d_status, s.status_cap, 4 * ch.n);
+    Scratch::ensure(s.d_boff, s.boff_cap, 8 * (ch.n + 1));
+    Scratch::ensure(s.d_coff, s.coff_cap, 8 * (ch.n + 1));
+    if (ch.nbytes)
+        cuda_check(cudaMemcpyAsync(static_cast<uint8_t*>(s.d_text) + shift, utf8 + ch.byte_lo, ch.nbytes,
+                                   cudaMemcpyHostToDevice, st), "H2D(text)");
+    cuda_check(cudaMemcpyAsync(s.d_off, byte_offsets + ch.s_lo, 8 * (ch.n + 1), cudaMemcpyHostToDevice, st), "H2D(offsets)");
+    BatchArgs& a = ch.a;
+    a = BatchArgs();
+    // offsets are absolute in the caller's buffer: bias the text pointer so that text[offset] is right
+    a.text = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(s.d_text) + shift - uintptr_t(ch.byte_lo));
+    a.offsets = static_cast<const uint64_t*>(s.d_off);
+    a.n_sent = ch.n;
+    bind_workspace(a, s.d_ws, ch.n);
+    a.status = static_cast<int32_t*>(s.d_status);
+    a.bound_offsets = static_cast<uint64_t*>(s.d_boff);
+    a.char_offsets = static_cast<uint64_t*>(s.d_coff);
+    cuda_check(launch_count(a, st), "launch(count)");
+    const size_t ng = (ch.n + kGroup - 1) / kGroup;
+    cuda_check(cudaMemcpyAsync(&s.h_totals[0], a.group_bound + ng, 8, cudaMemcpyDeviceToHost, st), "D2H(total)");
+    cuda_check(cudaMemcpyAsync(&s.h_totals[1], a.group_char + ng, 8, cudaMemcpyDeviceToHost, st), "D2H(total)");
+    if (!ch.counted) cuda_check(cudaEventCreateWithFlags(&ch.counted, cudaEventDisableTiming), "cudaEventCreate");
+    cuda_check(cudaEventRecord(ch.counted, st), "cudaEventRecord");
+}
+
+}  // namespace
 
 int vpt_predict_batch(const vpt_predictor* p, const uint8_t* utf8, const uint64_t* byte_offsets, size_t n_sent,
                       int32_t* scores_out, uint8_t* boundaries_out, size_t out_capacity, uint64_t* bound_offsets_out,
@@ -368,67 +455,78 @@ int vpt_predict_batch(const vpt_predictor* p, const uint8_t* utf8, const uint64_
     if (!byte_offsets || !bound_offsets_out)
         throw Error(kInvalidArgument, "InvalidArgumentError: byte_offsets/bound_offsets_out: must not be NULL");
     if (n_sent == 0) { bound_offsets_out[0] = 0; if (char_offsets_out) char_offsets_out[0] = 0; return kOk; }
-    const uint64_t base = byte_offsets[0], end = byte_offsets[n_sent];
-    if (end < base) throw Error(kInvalidArgument, "InvalidArgumentError: byte_offsets: must be non-decreasing");
-    const size_t nbytes = size_t(end - base);
-    if (nbytes && !utf8) throw Error(kInvalidArgument, "InvalidArgumentError: utf8: must not be NULL");
+    if (byte_offsets[n_sent] < byte_offsets[0])
+        throw Error(kInvalidArgument, "InvalidArgumentError: byte_offsets: must be non-decreasing");
+    if (byte_offsets[n_sent] > byte_offsets[0] && !utf8)
+        throw Error(kInvalidArgument, "InvalidArgumentError: utf8: must not be NULL");
     cuda_check(cudaSetDevice(p->device), "cudaSetDevice");
-    ScratchLease lease(*p);
-    Scratch& s = *lease.s;
-    cudaStream_t st = s.stream;
-    const WorkspaceLayout wl = workspace_layout(n_sent);
-    // the text is staged starting at a 16-byte aligned device address keeping base's low bits
-    const size_t shift = size_t(base & 15);
-    Scratch::ensure(s.d_text, s.text_cap, shift + nbytes + 64);
-    Scratch::ensure(s.d_off, s.off_cap, 8 * (n_sent + 1));
-    Scratch::ensure(s.d_ws, s.ws_cap, wl.total);
-    Scratch::ensure(s.d_status, s.status_cap, 4 * n_sent);
-    Scratch::ensure(s.d_boff, s.boff_cap, 8 * (n_sent + 1));
-    Scratch::ensure(s.d_coff, s.coff_cap, 8 * (n_sent + 1));
-    if (nbytes)
-        cuda_check(cudaMemcpyAsync(static_cast<uint8_t*>(s.d_text) + shift, utf8 + base, nbytes, cudaMemcpyHostToDevice, st),
-                   "H2D(text)");
-    cuda_check(cudaMemcpyAsync(s.d_off, byte_offsets, 8 * (n_sent + 1), cudaMemcpyHostToDevice, st), "H2D(offsets)");
-    BatchArgs a;
-    // offsets are absolute in the caller's buffer: bias the text pointer so that text[offset] is right
-    a.text = static_cast<const uint8_t*>(s.d_text) + shift - base;
-    a.offsets = static_cast<const uint64_t*>(s.d_off);
-    a.n_sent = n_sent;
-    bind_workspace(a, s.d_ws, n_sent);
-    a.status = static_cast<int32_t*>(s.d_status);
-    a.bound_offsets = static_cast<uint64_t*>(s.d_boff);
-    a.char_offsets = static_cast<uint64_t*>(s.d_coff);
-    cuda_check(launch_count(a, st), "launch(count)");
-    const size_t ng = (n_sent + kGroup - 1) / kGroup;
-    cuda_check(cudaMemcpyAsync(&s.h_totals[0], a.group_bound + ng, 8, cudaMemcpyDeviceToHost, st), "D2H(total)");
-    cuda_check(cudaMemcpyAsync(&s.h_totals[1], a.group_char + ng, 8, cudaMemcpyDeviceToHost, st), "D2H(total)");
-    cuda_check(cudaStreamSynchronize(st), "sync(count)");
-    const uint64_t nb = s.h_totals[0], nc = s.h_totals[1];
-    if (n_boundaries_out) *n_boundaries_out = nb;
-    if (n_chars_out) *n_chars_out = nc;
-    if (nb > out_capacity || (nb && !boundaries_out))
-        throw Error(kInvalidArgument, "InvalidArgumentError: out_capacity: too small for the batch");
-    const bool want_states = char_states_out || type_states_out;
-    if (want_states && nc > states_capacity)
-        throw Error(kInvalidArgument, "InvalidArgumentError: states_capacity: too small for the batch");
-    Scratch::ensure(s.d_scores, s.scores_cap, 4 * nb + 4);
-    Scratch::ensure(s.d_bounds, s.bounds_cap, nb + 4);
-    a.scores = static_cast<int32_t*>(s.d_scores);
-    a.boundaries = static_cast<uint8_t*>(s.d_bounds);
-    if (char_states_out) { Scratch::ensure(s.d_cst, s.cst_cap, 4 * nc + 4); a.char_states = static_cast<uint32_t*>(s.d_cst); }
-    if (type_states_out) { Scratch::ensure(s.d_tst, s.tst_cap, 4 * nc + 4); a.type_states = static_cast<uint32_t*>(s.d_tst); }
-    cuda_check(launch_score(p->dm, a, st), "launch(score)");
-    if (nb) {
-        if (scores_out) cuda_check(cudaMemcpyAsync(scores_out, s.d_scores, 4 * nb, cudaMemcpyDeviceToHost, st), "D2H(scores)");
-        cuda_check(cudaMemcpyAsync(boundaries_out, s.d_bounds, nb, cudaMemcpyDeviceToHost, st), "D2H(boundaries)");
+
+    // The batch is cut into chunks that flow through three streams so that the H2D copy of chunk c+2, the
+    // kernels of chunk c+1 and the D2H copy of chunk c overlap.  Each chunk is an independent batch on the
+    // device; its output offsets are rebased with the running totals (known on the host after its count pass).
+    const size_t nchunks = (n_sent + kChunkSentences - 1) / kChunkSentences;
+    constexpr int kDepth = 3;
+    std::unique_ptr<ScratchLease> lease[kDepth];
+    for (int i = 0; i < kDepth && size_t(i) < nchunks; ++i) lease[i].reset(new ScratchLease(*p));
+    std::vector<ChunkState> chunks(nchunks);
+    struct EventGuard {
+        std::vector<ChunkState>& c;
+        ~EventGuard() { for (auto& x : c) if (x.counted) cudaEventDestroy(x.counted); }
+    } guard{chunks};
+    for (size_t c = 0; c < nchunks; ++c) {
+        ChunkState& ch = chunks[c];
+        ch.s_lo = c * kChunkSentences;
+        ch.n = std::min(kChunkSentences, n_sent - ch.s_lo);
+        ch.byte_lo = byte_offsets[ch.s_lo];
+        if (byte_offsets[ch.s_lo + ch.n] < ch.byte_lo)
+            throw Error(kInvalidArgument, "InvalidArgumentError: byte_offsets: must be non-decreasing");
+        ch.nbytes = byte_offsets[ch.s_lo + ch.n] - ch.byte_lo;
     }
-    cuda_check(cudaMemcpyAsync(bound_offsets_out, s.d_boff, 8 * (n_sent + 1), cudaMemcpyDeviceToHost, st), "D2H(offsets)");
-    if (char_offsets_out)
-        cuda_check(cudaMemcpyAsync(char_offsets_out, s.d_coff, 8 * (n_sent + 1), cudaMemcpyDeviceToHost, st), "D2H(offsets)");
-    if (status_out) cuda_check(cudaMemcpyAsync(status_out, s.d_status, 4 * n_sent, cudaMemcpyDeviceToHost, st), "D2H(status)");
-    if (nc && char_states_out) cuda_check(cudaMemcpyAsync(char_states_out, s.d_cst, 4 * nc, cudaMemcpyDeviceToHost, st), "D2H(states)");
-    if (nc && type_states_out) cuda_check(cudaMemcpyAsync(type_states_out, s.d_tst, 4 * nc, cudaMemcpyDeviceToHost, st), "D2H(states)");
-    cuda_check(cudaStreamSynchronize(st), "sync(score)");
+    const bool want_states = char_states_out || type_states_out;
+    uint64_t nb_total = 0, nc_total = 0;
+    bool overflow = false;
+    for (size_t c = 0; c < std::min<size_t>(2, nchunks); ++c) chunk_count(*lease[c % kDepth]->s, chunks[c], utf8, byte_offsets);
+    for (size_t c = 0; c < nchunks; ++c) {
+        ChunkState& ch = chunks[c];
+        Scratch& s = *lease[c % kDepth]->s;
+        cudaStream_t st = s.stream;
+        cuda_check(cudaEventSynchronize(ch.counted), "sync(count)");
+        const uint64_t nb = s.h_totals[0], nc = s.h_totals[1];
+        if (nb_total + nb > out_capacity || (nb && !boundaries_out) || (want_states && nc_total + nc > states_capacity))
+            overflow = true;
+        if (!overflow) {
+            BatchArgs& a = ch.a;
+            Scratch::ensure(s.d_scores, s.scores_cap, 4 * nb + 4);
+            Scratch::ensure(s.d_bounds, s.bounds_cap, nb + 4);
+            a.scores = static_cast<int32_t*>(s.d_scores);
+            a.boundaries = static_cast<uint8_t*>(s.d_bounds);
+            if (char_states_out) { Scratch::ensure(s.d_cst, s.cst_cap, 4 * nc + 4); a.char_states = static_cast<uint32_t*>(s.d_cst); }
+            if (type_states_out) { Scratch::ensure(s.d_tst, s.tst_cap, 4 * nc + 4); a.type_states = static_cast<uint32_t*>(s.d_tst); }
+            a.bound_base = nb_total;
+            a.char_base = nc_total;
+            cuda_check(launch_score(p->dm, a, st), "launch(score)");
+            if (nb) {
+                if (scores_out) cuda_check(cudaMemcpyAsync(scores_out + nb_total, s.d_scores, 4 * nb, cudaMemcpyDeviceToHost, st), "D2H(scores)");
+                cuda_check(cudaMemcpyAsync(boundaries_out + nb_total, s.d_bounds, nb, cudaMemcpyDeviceToHost, st), "D2H(boundaries)");
+            }
+            // the last element of a chunk's offsets is the first of the next chunk's: copy n (+1 for the last chunk)
+            const size_t noff = ch.n + (c + 1 == nchunks ? 1 : 0);
+            cuda_check(cudaMemcpyAsync(bound_offsets_out + ch.s_lo, s.d_boff, 8 * noff, cudaMemcpyDeviceToHost, st), "D2H(offsets)");
+            if (char_offsets_out)
+                cuda_check(cudaMemcpyAsync(char_offsets_out + ch.s_lo, s.d_coff, 8 * noff, cudaMemcpyDeviceToHost, st), "D2H(offsets)");
+            if (status_out) cuda_check(cudaMemcpyAsync(status_out + ch.s_lo, s.d_status, 4 * ch.n, cudaMemcpyDeviceToHost, st), "D2H(status)");
+            if (nc && char_states_out) cuda_check(cudaMemcpyAsync(char_states_out + nc_total, s.d_cst, 4 * nc, cudaMemcpyDeviceToHost, st), "D2H(states)");
+            if (nc && type_states_out) cuda_check(cudaMemcpyAsync(type_states_out + nc_total, s.d_tst, 4 * nc, cudaMemcpyDeviceToHost, st), "D2H(states)");
+        }
+        nb_total += nb;
+        nc_total += nc;
+        if (c + 2 < nchunks) chunk_count(*lease[(c + 2) % kDepth]->s, chunks[c + 2], utf8, byte_offsets);
+    }
+    for (int i = 0; i < kDepth; ++i)
+        if (lease[i]) cuda_check(cudaStreamSynchronize(lease[i]->s->stream), "sync(score)");
+    if (n_boundaries_out) *n_boundaries_out = nb_total;
+    if (n_chars_out) *n_chars_out = nc_total;
+    if (overflow) throw Error(kInvalidArgument, "InvalidArgumentError: out_capacity/states_capacity: too small for the batch");
     return kOk;
     VPT_API_END
 }

@@ -9,7 +9,7 @@ namespace vpt {
 
 struct DevTable {
     const void* records = nullptr;     // nslots x 32 B (FastRecord or GeneralRecord)
-    const uint16_t* seeds = nullptr;   // nbuckets
+    const uint8_t* seeds = nullptr;    // nbuckets
     const uint32_t* slot_node = nullptr;
     const uint32_t* slot_pid = nullptr;
     const int32_t* pool = nullptr;     // general rows
@@ -27,6 +27,8 @@ struct DevModel {
     DevTable tt;                         // type patterns (automaton variant only)
     const int32_t* type_cache = nullptr; // 8^(2W) table (cache variant only)
     int32_t type_cache_window = 0;       // 0 = no cache table
+    const int32_t* type_a = nullptr;     // split tables for window 3 (T = A[t0..t3] + B[t2..t5]), or null
+    const int32_t* type_b = nullptr;
     int32_t bias = 0;
     int32_t char_window = 0;
     int32_t type_window = 0;
@@ -45,10 +47,13 @@ struct BatchArgs {
     uint32_t* local_char = nullptr;       // [n_sent] char offset inside its group
     uint64_t* group_bound = nullptr;      // [n_groups + 1]
     uint64_t* group_char = nullptr;       // [n_groups + 1]
+    uint32_t* ticket = nullptr;           // work counter of the persistent tile kernel (zeroed by the scan)
     // outputs
     int32_t* scores = nullptr;            // [sum(max(chars_i - 1, 0))]
     uint8_t* boundaries = nullptr;        // same length
-    uint64_t* bound_offsets = nullptr;    // [n_sent + 1]
+    uint64_t* bound_offsets = nullptr;    // [n_sent + 1]; values are chunk-local offsets + bound_base
+    uint64_t bound_base = 0;              // added to the bound_offsets / char_offsets written out
+    uint64_t char_base = 0;
     uint64_t* char_offsets = nullptr;     // [n_sent + 1] (nullable)
     uint32_t* char_states = nullptr;      // [sum(chars_i)] (nullable)
     uint32_t* type_states = nullptr;      // [sum(chars_i)] (nullable)
@@ -57,7 +62,9 @@ struct BatchArgs {
 constexpr int kGroup = 64;  // sentences per count-pass block
 
 // Launch helpers; all asynchronous on `stream`.  Return cudaError_t of the launch.
-cudaError_t launch_count(const BatchArgs& a, cudaStream_t stream);
+cudaError_t launch_count(const BatchArgs& a, cudaStream_t stream);  // count + scan
+cudaError_t launch_count_only(const BatchArgs& a, cudaStream_t stream);
+cudaError_t launch_scan_only(const BatchArgs& a, cudaStream_t stream);
 cudaError_t launch_score(const DevModel& m, const BatchArgs& a, cudaStream_t stream);
 // number of kernel launches issued by launch_count + launch_score for this model
 int launches_per_batch(const DevModel& m);

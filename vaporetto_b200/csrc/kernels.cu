@@ -10,13 +10,17 @@
 //   k_count        one warp per sentence: chars per sentence, validation (empty / NUL / bad UTF-8),
 //                  group-local exclusive offsets (64 sentences per CTA)
 //   k_scan_groups  one CTA: exclusive scan of the per-group totals
-//   k_score_fast   one warp per sentence, one lane per character: UTF-8 decode into a per-warp shared
-//                  ring, longest-suffix lookup in the perfect-hash node table (one 32-byte LDG.256 record
-//                  per probe), warp-shuffle gather of the 6-wide weight rows into per-boundary sums,
-//                  type-table add, bias, threshold, coalesced stores.
+//   k_tile_fast    one CTA per group of 64 sentences: the group's UTF-8 bytes are staged into shared memory
+//                  with one TMA bulk copy (cp.async.bulk + mbarrier); characters of all sentences are laid
+//                  out as one flat slot stream (zero separators between sentences) so every lane of every
+//                  warp owns one character: decode, longest-suffix lookup in the perfect-hash node table
+//                  (one 32-byte LDG.256 record per probe), warp-shuffle gather of the 6-wide weight rows
+//                  into per-boundary sums, type-table add, bias, threshold, coalesced stores.
+//   (fast_sentence_warp: one warp per sentence — fallback for groups too large for the tile buffers)
 //   k_score_general  same skeleton for models whose rows do not fit the inline window, for the type
 //                  automaton variant and for tag-state output: rows scatter with global atomics.
 // No tensor cores: integer indexing + scatter/gather add.
+#include <algorithm>
 #include <cstdint>
 
 #include <cuda_runtime.h>
@@ -48,11 +52,10 @@ __device__ __forceinline__ Rec32 load_record(const void* base, uint32_t slot) {
 }
 
 __device__ __forceinline__ uint32_t slot_of(const DevTable& t, uint64_t key) {
-    const uint64_t h = mix64(key + t.salt);
-    const uint32_t bucket = __umulhi(uint32_t(h >> 32), t.nbuckets);
-    const uint32_t seed = __ldg(t.seeds + bucket);
-    const uint64_t h2 = mix64(key ^ (uint64_t(seed) + 1) * 0x9E3779B97F4A7C15ULL);
-    return __umulhi(uint32_t(h2 >> 32), t.nslots);
+    uint32_t ha, hb;
+    key_hashes(key, t.salt, ha, hb);
+    const uint32_t seed = __ldg(t.seeds + bucket_of(ha, t.nbuckets));
+    return slot_with_seed(ha, hb, seed, t.nslots);
 }
 
 // One probe: returns true when the node with `key` exists; rec/slot are valid then.
@@ -162,24 +165,109 @@ __device__ __forceinline__ uint32_t prev_char(const uint8_t* __restrict__ text, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// TMA bulk copy + mbarrier helpers (PTX; SASS: UBLKCP / SYNCS)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // k_count
 // ------------------------------------------------------------------------------------------------
+constexpr int kCountTextCap = 24576;  // bytes of one group staged in shared memory by k_count
+
+// One CTA per group of 64 sentences.  The group's bytes are staged in shared memory with one TMA bulk copy
+// (groups larger than the buffer are read from global memory instead); each warp then counts and validates
+// its sentences: characters, NUL, malformed UTF-8.
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_count(BatchArgs a) {
+    __shared__ __align__(128) uint8_t s_text[kCountTextCap];
+    __shared__ uint64_t s_off[kGroup + 1];
     __shared__ uint32_t s_nout[kGroup], s_nch[kGroup];
+    __shared__ __align__(8) uint64_t s_bar;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint64_t gbase = uint64_t(blockIdx.x) * kGroup;
+    const int ns = int(min(uint64_t(kGroup), a.n_sent - gbase));
     const uint8_t* __restrict__ text = a.text;
+    if (threadIdx.x <= ns) s_off[threadIdx.x] = a.offsets[gbase + threadIdx.x];
+    if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+    __syncthreads();
+    const uint64_t a0 = s_off[0] & ~15ull;
+    const uint64_t span = (s_off[ns] - a0 + 15) & ~15ull;
+    const bool staged = span + 16 <= uint64_t(kCountTextCap);
+    if (staged && span) {
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(&s_bar, uint32_t(span));
+            tma_bulk_g2s(s_text, text + a0, uint32_t(span), &s_bar);
+        }
+        mbar_wait(&s_bar, 0);
+    }
     for (int i = warp; i < kGroup; i += kWarpsPerBlock) {
-        const uint64_t s = gbase + i;
         uint32_t nch = 0, nout = 0;
-        if (s < a.n_sent) {
-            const uint64_t b0 = a.offsets[s], b1 = a.offsets[s + 1];
+        if (i < ns) {
+            const uint64_t b0 = s_off[i], b1 = s_off[i + 1];
             uint32_t starts = 0, conts = 0, expect = 0, flags = 0;  // flags: 1 NUL, 2 malformed
             for (uint64_t wpos = b0 & ~3ull; wpos < b1; wpos += 128) {
                 const uint64_t addr = wpos + 4u * uint32_t(lane);
                 if (addr < b1) {
-                    const uint32_t lo = __ldg(reinterpret_cast<const uint32_t*>(text + addr));
-                    const uint32_t hi = (addr + 4 < b1) ? __ldg(reinterpret_cast<const uint32_t*>(text + addr + 4)) : 0u;
+                    uint32_t lo, hi = 0;
+                    if (staged) {
+                        lo = *reinterpret_cast<const uint32_t*>(s_text + (addr - a0));
+                        if (addr + 4 < b1) hi = *reinterpret_cast<const uint32_t*>(s_text + (addr + 4 - a0));
+                    } else {
+                        lo = __ldg(reinterpret_cast<const uint32_t*>(text + addr));
+                        if (addr + 4 < b1) hi = __ldg(reinterpret_cast<const uint32_t*>(text + addr + 4));
+                    }
+                    // ---- SWAR fast path over the 4 bytes of this word (V = the word and the 4 bytes after it) ----
+                    const uint32_t from = b0 > addr ? uint32_t(b0 - addr) : 0u;           // first byte inside
+                    const uint32_t to = b1 - addr < 4 ? uint32_t(b1 - addr) : 4u;         // one past the last
+                    const uint32_t im = (from >= 4 ? 0u : 0xFFFFFFFFu << (8 * from)) & (0xFFFFFFFFu >> (8 * (4 - to)));
+                    const uint32_t im80 = im & 0x80808080u;
+                    const uint32_t top2 = lo & (lo << 1);                                  // bit7 = b7&b6
+                    const uint32_t cont80 = lo & ~(lo << 1) & 0x80808080u;                 // 10xxxxxx
+                    const uint32_t l2 = top2 & im80;                                        // 11xxxxxx (any lead)
+                    const uint32_t l3 = top2 & (lo << 2) & im80;                            // 111xxxxx
+                    const uint32_t l4 = top2 & (lo << 2) & (lo << 3) & im80;                // 1111xxxx
+                    const uint32_t lz = (lo & im) | (0x20202020u & ~im);
+                    if ((lz - 0x01010101u) & ~lz & 0x80808080u) flags |= 1;                 // a NUL inside
+                    // bytes that need the exact per-byte rules: C0/C1, E0, ED, F0..FF (rare in real text)
+                    const uint32_t xe0 = lo ^ 0xE0E0E0E0u, xed = lo ^ 0xEDEDEDEDu, xc0 = (lo & 0xFEFEFEFEu) ^ 0xC0C0C0C0u;
+                    const uint32_t special = (l4 | ((xe0 - 0x01010101u) & ~xe0) | ((xed - 0x01010101u) & ~xed) |
+                                              ((xc0 - 0x01010101u) & ~xc0)) & im80;
+                    if (special == 0) {
+                        starts += __popc(im80 & ~cont80);
+                        conts += __popc(im80 & cont80);
+                        expect += __popc(l2) + __popc(l3);
+                        // every lead must be followed, inside the sentence, by its continuation bytes
+                        const uint64_t c64 = (uint64_t(hi & ~(hi << 1) & 0x80808080u) << 32) | cont80;
+                        const uint64_t avail = b1 - addr >= 8 ? ~0ull : (~0ull >> (8 * (8 - (b1 - addr))));
+                        const uint64_t okc = c64 & avail;
+                        const uint64_t need = (uint64_t(l2) << 8) | (uint64_t(l3) << 16);
+                        if (need & ~okc) flags |= 2;
+                    } else {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const uint64_t p = addr + j;
@@ -188,7 +276,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_count(BatchArgs a) {
                         const uint32_t b = x & 0xFF;
                         if ((b & 0xC0) == 0x80) { ++conts; continue; }
                         ++starts;
-                        if (b < 0x80) { if (b == 0) flags |= 1; continue; }
+                        if (b < 0x80) continue;
                         const uint32_t c1 = (x >> 8) & 0xFF, c2 = (x >> 16) & 0xFF, c3 = x >> 24;
                         uint32_t len;
                         bool ok;
@@ -207,6 +295,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_count(BatchArgs a) {
                         if (!ok) flags |= 2;
                         expect += len - 1;
                     }
+                    }
                 }
             }
 #pragma unroll
@@ -221,8 +310,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_count(BatchArgs a) {
             nout = nch > 0 ? nch - 1 : 0;
             const int st = (flags & 2) ? 3 : (flags & 1) ? 2 : (nch == 0 ? 1 : 0);
             if (lane == 0) {
-                a.n_chars[s] = nch;
-                a.status[s] = st;
+                a.n_chars[gbase + i] = nch;
+                a.status[gbase + i] = st;
             }
         }
         if (lane == 0) { s_nout[i] = nout; s_nch[i] = nch; }
@@ -240,7 +329,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_count(BatchArgs a) {
 }
 
 // Exclusive scan of the per-group totals (in place); element [ngroups] receives the grand total.
-__global__ void __launch_bounds__(1024) k_scan_groups(uint64_t* gb, uint64_t* gc, uint64_t ngroups) {
+__global__ void __launch_bounds__(1024) k_scan_groups(uint64_t* gb, uint64_t* gc, uint64_t ngroups, uint32_t* ticket) {
     __shared__ uint64_t s_wb[32], s_wc[32];
     __shared__ uint64_t s_carry[2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -274,7 +363,7 @@ __global__ void __launch_bounds__(1024) k_scan_groups(uint64_t* gb, uint64_t* gc
         if (threadIdx.x == 0) { s_carry[0] += s_wb[31]; s_carry[1] += s_wc[31]; }
         __syncthreads();
     }
-    if (threadIdx.x == 0) { gb[ngroups] = s_carry[0]; gc[ngroups] = s_carry[1]; }
+    if (threadIdx.x == 0) { gb[ngroups] = s_carry[0]; gc[ngroups] = s_carry[1]; *ticket = 0; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -297,11 +386,11 @@ __device__ __forceinline__ SentInfo sentence_info(const BatchArgs& a, uint64_t s
     si.obase = a.group_bound[grp] + a.local_bound[s];
     si.cbase = a.group_char[grp] + a.local_char[s];
     if (lane == 0) {
-        a.bound_offsets[s] = si.obase;
-        if (a.char_offsets) a.char_offsets[s] = si.cbase;
+        a.bound_offsets[s] = a.bound_base + si.obase;
+        if (a.char_offsets) a.char_offsets[s] = a.char_base + si.cbase;
         if (s + 1 == a.n_sent) {
-            a.bound_offsets[s + 1] = si.obase + si.nout;
-            if (a.char_offsets) a.char_offsets[s + 1] = si.cbase + si.n;
+            a.bound_offsets[s + 1] = a.bound_base + si.obase + si.nout;
+            if (a.char_offsets) a.char_offsets[s + 1] = a.char_base + si.cbase + si.n;
         }
     }
     return si;
@@ -360,12 +449,9 @@ __device__ __forceinline__ bool find_node(const DevTable& t, const Rings& r, con
 // ------------------------------------------------------------------------------------------------
 // k_score_fast
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) k_score_fast(DevModel m, BatchArgs a) {
-    __shared__ Rings s_rings[kWarpsPerBlock];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint64_t s = uint64_t(blockIdx.x) * kWarpsPerBlock + warp;
-    if (s >= a.n_sent) return;
-    Rings& r = s_rings[warp];
+// One warp scores one sentence, 32 characters per iteration (used by k_score_fast and as the fallback of
+// k_tile_fast for groups that do not fit the tile buffers).
+__device__ __forceinline__ void fast_sentence_warp(const DevModel& m, const BatchArgs& a, uint64_t s, Rings& r, int lane) {
     const SentInfo si = sentence_info(a, s, lane);
     const uint8_t* __restrict__ text = a.text;
     const uint32_t n = si.n;
@@ -432,6 +518,358 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_score_fast(DevModel m, 
     if (have_prev && prev_g + 1 < n) {
         a.scores[si.obase + prev_g] = prev_main;
         a.boundaries[si.obase + prev_g] = prev_main > 0 ? 1 : 0;
+    }
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) k_score_fast(DevModel m, BatchArgs a) {
+    __shared__ Rings s_rings[kWarpsPerBlock];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint64_t s = uint64_t(blockIdx.x) * kWarpsPerBlock + warp;
+    if (s >= a.n_sent) return;
+    fast_sentence_warp(m, a, s, s_rings[warp], lane);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// k_tile_fast — persistent: one 1024-thread CTA per SM = 4 independent 256-thread sub-blocks that pull
+// 64-sentence groups from a global ticket.  Shared by the 4 sub-blocks: the perfect-hash seed bytes and the
+// split type tables (staged once per CTA); private to each sub-block: the tile buffers below.
+// ------------------------------------------------------------------------------------------------
+constexpr int kSubThreads = 256;
+constexpr int kSubBlocks = 4;
+constexpr int kTileThreads = kSubThreads * kSubBlocks;
+constexpr int kTextCap = 12288;   // bytes of text staged per tile
+constexpr int kSlotCap = 3072;    // character slots (characters + separators) per tile
+constexpr int kSeedCap = 38400;   // seed bytes kept in shared memory (one per 8 nodes: ~307 K nodes)
+constexpr int kTypeSub = 4096;    // entries of each split type table
+constexpr uint32_t kSepPos = 0xFFFFu;
+
+struct TileTables {
+    uint64_t off[kGroup + 1];
+    uint64_t obase[kGroup];
+    uint64_t cbase[kGroup];
+    uint32_t lc[kGroup + 1];  // chars before sentence k inside the group
+    uint32_t nch[kGroup];
+    int32_t st[kGroup];
+    uint32_t ticket;
+    int32_t k1;               // end of the current sentence range
+    uint32_t pad[2];
+};
+
+// per-sub-block shared memory layout (bytes)
+constexpr int kOffText = 0;                              // text bytes, later per-slot partial sums (sc)
+constexpr int kOffCp = kOffText + kTextCap;              // code point per slot
+constexpr int kOffPos = kOffCp + 4 * kSlotCap;           // byte position per slot (u16), later spill arrays
+constexpr int kOffTy = kOffPos + 2 * kSlotCap;           // char type per slot (+ 32 guard bytes each side)
+constexpr int kOffKk = kOffTy + kSlotCap + 64;           // sentence-in-group per slot
+constexpr int kOffTab = kOffKk + kSlotCap;               // TileTables
+constexpr int kOffBar = kOffTab + ((int(sizeof(TileTables)) + 15) & ~15);
+constexpr int kSubBytes = (kOffBar + 16 + 127) & ~127;
+// CTA-shared part
+constexpr int kOffSeeds = 0;
+constexpr int kOffTypeA = kOffSeeds + kSeedCap;
+constexpr int kOffTypeB = kOffTypeA + 4 * kTypeSub;
+constexpr int kOffSub = kOffTypeB + 4 * kTypeSub;
+constexpr int kTileSmem = kOffSub + kSubBlocks * kSubBytes;
+static_assert(4 * kSlotCap <= kTextCap, "sc aliases the text buffer");
+static_assert(2 * (kSlotCap / 32) * 8 * 4 <= 2 * kSlotCap, "spill arrays alias the position buffer");
+static_assert(int(sizeof(Rings)) * (kSubThreads / 32) <= kOffPos, "fallback rings alias text+cp");
+static_assert(kTileSmem <= 227 * 1024, "shared memory budget");
+
+__device__ __forceinline__ void sub_sync(int sub) {
+    asm volatile("bar.sync %0, %1;" ::"r"(sub + 1), "r"(kSubThreads) : "memory");
+}
+
+template <bool kSeedsSmem>
+__device__ __forceinline__ uint32_t slot_of_t(const DevTable& t, const uint8_t* s_seeds, uint64_t key) {
+    uint32_t ha, hb;
+    key_hashes(key, t.salt, ha, hb);
+    const uint32_t b = bucket_of(ha, t.nbuckets);
+    const uint32_t seed = kSeedsSmem ? uint32_t(s_seeds[b]) : uint32_t(__ldg(t.seeds + b));
+    return slot_with_seed(ha, hb, seed, t.nslots);
+}
+
+__device__ __forceinline__ bool rec_matches(const Rec32& rec, uint64_t key) {
+    const uint64_t k = (uint64_t(rec.v[1]) << 32) | rec.v[0];
+    return (k & ~kExtFlag) == key;
+}
+
+// Completes the longest-suffix lookup for slot p given the (already loaded) record of the first probe.
+template <bool kSeedsSmem>
+__device__ __forceinline__ void lookup_finish(const DevTable& t, const uint8_t* s_seeds, const uint32_t* __restrict__ cp,
+                                              int p, uint32_t c1, uint32_t c2, uint32_t c3, Rec32 rec, uint32_t slot,
+                                              int32_t (&d)[kInlineWidth]) {
+    bool found = rec_matches(rec, shallow_key(c1, c2, c3));
+    const bool depth3 = found && c1 != 0;
+    if (!found && c1 != 0) {
+        const uint64_t key = shallow_key(0, c2, c3);
+        slot = slot_of_t<kSeedsSmem>(t, s_seeds, key);
+        rec = load_record(t.records, slot);
+        found = rec_matches(rec, key);
+    }
+    if (!found && c2 != 0) {
+        const uint64_t key = shallow_key(0, 0, c3);
+        slot = slot_of_t<kSeedsSmem>(t, s_seeds, key);
+        rec = load_record(t.records, slot);
+        found = rec_matches(rec, key);
+    }
+    if (depth3 && (rec.v[1] >> 31)) {
+        uint32_t node = __ldg(t.slot_node + slot);
+        for (int i = p - 3; cp[i] != 0; --i) {
+            const uint64_t key = deep_key(node, cp[i]);
+            const uint32_t nslot = slot_of_t<kSeedsSmem>(t, s_seeds, key);
+            const Rec32 nrec = load_record(t.records, nslot);
+            if (!rec_matches(nrec, key)) break;
+            rec = nrec;
+            if (!(rec.v[1] >> 31)) break;
+            node = __ldg(t.slot_node + nslot);
+        }
+    }
+    if (found) {
+#pragma unroll
+        for (int j = 0; j < kInlineWidth; ++j) d[j] = int32_t(rec.v[2 + j]);
+    }
+}
+
+// gather of the 6-wide rows of one 32-slot warp chunk: boundary (lane) <- row entry j of lane - r0 - j
+__device__ __forceinline__ void gather_store(const int32_t (&d)[kInlineWidth], int r0, int lane, int p, int32_t* s_sc,
+                                             int32_t* s_spill_prev, int32_t* s_spill_next) {
+    int32_t mainv = 0, to_prev = 0, to_next = 0;
+#pragma unroll
+    for (int j = 0; j < kInlineWidth; ++j) {
+        const int src = lane - r0 - j;
+        const int32_t v = __shfl_sync(kFull, d[j], src & 31);
+        if (src < 0) to_next += v;
+        else if (src >= 32) to_prev += v;
+        else mainv += v;
+    }
+    s_sc[p] = mainv;
+    const int wc = p >> 5;
+    if (lane >= 24) s_spill_prev[wc * 8 + lane - 24] = to_prev;
+    if (lane < 8) s_spill_next[wc * 8 + lane] = to_next;
+}
+
+template <bool kSeedsSmem>
+__global__ void __launch_bounds__(kTileThreads, 1) k_tile_fast(DevModel m, BatchArgs a, int gap) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* s_seeds = smem + kOffSeeds;
+    int32_t* s_type_a = reinterpret_cast<int32_t*>(smem + kOffTypeA);
+    int32_t* s_type_b = reinterpret_cast<int32_t*>(smem + kOffTypeB);
+    const int sub = threadIdx.x / kSubThreads;
+    const int tid = threadIdx.x % kSubThreads, warp = tid >> 5, lane = tid & 31;
+    uint8_t* sb = smem + kOffSub + sub * kSubBytes;
+    uint8_t* s_text = sb + kOffText;
+    int32_t* s_sc = reinterpret_cast<int32_t*>(sb + kOffText);
+    uint32_t* s_cp = reinterpret_cast<uint32_t*>(sb + kOffCp);
+    uint16_t* s_pos = reinterpret_cast<uint16_t*>(sb + kOffPos);
+    int32_t* s_spill_prev = reinterpret_cast<int32_t*>(sb + kOffPos);
+    int32_t* s_spill_next = s_spill_prev + (kSlotCap / 32) * 8;
+    uint8_t* s_ty = sb + kOffTy + 32;  // 32 guard bytes in front
+    uint8_t* s_kk = sb + kOffKk;
+    TileTables& T = *reinterpret_cast<TileTables*>(sb + kOffTab);
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(sb + kOffBar);
+    const uint8_t* __restrict__ text = a.text;
+
+    // ---- CTA-shared tables ----------------------------------------------------------------------------
+    const bool tsplit = m.type_a != nullptr && m.type_cache_window == 3;
+    if (kSeedsSmem) {
+        const uint32_t nwords = (m.ct.nbuckets + 3) / 4;
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(m.ct.seeds);
+        for (uint32_t i = threadIdx.x; i < nwords; i += kTileThreads) reinterpret_cast<uint32_t*>(s_seeds)[i] = __ldg(src + i);
+    }
+    if (tsplit) {
+        for (int i = threadIdx.x; i < kTypeSub; i += kTileThreads) {
+            s_type_a[i] = __ldg(m.type_a + i);
+            s_type_b[i] = __ldg(m.type_b + i);
+        }
+    }
+    if (tid == 0) mbar_init(s_bar, 1);
+    if (tid < 8) reinterpret_cast<uint32_t*>(sb + kOffTy)[tid] = 0;  // front guard of s_ty
+    __syncthreads();
+
+    const uint64_t ngroups = (a.n_sent + kGroup - 1) / kGroup;
+    const int r0 = m.ct.r0;
+    const int tw = m.type_cache_window;
+    uint32_t phase = 0;
+
+    for (;;) {
+        if (tid == 0) T.ticket = atomicAdd(a.ticket, 1u);
+        sub_sync(sub);
+        const uint64_t grp = T.ticket;
+        if (grp >= ngroups) break;
+        const uint64_t s0 = grp * kGroup;
+        const int ns = int(min(uint64_t(kGroup), a.n_sent - s0));
+
+        // ---- per-sentence tables -----------------------------------------------------------------------
+        if (tid <= ns) T.off[tid] = a.offsets[s0 + tid];
+        if (tid < ns) {
+            const uint64_t s = s0 + tid;
+            const uint32_t n = a.n_chars[s];
+            const uint32_t lc = a.local_char[s], lb = a.local_bound[s];
+            const uint64_t ob = a.group_bound[grp] + lb, cb = a.group_char[grp] + lc;
+            T.nch[tid] = n;
+            T.lc[tid] = lc;
+            T.st[tid] = a.status[s];
+            T.obase[tid] = ob;
+            T.cbase[tid] = cb;
+            a.bound_offsets[s] = a.bound_base + ob;
+            if (a.char_offsets) a.char_offsets[s] = a.char_base + cb;
+            if (s + 1 == a.n_sent) {
+                a.bound_offsets[s + 1] = a.bound_base + ob + (n > 0 ? n - 1 : 0);
+                if (a.char_offsets) a.char_offsets[s + 1] = a.char_base + cb + n;
+            }
+        }
+        if (tid == 0) T.lc[ns] = uint32_t(a.group_char[grp + 1] - a.group_char[grp]);
+        sub_sync(sub);
+
+        for (int k0 = 0; k0 < ns;) {
+            // ---- choose the longest sentence range [k0, k1) that fits the tile buffers ---------------------
+            // (the fit test is monotone in the range end: the first sentence that does not fit ends the range)
+            if (tid == 0) T.k1 = ns;
+            sub_sync(sub);
+            if (tid >= k0 && tid < ns) {
+                const uint64_t ra0 = T.off[k0] & ~15ull;
+                const uint64_t rspan = (T.off[tid + 1] - ra0 + 15) & ~15ull;
+                const int slots = gap + int(T.lc[tid + 1] - T.lc[k0]) + gap * (tid + 1 - k0);
+                if (rspan + 16 > uint64_t(kTextCap) || ((slots + 8 + 255) & ~255) > kSlotCap) atomicMin(&T.k1, tid);
+            }
+            sub_sync(sub);
+            const bool single = T.k1 == k0;
+            const int k1 = single ? k0 + 1 : T.k1;
+            if (single) {
+                // a single sentence larger than the tile buffers: one warp walks it in 32-character steps
+                Rings* rings = reinterpret_cast<Rings*>(sb);
+                if (warp == 0) fast_sentence_warp(m, a, s0 + k0, rings[0], lane);
+                sub_sync(sub);
+                k0 = k1;
+                continue;
+            }
+            const uint64_t a0 = T.off[k0] & ~15ull;
+            const uint32_t span = uint32_t((T.off[k1] - a0 + 15) & ~15ull);
+            const int S = gap + int(T.lc[k1] - T.lc[k0]) + gap * (k1 - k0);
+            const int Sround = (S + 8 + 255) & ~255;
+            const uint32_t lc0 = T.lc[k0];
+
+            // ---- stage the range's bytes: one TMA bulk copy --------------------------------------------------
+            if (tid == 0 && span) {
+                mbar_expect_tx(s_bar, span);
+                tma_bulk_g2s(s_text, text + a0, span, s_bar);
+            }
+            for (int i = tid; i < Sround / 2; i += kSubThreads) reinterpret_cast<uint32_t*>(s_pos)[i] = 0xFFFFFFFFu;
+            sub_sync(sub);
+            if (span) {
+                mbar_wait(s_bar, phase);
+                phase ^= 1;
+            }
+
+            // ---- pass A: byte position and sentence of every character slot ---------------------------------
+            for (int k = k0 + warp; k < k1; k += kSubThreads / 32) {
+                if (T.st[k] != 0) {
+                    const uint32_t nout = T.nch[k] > 0 ? T.nch[k] - 1 : 0;
+                    for (uint32_t i = lane; i < nout; i += 32) { a.scores[T.obase[k] + i] = 0; a.boundaries[T.obase[k] + i] = 0; }
+                    if (a.char_states) for (uint32_t i = lane; i < T.nch[k]; i += 32) a.char_states[T.cbase[k] + i] = kNoPattern;
+                    if (a.type_states) for (uint32_t i = lane; i < T.nch[k]; i += 32) a.type_states[T.cbase[k] + i] = kNoPattern;
+                    continue;
+                }
+                const uint32_t rb0 = uint32_t(T.off[k] - a0), rb1 = uint32_t(T.off[k + 1] - a0);
+                uint32_t idx = uint32_t(gap) + (T.lc[k] - lc0) + uint32_t(gap) * uint32_t(k - k0);
+                for (uint32_t w = rb0 & ~3u; w < rb1; w += 128) {
+                    const uint32_t addr = w + 4u * uint32_t(lane);
+                    const uint32_t lo = addr < rb1 ? *reinterpret_cast<const uint32_t*>(s_text + addr) : 0u;
+                    // start-of-character bytes of this word that lie inside the sentence
+                    uint32_t smask = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t p = addr + j;
+                        if (p >= rb0 && p < rb1 && ((lo >> (8 * j)) & 0xC0) != 0x80) smask |= 1u << j;
+                    }
+                    const uint32_t cnt = __popc(smask);
+                    const uint32_t incl = warp_incl_scan(cnt, lane);
+                    uint32_t at = idx + incl - cnt;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (smask & (1u << j)) {
+                            s_pos[at] = uint16_t(addr + j);
+                            s_kk[at] = uint8_t(k);
+                            ++at;
+                        }
+                    }
+                    idx += __shfl_sync(kFull, incl, 31);
+                }
+            }
+            sub_sync(sub);
+
+            // ---- pass B: one thread per slot: decode the code point and its type -----------------------------
+            for (int p = tid; p < Sround; p += kSubThreads) {
+                const uint32_t pos = s_pos[p];
+                uint32_t c = 0, ty = 0;
+                if (pos != kSepPos) {
+                    const uint32_t al = pos & ~3u;
+                    const uint32_t lo = *reinterpret_cast<const uint32_t*>(s_text + al);
+                    const uint32_t hi = *reinterpret_cast<const uint32_t*>(s_text + al + 4);
+                    c = decode_cp(__funnelshift_r(lo, hi, 8 * (pos & 3u)));
+                    ty = char_type(c);
+                }
+                s_cp[p] = c;
+                s_ty[p] = uint8_t(ty);
+            }
+            sub_sync(sub);
+
+            // ---- pass C: node lookup + warp-shuffle gather, two slots per thread in flight --------------------
+            for (int base = 0; base < Sround; base += 2 * kSubThreads) {
+                const int pA = base + tid, pB = pA + kSubThreads;
+                const bool hasB = pB < Sround;  // uniform: Sround is a multiple of 256
+                int32_t dA[kInlineWidth], dB[kInlineWidth];
+#pragma unroll
+                for (int j = 0; j < kInlineWidth; ++j) dA[j] = dB[j] = 0;
+                uint32_t a1 = 0, a2 = 0, b1 = 0, b2 = 0, slA = 0, slB = 0;
+                const uint32_t a3 = m.ct.present ? s_cp[pA] : 0u;
+                const uint32_t b3 = (m.ct.present && hasB) ? s_cp[pB] : 0u;
+                Rec32 rA, rB;
+                if (a3) {
+                    a2 = s_cp[pA - 1];
+                    a1 = a2 ? s_cp[pA - 2] : 0u;
+                    slA = slot_of_t<kSeedsSmem>(m.ct, s_seeds, shallow_key(a1, a2, a3));
+                    rA = load_record(m.ct.records, slA);
+                }
+                if (b3) {
+                    b2 = s_cp[pB - 1];
+                    b1 = b2 ? s_cp[pB - 2] : 0u;
+                    slB = slot_of_t<kSeedsSmem>(m.ct, s_seeds, shallow_key(b1, b2, b3));
+                    rB = load_record(m.ct.records, slB);
+                }
+                if (a3) lookup_finish<kSeedsSmem>(m.ct, s_seeds, s_cp, pA, a1, a2, a3, rA, slA, dA);
+                if (b3) lookup_finish<kSeedsSmem>(m.ct, s_seeds, s_cp, pB, b1, b2, b3, rB, slB, dB);
+                gather_store(dA, r0, lane, pA, s_sc, s_spill_prev, s_spill_next);
+                if (hasB) gather_store(dB, r0, lane, pB, s_sc, s_spill_prev, s_spill_next);
+            }
+            sub_sync(sub);
+
+            // ---- pass D: one thread per boundary: spills, type table, bias, threshold, store ------------------
+            const int nwc = Sround >> 5;
+            for (int p = tid; p < Sround - 1; p += kSubThreads) {
+                if (s_cp[p] == 0) continue;
+                const int k = s_kk[p];
+                const uint32_t g = uint32_t(p) - (uint32_t(gap) + (T.lc[k] - lc0) + uint32_t(gap) * uint32_t(k - k0));
+                if (a.char_states) a.char_states[T.cbase[k] + g] = kNoPattern;
+                if (a.type_states) a.type_states[T.cbase[k] + g] = kNoPattern;
+                if (s_cp[p + 1] == 0) continue;
+                const int wc = p >> 5, ln = p & 31;
+                int32_t v = s_sc[p] + m.bias;
+                if (ln >= 24 && wc + 1 < nwc) v += s_spill_prev[(wc + 1) * 8 + ln - 24];
+                if (ln < 8 && wc > 0) v += s_spill_next[(wc - 1) * 8 + ln];
+                if (tw > 0) {
+                    uint32_t idx = 0;
+                    for (int q = p - tw + 1; q <= p + tw; ++q) idx = (idx << 3) | s_ty[q];
+                    v += tsplit ? s_type_a[idx >> 6] + s_type_b[idx & 4095u] : __ldg(m.type_cache + idx);
+                }
+                const uint64_t o = T.obase[k] + g;
+                a.scores[o] = v;
+                a.boundaries[o] = v > 0 ? 1 : 0;
+            }
+            sub_sync(sub);
+            k0 = k1;
+        }
     }
 }
 
@@ -535,23 +973,65 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_score_general(DevModel 
 
 }  // namespace
 
-cudaError_t launch_count(const BatchArgs& a, cudaStream_t stream) {
+cudaError_t launch_count_only(const BatchArgs& a, cudaStream_t stream) {
     if (a.n_sent == 0) return cudaSuccess;
     const uint64_t ngroups = (a.n_sent + kGroup - 1) / kGroup;
     k_count<<<unsigned(ngroups), kWarpsPerBlock * 32, 0, stream>>>(a);
-    k_scan_groups<<<1, 1024, 0, stream>>>(a.group_bound, a.group_char, ngroups);
     return cudaGetLastError();
+}
+
+cudaError_t launch_scan_only(const BatchArgs& a, cudaStream_t stream) {
+    if (a.n_sent == 0) return cudaSuccess;
+    const uint64_t ngroups = (a.n_sent + kGroup - 1) / kGroup;
+    k_scan_groups<<<1, 1024, 0, stream>>>(a.group_bound, a.group_char, ngroups, a.ticket);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_count(const BatchArgs& a, cudaStream_t stream) {
+    cudaError_t e = launch_count_only(a, stream);
+    return e != cudaSuccess ? e : launch_scan_only(a, stream);
 }
 
 static bool use_fast(const DevModel& m) {
     return (!m.ct.present || m.ct.fast) && !m.tt.present && !m.emit_states;
 }
 
+// separator slots between sentences of a tile so that neither the weight-row gather (window
+// [r0, r0+6)) nor the type window can reach a neighbouring sentence
+static int tile_gap(const DevModel& m) {
+    const int r0 = m.ct.present ? m.ct.r0 : 0;
+    return std::max(std::max(2, m.type_cache_window - 1), std::max(-r0 - 1, r0 + kInlineWidth - 1));
+}
+
+static bool use_tile(const DevModel& m) {
+    if (!use_fast(m)) return false;
+    const int r0 = m.ct.present ? m.ct.r0 : 0;
+    return r0 >= -8 && r0 <= 2 && tile_gap(m) <= 8 && m.type_cache_window <= 3;
+}
+
 cudaError_t launch_score(const DevModel& m, const BatchArgs& a, cudaStream_t stream) {
     if (a.n_sent == 0) return cudaSuccess;
     const uint64_t nblocks = (a.n_sent + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    if (use_fast(m)) k_score_fast<<<unsigned(nblocks), kWarpsPerBlock * 32, 0, stream>>>(m, a);
-    else k_score_general<<<unsigned(nblocks), kWarpsPerBlock * 32, 0, stream>>>(m, a);
+    if (use_tile(m)) {
+        static int n_sm = 0;
+        if (n_sm == 0) {
+            int dev = 0;
+            cudaError_t e = cudaGetDevice(&dev);
+            if (e == cudaSuccess) e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tile_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tile_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem);
+            if (e != cudaSuccess) { n_sm = 0; return e; }
+        }
+        const uint64_t ngroups = (a.n_sent + kGroup - 1) / kGroup;
+        const unsigned grid = unsigned(std::min<uint64_t>(uint64_t(n_sm), (ngroups + kSubBlocks - 1) / kSubBlocks));
+        const bool seeds_smem = m.ct.present && m.ct.nbuckets <= uint32_t(kSeedCap);
+        if (seeds_smem) k_tile_fast<true><<<grid, kTileThreads, kTileSmem, stream>>>(m, a, tile_gap(m));
+        else k_tile_fast<false><<<grid, kTileThreads, kTileSmem, stream>>>(m, a, tile_gap(m));
+    } else if (use_fast(m)) {
+        k_score_fast<<<unsigned(nblocks), kWarpsPerBlock * 32, 0, stream>>>(m, a);
+    } else {
+        k_score_general<<<unsigned(nblocks), kWarpsPerBlock * 32, 0, stream>>>(m, a);
+    }
     return cudaGetLastError();
 }
 

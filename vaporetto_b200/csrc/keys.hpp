@@ -44,4 +44,23 @@ VPT_HD uint64_t deep_key(uint32_t parent_id, uint32_t sym) {
     return ((kDeepMarker + (uint64_t(parent_id) >> 21)) << 42) | ((uint64_t(parent_id) & 0x1FFFFF) << 21) | uint64_t(sym);
 }
 
+// Hash-and-displace perfect hash (32-bit arithmetic: cheap on the GPU).  A key is reduced to two mixed
+// 32-bit hashes; the first picks the bucket, the bucket's 16-bit seed displaces the second into the slot.
+VPT_HD void key_hashes(uint64_t key, uint64_t salt, uint32_t& ha, uint32_t& hb) {
+    const uint32_t lo = uint32_t(key) ^ uint32_t(salt), hi = uint32_t(key >> 32) ^ uint32_t(salt >> 32);
+    uint32_t a = (lo * 0x9E3779B1u) ^ (hi * 0x85EBCA77u);
+    a ^= a >> 15;
+    a *= 0xC2B2AE3Du;
+    ha = a;
+    hb = lo * 0x27D4EB2Fu + hi * 0x165667B1u;
+}
+VPT_HD uint32_t mulhi32(uint32_t a, uint32_t b) { return uint32_t((uint64_t(a) * b) >> 32); }
+VPT_HD uint32_t bucket_of(uint32_t ha, uint32_t nbuckets) { return mulhi32(ha, nbuckets); }
+VPT_HD uint32_t slot_with_seed(uint32_t ha, uint32_t hb, uint32_t seed, uint32_t nslots) {
+    uint32_t v = hb + seed * (ha | 1u);
+    v ^= v >> 15;
+    v *= 0x85EBCA6Bu;
+    return mulhi32(v, nslots);
+}
+
 }  // namespace vpt

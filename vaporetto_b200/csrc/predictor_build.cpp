@@ -32,7 +32,7 @@ void write_table(BlobWriter& w, const NodeTable& t, size_t n_patterns, BlobTable
     bt.n_nodes = t.n_nodes;
     bt.n_patterns = uint32_t(n_patterns);
     bt.rec_off = w.add(t.records.data(), t.records.size());
-    bt.seeds_off = w.add(t.seeds.data(), t.seeds.size() * 2);
+    bt.seeds_off = w.add(t.seeds.data(), t.seeds.size());
     bt.node_off = w.add(t.slot_node.data(), t.slot_node.size() * 4);
     bt.pid_off = w.add(t.slot_pid.data(), t.slot_pid.size() * 4);
     bt.pool_off = w.add(t.pool.data(), t.pool.size() * 4);
@@ -111,7 +111,14 @@ HostPredictor build_host_predictor(const Model& m, bool predict_tags) {
     h.max_char_pattern_len = int32_t(cps.max_len);
     write_table(w, ctab, cps.raw.size(), h.ct);
     write_table(w, ttab, tps.raw.size(), h.tt);
-    if (type_variant == 2) h.type_cache_off = w.add(tcache.data(), tcache.size() * 4);
+    if (type_variant == 2) {
+        h.type_cache_off = w.add(tcache.data(), tcache.size() * 4);
+        std::vector<int32_t> ta, tb;
+        if (build_type_split(m.type_ngrams, m.type_window, ta, tb)) {
+            h.type_a_off = w.add(ta.data(), ta.size() * 4);
+            h.type_b_off = w.add(tb.data(), tb.size() * 4);
+        }
+    }
     w.buf.resize(align_up(w.buf.size(), 256));
     h.total_bytes = w.buf.size();
     memcpy(w.buf.data(), &h, sizeof h);

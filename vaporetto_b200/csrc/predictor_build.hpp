@@ -11,7 +11,7 @@
 
 namespace vpt {
 
-constexpr char kBlobMagic[8] = {'V', 'P', 'T', 'B', '2', '0', '0', '\1'};
+constexpr char kBlobMagic[8] = {'V', 'P', 'T', 'B', '2', '0', '0', '\2'};
 
 struct BlobTable {
     uint64_t rec_off, seeds_off, node_off, pid_off, pool_off;
@@ -28,6 +28,7 @@ struct BlobHeader {
     int32_t bias, char_window, type_window, type_cache_window;
     int32_t emit_states, char_variant, type_variant, max_char_pattern_len;
     uint64_t type_cache_off;
+    uint64_t type_a_off, type_b_off;  // split tables (0 = absent)
     BlobTable ct, tt;
 };
 
