@@ -307,71 +307,109 @@ struct Merger {
 };
 
 // ---------------------------------------------------------------------------
-// Aho-Corasick over bytes (semantics of daachorse; see header).
+// Aho-Corasick over symbols (code points for the char scorer — the reference's default
+// `charwise-pma` feature — or type bytes for the type scorer).  Semantics of daachorse; see header.
+// goto function: open-addressing hash (state, symbol) -> state; classic failure links.
 // ---------------------------------------------------------------------------
 struct AC {
-    struct Node {
-        vector<std::pair<uint8_t, int>> ch;  // sorted by byte
-        int fail = 0;
-        int out = -1;       // longest pattern ending at this state (own, else via suffix)
-        int own = -1;       // pattern ending exactly here
-        int out_link = -1;  // next shorter pattern-bearing suffix state
-    };
-    vector<Node> nodes;
-    vector<int> root_next;  // 256 direct transitions from the root
-    void build(const vector<string>& pats) {
-        nodes.assign(1, Node());
+    vector<int32_t> fail, out, own, depth;
+    vector<uint64_t> hkey;   // (state << 21 | symbol) + 1, 0 = empty
+    vector<int32_t> hval;
+    uint64_t hmask = 0;
+    static inline uint64_t hmix(uint64_t x) {
+        x ^= x >> 29; x *= 0xbf58476d1ce4e5b9ULL; x ^= x >> 32;
+        return x;
+    }
+    inline int find(int s, uint32_t c) const {
+        const uint64_t k = ((uint64_t(uint32_t(s)) << 21) | c) + 1;
+        for (uint64_t i = hmix(k) & hmask;; i = (i + 1) & hmask) {
+            if (hkey[i] == k) return hval[i];
+            if (hkey[i] == 0) return -1;
+        }
+    }
+    void insert(int s, uint32_t c, int v) {
+        const uint64_t k = ((uint64_t(uint32_t(s)) << 21) | c) + 1;
+        uint64_t i = hmix(k) & hmask;
+        while (hkey[i] != 0) i = (i + 1) & hmask;
+        hkey[i] = k;
+        hval[i] = v;
+    }
+    static vector<uint32_t> symbols(const string& p, bool utf8) {
+        vector<uint32_t> v;
+        if (!utf8) { for (unsigned char c : p) v.push_back(c); return v; }
+        for (size_t i = 0; i < p.size();) {
+            uint8_t b = uint8_t(p[i]);
+            int l = b < 0x80 ? 1 : b < 0xE0 ? 2 : b < 0xF0 ? 3 : 4;
+            uint32_t cp = l == 1 ? b : l == 2 ? (b & 0x1F) : l == 3 ? (b & 0x0F) : (b & 0x07);
+            for (int k = 1; k < l; ++k) cp = (cp << 6) | (uint8_t(p[i + k]) & 0x3F);
+            v.push_back(cp);
+            i += size_t(l);
+        }
+        return v;
+    }
+    void build(const vector<string>& pats, bool utf8) {
+        size_t total = 1;
+        for (auto& p : pats) total += p.size();
+        size_t cap = 16;
+        while (cap < total * 2) cap <<= 1;
+        hkey.assign(cap, 0);
+        hval.assign(cap, 0);
+        hmask = cap - 1;
+        fail.assign(1, 0); out.assign(1, -1); own.assign(1, -1); depth.assign(1, 0);
+        vector<vector<std::pair<uint32_t, int>>> kids(1);
         for (size_t i = 0; i < pats.size(); ++i) {
             if (pats[i].empty()) throw Error(INVALID_MODEL, "failed to build the automaton");
             int s = 0;
-            for (unsigned char c : pats[i]) {
-                int nx = -1;
-                for (auto& e : nodes[s].ch) if (e.first == c) { nx = e.second; break; }
+            for (uint32_t c : symbols(pats[i], utf8)) {
+                int nx = find(s, c);
                 if (nx < 0) {
-                    nx = int(nodes.size());
-                    nodes.push_back(Node());
-                    nodes[s].ch.emplace_back(c, nx);
+                    nx = int(fail.size());
+                    fail.push_back(0); out.push_back(-1); own.push_back(-1); depth.push_back(depth[s] + 1);
+                    kids.emplace_back();
+                    kids[s].emplace_back(c, nx);
+                    insert(s, c, nx);
                 }
                 s = nx;
             }
-            if (nodes[s].own >= 0) throw Error(INVALID_MODEL, "failed to build the automaton");  // duplicate
-            nodes[s].own = int(i);
+            if (own[s] >= 0) throw Error(INVALID_MODEL, "failed to build the automaton");  // duplicate pattern
+            own[s] = int(i);
         }
-        for (auto& nd : nodes) std::sort(nd.ch.begin(), nd.ch.end());
         vector<int> q;
-        for (auto& e : nodes[0].ch) { nodes[e.second].fail = 0; q.push_back(e.second); }
+        for (auto& e : kids[0]) { fail[e.second] = 0; q.push_back(e.second); }
         for (size_t h = 0; h < q.size(); ++h) {
-            int s = q[h];
-            Node& ns = nodes[s];
-            int f = ns.fail;
-            ns.out = ns.own >= 0 ? ns.own : nodes[f].out;
-            ns.out_link = nodes[f].own >= 0 ? f : nodes[f].out_link;
-            for (auto& e : ns.ch) {
-                int t = ns.fail;
-                int nx;
-                while ((nx = child(t, e.first)) < 0 && t != 0) t = nodes[t].fail;
-                nodes[e.second].fail = nx < 0 ? 0 : nx;
+            const int s = q[h];
+            out[s] = own[s] >= 0 ? own[s] : out[fail[s]];
+            for (auto& e : kids[s]) {
+                int t = fail[s], nx;
+                while ((nx = find(t, e.first)) < 0 && t != 0) t = fail[t];
+                fail[e.second] = nx < 0 ? 0 : nx;
                 q.push_back(e.second);
             }
         }
-        root_next.assign(256, 0);
-        for (auto& e : nodes[0].ch) root_next[e.first] = e.second;
-    }
-    int child(int s, uint8_t c) const {
-        const auto& ch = nodes[s].ch;
-        if (ch.size() <= 8) {
-            for (auto& e : ch) if (e.first == c) return e.second;
-            return -1;
+        // rehash compactly (2 slots per transition) and pack key+value side by side for the walk
+        size_t ncap = 16;
+        while (ncap < fail.size() * 2) ncap <<= 1;
+        vector<uint64_t> ok;
+        vector<int32_t> ov;
+        ok.swap(hkey);
+        ov.swap(hval);
+        hkey.assign(ncap, 0);
+        hval.assign(ncap, 0);
+        hmask = ncap - 1;
+        for (size_t i = 0; i < ok.size(); ++i) {
+            if (!ok[i]) continue;
+            uint64_t j = hmix(ok[i]) & hmask;
+            while (hkey[j] != 0) j = (j + 1) & hmask;
+            hkey[j] = ok[i];
+            hval[j] = ov[i];
         }
-        auto it = std::lower_bound(ch.begin(), ch.end(), std::make_pair(c, -1));
-        return (it != ch.end() && it->first == c) ? it->second : -1;
     }
-    inline int step(int s, uint8_t c) const {
+    inline int step(int s, uint32_t c) const {
         for (;;) {
-            if (s == 0) return root_next[c];
-            int nx = child(s, c);
+            const int nx = find(s, c);
             if (nx >= 0) return nx;
-            s = nodes[s].fail;
+            if (s == 0) return 0;
+            s = fail[s];
         }
     }
 };
@@ -392,6 +430,7 @@ static inline uint8_t get_type(uint32_t c) {
 // Sentence state touched by predict (sentence.rs:85-101)
 struct Sentence {
     string text;
+    vector<uint32_t> chars;  // code points
     vector<uint8_t> char_types;
     vector<uint8_t> boundaries;
     vector<int32_t> boundary_scores;  // padded strip
@@ -402,7 +441,7 @@ struct Sentence {
     // Sentence::parse_raw (sentence.rs:160-196); text must be valid UTF-8
     void parse_raw(const char* s, size_t nbytes) {
         text.assign(s, nbytes);
-        char_types.clear(); boundaries.clear(); str_to_char_pos.clear(); char_to_str_pos.clear();
+        chars.clear(); char_types.clear(); boundaries.clear(); str_to_char_pos.clear(); char_to_str_pos.clear();
         boundary_scores.clear(); char_pma_states.clear(); type_pma_states.clear(); score_padding = 0;
         if (!valid_utf8(text)) throw Error(INVALID_ARGUMENT, "InvalidArgumentError: text: must be valid UTF-8");
         char_to_str_pos.push_back(0);
@@ -416,6 +455,7 @@ struct Sentence {
             else { cp = b & 0x07; l = 4; }
             for (int k = 1; k < l; ++k) cp = (cp << 6) | (uint8_t(s[pos + k]) & 0x3F);
             if (cp == 0) throw Error(INVALID_ARGUMENT, "InvalidArgumentError: text: must not contain NULL");
+            chars.push_back(cp);
             char_types.push_back(get_type(cp));
             pos += l;
             char_to_str_pos.push_back(uint32_t(pos));
@@ -459,9 +499,14 @@ static inline void add_tag_vec(const vector<int32_t>& w, vector<int32_t>& ys) {
 struct PmaScorer {
     AC pma;
     vector<std::optional<PW>> weights;
+    // flat copy of `weights` for the hot loop: offset, begin, length (len < 0: no boundary weight)
+    vector<int32_t> w_off, w_len;
+    vector<uint32_t> w_begin;
+    vector<int32_t> w_data;
     TagTable tag_weight;
     bool tag_variant = false;
     bool is_char = true;
+    vector<string> pattern_strings;
 
     void build(const vector<NgramData>& ngrams, const vector<WordWeightRecord>& dict, uint8_t window,
                const vector<const vector<TagNgramData>*>& tag_ngrams, bool is_char_) {
@@ -499,7 +544,13 @@ struct PmaScorer {
                 tag_weight.t[kv.first.first][kv.first.second][uint32_t(i)] = kv.second;
             }
         }
-        pma.build(pats);
+        pattern_strings = pats;
+        pma.build(pats, is_char);
+        for (auto& w : weights) {
+            w_begin.push_back(uint32_t(w_data.size()));
+            if (w) { w_off.push_back(w->offset); w_len.push_back(int32_t(w->weight.size())); w_data.insert(w_data.end(), w->weight.begin(), w->weight.end()); }
+            else { w_off.push_back(0); w_len.push_back(-1); }
+        }
     }
 
     // add_scores: walk, longest match per end position (boundary_scorer.rs:93-113 etc.)
@@ -510,25 +561,26 @@ struct PmaScorer {
             states->assign(s.len(), 0xFFFFFFFFu);
         }
         int st = 0;
-        if (is_char) {
-            const size_t nb = s.text.size();
-            for (size_t i = 0; i < nb; ++i) {
-                st = pma.step(st, uint8_t(s.text[i]));
-                int p = pma.nodes[st].out;
-                if (p < 0) continue;
-                size_t end = s.str_to_char_pos[i + 1];
-                if (weights[p]) add_score(*weights[p], long(end + s.score_padding) - 1, s.boundary_scores);
-                if (states) (*states)[end - 1] = uint32_t(p);
+        const size_t n = s.len();
+        const long ny = long(s.boundary_scores.size());
+        int32_t* ys = s.boundary_scores.data();
+        for (size_t i = 0; i < n; ++i) {
+            st = pma.step(st, is_char ? s.chars[i] : uint32_t(s.char_types[i]));
+            const int p = pma.out[st];
+            if (p < 0) continue;
+            const size_t end = i + 1;  // char index (== str_to_char_pos[m.end()] of the bytewise reference path)
+            if (w_len[p] >= 0) {
+                // PositionalWeight::add_score (predictor.rs:176-213), ragged add clipped at both strip ends
+                const long pos = long(end + s.score_padding) - 1 + w_off[p];
+                const int32_t* w = w_data.data() + w_begin[p];
+                for (long k = 0; k < w_len[p]; ++k) {
+                    const long q = pos + k;
+                    if (q < 0) continue;
+                    if (q >= ny) break;
+                    ys[q] = wadd(ys[q], w[k]);
+                }
             }
-        } else {
-            for (size_t i = 0; i < s.char_types.size(); ++i) {
-                st = pma.step(st, s.char_types[i]);
-                int p = pma.nodes[st].out;
-                if (p < 0) continue;
-                size_t end = i + 1;
-                if (weights[p]) add_score(*weights[p], long(end + s.score_padding) - 1, s.boundary_scores);
-                if (states) (*states)[end - 1] = uint32_t(p);
-            }
+            if (states) (*states)[end - 1] = uint32_t(p);
         }
     }
 
@@ -789,11 +841,7 @@ long ora_dump_patterns(const void* p, int which, char* buf, size_t cap) {
     string out;
     // recover pattern strings by walking the trie
     vector<string> pats(sc->weights.size());
-    struct Rec { static void go(const AC& ac, int s, string& cur, vector<string>& pats) {
-        if (ac.nodes[s].own >= 0) pats[size_t(ac.nodes[s].own)] = cur;
-        for (auto& e : ac.nodes[s].ch) { cur.push_back(char(e.first)); go(ac, e.second, cur, pats); cur.pop_back(); }
-    } };
-    string cur; Rec::go(sc->pma, 0, cur, pats);
+    pats = sc->pattern_strings;
     for (size_t i = 0; i < pats.size(); ++i) {
         out += pats[i]; out += '\t';
         if (sc->weights[i]) {
