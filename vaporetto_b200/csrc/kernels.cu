@@ -225,13 +225,18 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_count(BatchArgs a) {
         }
         mbar_wait(&s_bar, 0);
     }
-    for (int i = warp; i < kGroup; i += kWarpsPerBlock) {
+    // each warp scores 4 sentences at a time: 8 lanes per sentence, 32 bytes per sentence per iteration
+    const int quad = lane >> 3, l8 = lane & 7;
+    for (int it = 0; it < kGroup / (kWarpsPerBlock * 4); ++it) {
+        const int i = (warp * (kGroup / kWarpsPerBlock)) + it * 4 + quad;
         uint32_t nch = 0, nout = 0;
-        if (i < ns) {
-            const uint64_t b0 = s_off[i], b1 = s_off[i + 1];
+        {
+            // lanes of a quad beyond the group's last sentence run an empty range (all 32 lanes must reach
+            // the shuffles below)
+            const uint64_t b0 = i < ns ? s_off[i] : 0, b1 = i < ns ? s_off[i + 1] : 0;
             uint32_t starts = 0, conts = 0, expect = 0, flags = 0;  // flags: 1 NUL, 2 malformed
-            for (uint64_t wpos = b0 & ~3ull; wpos < b1; wpos += 128) {
-                const uint64_t addr = wpos + 4u * uint32_t(lane);
+            for (uint64_t wpos = b0 & ~3ull; wpos < b1; wpos += 32) {
+                const uint64_t addr = wpos + 4u * uint32_t(l8);
                 if (addr < b1) {
                     uint32_t lo, hi = 0;
                     if (staged) {
@@ -299,22 +304,22 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_count(BatchArgs a) {
                 }
             }
 #pragma unroll
-            for (int d = 16; d > 0; d >>= 1) {
+            for (int d = 4; d > 0; d >>= 1) {
                 starts += __shfl_xor_sync(kFull, starts, d);
                 conts += __shfl_xor_sync(kFull, conts, d);
                 expect += __shfl_xor_sync(kFull, expect, d);
                 flags |= __shfl_xor_sync(kFull, flags, d);
             }
             if (conts != expect) flags |= 2;
-            nch = starts;
+            nch = i < ns ? starts : 0;
             nout = nch > 0 ? nch - 1 : 0;
             const int st = (flags & 2) ? 3 : (flags & 1) ? 2 : (nch == 0 ? 1 : 0);
-            if (lane == 0) {
+            if (l8 == 0 && i < ns) {
                 a.n_chars[gbase + i] = nch;
                 a.status[gbase + i] = st;
             }
         }
-        if (lane == 0) { s_nout[i] = nout; s_nch[i] = nch; }
+        if (l8 == 0) { s_nout[i] = nout; s_nch[i] = nch; }
     }
     __syncthreads();
     if (warp == 0) {
@@ -549,6 +554,8 @@ struct TileTables {
     uint64_t obase[kGroup];
     uint64_t cbase[kGroup];
     uint32_t lc[kGroup + 1];  // chars before sentence k inside the group
+    int64_t odelta[kGroup];   // output index of a boundary = its slot + odelta[sentence]
+    int64_t cdelta[kGroup];   // state index of a character = its slot + cdelta[sentence]
     uint32_t nch[kGroup];
     int32_t st[kGroup];
     uint32_t ticket;
@@ -632,8 +639,12 @@ __device__ __forceinline__ void lookup_finish(const DevTable& t, const uint8_t* 
 }
 
 // gather of the 6-wide rows of one 32-slot warp chunk: boundary (lane) <- row entry j of lane - r0 - j
-__device__ __forceinline__ void gather_store(const int32_t (&d)[kInlineWidth], int r0, int lane, int p, int32_t* s_sc,
+// (kR0 = compile-time window start for the common char-window-3 model, kRuntimeR0 = use the argument)
+constexpr int kRuntimeR0 = 99;
+template <int kR0>
+__device__ __forceinline__ void gather_store(const int32_t (&d)[kInlineWidth], int r0_arg, int lane, int p, int32_t* s_sc,
                                              int32_t* s_spill_prev, int32_t* s_spill_next) {
+    const int r0 = kR0 == kRuntimeR0 ? r0_arg : kR0;
     int32_t mainv = 0, to_prev = 0, to_next = 0;
 #pragma unroll
     for (int j = 0; j < kInlineWidth; ++j) {
@@ -649,7 +660,7 @@ __device__ __forceinline__ void gather_store(const int32_t (&d)[kInlineWidth], i
     if (lane < 8) s_spill_next[wc * 8 + lane] = to_next;
 }
 
-template <bool kSeedsSmem>
+template <bool kSeedsSmem, int kR0>
 __global__ void __launch_bounds__(kTileThreads, 1) k_tile_fast(DevModel m, BatchArgs a, int gap) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* s_seeds = smem + kOffSeeds;
@@ -756,6 +767,11 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_fast(DevModel m, Batch
                 tma_bulk_g2s(s_text, text + a0, span, s_bar);
             }
             for (int i = tid; i < Sround / 2; i += kSubThreads) reinterpret_cast<uint32_t*>(s_pos)[i] = 0xFFFFFFFFu;
+            if (tid >= k0 && tid < k1) {
+                const int64_t slot0 = int64_t(gap) + int64_t(T.lc[tid] - lc0) + int64_t(gap) * (tid - k0);
+                T.odelta[tid] = int64_t(T.obase[tid]) - slot0;
+                T.cdelta[tid] = int64_t(T.cbase[tid]) - slot0;
+            }
             sub_sync(sub);
             if (span) {
                 mbar_wait(s_bar, phase);
@@ -840,8 +856,8 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_fast(DevModel m, Batch
                 }
                 if (a3) lookup_finish<kSeedsSmem>(m.ct, s_seeds, s_cp, pA, a1, a2, a3, rA, slA, dA);
                 if (b3) lookup_finish<kSeedsSmem>(m.ct, s_seeds, s_cp, pB, b1, b2, b3, rB, slB, dB);
-                gather_store(dA, r0, lane, pA, s_sc, s_spill_prev, s_spill_next);
-                if (hasB) gather_store(dB, r0, lane, pB, s_sc, s_spill_prev, s_spill_next);
+                gather_store<kR0>(dA, r0, lane, pA, s_sc, s_spill_prev, s_spill_next);
+                if (hasB) gather_store<kR0>(dB, r0, lane, pB, s_sc, s_spill_prev, s_spill_next);
             }
             sub_sync(sub);
 
@@ -850,9 +866,8 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_fast(DevModel m, Batch
             for (int p = tid; p < Sround - 1; p += kSubThreads) {
                 if (s_cp[p] == 0) continue;
                 const int k = s_kk[p];
-                const uint32_t g = uint32_t(p) - (uint32_t(gap) + (T.lc[k] - lc0) + uint32_t(gap) * uint32_t(k - k0));
-                if (a.char_states) a.char_states[T.cbase[k] + g] = kNoPattern;
-                if (a.type_states) a.type_states[T.cbase[k] + g] = kNoPattern;
+                if (a.char_states) a.char_states[int64_t(p) + T.cdelta[k]] = kNoPattern;
+                if (a.type_states) a.type_states[int64_t(p) + T.cdelta[k]] = kNoPattern;
                 if (s_cp[p + 1] == 0) continue;
                 const int wc = p >> 5, ln = p & 31;
                 int32_t v = s_sc[p] + m.bias;
@@ -863,7 +878,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_fast(DevModel m, Batch
                     for (int q = p - tw + 1; q <= p + tw; ++q) idx = (idx << 3) | s_ty[q];
                     v += tsplit ? s_type_a[idx >> 6] + s_type_b[idx & 4095u] : __ldg(m.type_cache + idx);
                 }
-                const uint64_t o = T.obase[k] + g;
+                const int64_t o = int64_t(p) + T.odelta[k];
                 a.scores[o] = v;
                 a.boundaries[o] = v > 0 ? 1 : 0;
             }
@@ -1018,15 +1033,21 @@ cudaError_t launch_score(const DevModel& m, const BatchArgs& a, cudaStream_t str
             int dev = 0;
             cudaError_t e = cudaGetDevice(&dev);
             if (e == cudaSuccess) e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tile_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tile_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tile_fast<true, -3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tile_fast<false, -3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tile_fast<true, kRuntimeR0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tile_fast<false, kRuntimeR0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem);
             if (e != cudaSuccess) { n_sm = 0; return e; }
         }
         const uint64_t ngroups = (a.n_sent + kGroup - 1) / kGroup;
         const unsigned grid = unsigned(std::min<uint64_t>(uint64_t(n_sm), (ngroups + kSubBlocks - 1) / kSubBlocks));
         const bool seeds_smem = m.ct.present && m.ct.nbuckets <= uint32_t(kSeedCap);
-        if (seeds_smem) k_tile_fast<true><<<grid, kTileThreads, kTileSmem, stream>>>(m, a, tile_gap(m));
-        else k_tile_fast<false><<<grid, kTileThreads, kTileSmem, stream>>>(m, a, tile_gap(m));
+        const bool r3 = m.ct.present && m.ct.r0 == -3;
+        const int gap = tile_gap(m);
+        if (seeds_smem && r3) k_tile_fast<true, -3><<<grid, kTileThreads, kTileSmem, stream>>>(m, a, gap);
+        else if (seeds_smem) k_tile_fast<true, kRuntimeR0><<<grid, kTileThreads, kTileSmem, stream>>>(m, a, gap);
+        else if (r3) k_tile_fast<false, -3><<<grid, kTileThreads, kTileSmem, stream>>>(m, a, gap);
+        else k_tile_fast<false, kRuntimeR0><<<grid, kTileThreads, kTileSmem, stream>>>(m, a, gap);
     } else if (use_fast(m)) {
         k_score_fast<<<unsigned(nblocks), kWarpsPerBlock * 32, 0, stream>>>(m, a);
     } else {
