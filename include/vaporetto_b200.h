@@ -92,6 +92,10 @@ int vpt_predictor_get_info(const vpt_predictor* predictor, vpt_predictor_info* o
  * (Replaces `Predictor::serialize_to_vec` / `deserialize_from_slice_unchecked`, predictor.rs:640-664, whose
  * daachorse-private layout is not reproducible; the blob format is this library's own.)
  * Predictors made from a blob score boundaries; tag prediction needs vpt_predictor_new. */
+/* Host-only build of the flat model (no CUDA device needed): what vpt_predictor_new uploads.  Consumes `model`.
+ * The returned buffer is released with vpt_blob_free. */
+int vpt_blob_build(vpt_model* model, int predict_tags, uint8_t** blob_out, uint64_t* len_out);
+void vpt_blob_free(uint8_t* blob);
 uint64_t vpt_predictor_blob_size(const vpt_predictor* predictor);
 int vpt_predictor_blob_export(const vpt_predictor* predictor, void* dst, uint64_t capacity);
 int vpt_predictor_from_blob(const void* blob, uint64_t len, int device, vpt_predictor** out);

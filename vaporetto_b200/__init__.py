@@ -13,7 +13,7 @@ from typing import List, Optional, Sequence
 import numpy as np
 
 __all__ = ["Model", "Predictor", "Sentence", "VaporettoError", "CharacterBoundary", "CharacterType", "lib", "build",
-           "BatchResult"]
+           "BatchResult", "build_blob", "shard_by_bytes"]
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_PKG, "libvaporetto_b200.so")
@@ -69,6 +69,8 @@ ABI = [
     ("vpt_predictor_new", C.c_int, [_P, C.c_int, C.c_int, C.POINTER(_P)]),
     ("vpt_predictor_free", None, [_P]),
     ("vpt_predictor_get_info", C.c_int, [_P, C.POINTER(_Info)]),
+    ("vpt_blob_build", C.c_int, [_P, C.c_int, C.POINTER(_P), C.POINTER(C.c_uint64)]),
+    ("vpt_blob_free", None, [_P]),
     ("vpt_predictor_blob_size", C.c_uint64, [_P]),
     ("vpt_predictor_blob_export", C.c_int, [_P, _P, C.c_uint64]),
     ("vpt_predictor_from_blob", C.c_int, [_P, C.c_uint64, C.c_int, C.POINTER(_P)]),
@@ -148,6 +150,32 @@ class Model:
         if getattr(self, "_h", None):
             lib().vpt_model_free(self._h)
             self._h = None
+
+
+def build_blob(model: Model, predict_tags: bool = False) -> np.ndarray:
+    """Host-only build of the flat device model (vpt_blob_build); consumes `model`.  The blob can be broadcast
+    as bytes and turned into a predictor on every rank with Predictor.from_blob."""
+    out = _P()
+    n = C.c_uint64()
+    _check(lib().vpt_blob_build(model._take(), int(predict_tags), C.byref(out), C.byref(n)))
+    try:
+        return np.ctypeslib.as_array(C.cast(out, C.POINTER(C.c_uint8)), shape=(n.value,)).copy()
+    finally:
+        lib().vpt_blob_free(out)
+
+
+def shard_by_bytes(offsets, rank: int, world: int):
+    """Contiguous sentence range [lo, hi) of `rank` when a batch is split over `world` ranks balanced by bytes
+    (SURVEY.md §8e).  Every sentence belongs to exactly one rank."""
+    off = np.asarray(offsets, np.uint64)
+    n = off.size - 1
+    total = int(off[-1] - off[0])
+    cuts = [int(np.searchsorted(off, int(off[0]) + total * r // world, side="left")) for r in range(world + 1)]
+    cuts[0], cuts[-1] = 0, n
+    cuts = [min(max(c, 0), n) for c in cuts]
+    for i in range(1, world + 1):
+        cuts[i] = max(cuts[i], cuts[i - 1])
+    return cuts[rank], cuts[rank + 1]
 
 
 class BatchResult:

@@ -3,6 +3,7 @@
 #include "../../include/vaporetto_b200.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -294,6 +295,23 @@ int vpt_predictor_get_info(const vpt_predictor* p, vpt_predictor_info* o) {
     return kOk;
     VPT_API_END
 }
+
+int vpt_blob_build(vpt_model* model, int predict_tags, uint8_t** blob_out, uint64_t* len_out) {
+    std::unique_ptr<vpt_model> owned(model);
+    VPT_API_BEGIN
+    if (!model || !blob_out || !len_out) throw Error(kInvalidArgument, "InvalidArgumentError: model/out: must not be NULL");
+    *blob_out = nullptr;
+    HostPredictor hp = build_host_predictor(owned->m, predict_tags != 0);
+    uint8_t* buf = static_cast<uint8_t*>(malloc(hp.blob.size()));
+    if (!buf) throw Error(kInternal, "internal error: out of memory");
+    memcpy(buf, hp.blob.data(), hp.blob.size());
+    *blob_out = buf;
+    *len_out = hp.blob.size();
+    return kOk;
+    VPT_API_END
+}
+
+void vpt_blob_free(uint8_t* blob) { free(blob); }
 
 uint64_t vpt_predictor_blob_size(const vpt_predictor* p) { return p ? p->blob.size() : 0; }
 
