@@ -39,14 +39,16 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
-def get_model(n_patterns: int, sample: int) -> bytes:
+def get_model(n_patterns: int, sample: int, config: int = 2) -> bytes:
     from vpt_testlib import synth
     os.makedirs(CACHE, exist_ok=True)
-    fn = os.path.join(CACHE, f"bccwj_shaped_{n_patterns}_{sample}.bin")
+    tag = {2: "bccwj_shaped", 3: "bccwj_tags_shaped", 4: "kytea_shaped"}[config]
+    fn = os.path.join(CACHE, f"{tag}_{n_patterns}_{sample}.bin")
     if os.path.exists(fn):
         return open(fn, "rb").read()
     t = time.time()
-    m = synth.gen_model_bccwj_shaped(n_patterns=n_patterns, sample_sentences=sample)
+    m = synth.gen_model_bccwj_shaped(n_patterns=n_patterns, sample_sentences=sample,
+                                     dict_words=500_000 if config == 4 else 0, tag_models=20_000 if config == 3 else 0)
     log(f"[bench] generated model ({len(m)} bytes) in {time.time() - t:.1f}s")
     try:
         with open(fn + ".tmp", "wb") as f:
@@ -116,11 +118,11 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_baseline(model_bytes: bytes, text, offs, budget_s: float = 12.0):
+def cpu_baseline(model_bytes: bytes, text, offs, budget_s: float = 12.0, predict_tags: bool = False):
     """Reference algorithm (C++ restatement, oracle/) on the host cores over a bounded sample of the workload."""
     from vpt_testlib.oracle import OraclePredictor
     t = time.time()
-    o = OraclePredictor(model_bytes)
+    o = OraclePredictor(model_bytes, predict_tags=predict_tags)
     build_s = time.time() - t
     n = len(offs) - 1
     ncores = os.cpu_count() or 1
@@ -133,7 +135,7 @@ def cpu_baseline(model_bytes: bytes, text, offs, budget_s: float = 12.0):
     est = mb1 * ncores * 0.7
     nall = int(min(n, max(n1, est * 1e6 * budget_s / 120.0)))
     sub = offs[: nall + 1]
-    dta = o.time_batch(text, sub, nthreads=ncores)
+    dta = min(o.time_batch(text, sub, nthreads=ncores) for _ in range(3))
     mba = float(sub[-1] - sub[0]) / dta / 1e6
     return {"value": round(mba, 2), "unit": "MB/s", "cores": ncores, "kind": "port",
             "sample": f"{nall} of the step's sentences, {ncores} threads ({dta:.2f}s); single thread "
@@ -147,10 +149,10 @@ def run_reference(args, rank, world):
     """--impl reference: the reference's CPU algorithm on the host cores, rank 0 only."""
     if rank != 0:
         return
-    model_bytes = get_model(args.patterns, args.model_sample)
+    model_bytes = get_model(args.patterns, args.model_sample, args.config)
     text, offs, _ = get_text(min(args.sentences, 400_000), 0, args.ragged)
     from vpt_testlib.oracle import OraclePredictor
-    o = OraclePredictor(model_bytes)
+    o = OraclePredictor(model_bytes, predict_tags=False)
     ncores = os.cpu_count() or 1
     n = len(offs) - 1
     # size each step for ~2 s of CPU work
@@ -179,9 +181,11 @@ def run_reference(args, rank, world):
 
 
 def workload_config(args, n_sent):
-    return {"workload": "BASELINE configs[1]: bccwj-suw-shaped model (W=3/3, %d char 1-3-gram patterns, 258 type "
-                        "n-grams, no dict, no tags), synthetic JP sentences%s" %
-                        (args.patterns, " (ragged lognormal lengths)" if args.ragged else " of 40 chars"),
+    extra = {2: "no dict, no tags", 3: "no dict, 20000 tag models, predict_tags (pattern-id states emitted)",
+             4: "500000-word KyTea-shaped dictionary, no tags"}[args.config]
+    return {"workload": "BASELINE configs[%d]: bccwj-suw-shaped model (W=3/3, %d char 1-3-gram patterns, 258 type "
+                        "n-grams, %s), synthetic JP sentences%s" %
+                        (args.config - 1, args.patterns, extra, " (ragged lognormal lengths)" if args.ragged else " of 40 chars"),
             "sentences_per_gpu": n_sent, "parallelism": "dp%d (sentences sharded, NCCL model broadcast only)" % args.gpus,
             "l2": "batch (115 MB in + 195 MB out per GPU) exceeds L2; no flush needed"}
 
@@ -196,6 +200,9 @@ def main():
     ap.add_argument("--patterns", type=int, default=300_000)
     ap.add_argument("--model-sample", type=int, default=2_000_000)
     ap.add_argument("--ragged", action="store_true")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4],
+                    help="BASELINE.json config: 2 bccwj-suw-shaped (default, the headline), 3 + tag models (states "
+                         "emitted), 4 KyTea-shaped (+ 500K-word dictionary)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=5)
     args = ap.parse_args()
@@ -222,9 +229,9 @@ def main():
     # ---- model: rank 0 parses/builds, the flat blob is broadcast once over NCCL -------------------------
     L = vb.lib()
     if rank == 0:
-        model_bytes = get_model(args.patterns, args.model_sample)
+        model_bytes = get_model(args.patterns, args.model_sample, args.config)
         t = time.time()
-        pred = vb.Predictor(vb.Model.read(model_bytes), device=local_rank)
+        pred = vb.Predictor(vb.Model.read(model_bytes), predict_tags=args.config == 3, device=local_rank)
         log(f"[bench] predictor built in {time.time() - t:.1f}s: {pred.info}")
         blob = pred.export_blob()
     if world > 1:
@@ -236,7 +243,7 @@ def main():
         dist.broadcast(tb, 0)
         if rank != 0:
             pred = vb.Predictor.from_blob(tb.cpu().numpy(), device=local_rank)
-    assert pred.info["fast_path"] == 1, "config-2 model must take the fast kernel"
+    assert args.config != 2 or pred.info["fast_path"] == 1, "config-2 model must take the fast kernel"
 
     # ---- data ------------------------------------------------------------------------------------------
     text, offs, _ = get_text(args.sentences, rank, args.ragged)
@@ -252,11 +259,18 @@ def main():
     d_status = torch.empty(n, dtype=torch.int32, device=dev)
     stream = torch.cuda.current_stream()
     sp = C.c_void_p(stream.cuda_stream)
+    want_states = args.config == 3  # config 3: pattern-id states are part of the output (tag prediction input)
+    d_cst = torch.empty(nbytes, dtype=torch.int32, device=dev) if want_states else None
+    d_tst = torch.empty(nbytes, dtype=torch.int32, device=dev) if want_states else None
+    d_coff = torch.empty(n + 1, dtype=torch.int64, device=dev) if want_states else None
+    p_cst = d_cst.data_ptr() if want_states else None
+    p_tst = d_tst.data_ptr() if want_states else None
+    p_coff = d_coff.data_ptr() if want_states else None
 
     def step_dev():
         rc = L.vpt_predict_batch_dev(pred._h, d_text.data_ptr(), d_off.data_ptr(), n, ws.data_ptr(), ws.numel(),
                                      d_scores.data_ptr(), d_bounds.data_ptr(), d_boff.data_ptr(), d_status.data_ptr(),
-                                     None, None, None, sp)
+                                     p_cst, p_tst, p_coff, sp)
         if rc:
             raise RuntimeError(L.vpt_last_error().decode())
 
@@ -289,7 +303,7 @@ def main():
     for _ in range(reps):
         rc = L.vpt_predict_batch_dev_profiled(pred._h, d_text.data_ptr(), d_off.data_ptr(), n, ws.data_ptr(), ws.numel(),
                                               d_scores.data_ptr(), d_bounds.data_ptr(), d_boff.data_ptr(),
-                                              d_status.data_ptr(), None, None, None, sp, stage)
+                                              d_status.data_ptr(), p_cst, p_tst, p_coff, sp, stage)
         if rc:
             raise RuntimeError(L.vpt_last_error().decode())
         stage_acc += np.array(list(stage))
@@ -313,11 +327,17 @@ def main():
     h_boff = torch.empty(n + 1, dtype=torch.int64).pin_memory()
     h_status = torch.empty(n, dtype=torch.int32).pin_memory()
     nb_out, nc_out = C.c_uint64(), C.c_uint64()
+    n_chars_total = n_bound + n  # every sentence is non-empty
+    h_cst = torch.empty(n_chars_total, dtype=torch.int32).pin_memory() if want_states else None
+    h_tst = torch.empty(n_chars_total, dtype=torch.int32).pin_memory() if want_states else None
+    h_coff = torch.empty(n + 1, dtype=torch.int64).pin_memory() if want_states else None
 
     def step_e2e():
         rc = L.vpt_predict_batch(pred._h, h_text.data_ptr(), h_off.data_ptr(), n, h_scores.data_ptr(),
-                                 h_bounds.data_ptr(), n_bound, h_boff.data_ptr(), h_status.data_ptr(), None, None, 0,
-                                 None, C.byref(nb_out), C.byref(nc_out))
+                                 h_bounds.data_ptr(), n_bound, h_boff.data_ptr(), h_status.data_ptr(),
+                                 h_cst.data_ptr() if want_states else None, h_tst.data_ptr() if want_states else None,
+                                 n_chars_total if want_states else 0, h_coff.data_ptr() if want_states else None,
+                                 C.byref(nb_out), C.byref(nc_out))
         if rc:
             raise RuntimeError(L.vpt_last_error().decode())
 
@@ -336,7 +356,7 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = total_bytes * args.e2e_steps / float(te.item()) / 1e6
     h2d = nbytes + 8 * (n + 1)
-    d2h = 4 * n_bound + n_bound + 8 * (n + 1) + 4 * n + 16
+    d2h = 4 * n_bound + n_bound + 8 * (n + 1) + 4 * n + 16 + (8 * n_chars_total + 8 * (n + 1) if want_states else 0)
 
     if rank == 0:
         peaks = {}
@@ -348,10 +368,12 @@ def main():
         peak_src = "MEASURED_PEAKS.json hbm_gbs (burst copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         alg_bytes = nbytes + 8 * n + 5 * n_bound  # read B+8 per sentence, write 4(n-1)+(n-1)
         score_ms = float(stage_ms[2])
+        kernel_name = "k_tile_fast" if pred.info["fast_path"] else "k_score_general"
         achieved = alg_bytes / (score_ms / 1e3) / 1e9
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_score_fast_bytes_per_launch")
+            if args.config == 2 and args.sentences == 1_000_000:
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_score_fast_bytes_per_launch")
         except Exception:
             pass
         out = {
@@ -359,11 +381,11 @@ def main():
             "warmup": args.warmup, "ms_per_step": round(ms_all / args.steps, 4), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "i32", "data": "synthetic",
             "config": workload_config(args, n),
-            "roofline": {"bound": "hbm", "kernel": "k_score_fast", "achieved": round(achieved, 1), "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": round(achieved, 1), "peak": peak,
                          "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": round(score_ms, 4),
                          "stage_ms": {"k_count": round(float(stage_ms[0]), 4), "k_scan_groups": round(float(stage_ms[1]), 4),
-                                      "k_score_fast": round(score_ms, 4)},
+                                      kernel_name: round(score_ms, 4)},
                          "read_only_GBps": round((nbytes + 8 * n) / (score_ms / 1e3) / 1e9, 1),
                          "whole_step_frac": round(alg_bytes / (ms_all / args.steps / 1e3) / 1e9 / peak, 4)},
             "e2e": {"value": round(e2e_value, 1), "unit": "MB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -373,8 +395,12 @@ def main():
             "bit_exact_checked": True,
         }
         if world == 1 and not args.no_cpu_baseline:
-            model_bytes = get_model(args.patterns, args.model_sample)
-            cb, oracle = cpu_baseline(model_bytes, text, offs)
+            model_bytes = get_model(args.patterns, args.model_sample, args.config)
+            # (config 3: the oracle restates the reference's build-time tag merge literally, which takes minutes on
+            #  20 000 tag models; the CPU arm therefore scores boundaries with predict_tags = false)
+            cb, oracle = cpu_baseline(model_bytes, text, offs, predict_tags=False)
+            if args.config == 3:
+                cb["sample"] += "; predict_tags = false on the CPU arm (boundary scores are identical)"
             out["cpu_baseline"] = cb
             # parity spot check of this very run against the oracle
             idx = np.arange(0, n, max(1, n // 200))[:200]

@@ -67,7 +67,8 @@ void vpt_model_free(vpt_model* model);
 
 /* `Predictor::new(model: Model, predict_tags: bool) -> Result<Predictor>` (predictor.rs:450-508).
  * Consumes `model` (it is freed, success or failure), builds the merged weight rows and the flat device
- * tables, and uploads them to CUDA device `device`. */
+ * tables, and uploads them to CUDA device `device`.  device = -1 creates a host-only handle (tag prediction and
+ * Sentence helpers work, every scoring entry point fails with VPT_CUDA_ERROR — there is no CPU scoring path). */
 int vpt_predictor_new(vpt_model* model, int predict_tags, int device, vpt_predictor** out);
 void vpt_predictor_free(vpt_predictor* predictor);
 

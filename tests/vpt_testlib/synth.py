@@ -169,10 +169,12 @@ def _encode_ngram_list(ngram_bytes, weight_rows) -> bytes:
 
 
 def gen_model_bccwj_shaped(n_patterns: int = 300_000, sample_sentences: int = 2_000_000, window: int = 3,
-                           seed: int = MODEL_SEED, dict_words: int = 0, return_parts: bool = False) -> bytes:
+                           seed: int = MODEL_SEED, dict_words: int = 0, tag_models: int = 0) -> bytes:
     """bccwj-suw-shaped model (BASELINE config 2): the n_patterns most frequent char 1/2/3-grams of a synthetic
     sample, all 6+36+216 type 1-3-grams, W=3 both, no tags; `dict_words` > 0 adds a KyTea-shaped dictionary
-    (config 4: lengths {1:2%,2:30%,3:25%,4:18%,5-7:17%,8-16:8%}, weights [L, I.., R] in 4 length buckets)."""
+    (config 4: lengths {1:2%,2:30%,3:25%,4:18%,5-7:17%,8-16:8%}, weights [L, I.., R] in 4 length buckets);
+    `tag_models` > 0 adds unidic_pos-shaped tag models (config 3: tokens = 1-4-char strings, 1-2 tag slots of 2-8
+    candidates, 0-30 char and 0-10 type tag n-grams each with one rel_position in [0, 3])."""
     L = 40
     cps = gen_codepoints(sample_sentences, L, TEXT_SEED ^ 0x77).reshape(sample_sentences, L)
     allk, allc, alln = [], [], []
@@ -245,6 +247,72 @@ def gen_model_bccwj_shaped(n_patterns: int = 300_000, sample_sentences: int = 2_
             body.append(varint(len(wb)) + wb + varint(len(ws)) + b"".join(zigzag(x) for x in ws) + varint(0))
         dparts = [varint(n_real)] + body
     bias = int(splitmix64(seed, 1, 40)[0] % np.uint64(65535)) - 32767
+    tparts = [varint(0)]
+    if tag_models:
+        r = splitmix64(seed, tag_models * 8, 50).reshape(tag_models, 8)
+        tok_len = (r[:, 0] % np.uint64(4)).astype(np.int64) + 1
+        tok_cps = gen_codepoints(tag_models, tok_len, TEXT_SEED ^ 0x55)
+        tstart = np.zeros(tag_models + 1, np.int64)
+        np.cumsum(tok_len, out=tstart[1:])
+        n_char_ng = (r[:, 1] % np.uint64(31)).astype(np.int64)
+        n_type_ng = (r[:, 2] % np.uint64(11)).astype(np.int64)
+        ng_total = int(n_char_ng.sum())
+        ng_len = (splitmix64(seed, ng_total, 51) % np.uint64(3)).astype(np.int64) + 1
+        ng_cps = gen_codepoints(ng_total, ng_len, TEXT_SEED ^ 0x66)
+        ng_start = np.zeros(ng_total + 1, np.int64)
+        np.cumsum(ng_len, out=ng_start[1:])
+        ng_rel = (splitmix64(seed, ng_total, 52) % np.uint64(window + 1)).astype(np.int64)
+        tng_total = int(n_type_ng.sum())
+        tng_r = splitmix64(seed, tng_total * 4, 53).reshape(tng_total, 4) if tng_total else np.zeros((0, 4), np.uint64)
+        cache = {}
+        seen = set()
+        body = []
+        ci = ti = 0
+        wsrc = (splitmix64(seed, 1 << 16, 54) % np.uint64(2001)).astype(np.int64) - 1000
+        wpos = 0
+
+        def wvec(k):
+            nonlocal wpos
+            if wpos + k > len(wsrc):
+                wpos = 0
+            v = wsrc[wpos:wpos + k]
+            wpos += k
+            return v
+
+        for i in range(tag_models):
+            tok = b"".join(cache.setdefault(int(c), _cp_to_utf8_bytes(c)) for c in tok_cps[tstart[i]:tstart[i + 1]])
+            nc, nt = int(n_char_ng[i]), int(n_type_ng[i])
+            if tok in seen:
+                ci += nc
+                ti += nt
+                continue
+            seen.add(tok)
+            nslots = int(r[i, 3] % np.uint64(2)) + 1
+            cands = [int(r[i, 4 + s] % np.uint64(7)) + 2 for s in range(nslots)]
+            slen = sum(cands)
+            p = [varint(len(tok)), tok, varint(nslots)]
+            for s_, c_ in enumerate(cands):
+                p.append(varint(c_))
+                for k in range(c_):
+                    t = b"T%d_%d" % (s_, k)
+                    p.append(varint(len(t)) + t)
+            p.append(varint(nc))
+            for j in range(nc):
+                g = b"".join(cache.setdefault(int(c), _cp_to_utf8_bytes(c)) for c in ng_cps[ng_start[ci + j]:ng_start[ci + j + 1]])
+                p.append(varint(len(g)) + g + varint(1) + bytes([int(ng_rel[ci + j])]) + varint(slen) +
+                         b"".join(zigzag(int(x)) for x in wvec(slen)))
+            ci += nc
+            p.append(varint(nt))
+            for j in range(nt):
+                rr = tng_r[ti + j]
+                ln = int(rr[0] % np.uint64(3)) + 1
+                g = bytes(int(rr[1 + q] % np.uint64(6)) + 1 for q in range(ln))
+                p.append(varint(len(g)) + g + varint(1) + bytes([int(rr[0] >> np.uint64(8)) % (window + 1)]) + varint(slen) +
+                         b"".join(zigzag(int(x)) for x in wvec(slen)))
+            ti += nt
+            p.append(varint(slen) + b"".join(zigzag(int(x)) for x in wvec(slen)))
+            body.append(b"".join(p))
+        tparts = [varint(len(body))] + body
     out = b"".join([MODEL_MAGIC, char_part, type_part, b"".join(dparts), zigzag(bias), bytes([window]), bytes([window]),
-                    varint(0)])
+                    b"".join(tparts)])
     return out

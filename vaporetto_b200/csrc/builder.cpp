@@ -143,13 +143,23 @@ PatternSet build_patterns(const std::vector<NgramEntry>& ngrams, const std::vect
     std::iota(order.begin(), order.end(), 0u);
     std::stable_sort(order.begin(), order.end(),
                      [&](uint32_t a, uint32_t b) { return ps.raw[a].size() < ps.raw[b].size(); });
+    //    Tag weights are NOT materialised along the suffix chain (a frequent unigram tag n-gram would be copied
+    //    into every longer pattern): each pattern keeps its own entries plus a link to its longest proper
+    //    suffix pattern, and vpt_fill_tags evaluates the reference's merge (predictor.rs:242-262) lazily.
+    ps.suffix_link.assign(n, kNoPattern);
     for (uint32_t p : order) {
         const std::string& s = ps.raw[p];
         for (size_t j = 1; j < s.size(); ++j) {
             if (utf8 && (uint8_t(s[j]) & 0xC0) == 0x80) continue;
             auto it = index.find(s.substr(j));
             if (it != index.end()) {
-                accumulate(*own[p], *own[it->second]);
+                Entry& dst = *own[p];
+                const Entry& src = *own[it->second];
+                if (src.has_weight) {
+                    if (dst.has_weight) accumulate(dst.weight, src.weight);
+                    else { dst.weight = src.weight; dst.has_weight = true; }
+                }
+                ps.suffix_link[p] = it->second;
                 break;
             }
         }

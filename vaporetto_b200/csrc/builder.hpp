@@ -29,8 +29,9 @@ struct Row {
     std::vector<int32_t> w;
 };
 
-// Per-pattern tag weights, suffix-merged like the boundary rows
-// (PositionalWeightWithTag, predictor.rs:217-262): (token_id, rel_position) -> weights.
+// Per-pattern tag weights (PositionalWeightWithTag::tag_info, predictor.rs:217-262): (token_id, rel_position) ->
+// weights.  The reference suffix-merges them at build time; here the merge is evaluated at lookup time along
+// `suffix_link` (same result, without copying a short pattern's entries into every longer pattern).
 using TagInfo = std::vector<std::pair<std::pair<uint32_t, uint8_t>, std::vector<int32_t>>>;
 
 struct PatternSet {
@@ -38,7 +39,8 @@ struct PatternSet {
     std::vector<std::string> raw;              // pattern bytes, sorted byte-lexicographically; index = pattern id
     std::vector<std::vector<uint32_t>> syms;   // the same patterns as symbol sequences
     std::vector<Row> rows;                     // merged boundary rows (zero-trimmed)
-    std::vector<TagInfo> tags;                 // merged tag weights per pattern (tag variant only)
+    std::vector<TagInfo> tags;                 // the pattern's OWN tag weights (tag variant only; not suffix-merged)
+    std::vector<uint32_t> suffix_link;         // longest proper suffix that is a pattern, or kNoPattern
     bool tag_variant = false;
     size_t max_len = 0;                        // longest pattern in symbols
 };

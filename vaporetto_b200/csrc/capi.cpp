@@ -118,6 +118,7 @@ DevTable dev_table(const BlobTable& bt, const uint8_t* base) {
 }
 
 void upload(vpt_predictor& p) {
+    if (p.device == -1) return;  // host-only handle (tag prediction / Sentence helpers); cannot score
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
@@ -227,12 +228,42 @@ void add_truncated(const std::vector<int32_t>& w, std::vector<int32_t>& ys) {  /
     for (size_t i = 0; i < n; ++i) ys[i] = wrapping_add(ys[i], w[i]);
 }
 
-void add_tag_scores(const TagWeightMap& tw, uint32_t token, size_t pos, const uint32_t* states, size_t n,
-                    std::vector<int32_t>& scores) {  // boundary_tag_scorer.rs:154-174
+// Tag weight of pattern `pid` for one (token, rel) table, as the reference's build-time suffix merge would have
+// produced it (PositionalWeightWithTag +=, predictor.rs:242-262, applied along the chain of suffix patterns,
+// char_scorer.rs:50-78): a pattern's own vector plus the merged vector of its longest suffix pattern truncated
+// to the own length; without an own vector, the suffix's merged vector unchanged.
+bool merged_tag_weight(const std::unordered_map<uint32_t, std::vector<int32_t>>& table,
+                       const std::vector<uint32_t>& suffix_link, uint32_t pid, std::vector<int32_t>& out) {
+    // collect the chain entries (longest pattern first)
+    const std::vector<int32_t>* chain[64];
+    int n = 0;
+    for (uint32_t q = pid; q != kNoPattern; q = suffix_link[q]) {
+        auto it = table.find(q);
+        if (it != table.end()) {
+            if (n == 64) break;  // patterns are far shorter than 64 symbols per chain in practice
+            chain[n++] = &it->second;
+        }
+    }
+    if (n == 0) return false;
+    // evaluate from the shortest suffix outwards
+    out = *chain[n - 1];
+    for (int i = n - 2; i >= 0; --i) {
+        std::vector<int32_t> cur = *chain[i];
+        const size_t m = std::min(cur.size(), out.size());
+        for (size_t k = 0; k < m; ++k) cur[k] = wrapping_add(cur[k], out[k]);
+        out.swap(cur);
+    }
+    return true;
+}
+
+void add_tag_scores(const TagWeightMap& tw, const std::vector<uint32_t>& suffix_link, uint32_t token, size_t pos,
+                    const uint32_t* states, size_t n, std::vector<int32_t>& scores) {  // boundary_tag_scorer.rs:154-174
     const auto& per_rel = tw[token];
+    std::vector<int32_t> w;
     for (size_t r = 0; r < per_rel.size() && pos + r < n; ++r) {
-        auto it = per_rel[r].find(states[pos + r]);
-        if (it != per_rel[r].end()) add_truncated(it->second, scores);
+        const uint32_t pid = states[pos + r];
+        if (pid == kNoPattern || pid >= suffix_link.size() || per_rel[r].empty()) continue;
+        if (merged_tag_weight(per_rel[r], suffix_link, pid, w)) add_truncated(w, scores);
     }
 }
 
@@ -346,11 +377,18 @@ int vpt_predictor_from_blob(const void* blob, uint64_t len, int device, vpt_pred
 
 uint64_t vpt_workspace_size(size_t n_sent) { return workspace_layout(n_sent).total; }
 
+static void require_device(const vpt_predictor* p) {
+    if (!p) throw Error(kInvalidArgument, "InvalidArgumentError: predictor: must not be NULL");
+    if (p->device < 0 || !p->d_blob)
+        throw Error(kCudaError, "this predictor was created without a CUDA device (device = -1): it cannot score; "
+                                "vaporetto_b200 has no CPU fallback");
+}
+
 static void run_batch_dev(const vpt_predictor* p, const uint8_t* d_utf8, const uint64_t* d_byte_offsets, size_t n_sent,
                           void* d_workspace, uint64_t workspace_bytes, int32_t* d_scores, uint8_t* d_boundaries,
                           uint64_t* d_bound_offsets, int32_t* d_status, uint32_t* d_char_states,
                           uint32_t* d_type_states, uint64_t* d_char_offsets, void* cuda_stream, float* stage_ms) {
-    if (!p) throw Error(kInvalidArgument, "InvalidArgumentError: predictor: must not be NULL");
+    require_device(p);
     if (stage_ms) stage_ms[0] = stage_ms[1] = stage_ms[2] = 0.f;
     if (n_sent == 0) return;
     if (!d_utf8 || !d_byte_offsets || !d_workspace || !d_scores || !d_boundaries || !d_bound_offsets || !d_status)
@@ -467,7 +505,7 @@ int vpt_predict_batch(const vpt_predictor* p, const uint8_t* utf8, const uint64_
                       size_t states_capacity, uint64_t* char_offsets_out, uint64_t* n_boundaries_out,
                       uint64_t* n_chars_out) {
     VPT_API_BEGIN
-    if (!p) throw Error(kInvalidArgument, "InvalidArgumentError: predictor: must not be NULL");
+    require_device(p);
     if (n_boundaries_out) *n_boundaries_out = 0;
     if (n_chars_out) *n_chars_out = 0;
     if (!byte_offsets || !bound_offsets_out)
@@ -626,8 +664,8 @@ int vpt_fill_tags(const vpt_predictor* p, const uint8_t* utf8, size_t n_bytes, c
         const TagPredictorHost& tp = p->tag_preds[tid];
         scores.assign(tp.bias.size(), 0);
         add_truncated(tp.bias, scores);
-        if (p->char_tags) add_tag_scores(p->char_tag_weight, tid, last, char_states, n, scores);
-        if (p->type_tags) add_tag_scores(p->type_tag_weight, tid, last, type_states, n, scores);
+        if (p->char_tags) add_tag_scores(p->char_tag_weight, p->char_suffix_link, tid, last, char_states, n, scores);
+        if (p->type_tags) add_tag_scores(p->type_tag_weight, p->type_suffix_link, tid, last, type_states, n, scores);
         // TagPredictor::predict (predictor.rs:286-304): first strict maximum per slot with >= 2 candidates
         size_t off = 0;
         for (size_t k = 0; k < tp.tags.size() && k < nt; ++k) {

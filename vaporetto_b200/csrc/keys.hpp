@@ -48,11 +48,15 @@ VPT_HD uint64_t deep_key(uint32_t parent_id, uint32_t sym) {
 // 32-bit hashes; the first picks the bucket, the bucket's 16-bit seed displaces the second into the slot.
 VPT_HD void key_hashes(uint64_t key, uint64_t salt, uint32_t& ha, uint32_t& hb) {
     const uint32_t lo = uint32_t(key) ^ uint32_t(salt), hi = uint32_t(key >> 32) ^ uint32_t(salt >> 32);
-    uint32_t a = (lo * 0x9E3779B1u) ^ (hi * 0x85EBCA77u);
+    // multiplication only carries differences upwards, so each half is folded (>> 16) into the other before
+    // the second multiply: keys that differ only in high bits (deep vs shallow keys) still separate
+    const uint32_t t = hi * 0x85EBCA77u;
+    uint32_t a = (lo ^ t ^ (t >> 16)) * 0x9E3779B1u;
     a ^= a >> 15;
-    a *= 0xC2B2AE3Du;
-    ha = a;
-    hb = lo * 0x27D4EB2Fu + hi * 0x165667B1u;
+    ha = a * 0xC2B2AE3Du;
+    const uint32_t u = lo * 0x27D4EB2Fu;
+    uint32_t b = (hi ^ u ^ (u >> 15)) * 0x165667B1u;
+    hb = b ^ (b >> 16);
 }
 VPT_HD uint32_t mulhi32(uint32_t a, uint32_t b) { return uint32_t((uint64_t(a) * b) >> 32); }
 VPT_HD uint32_t bucket_of(uint32_t ha, uint32_t nbuckets) { return mulhi32(ha, nbuckets); }

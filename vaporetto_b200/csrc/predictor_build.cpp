@@ -93,8 +93,8 @@ HostPredictor build_host_predictor(const Model& m, bool predict_tags) {
     if (has_char && ctab.fast && (ttab.present)) ctab = build_node_table(cps, true);
 
     if (tags) {
-        if (has_char) { p->char_tag_weight = collect_tag_weights(cps, m.tag_models.size(), m.char_window); p->char_tags = true; }
-        if (type_variant == 3) { p->type_tag_weight = collect_tag_weights(tps, m.tag_models.size(), m.type_window); p->type_tags = true; }
+        if (has_char) { p->char_tag_weight = collect_tag_weights(cps, m.tag_models.size(), m.char_window); p->char_suffix_link = cps.suffix_link; p->char_tags = true; }
+        if (type_variant == 3) { p->type_tag_weight = collect_tag_weights(tps, m.tag_models.size(), m.type_window); p->type_suffix_link = tps.suffix_link; p->type_tags = true; }
     }
 
     BlobWriter w;

@@ -49,7 +49,8 @@ struct HostPredictor {
     size_t n_tags = 0;
     std::unordered_map<std::string, uint32_t> token_ids;
     std::vector<TagPredictorHost> tag_preds;
-    TagWeightMap char_tag_weight, type_tag_weight;
+    TagWeightMap char_tag_weight, type_tag_weight;      // own (un-merged) entries per pattern id
+    std::vector<uint32_t> char_suffix_link, type_suffix_link;
     bool char_tags = false, type_tags = false;
 };
 
