@@ -455,7 +455,15 @@ int vpt_predict_batch_dev_profiled(const vpt_predictor* p, const uint8_t* d_utf8
 
 namespace {
 
-constexpr size_t kChunkSentences = 65536;  // sentences per pipelined chunk of vpt_predict_batch
+// sentences per pipelined chunk of vpt_predict_batch (tuning knob: env VPT_CHUNK_SENTENCES)
+size_t chunk_sentences() {
+    static const size_t v = [] {
+        const char* e = getenv("VPT_CHUNK_SENTENCES");
+        const long long x = e ? atoll(e) : 0;
+        return x >= 1024 ? size_t(x) : size_t(65536);
+    }();
+    return v;
+}
 
 struct ChunkState {
     size_t s_lo = 0, n = 0;       // sentence range
@@ -520,6 +528,7 @@ int vpt_predict_batch(const vpt_predictor* p, const uint8_t* utf8, const uint64_
     // The batch is cut into chunks that flow through three streams so that the H2D copy of chunk c+2, the
     // kernels of chunk c+1 and the D2H copy of chunk c overlap.  Each chunk is an independent batch on the
     // device; its output offsets are rebased with the running totals (known on the host after its count pass).
+    const size_t kChunkSentences = chunk_sentences();
     const size_t nchunks = (n_sent + kChunkSentences - 1) / kChunkSentences;
     constexpr int kDepth = 3;
     std::unique_ptr<ScratchLease> lease[kDepth];

@@ -601,40 +601,19 @@ __device__ __forceinline__ bool rec_matches(const Rec32& rec, uint64_t key) {
     return (k & ~kExtFlag) == key;
 }
 
-// Completes the longest-suffix lookup for slot p given the (already loaded) record of the first probe.
+// Continues a depth-3 hit backwards through the text for patterns longer than three characters (rare).
 template <bool kSeedsSmem>
-__device__ __forceinline__ void lookup_finish(const DevTable& t, const uint8_t* s_seeds, const uint32_t* __restrict__ cp,
-                                              int p, uint32_t c1, uint32_t c2, uint32_t c3, Rec32 rec, uint32_t slot,
-                                              int32_t (&d)[kInlineWidth]) {
-    bool found = rec_matches(rec, shallow_key(c1, c2, c3));
-    const bool depth3 = found && c1 != 0;
-    if (!found && c1 != 0) {
-        const uint64_t key = shallow_key(0, c2, c3);
-        slot = slot_of_t<kSeedsSmem>(t, s_seeds, key);
-        rec = load_record(t.records, slot);
-        found = rec_matches(rec, key);
-    }
-    if (!found && c2 != 0) {
-        const uint64_t key = shallow_key(0, 0, c3);
-        slot = slot_of_t<kSeedsSmem>(t, s_seeds, key);
-        rec = load_record(t.records, slot);
-        found = rec_matches(rec, key);
-    }
-    if (depth3 && (rec.v[1] >> 31)) {
-        uint32_t node = __ldg(t.slot_node + slot);
-        for (int i = p - 3; cp[i] != 0; --i) {
-            const uint64_t key = deep_key(node, cp[i]);
-            const uint32_t nslot = slot_of_t<kSeedsSmem>(t, s_seeds, key);
-            const Rec32 nrec = load_record(t.records, nslot);
-            if (!rec_matches(nrec, key)) break;
-            rec = nrec;
-            if (!(rec.v[1] >> 31)) break;
-            node = __ldg(t.slot_node + nslot);
-        }
-    }
-    if (found) {
-#pragma unroll
-        for (int j = 0; j < kInlineWidth; ++j) d[j] = int32_t(rec.v[2 + j]);
+__device__ __forceinline__ void deep_walk(const DevTable& t, const uint8_t* s_seeds, const uint32_t* __restrict__ cp, int p,
+                                          uint32_t slot, Rec32& rec) {
+    uint32_t node = __ldg(t.slot_node + slot);
+    for (int i = p - 3; cp[i] != 0; --i) {
+        const uint64_t key = deep_key(node, cp[i]);
+        const uint32_t nslot = slot_of_t<kSeedsSmem>(t, s_seeds, key);
+        const Rec32 nrec = load_record(t.records, nslot);
+        if (!rec_matches(nrec, key)) break;
+        rec = nrec;
+        if (!(rec.v[1] >> 31)) break;
+        node = __ldg(t.slot_node + nslot);
     }
 }
 
@@ -854,8 +833,35 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_fast(DevModel m, Batch
                     slB = slot_of_t<kSeedsSmem>(m.ct, s_seeds, shallow_key(b1, b2, b3));
                     rB = load_record(m.ct.records, slB);
                 }
-                if (a3) lookup_finish<kSeedsSmem>(m.ct, s_seeds, s_cp, pA, a1, a2, a3, rA, slA, dA);
-                if (b3) lookup_finish<kSeedsSmem>(m.ct, s_seeds, s_cp, pB, b1, b2, b3, rB, slB, dB);
+                // resolve both slots level by level so that the fallback probes of A and B are in flight together
+                bool fA = a3 != 0 && rec_matches(rA, shallow_key(a1, a2, a3));
+                bool fB = b3 != 0 && rec_matches(rB, shallow_key(b1, b2, b3));
+                const bool deepA = fA && a1 != 0 && (rA.v[1] >> 31), deepB = fB && b1 != 0 && (rB.v[1] >> 31);
+                {   // two-character suffixes
+                    const bool nA = a3 != 0 && !fA && a1 != 0, nB = b3 != 0 && !fB && b1 != 0;
+                    const uint64_t kA = shallow_key(0, a2, a3), kB = shallow_key(0, b2, b3);
+                    // (a slot that still needs a probe has no use for its previous record: load in place)
+                    if (nA) rA = load_record(m.ct.records, slot_of_t<kSeedsSmem>(m.ct, s_seeds, kA));
+                    if (nB) rB = load_record(m.ct.records, slot_of_t<kSeedsSmem>(m.ct, s_seeds, kB));
+                    if (nA) fA = rec_matches(rA, kA);
+                    if (nB) fB = rec_matches(rB, kB);
+                }
+                {   // single characters
+                    const bool nA = a3 != 0 && !fA && a2 != 0, nB = b3 != 0 && !fB && b2 != 0;
+                    const uint64_t kA = shallow_key(0, 0, a3), kB = shallow_key(0, 0, b3);
+                    // (a slot that still needs a probe has no use for its previous record: load in place)
+                    if (nA) rA = load_record(m.ct.records, slot_of_t<kSeedsSmem>(m.ct, s_seeds, kA));
+                    if (nB) rB = load_record(m.ct.records, slot_of_t<kSeedsSmem>(m.ct, s_seeds, kB));
+                    if (nA) fA = rec_matches(rA, kA);
+                    if (nB) fB = rec_matches(rB, kB);
+                }
+                if (deepA) deep_walk<kSeedsSmem>(m.ct, s_seeds, s_cp, pA, slA, rA);
+                if (deepB) deep_walk<kSeedsSmem>(m.ct, s_seeds, s_cp, pB, slB, rB);
+#pragma unroll
+                for (int j = 0; j < kInlineWidth; ++j) {
+                    dA[j] = fA ? int32_t(rA.v[2 + j]) : 0;
+                    dB[j] = fB ? int32_t(rB.v[2 + j]) : 0;
+                }
                 gather_store<kR0>(dA, r0, lane, pA, s_sc, s_spill_prev, s_spill_next);
                 if (hasB) gather_store<kR0>(dB, r0, lane, pB, s_sc, s_spill_prev, s_spill_next);
             }
