@@ -536,6 +536,110 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_score_fast(DevModel m, 
 
 
 // ------------------------------------------------------------------------------------------------
+// k_score_general (one warp per sentence)
+// ------------------------------------------------------------------------------------------------
+template <bool kTypes>
+__device__ __forceinline__ void scatter_general(const DevTable& t, const Rings& r, const uint8_t* __restrict__ text,
+                                                const SentInfo& si, uint32_t g, int32_t* scores, uint32_t* states) {
+    Rec32 rec;
+    uint32_t slot;
+    uint32_t pid = kNoPattern;
+    if (find_node<kTypes>(t, r, text, si.b0, g, rec, slot)) {
+        pid = rec.v[2];
+        const uint32_t row = rec.v[3];
+        if (row != kNoPattern) {
+            const int32_t off = int32_t(rec.v[4]);
+            const uint32_t len = rec.v[5];
+            for (uint32_t k = 0; k < len; ++k) {
+                const int64_t i = int64_t(g) + off + int64_t(k);
+                if (i >= 0 && i < int64_t(si.nout)) atomicAdd(scores + si.obase + i, __ldg(t.pool + row + k));
+            }
+        }
+    }
+    if (states) states[si.cbase + g] = pid;
+}
+
+// One warp scores one sentence with the general (pooled-row) tables: rows of any length scatter with global
+// atomics, pattern-id states are emitted, the type automaton variant is supported.  Used by k_score_general and
+// as the fallback of k_tile for single sentences larger than the tile buffers.
+__device__ __forceinline__ void general_sentence_warp(const DevModel& m, const BatchArgs& a, uint64_t s, Rings& r, int lane) {
+    const SentInfo si = sentence_info(a, s, lane);
+    const uint8_t* __restrict__ text = a.text;
+    const uint32_t n = si.n;
+    uint32_t* cstates = a.char_states;
+    uint32_t* tstates = a.type_states;
+    if (si.status != 0) {
+        for (uint32_t i = lane; i < si.nout; i += 32) { a.scores[si.obase + i] = 0; a.boundaries[si.obase + i] = 0; }
+        if (cstates) for (uint32_t i = lane; i < n; i += 32) cstates[si.cbase + i] = kNoPattern;
+        if (tstates) for (uint32_t i = lane; i < n; i += 32) tstates[si.cbase + i] = kNoPattern;
+        return;
+    }
+    const int tw = m.type_cache_window;
+    // pass 1: scores = bias + type table; states = none
+    {
+        uint64_t wpos = si.b0 & ~3ull;
+        uint32_t nd = 0;
+        for (uint32_t cb = 0; cb < n; cb += 32) {
+            const uint32_t need = min(n, cb + 32u + uint32_t(tw));
+            while (nd < need && wpos < si.b1) {
+                nd += decode_window(text, wpos, si.b0, si.b1, nd, r, lane);
+                wpos += 128;
+            }
+            __syncwarp();
+            const uint32_t g = cb + lane;
+            if (g + 1 < n) {
+                int32_t v = m.bias;
+                if (tw > 0) v += __ldg(m.type_cache + type_index(r, int64_t(g), n, tw));
+                a.scores[si.obase + g] = v;
+            }
+            if (g < n) {
+                if (cstates) cstates[si.cbase + g] = kNoPattern;
+                if (tstates) tstates[si.cbase + g] = kNoPattern;
+            }
+            __syncwarp();
+        }
+    }
+    __threadfence();
+    __syncwarp();
+    // pass 2: pattern rows
+    if (m.ct.present || m.tt.present) {
+        uint64_t wpos = si.b0 & ~3ull;
+        uint32_t nd = 0;
+        for (uint32_t cb = 0; cb < n; cb += 32) {
+            const uint32_t need = min(n, cb + 32u);
+            while (nd < need && wpos < si.b1) {
+                nd += decode_window(text, wpos, si.b0, si.b1, nd, r, lane);
+                wpos += 128;
+            }
+            __syncwarp();
+            const uint32_t g = cb + lane;
+            if (g < n) {
+                if (m.ct.present)
+                    scatter_general<false>(m.ct, r, text, si, g, a.scores, m.emit_states ? cstates : nullptr);
+                if (m.tt.present)
+                    scatter_general<true>(m.tt, r, text, si, g, a.scores, m.emit_states ? tstates : nullptr);
+            }
+            __syncwarp();
+        }
+    }
+    __threadfence();
+    __syncwarp();
+    // pass 3: threshold
+    for (uint32_t i = lane; i < si.nout; i += 32) {
+        const int32_t v = __ldcg(a.scores + si.obase + i);
+        a.boundaries[si.obase + i] = v > 0 ? 1 : 0;
+    }
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) k_score_general(DevModel m, BatchArgs a) {
+    __shared__ Rings s_rings[kWarpsPerBlock];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint64_t s = uint64_t(blockIdx.x) * kWarpsPerBlock + warp;
+    if (s >= a.n_sent) return;
+    general_sentence_warp(m, a, s, s_rings[warp], lane);
+}
+
+// ------------------------------------------------------------------------------------------------
 // k_tile_fast — persistent: one 1024-thread CTA per SM = 4 independent 256-thread sub-blocks that pull
 // 64-sentence groups from a global ticket.  Shared by the 4 sub-blocks: the perfect-hash seed bytes and the
 // split type tables (staged once per CTA); private to each sub-block: the tile buffers below.
@@ -639,7 +743,56 @@ __device__ __forceinline__ void gather_store(const int32_t (&d)[kInlineWidth], i
     if (lane < 8) s_spill_next[wc * 8 + lane] = to_next;
 }
 
-template <bool kSeedsSmem, int kR0>
+// General-table lookup + scatter for slot p of the flat slot stream: the row of the longest pattern ending at p
+// adds w[k] to boundary slot p + off + k, restricted to the boundary slots [lo_slot, hi_slot) of p's sentence
+// (what falls outside lands in the reference's strip padding or is clipped: predictor.rs:181-201).
+template <bool kSeedsSmem, bool kTypes>
+__device__ __forceinline__ void tile_scatter(const DevTable& t, const uint8_t* s_seeds, const uint32_t* __restrict__ cp,
+                                             const uint8_t* __restrict__ ty, int p, int lo_slot, int hi_slot, int32_t* s_sc,
+                                             uint32_t* state_out) {
+    auto sym = [&](int i) -> uint32_t { return kTypes ? uint32_t(ty[i]) : cp[i]; };
+    const uint32_t c3 = sym(p), c2 = sym(p - 1);
+    const uint32_t c1 = c2 ? sym(p - 2) : 0u;
+    uint64_t key = shallow_key(c1, c2, c3);
+    Rec32 rec = load_record(t.records, slot_of_t<kSeedsSmem>(t, s_seeds, key));
+    bool found = rec_matches(rec, key);
+    const bool depth3 = found && c1 != 0;
+    if (!found && c1 != 0) {
+        key = shallow_key(0, c2, c3);
+        rec = load_record(t.records, slot_of_t<kSeedsSmem>(t, s_seeds, key));
+        found = rec_matches(rec, key);
+    }
+    if (!found && c2 != 0) {
+        key = shallow_key(0, 0, c3);
+        rec = load_record(t.records, slot_of_t<kSeedsSmem>(t, s_seeds, key));
+        found = rec_matches(rec, key);
+    }
+    if (depth3 && (rec.v[1] >> 31)) {
+        for (int i = p - 3; sym(i) != 0; --i) {
+            key = deep_key(rec.v[6], sym(i));  // general records carry their node id
+            const Rec32 nrec = load_record(t.records, slot_of_t<kSeedsSmem>(t, s_seeds, key));
+            if (!rec_matches(nrec, key)) break;
+            rec = nrec;
+            if (!(rec.v[1] >> 31)) break;
+        }
+    }
+    uint32_t pid = kNoPattern;
+    if (found) {
+        pid = rec.v[2];
+        const uint32_t row = rec.v[3];
+        if (row != kNoPattern) {
+            const int off = int(rec.v[4]);
+            const int len = int(rec.v[5]);
+            int k_lo = lo_slot - (p + off), k_hi = hi_slot - (p + off);
+            if (k_lo < 0) k_lo = 0;
+            if (k_hi > len) k_hi = len;
+            for (int k = k_lo; k < k_hi; ++k) atomicAdd(s_sc + p + off + k, __ldg(t.pool + row + k));
+        }
+    }
+    if (state_out) *state_out = pid;
+}
+
+template <bool kSeedsSmem, int kR0, bool kGeneral>
 __global__ void __launch_bounds__(kTileThreads, 1) k_tile_fast(DevModel m, BatchArgs a, int gap) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* s_seeds = smem + kOffSeeds;
@@ -729,7 +882,10 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_fast(DevModel m, Batch
             if (single) {
                 // a single sentence larger than the tile buffers: one warp walks it in 32-character steps
                 Rings* rings = reinterpret_cast<Rings*>(sb);
-                if (warp == 0) fast_sentence_warp(m, a, s0 + k0, rings[0], lane);
+                if (warp == 0) {
+                    if (kGeneral) general_sentence_warp(m, a, s0 + k0, rings[0], lane);
+                    else fast_sentence_warp(m, a, s0 + k0, rings[0], lane);
+                }
                 sub_sync(sub);
                 k0 = k1;
                 continue;
@@ -810,60 +966,81 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_fast(DevModel m, Batch
             }
             sub_sync(sub);
 
+            if constexpr (kGeneral) {
+                // ---- pass C (general tables): rows of any offset/length scatter into the per-slot sums with
+                //      shared-memory atomics; pattern-id states go straight to global memory ----------------------
+                for (int p = tid; p < Sround; p += kSubThreads) s_sc[p] = 0;
+                sub_sync(sub);
+                uint32_t* cst = m.emit_states ? a.char_states : nullptr;
+                uint32_t* tst = m.emit_states ? a.type_states : nullptr;
+                for (int p = tid; p < Sround; p += kSubThreads) {
+                    if (s_cp[p] == 0) continue;
+                    const int k = s_kk[p];
+                    const int lo_slot = int(int64_t(T.obase[k]) - T.odelta[k]);       // first slot of the sentence
+                    const int hi_slot = lo_slot + int(T.nch[k]) - 1;                  // boundary slots [lo, hi)
+                    if (m.ct.present)
+                        tile_scatter<kSeedsSmem, false>(m.ct, s_seeds, s_cp, s_ty, p, lo_slot, hi_slot, s_sc,
+                                                        cst ? cst + (int64_t(p) + T.cdelta[k]) : nullptr);
+                    if (m.tt.present)
+                        tile_scatter<false, true>(m.tt, s_seeds, s_cp, s_ty, p, lo_slot, hi_slot, s_sc,
+                                                  tst ? tst + (int64_t(p) + T.cdelta[k]) : nullptr);
+                }
+            } else {
             // ---- pass C: node lookup + warp-shuffle gather, two slots per thread in flight --------------------
-            for (int base = 0; base < Sround; base += 2 * kSubThreads) {
-                const int pA = base + tid, pB = pA + kSubThreads;
-                const bool hasB = pB < Sround;  // uniform: Sround is a multiple of 256
-                int32_t dA[kInlineWidth], dB[kInlineWidth];
-#pragma unroll
-                for (int j = 0; j < kInlineWidth; ++j) dA[j] = dB[j] = 0;
-                uint32_t a1 = 0, a2 = 0, b1 = 0, b2 = 0, slA = 0, slB = 0;
-                const uint32_t a3 = m.ct.present ? s_cp[pA] : 0u;
-                const uint32_t b3 = (m.ct.present && hasB) ? s_cp[pB] : 0u;
-                Rec32 rA, rB;
-                if (a3) {
-                    a2 = s_cp[pA - 1];
-                    a1 = a2 ? s_cp[pA - 2] : 0u;
-                    slA = slot_of_t<kSeedsSmem>(m.ct, s_seeds, shallow_key(a1, a2, a3));
-                    rA = load_record(m.ct.records, slA);
+                for (int base = 0; base < Sround; base += 2 * kSubThreads) {
+                    const int pA = base + tid, pB = pA + kSubThreads;
+                    const bool hasB = pB < Sround;  // uniform: Sround is a multiple of 256
+                    int32_t dA[kInlineWidth], dB[kInlineWidth];
+    #pragma unroll
+                    for (int j = 0; j < kInlineWidth; ++j) dA[j] = dB[j] = 0;
+                    uint32_t a1 = 0, a2 = 0, b1 = 0, b2 = 0, slA = 0, slB = 0;
+                    const uint32_t a3 = m.ct.present ? s_cp[pA] : 0u;
+                    const uint32_t b3 = (m.ct.present && hasB) ? s_cp[pB] : 0u;
+                    Rec32 rA, rB;
+                    if (a3) {
+                        a2 = s_cp[pA - 1];
+                        a1 = a2 ? s_cp[pA - 2] : 0u;
+                        slA = slot_of_t<kSeedsSmem>(m.ct, s_seeds, shallow_key(a1, a2, a3));
+                        rA = load_record(m.ct.records, slA);
+                    }
+                    if (b3) {
+                        b2 = s_cp[pB - 1];
+                        b1 = b2 ? s_cp[pB - 2] : 0u;
+                        slB = slot_of_t<kSeedsSmem>(m.ct, s_seeds, shallow_key(b1, b2, b3));
+                        rB = load_record(m.ct.records, slB);
+                    }
+                    // resolve both slots level by level so that the fallback probes of A and B are in flight together
+                    bool fA = a3 != 0 && rec_matches(rA, shallow_key(a1, a2, a3));
+                    bool fB = b3 != 0 && rec_matches(rB, shallow_key(b1, b2, b3));
+                    const bool deepA = fA && a1 != 0 && (rA.v[1] >> 31), deepB = fB && b1 != 0 && (rB.v[1] >> 31);
+                    {   // two-character suffixes
+                        const bool nA = a3 != 0 && !fA && a1 != 0, nB = b3 != 0 && !fB && b1 != 0;
+                        const uint64_t kA = shallow_key(0, a2, a3), kB = shallow_key(0, b2, b3);
+                        // (a slot that still needs a probe has no use for its previous record: load in place)
+                        if (nA) rA = load_record(m.ct.records, slot_of_t<kSeedsSmem>(m.ct, s_seeds, kA));
+                        if (nB) rB = load_record(m.ct.records, slot_of_t<kSeedsSmem>(m.ct, s_seeds, kB));
+                        if (nA) fA = rec_matches(rA, kA);
+                        if (nB) fB = rec_matches(rB, kB);
+                    }
+                    {   // single characters
+                        const bool nA = a3 != 0 && !fA && a2 != 0, nB = b3 != 0 && !fB && b2 != 0;
+                        const uint64_t kA = shallow_key(0, 0, a3), kB = shallow_key(0, 0, b3);
+                        // (a slot that still needs a probe has no use for its previous record: load in place)
+                        if (nA) rA = load_record(m.ct.records, slot_of_t<kSeedsSmem>(m.ct, s_seeds, kA));
+                        if (nB) rB = load_record(m.ct.records, slot_of_t<kSeedsSmem>(m.ct, s_seeds, kB));
+                        if (nA) fA = rec_matches(rA, kA);
+                        if (nB) fB = rec_matches(rB, kB);
+                    }
+                    if (deepA) deep_walk<kSeedsSmem>(m.ct, s_seeds, s_cp, pA, slA, rA);
+                    if (deepB) deep_walk<kSeedsSmem>(m.ct, s_seeds, s_cp, pB, slB, rB);
+    #pragma unroll
+                    for (int j = 0; j < kInlineWidth; ++j) {
+                        dA[j] = fA ? int32_t(rA.v[2 + j]) : 0;
+                        dB[j] = fB ? int32_t(rB.v[2 + j]) : 0;
+                    }
+                    gather_store<kR0>(dA, r0, lane, pA, s_sc, s_spill_prev, s_spill_next);
+                    if (hasB) gather_store<kR0>(dB, r0, lane, pB, s_sc, s_spill_prev, s_spill_next);
                 }
-                if (b3) {
-                    b2 = s_cp[pB - 1];
-                    b1 = b2 ? s_cp[pB - 2] : 0u;
-                    slB = slot_of_t<kSeedsSmem>(m.ct, s_seeds, shallow_key(b1, b2, b3));
-                    rB = load_record(m.ct.records, slB);
-                }
-                // resolve both slots level by level so that the fallback probes of A and B are in flight together
-                bool fA = a3 != 0 && rec_matches(rA, shallow_key(a1, a2, a3));
-                bool fB = b3 != 0 && rec_matches(rB, shallow_key(b1, b2, b3));
-                const bool deepA = fA && a1 != 0 && (rA.v[1] >> 31), deepB = fB && b1 != 0 && (rB.v[1] >> 31);
-                {   // two-character suffixes
-                    const bool nA = a3 != 0 && !fA && a1 != 0, nB = b3 != 0 && !fB && b1 != 0;
-                    const uint64_t kA = shallow_key(0, a2, a3), kB = shallow_key(0, b2, b3);
-                    // (a slot that still needs a probe has no use for its previous record: load in place)
-                    if (nA) rA = load_record(m.ct.records, slot_of_t<kSeedsSmem>(m.ct, s_seeds, kA));
-                    if (nB) rB = load_record(m.ct.records, slot_of_t<kSeedsSmem>(m.ct, s_seeds, kB));
-                    if (nA) fA = rec_matches(rA, kA);
-                    if (nB) fB = rec_matches(rB, kB);
-                }
-                {   // single characters
-                    const bool nA = a3 != 0 && !fA && a2 != 0, nB = b3 != 0 && !fB && b2 != 0;
-                    const uint64_t kA = shallow_key(0, 0, a3), kB = shallow_key(0, 0, b3);
-                    // (a slot that still needs a probe has no use for its previous record: load in place)
-                    if (nA) rA = load_record(m.ct.records, slot_of_t<kSeedsSmem>(m.ct, s_seeds, kA));
-                    if (nB) rB = load_record(m.ct.records, slot_of_t<kSeedsSmem>(m.ct, s_seeds, kB));
-                    if (nA) fA = rec_matches(rA, kA);
-                    if (nB) fB = rec_matches(rB, kB);
-                }
-                if (deepA) deep_walk<kSeedsSmem>(m.ct, s_seeds, s_cp, pA, slA, rA);
-                if (deepB) deep_walk<kSeedsSmem>(m.ct, s_seeds, s_cp, pB, slB, rB);
-#pragma unroll
-                for (int j = 0; j < kInlineWidth; ++j) {
-                    dA[j] = fA ? int32_t(rA.v[2 + j]) : 0;
-                    dB[j] = fB ? int32_t(rB.v[2 + j]) : 0;
-                }
-                gather_store<kR0>(dA, r0, lane, pA, s_sc, s_spill_prev, s_spill_next);
-                if (hasB) gather_store<kR0>(dB, r0, lane, pB, s_sc, s_spill_prev, s_spill_next);
             }
             sub_sync(sub);
 
@@ -872,13 +1049,15 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_fast(DevModel m, Batch
             for (int p = tid; p < Sround - 1; p += kSubThreads) {
                 if (s_cp[p] == 0) continue;
                 const int k = s_kk[p];
-                if (a.char_states) a.char_states[int64_t(p) + T.cdelta[k]] = kNoPattern;
-                if (a.type_states) a.type_states[int64_t(p) + T.cdelta[k]] = kNoPattern;
+                if (a.char_states && !(kGeneral && m.emit_states && m.ct.present)) a.char_states[int64_t(p) + T.cdelta[k]] = kNoPattern;
+                if (a.type_states && !(kGeneral && m.emit_states && m.tt.present)) a.type_states[int64_t(p) + T.cdelta[k]] = kNoPattern;
                 if (s_cp[p + 1] == 0) continue;
                 const int wc = p >> 5, ln = p & 31;
                 int32_t v = s_sc[p] + m.bias;
-                if (ln >= 24 && wc + 1 < nwc) v += s_spill_prev[(wc + 1) * 8 + ln - 24];
-                if (ln < 8 && wc > 0) v += s_spill_next[(wc - 1) * 8 + ln];
+                if (!kGeneral) {
+                    if (ln >= 24 && wc + 1 < nwc) v += s_spill_prev[(wc + 1) * 8 + ln - 24];
+                    if (ln < 8 && wc > 0) v += s_spill_next[(wc - 1) * 8 + ln];
+                }
                 if (tw > 0) {
                     uint32_t idx = 0;
                     for (int q = p - tw + 1; q <= p + tw; ++q) idx = (idx << 3) | s_ty[q];
@@ -891,104 +1070,6 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_fast(DevModel m, Batch
             sub_sync(sub);
             k0 = k1;
         }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// k_score_general
-// ------------------------------------------------------------------------------------------------
-template <bool kTypes>
-__device__ __forceinline__ void scatter_general(const DevTable& t, const Rings& r, const uint8_t* __restrict__ text,
-                                                const SentInfo& si, uint32_t g, int32_t* scores, uint32_t* states) {
-    Rec32 rec;
-    uint32_t slot;
-    uint32_t pid = kNoPattern;
-    if (find_node<kTypes>(t, r, text, si.b0, g, rec, slot)) {
-        pid = rec.v[2];
-        const uint32_t row = rec.v[3];
-        if (row != kNoPattern) {
-            const int32_t off = int32_t(rec.v[4]);
-            const uint32_t len = rec.v[5];
-            for (uint32_t k = 0; k < len; ++k) {
-                const int64_t i = int64_t(g) + off + int64_t(k);
-                if (i >= 0 && i < int64_t(si.nout)) atomicAdd(scores + si.obase + i, __ldg(t.pool + row + k));
-            }
-        }
-    }
-    if (states) states[si.cbase + g] = pid;
-}
-
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) k_score_general(DevModel m, BatchArgs a) {
-    __shared__ Rings s_rings[kWarpsPerBlock];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint64_t s = uint64_t(blockIdx.x) * kWarpsPerBlock + warp;
-    if (s >= a.n_sent) return;
-    Rings& r = s_rings[warp];
-    const SentInfo si = sentence_info(a, s, lane);
-    const uint8_t* __restrict__ text = a.text;
-    const uint32_t n = si.n;
-    uint32_t* cstates = a.char_states;
-    uint32_t* tstates = a.type_states;
-    if (si.status != 0) {
-        for (uint32_t i = lane; i < si.nout; i += 32) { a.scores[si.obase + i] = 0; a.boundaries[si.obase + i] = 0; }
-        if (cstates) for (uint32_t i = lane; i < n; i += 32) cstates[si.cbase + i] = kNoPattern;
-        if (tstates) for (uint32_t i = lane; i < n; i += 32) tstates[si.cbase + i] = kNoPattern;
-        return;
-    }
-    const int tw = m.type_cache_window;
-    // pass 1: scores = bias + type table; states = none
-    {
-        uint64_t wpos = si.b0 & ~3ull;
-        uint32_t nd = 0;
-        for (uint32_t cb = 0; cb < n; cb += 32) {
-            const uint32_t need = min(n, cb + 32u + uint32_t(tw));
-            while (nd < need && wpos < si.b1) {
-                nd += decode_window(text, wpos, si.b0, si.b1, nd, r, lane);
-                wpos += 128;
-            }
-            __syncwarp();
-            const uint32_t g = cb + lane;
-            if (g + 1 < n) {
-                int32_t v = m.bias;
-                if (tw > 0) v += __ldg(m.type_cache + type_index(r, int64_t(g), n, tw));
-                a.scores[si.obase + g] = v;
-            }
-            if (g < n) {
-                if (cstates) cstates[si.cbase + g] = kNoPattern;
-                if (tstates) tstates[si.cbase + g] = kNoPattern;
-            }
-            __syncwarp();
-        }
-    }
-    __threadfence();
-    __syncwarp();
-    // pass 2: pattern rows
-    if (m.ct.present || m.tt.present) {
-        uint64_t wpos = si.b0 & ~3ull;
-        uint32_t nd = 0;
-        for (uint32_t cb = 0; cb < n; cb += 32) {
-            const uint32_t need = min(n, cb + 32u);
-            while (nd < need && wpos < si.b1) {
-                nd += decode_window(text, wpos, si.b0, si.b1, nd, r, lane);
-                wpos += 128;
-            }
-            __syncwarp();
-            const uint32_t g = cb + lane;
-            if (g < n) {
-                if (m.ct.present)
-                    scatter_general<false>(m.ct, r, text, si, g, a.scores, m.emit_states ? cstates : nullptr);
-                if (m.tt.present)
-                    scatter_general<true>(m.tt, r, text, si, g, a.scores, m.emit_states ? tstates : nullptr);
-            }
-            __syncwarp();
-        }
-    }
-    __threadfence();
-    __syncwarp();
-    // pass 3: threshold
-    for (uint32_t i = lane; i < si.nout; i += 32) {
-        const int32_t v = __ldcg(a.scores + si.obase + i);
-        a.boundaries[si.obase + i] = v > 0 ? 1 : 0;
     }
 }
 
@@ -1018,47 +1099,65 @@ static bool use_fast(const DevModel& m) {
 }
 
 // separator slots between sentences of a tile so that neither the weight-row gather (window
-// [r0, r0+6)) nor the type window can reach a neighbouring sentence
+// [r0, r0+6)) nor the type window can reach a neighbouring sentence (general tables clip rows per sentence)
 static int tile_gap(const DevModel& m) {
+    const int tw = std::max(2, m.type_cache_window - 1);
+    if (!use_fast(m)) return tw;
     const int r0 = m.ct.present ? m.ct.r0 : 0;
-    return std::max(std::max(2, m.type_cache_window - 1), std::max(-r0 - 1, r0 + kInlineWidth - 1));
+    return std::max(tw, std::max(-r0 - 1, r0 + kInlineWidth - 1));
 }
 
-static bool use_tile(const DevModel& m) {
+static bool tile_fast_ok(const DevModel& m) {
     if (!use_fast(m)) return false;
     const int r0 = m.ct.present ? m.ct.r0 : 0;
     return r0 >= -8 && r0 <= 2 && tile_gap(m) <= 8 && m.type_cache_window <= 3;
 }
 
+template <bool kSeeds, int kR0, bool kGeneral>
+static cudaError_t launch_tile(const DevModel& m, const BatchArgs& a, cudaStream_t stream, int n_sm) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_tile_fast<kSeeds, kR0, kGeneral>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    const uint64_t ngroups = (a.n_sent + kGroup - 1) / kGroup;
+    const unsigned grid = unsigned(std::min<uint64_t>(uint64_t(n_sm), (ngroups + kSubBlocks - 1) / kSubBlocks));
+    k_tile_fast<kSeeds, kR0, kGeneral><<<grid, kTileThreads, kTileSmem, stream>>>(m, a, tile_gap(m));
+    return cudaGetLastError();
+}
+
 cudaError_t launch_score(const DevModel& m, const BatchArgs& a, cudaStream_t stream) {
     if (a.n_sent == 0) return cudaSuccess;
-    const uint64_t nblocks = (a.n_sent + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    if (use_tile(m)) {
-        static int n_sm = 0;
-        if (n_sm == 0) {
-            int dev = 0;
-            cudaError_t e = cudaGetDevice(&dev);
-            if (e == cudaSuccess) e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tile_fast<true, -3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tile_fast<false, -3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tile_fast<true, kRuntimeR0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tile_fast<false, kRuntimeR0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem);
-            if (e != cudaSuccess) { n_sm = 0; return e; }
-        }
-        const uint64_t ngroups = (a.n_sent + kGroup - 1) / kGroup;
-        const unsigned grid = unsigned(std::min<uint64_t>(uint64_t(n_sm), (ngroups + kSubBlocks - 1) / kSubBlocks));
-        const bool seeds_smem = m.ct.present && m.ct.nbuckets <= uint32_t(kSeedCap);
-        const bool r3 = m.ct.present && m.ct.r0 == -3;
-        const int gap = tile_gap(m);
-        if (seeds_smem && r3) k_tile_fast<true, -3><<<grid, kTileThreads, kTileSmem, stream>>>(m, a, gap);
-        else if (seeds_smem) k_tile_fast<true, kRuntimeR0><<<grid, kTileThreads, kTileSmem, stream>>>(m, a, gap);
-        else if (r3) k_tile_fast<false, -3><<<grid, kTileThreads, kTileSmem, stream>>>(m, a, gap);
-        else k_tile_fast<false, kRuntimeR0><<<grid, kTileThreads, kTileSmem, stream>>>(m, a, gap);
-    } else if (use_fast(m)) {
-        k_score_fast<<<unsigned(nblocks), kWarpsPerBlock * 32, 0, stream>>>(m, a);
-    } else {
-        k_score_general<<<unsigned(nblocks), kWarpsPerBlock * 32, 0, stream>>>(m, a);
+    static int n_sm = 0;
+    if (n_sm == 0) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) { n_sm = 0; return e; }
     }
+    const bool seeds_smem = m.ct.present && m.ct.nbuckets <= uint32_t(kSeedCap);
+    if (tile_fast_ok(m)) {
+        const bool r3 = m.ct.present && m.ct.r0 == -3;
+        if (seeds_smem && r3) return launch_tile<true, -3, false>(m, a, stream, n_sm);
+        if (seeds_smem) return launch_tile<true, kRuntimeR0, false>(m, a, stream, n_sm);
+        if (r3) return launch_tile<false, -3, false>(m, a, stream, n_sm);
+        return launch_tile<false, kRuntimeR0, false>(m, a, stream, n_sm);
+    }
+    if (use_fast(m)) {  // inline rows with an unusual window: one warp per sentence
+        const uint64_t nblocks = (a.n_sent + kWarpsPerBlock - 1) / kWarpsPerBlock;
+        k_score_fast<<<unsigned(nblocks), kWarpsPerBlock * 32, 0, stream>>>(m, a);
+        return cudaGetLastError();
+    }
+    // general tables through the tile kernel pay off for shallow pattern sets (n-gram models with tags); deep
+    // dictionaries (long rows, backward walks, seed array too large for shared memory) are faster one warp per
+    // sentence (measured: BASELINE.md configs 3 and 4)
+    if (m.type_cache_window <= 3 && m.ct.max_depth <= 3 && m.tt.max_depth <= 4) {
+        if (seeds_smem) return launch_tile<true, kRuntimeR0, true>(m, a, stream, n_sm);
+        return launch_tile<false, kRuntimeR0, true>(m, a, stream, n_sm);
+    }
+    const uint64_t nblocks = (a.n_sent + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    k_score_general<<<unsigned(nblocks), kWarpsPerBlock * 32, 0, stream>>>(m, a);
     return cudaGetLastError();
 }
 
