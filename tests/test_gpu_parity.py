@@ -161,6 +161,39 @@ def test_edge_cases():
         assert msg in str(e.value)
 
 
+@pytest.mark.parametrize("kind", ["fast", "general_dict", "general_tags"])
+def test_long_sentences_and_tile_splitting(kind):
+    """Sentences longer than one tile (slots / bytes), groups that must be split into several ranges, and
+    mixtures of tiny and huge sentences inside one 64-sentence group."""
+    rng = np.random.default_rng(11)
+    if kind == "fast":
+        mb = synth.gen_model_bccwj_shaped(n_patterns=8000, sample_sentences=20000)
+        tags = False
+    elif kind == "general_dict":
+        mb = synth.gen_model_bccwj_shaped(n_patterns=8000, sample_sentences=20000, dict_words=5000)
+        tags = False
+    else:
+        mb = synth.gen_model_bccwj_shaped(n_patterns=8000, sample_sentences=20000, tag_models=200)
+        tags = True
+    p, o = make(mb, tags=tags), OraclePredictor(mb, predict_tags=tags)
+    lens = [1, 2, 5000, 3, 40, 3100, 3064, 3065, 12, 20000, 1, 700, 2900, 2900, 64, 1] + list(rng.integers(1, 400, size=150))
+    lens += [4200] * 3 + list(rng.integers(1, 80, size=70))
+    cps = synth.gen_codepoints(len(lens), np.array(lens), seed=99)
+    text, offs = synth.encode_utf8(cps, np.array(lens))
+    r = check_batch(p, o, text, offs, want_states=tags)
+    if tags:
+        for i in (2, 9, 11):
+            s = bytes(text[int(offs[i]):int(offs[i + 1])]).decode()
+            _, _, ocs, ots = o.predict(s, states=True)
+            c0 = int(r.char_offsets[i])
+            assert np.array_equal(r.char_states[c0:c0 + len(ocs)], ocs)
+            assert np.array_equal(r.type_states[c0:c0 + len(ots)], ots)
+    # all-ASCII sentence of 13 000 bytes: bytes exceed the tile text buffer while slots do too
+    big = ("abc 123 " * 1700)
+    rb = p.predict_batch(np.frombuffer(big.encode(), np.uint8), np.array([0, len(big)], np.uint64))
+    assert rb.scores.tolist() == o.predict(big)[0].tolist()
+
+
 def test_utf8_validation_matches_strict_decoder():
     """status 3 <=> the bytes are not valid UTF-8 (Python's strict decoder = Rust's str validity rules:
     no overlongs, no surrogates, <= U+10FFFF); 2 <=> valid but contains NUL; 1 <=> empty."""

@@ -1113,13 +1113,15 @@ static bool tile_fast_ok(const DevModel& m) {
     return r0 >= -8 && r0 <= 2 && tile_gap(m) <= 8 && m.type_cache_window <= 3;
 }
 
+constexpr int kMaxDevices = 64;
+
 template <bool kSeeds, int kR0, bool kGeneral>
-static cudaError_t launch_tile(const DevModel& m, const BatchArgs& a, cudaStream_t stream, int n_sm) {
-    static bool attr_set = false;
-    if (!attr_set) {
+static cudaError_t launch_tile(const DevModel& m, const BatchArgs& a, cudaStream_t stream, int dev, int n_sm) {
+    static bool attr_set[kMaxDevices] = {};  // the opt-in shared memory size is a per-device function attribute
+    if (!attr_set[dev]) {
         cudaError_t e = cudaFuncSetAttribute(k_tile_fast<kSeeds, kR0, kGeneral>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem);
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        attr_set[dev] = true;
     }
     const uint64_t ngroups = (a.n_sent + kGroup - 1) / kGroup;
     const unsigned grid = unsigned(std::min<uint64_t>(uint64_t(n_sm), (ngroups + kSubBlocks - 1) / kSubBlocks));
@@ -1129,20 +1131,25 @@ static cudaError_t launch_tile(const DevModel& m, const BatchArgs& a, cudaStream
 
 cudaError_t launch_score(const DevModel& m, const BatchArgs& a, cudaStream_t stream) {
     if (a.n_sent == 0) return cudaSuccess;
-    static int n_sm = 0;
-    if (n_sm == 0) {
-        int dev = 0;
-        cudaError_t e = cudaGetDevice(&dev);
-        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        if (e != cudaSuccess) { n_sm = 0; return e; }
+    static int sm_count[kMaxDevices] = {};
+    int dev = 0;
+    cudaError_t e0 = cudaGetDevice(&dev);
+    if (e0 != cudaSuccess) return e0;
+    if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+    if (sm_count[dev] == 0) {
+        int v = 0;
+        e0 = cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        if (e0 != cudaSuccess) return e0;
+        sm_count[dev] = v;
     }
+    const int n_sm = sm_count[dev];
     const bool seeds_smem = m.ct.present && m.ct.nbuckets <= uint32_t(kSeedCap);
     if (tile_fast_ok(m)) {
         const bool r3 = m.ct.present && m.ct.r0 == -3;
-        if (seeds_smem && r3) return launch_tile<true, -3, false>(m, a, stream, n_sm);
-        if (seeds_smem) return launch_tile<true, kRuntimeR0, false>(m, a, stream, n_sm);
-        if (r3) return launch_tile<false, -3, false>(m, a, stream, n_sm);
-        return launch_tile<false, kRuntimeR0, false>(m, a, stream, n_sm);
+        if (seeds_smem && r3) return launch_tile<true, -3, false>(m, a, stream, dev, n_sm);
+        if (seeds_smem) return launch_tile<true, kRuntimeR0, false>(m, a, stream, dev, n_sm);
+        if (r3) return launch_tile<false, -3, false>(m, a, stream, dev, n_sm);
+        return launch_tile<false, kRuntimeR0, false>(m, a, stream, dev, n_sm);
     }
     if (use_fast(m)) {  // inline rows with an unusual window: one warp per sentence
         const uint64_t nblocks = (a.n_sent + kWarpsPerBlock - 1) / kWarpsPerBlock;
@@ -1153,8 +1160,8 @@ cudaError_t launch_score(const DevModel& m, const BatchArgs& a, cudaStream_t str
     // dictionaries (long rows, backward walks, seed array too large for shared memory) are faster one warp per
     // sentence (measured: BASELINE.md configs 3 and 4)
     if (m.type_cache_window <= 3 && m.ct.max_depth <= 3 && m.tt.max_depth <= 4) {
-        if (seeds_smem) return launch_tile<true, kRuntimeR0, true>(m, a, stream, n_sm);
-        return launch_tile<false, kRuntimeR0, true>(m, a, stream, n_sm);
+        if (seeds_smem) return launch_tile<true, kRuntimeR0, true>(m, a, stream, dev, n_sm);
+        return launch_tile<false, kRuntimeR0, true>(m, a, stream, dev, n_sm);
     }
     const uint64_t nblocks = (a.n_sent + kWarpsPerBlock - 1) / kWarpsPerBlock;
     k_score_general<<<unsigned(nblocks), kWarpsPerBlock * 32, 0, stream>>>(m, a);
