@@ -22,6 +22,7 @@ struct Tab {
     const uint32_t* rec(uint32_t slot) const { return reinterpret_cast<const uint32_t*>(base + bt->rec_off + size_t(slot) * 32); }
     const uint32_t* slot_node() const { return reinterpret_cast<const uint32_t*>(base + bt->node_off); }
     const int32_t* pool() const { return reinterpret_cast<const int32_t*>(base + bt->pool_off); }
+    const uint32_t* slot_pid() const { return reinterpret_cast<const uint32_t*>(base + bt->pid_off); }
     bool probe(uint64_t key, const uint32_t*& r, uint32_t& slot) const {
         slot = table_slot(geom(), seeds(), key);
         r = rec(slot);
@@ -81,7 +82,7 @@ long emul_predict(const uint8_t* model, size_t model_len, int predict_tags, cons
         std::vector<uint32_t> tys(n);
         for (size_t i = 0; i < n; ++i) tys[i] = ctype(cps[i]);
         const long nout = long(n) - 1;
-        const bool fast = (!h.ct.present || h.ct.fast) && !h.tt.present && !h.emit_states;
+        const bool fast = (!h.ct.present || h.ct.fast) && !h.tt.present;
         if (info) { info[0] = fast; info[1] = h.char_variant; info[2] = h.type_variant; }
         for (long i = 0; i < nout; ++i) {
             int32_t v = h.bias;
@@ -104,7 +105,13 @@ long emul_predict(const uint8_t* model, size_t model_len, int predict_tags, cons
         }
         for (size_t g = 0; g < n; ++g) {
             if (cstates) cstates[g] = kNoPattern;
-            if (tstates) tstates[g] = kNoPattern;
+            if (tstates) {
+                tstates[g] = kNoPattern;
+                if (h.emit_states && h.type_state3_off) {
+                    const uint32_t t2 = g >= 1 ? tys[g - 1] : 0, t1 = (g >= 2 && t2) ? tys[g - 2] : 0;
+                    tstates[g] = reinterpret_cast<const uint32_t*>(base + h.type_state3_off)[(t1 << 6) | (t2 << 3) | tys[g]];
+                }
+            }
         }
         for (int which = 0; which < 2; ++which) {
             const Tab& t = which ? tt : ct;
@@ -114,6 +121,7 @@ long emul_predict(const uint8_t* model, size_t model_len, int predict_tags, cons
                 const uint32_t* rec; uint32_t slot;
                 if (!find_node(t, sym, g, rec, slot)) continue;
                 if (t.bt->fast) {
+                    if (h.emit_states && which == 0 && cstates) cstates[g] = t.slot_pid()[slot];
                     for (int j = 0; j < kInlineWidth; ++j) {
                         long i = long(g) + t.bt->r0 + j;
                         if (i >= 0 && i < nout) scores[i] = wrapping_add(scores[i], int32_t(rec[2 + j]));

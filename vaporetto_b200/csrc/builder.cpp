@@ -263,6 +263,25 @@ bool build_type_split(const std::vector<NgramEntry>& type_ngrams, uint8_t window
     return true;
 }
 
+bool build_type_state3(const PatternSet& tps, std::vector<uint32_t>& table) {
+    if (tps.max_len > 3) return false;
+    table.assign(512, kNoPattern);
+    std::unordered_map<std::string, uint32_t> index;
+    for (size_t i = 0; i < tps.raw.size(); ++i) index.emplace(tps.raw[i], uint32_t(i));
+    for (uint32_t code = 0; code < 512; ++code) {
+        const uint8_t t1 = uint8_t(code >> 6), t2 = uint8_t((code >> 3) & 7), t3 = uint8_t(code & 7);
+        if (t3 == 0) continue;
+        // longest suffix of (t1 t2 t3) that is a pattern; a zero type ends the context (sentence start)
+        std::string s3{char(t1), char(t2), char(t3)}, s2{char(t2), char(t3)}, s1{char(t3)};
+        uint32_t pid = kNoPattern;
+        if (t1 != 0 && t2 != 0 && index.count(s3)) pid = index[s3];
+        else if (t2 != 0 && index.count(s2)) pid = index[s2];
+        else if (index.count(s1)) pid = index[s1];
+        table[code] = pid;
+    }
+    return true;
+}
+
 uint32_t table_slot(const TableGeom& g, const uint8_t* seeds, uint64_t key) {
     uint32_t ha, hb;
     key_hashes(key, g.salt, ha, hb);
@@ -327,7 +346,7 @@ bool place_keys(const std::vector<uint64_t>& keys, TableGeom& g, std::vector<uin
 
 }  // namespace
 
-NodeTable build_node_table(const PatternSet& ps, bool force_general) {
+NodeTable build_node_table(const PatternSet& ps, bool force_general, uint32_t bucket_cap) {
     NodeTable t;
     if (ps.raw.empty()) return t;
     t.present = true;
@@ -376,7 +395,7 @@ NodeTable build_node_table(const PatternSet& ps, bool force_general) {
         if (!any) { t.rel_min = lo; t.rel_max = hi; any = true; }
         else { t.rel_min = std::min(t.rel_min, lo); t.rel_max = std::max(t.rel_max, hi); }
     }
-    t.fast = !force_general && !ps.tag_variant && (!any || t.rel_max - t.rel_min <= kInlineWidth);
+    t.fast = !force_general && (!any || t.rel_max - t.rel_min <= kInlineWidth);
     t.r0 = any ? t.rel_min : 0;
     if (t.r0 < -24 || t.r0 > 18) t.fast = false;  // shuffle gather reaches at most one warp left/right
 
@@ -393,6 +412,16 @@ NodeTable build_node_table(const PatternSet& ps, bool force_general) {
     // on failure retry with another salt and a sparser table, then with smaller buckets.
     static const double kAlpha[] = {0.60, 0.50, 0.42, 0.35, 0.30, 0.30, 0.25, 0.25, 0.20, 0.15};
     static const double kLambda[] = {8.0, 8.0, 8.0, 8.0, 8.0, 6.0, 6.0, 4.0, 4.0, 3.0};
+    // Tables slightly too large for the kernel's shared seed buffer first try fatter buckets (<= 12 keys) on a
+    // sparse table so that the seeds still fit.
+    if (bucket_cap && double(n) / 8.0 + 1.0 > double(bucket_cap) && double(n) / 12.0 < double(bucket_cap)) {
+        for (int attempt = 0; attempt < 2 && !ok; ++attempt) {
+            t.geom.nslots = uint32_t(double(n) / (attempt ? 0.25 : 0.33) + 1.0);
+            t.geom.nbuckets = bucket_cap;
+            t.geom.salt = 0x7f4a7c159e3779b9ULL * uint64_t(attempt + 1);
+            ok = place_keys(keys, t.geom, t.seeds, slot_of_key);
+        }
+    }
     for (int attempt = 0; attempt < 10 && !ok; ++attempt) {
         t.geom.nslots = uint32_t(std::max<double>(16.0, double(n) / kAlpha[attempt] + 1.0));
         t.geom.nbuckets = uint32_t(std::max<double>(1.0, double(n) / kLambda[attempt] + 1.0));

@@ -64,8 +64,13 @@ struct NodeTable {
 PatternSet build_patterns(const std::vector<NgramEntry>& ngrams, const std::vector<DictEntry>* dict, uint8_t window,
                           const std::vector<const std::vector<TagNgramEntry>*>& tag_ngrams, bool utf8);
 
-// Reversed-pattern trie -> perfect-hash table.  `force_general` disables the inline format.
-NodeTable build_node_table(const PatternSet& ps, bool force_general);
+// Reversed-pattern trie -> perfect-hash table.  `force_general` disables the inline format; `bucket_cap` is the
+// number of seed bytes the kernel can keep in shared memory (0 = no preference).
+NodeTable build_node_table(const PatternSet& ps, bool force_general, uint32_t bucket_cap = 0);
+
+// Tag variant of the type scorer with patterns of at most 3 types: pattern id of the longest pattern ending at
+// a character as a direct table over the 9-bit code (t[-2] t[-1] t[0]), zero = before the sentence start.
+bool build_type_state3(const PatternSet& tps, std::vector<uint32_t>& table);
 
 // Type score table of TypeScorerBoundaryCache::new (type_scorer/boundary_scorer_cache.rs:22-56).
 std::vector<int32_t> build_type_cache(const std::vector<NgramEntry>& type_ngrams, uint8_t window);

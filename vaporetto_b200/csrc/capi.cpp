@@ -137,6 +137,7 @@ void upload(vpt_predictor& p) {
     p.dm.type_cache = h.type_cache_window ? reinterpret_cast<const int32_t*>(base + h.type_cache_off) : nullptr;
     p.dm.type_a = h.type_a_off ? reinterpret_cast<const int32_t*>(base + h.type_a_off) : nullptr;
     p.dm.type_b = h.type_b_off ? reinterpret_cast<const int32_t*>(base + h.type_b_off) : nullptr;
+    p.dm.type_state3 = h.type_state3_off ? reinterpret_cast<const uint32_t*>(base + h.type_state3_off) : nullptr;
     p.dm.bias = h.bias;
     p.dm.char_window = h.char_window;
     p.dm.type_window = h.type_window;
@@ -312,7 +313,7 @@ int vpt_predictor_get_info(const vpt_predictor* p, vpt_predictor_info* o) {
     o->n_tags = int32_t(p->n_tags);
     o->char_scorer = p->hdr.char_variant;
     o->type_scorer = p->hdr.type_variant;
-    o->fast_path = (!p->dm.ct.present || p->dm.ct.fast) && !p->dm.tt.present && !p->dm.emit_states;
+    o->fast_path = (!p->hdr.ct.present || p->hdr.ct.fast) && !p->hdr.tt.present;
     o->bias = p->hdr.bias;
     o->char_window = p->hdr.char_window;
     o->type_window = p->hdr.type_window;

@@ -29,6 +29,7 @@ struct DevModel {
     int32_t type_cache_window = 0;       // 0 = no cache table
     const int32_t* type_a = nullptr;     // split tables for window 3 (T = A[t0..t3] + B[t2..t5]), or null
     const int32_t* type_b = nullptr;
+    const uint32_t* type_state3 = nullptr;  // tag variant: pattern id by (t[-2] t[-1] t[0]) code, or null
     int32_t bias = 0;
     int32_t char_window = 0;
     int32_t type_window = 0;

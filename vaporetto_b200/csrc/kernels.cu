@@ -485,12 +485,14 @@ __device__ __forceinline__ void fast_sentence_warp(const DevModel& m, const Batc
         int32_t d[kInlineWidth];
 #pragma unroll
         for (int j = 0; j < kInlineWidth; ++j) d[j] = 0;
+        uint32_t cstate = kNoPattern;
         if (active && m.ct.present) {
             Rec32 rec;
             uint32_t slot;
             if (find_node<false>(m.ct, r, text, si.b0, g, rec, slot)) {
 #pragma unroll
                 for (int j = 0; j < kInlineWidth; ++j) d[j] = int32_t(rec.v[2 + j]);
+                if (m.emit_states && a.char_states) cstate = __ldg(m.ct.slot_pid + slot);
             }
         }
         // gather: boundary (lane) <- row entry j of the source lane (lane - r0 - j); sources that fall
@@ -512,8 +514,15 @@ __device__ __forceinline__ void fast_sentence_warp(const DevModel& m, const Batc
             a.scores[si.obase + prev_g] = fin;
             a.boundaries[si.obase + prev_g] = fin > 0 ? 1 : 0;
         }
-        if (a.char_states && active) a.char_states[si.cbase + g] = kNoPattern;
-        if (a.type_states && active) a.type_states[si.cbase + g] = kNoPattern;
+        if (a.char_states && active) a.char_states[si.cbase + g] = cstate;
+        if (a.type_states && active) {
+            uint32_t ts = kNoPattern;
+            if (m.emit_states && m.type_state3) {
+                const uint32_t t2 = g >= 1 ? r.ty[(g - 1) & kRingMask] : 0u, t1 = (g >= 2 && t2) ? r.ty[(g - 2) & kRingMask] : 0u;
+                ts = __ldg(m.type_state3 + ((t1 << 6) | (t2 << 3) | r.ty[g & kRingMask]));
+            }
+            a.type_states[si.cbase + g] = ts;
+        }
         prev_main = mainv;
         prev_g = g;
         have_prev = true;
@@ -594,7 +603,15 @@ __device__ __forceinline__ void general_sentence_warp(const DevModel& m, const B
             }
             if (g < n) {
                 if (cstates) cstates[si.cbase + g] = kNoPattern;
-                if (tstates) tstates[si.cbase + g] = kNoPattern;
+                if (tstates) {
+                    uint32_t ts = kNoPattern;
+                    if (m.emit_states && m.type_state3) {  // tag variant with short type patterns: direct table
+                        const uint32_t t2 = g >= 1 ? r.ty[(g - 1) & kRingMask] : 0u;
+                        const uint32_t t1 = (g >= 2 && t2) ? r.ty[(g - 2) & kRingMask] : 0u;
+                        ts = __ldg(m.type_state3 + ((t1 << 6) | (t2 << 3) | r.ty[g & kRingMask]));
+                    }
+                    tstates[si.cbase + g] = ts;
+                }
             }
             __syncwarp();
         }
@@ -708,7 +725,7 @@ __device__ __forceinline__ bool rec_matches(const Rec32& rec, uint64_t key) {
 // Continues a depth-3 hit backwards through the text for patterns longer than three characters (rare).
 template <bool kSeedsSmem>
 __device__ __forceinline__ void deep_walk(const DevTable& t, const uint8_t* s_seeds, const uint32_t* __restrict__ cp, int p,
-                                          uint32_t slot, Rec32& rec) {
+                                          uint32_t& slot, Rec32& rec) {
     uint32_t node = __ldg(t.slot_node + slot);
     for (int i = p - 3; cp[i] != 0; --i) {
         const uint64_t key = deep_key(node, cp[i]);
@@ -716,6 +733,7 @@ __device__ __forceinline__ void deep_walk(const DevTable& t, const uint8_t* s_se
         const Rec32 nrec = load_record(t.records, nslot);
         if (!rec_matches(nrec, key)) break;
         rec = nrec;
+        slot = nslot;
         if (!(rec.v[1] >> 31)) break;
         node = __ldg(t.slot_node + nslot);
     }
@@ -1017,8 +1035,8 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_fast(DevModel m, Batch
                         const bool nA = a3 != 0 && !fA && a1 != 0, nB = b3 != 0 && !fB && b1 != 0;
                         const uint64_t kA = shallow_key(0, a2, a3), kB = shallow_key(0, b2, b3);
                         // (a slot that still needs a probe has no use for its previous record: load in place)
-                        if (nA) rA = load_record(m.ct.records, slot_of_t<kSeedsSmem>(m.ct, s_seeds, kA));
-                        if (nB) rB = load_record(m.ct.records, slot_of_t<kSeedsSmem>(m.ct, s_seeds, kB));
+                        if (nA) { slA = slot_of_t<kSeedsSmem>(m.ct, s_seeds, kA); rA = load_record(m.ct.records, slA); }
+                        if (nB) { slB = slot_of_t<kSeedsSmem>(m.ct, s_seeds, kB); rB = load_record(m.ct.records, slB); }
                         if (nA) fA = rec_matches(rA, kA);
                         if (nB) fB = rec_matches(rB, kB);
                     }
@@ -1026,13 +1044,18 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_fast(DevModel m, Batch
                         const bool nA = a3 != 0 && !fA && a2 != 0, nB = b3 != 0 && !fB && b2 != 0;
                         const uint64_t kA = shallow_key(0, 0, a3), kB = shallow_key(0, 0, b3);
                         // (a slot that still needs a probe has no use for its previous record: load in place)
-                        if (nA) rA = load_record(m.ct.records, slot_of_t<kSeedsSmem>(m.ct, s_seeds, kA));
-                        if (nB) rB = load_record(m.ct.records, slot_of_t<kSeedsSmem>(m.ct, s_seeds, kB));
+                        if (nA) { slA = slot_of_t<kSeedsSmem>(m.ct, s_seeds, kA); rA = load_record(m.ct.records, slA); }
+                        if (nB) { slB = slot_of_t<kSeedsSmem>(m.ct, s_seeds, kB); rB = load_record(m.ct.records, slB); }
                         if (nA) fA = rec_matches(rA, kA);
                         if (nB) fB = rec_matches(rB, kB);
                     }
                     if (deepA) deep_walk<kSeedsSmem>(m.ct, s_seeds, s_cp, pA, slA, rA);
                     if (deepB) deep_walk<kSeedsSmem>(m.ct, s_seeds, s_cp, pB, slB, rB);
+                    if (m.emit_states && a.char_states) {
+                        // pattern id of the longest match (tag prediction input): side array indexed by the final slot
+                        if (a3) a.char_states[int64_t(pA) + T.cdelta[s_kk[pA]]] = fA ? __ldg(m.ct.slot_pid + slA) : kNoPattern;
+                        if (b3) a.char_states[int64_t(pB) + T.cdelta[s_kk[pB]]] = fB ? __ldg(m.ct.slot_pid + slB) : kNoPattern;
+                    }
     #pragma unroll
                     for (int j = 0; j < kInlineWidth; ++j) {
                         dA[j] = fA ? int32_t(rA.v[2 + j]) : 0;
@@ -1049,8 +1072,16 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_fast(DevModel m, Batch
             for (int p = tid; p < Sround - 1; p += kSubThreads) {
                 if (s_cp[p] == 0) continue;
                 const int k = s_kk[p];
-                if (a.char_states && !(kGeneral && m.emit_states && m.ct.present)) a.char_states[int64_t(p) + T.cdelta[k]] = kNoPattern;
-                if (a.type_states && !(kGeneral && m.emit_states && m.tt.present)) a.type_states[int64_t(p) + T.cdelta[k]] = kNoPattern;
+                // states not produced by pass C: "no pattern" (non-tag predictors), or the direct type-state table
+                if (a.char_states && !(m.emit_states && m.ct.present)) a.char_states[int64_t(p) + T.cdelta[k]] = kNoPattern;
+                if (a.type_states && !(kGeneral && m.emit_states && m.tt.present)) {
+                    uint32_t ts = kNoPattern;
+                    if (m.emit_states && m.type_state3) {
+                        const uint32_t t2 = s_ty[p - 1], t1 = t2 ? uint32_t(s_ty[p - 2]) : 0u;
+                        ts = __ldg(m.type_state3 + ((t1 << 6) | (t2 << 3) | s_ty[p]));
+                    }
+                    a.type_states[int64_t(p) + T.cdelta[k]] = ts;
+                }
                 if (s_cp[p + 1] == 0) continue;
                 const int wc = p >> 5, ln = p & 31;
                 int32_t v = s_sc[p] + m.bias;
@@ -1095,7 +1126,7 @@ cudaError_t launch_count(const BatchArgs& a, cudaStream_t stream) {
 }
 
 static bool use_fast(const DevModel& m) {
-    return (!m.ct.present || m.ct.fast) && !m.tt.present && !m.emit_states;
+    return (!m.ct.present || m.ct.fast) && !m.tt.present;
 }
 
 // separator slots between sentences of a tile so that neither the weight-row gather (window

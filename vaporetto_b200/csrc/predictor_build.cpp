@@ -79,19 +79,42 @@ HostPredictor build_host_predictor(const Model& m, bool predict_tags) {
     PatternSet cps, tps;
     NodeTable ctab, ttab;
     std::vector<int32_t> tcache;
-    const bool need_general = tags || type_variant == 1 || type_variant == 3;
-    if (has_char) {
-        cps = build_patterns(m.char_ngrams, &m.dict, m.char_window, tag_char, true);
-        ctab = build_node_table(cps, need_general);
-    }
+    std::vector<uint32_t> tstate3;
+    constexpr uint32_t kSeedBudget = 37888;  // seed bytes the tile kernel keeps in shared memory (kernels.cu kSeedCap)
+    // Type scorer.  The boundary scores of the automaton variants equal the cached table's whenever the window is
+    // <= 3 (sum of all boundary n-gram occurrences either way), so tag predictors with short type patterns use the
+    // table for scores and a 512-entry direct table for the pattern-id states; only windows > 3 or long tag type
+    // n-grams need the type node table on the device.
+    bool type_table_on_device = false;
     if (type_variant == 2) tcache = build_type_cache(m.type_ngrams, m.type_window);
     else if (type_variant != 0) {
         tps = build_patterns(m.type_ngrams, nullptr, m.type_window, tag_type, false);
-        ttab = build_node_table(tps, true);
+        bool light = false;
+        // (exact only when every boundary weight vector lies inside the 2W window: the table indexes weights by
+        //  window position, the automaton variant adds whatever the row holds)
+        bool in_window = true;
+        for (const auto& d : m.type_ngrams)
+            in_window = in_window && d.ngram.size() <= size_t(2 * m.type_window) &&
+                        d.weights.size() + d.ngram.size() <= size_t(2 * m.type_window) + 1;
+        if (type_variant == 3 && m.type_window <= 3 && in_window && build_type_state3(tps, tstate3)) {
+            try {
+                tcache = build_type_cache(m.type_ngrams, m.type_window);
+                light = true;
+            } catch (const Error&) {  // duplicate boundary n-grams: the merger adds them, the cache builder rejects them
+                tstate3.clear();
+            }
+        }
+        if (!light) {
+            ttab = build_node_table(tps, true);
+            type_table_on_device = true;
+        }
     }
-    // a general-format type table forces the general kernel, which needs a general char table
-    if (has_char && ctab.fast && (ttab.present)) ctab = build_node_table(cps, true);
-
+    // a general-format type table forces the general kernels, which need general char records
+    const bool need_general = type_table_on_device;
+    if (has_char) {
+        cps = build_patterns(m.char_ngrams, &m.dict, m.char_window, tag_char, true);
+        ctab = build_node_table(cps, need_general, kSeedBudget);
+    }
     if (tags) {
         if (has_char) { p->char_tag_weight = collect_tag_weights(cps, m.tag_models.size(), m.char_window); p->char_suffix_link = cps.suffix_link; p->char_tags = true; }
         if (type_variant == 3) { p->type_tag_weight = collect_tag_weights(tps, m.tag_models.size(), m.type_window); p->type_suffix_link = tps.suffix_link; p->type_tags = true; }
@@ -104,14 +127,15 @@ HostPredictor build_host_predictor(const Model& m, bool predict_tags) {
     h.bias = m.bias;
     h.char_window = m.char_window;
     h.type_window = m.type_window;
-    h.type_cache_window = type_variant == 2 ? m.type_window : 0;
+    h.type_cache_window = tcache.empty() ? 0 : m.type_window;
     h.emit_states = tags ? 1 : 0;
     h.char_variant = char_variant;
     h.type_variant = type_variant;
     h.max_char_pattern_len = int32_t(cps.max_len);
     write_table(w, ctab, cps.raw.size(), h.ct);
     write_table(w, ttab, tps.raw.size(), h.tt);
-    if (type_variant == 2) {
+    if (!tstate3.empty()) h.type_state3_off = w.add(tstate3.data(), tstate3.size() * 4);
+    if (!tcache.empty()) {
         h.type_cache_off = w.add(tcache.data(), tcache.size() * 4);
         std::vector<int32_t> ta, tb;
         if (build_type_split(m.type_ngrams, m.type_window, ta, tb)) {

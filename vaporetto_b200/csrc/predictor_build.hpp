@@ -11,7 +11,7 @@
 
 namespace vpt {
 
-constexpr char kBlobMagic[8] = {'V', 'P', 'T', 'B', '2', '0', '0', '\2'};
+constexpr char kBlobMagic[8] = {'V', 'P', 'T', 'B', '2', '0', '0', '\3'};
 
 struct BlobTable {
     uint64_t rec_off, seeds_off, node_off, pid_off, pool_off;
@@ -29,6 +29,7 @@ struct BlobHeader {
     int32_t emit_states, char_variant, type_variant, max_char_pattern_len;
     uint64_t type_cache_off;
     uint64_t type_a_off, type_b_off;  // split tables (0 = absent)
+    uint64_t type_state3_off;         // 512-entry type state table (0 = absent)
     BlobTable ct, tt;
 };
 
