@@ -666,7 +666,7 @@ constexpr int kSubBlocks = 4;
 constexpr int kTileThreads = kSubThreads * kSubBlocks;
 constexpr int kTextCap = 12288;   // bytes of text staged per tile
 constexpr int kSlotCap = 3072;    // character slots (characters + separators) per tile
-constexpr int kSeedCap = 38400;   // seed bytes kept in shared memory (one per 8 nodes: ~307 K nodes)
+constexpr int kSeedCap = 37632;   // seed bytes kept in shared memory (one per 8 nodes: ~300 K nodes)
 constexpr int kTypeSub = 4096;    // entries of each split type table
 constexpr uint32_t kSepPos = 0xFFFFu;
 
@@ -678,7 +678,7 @@ struct TileTables {
     int64_t odelta[kGroup];   // output index of a boundary = its slot + odelta[sentence]
     int64_t cdelta[kGroup];   // state index of a character = its slot + cdelta[sentence]
     uint32_t nch[kGroup];
-    int32_t st[kGroup];
+    int8_t st[kGroup];
     uint32_t ticket;
     int32_t k1;               // end of the current sentence range
     uint32_t pad[2];
@@ -692,12 +692,13 @@ constexpr int kOffTy = kOffPos + 2 * kSlotCap;           // char type per slot (
 constexpr int kOffKk = kOffTy + kSlotCap + 64;           // sentence-in-group per slot
 constexpr int kOffTab = kOffKk + kSlotCap;               // TileTables
 constexpr int kOffBar = kOffTab + ((int(sizeof(TileTables)) + 15) & ~15);
-constexpr int kSubBytes = (kOffBar + 16 + 127) & ~127;
+constexpr int kSubBytes = (kOffBar + 16 + 15) & ~15;
 // CTA-shared part
 constexpr int kOffSeeds = 0;
 constexpr int kOffTypeA = kOffSeeds + kSeedCap;
 constexpr int kOffTypeB = kOffTypeA + 4 * kTypeSub;
-constexpr int kOffSub = kOffTypeB + 4 * kTypeSub;
+constexpr int kOffTyTab = kOffTypeB + 4 * kTypeSub;  // character-type page table (256 B) + 3 sub-tables (768 B)
+constexpr int kOffSub = kOffTyTab + 1024;
 constexpr int kTileSmem = kOffSub + kSubBlocks * kSubBytes;
 static_assert(4 * kSlotCap <= kTextCap, "sc aliases the text buffer");
 static_assert(2 * (kSlotCap / 32) * 8 * 4 <= 2 * kSlotCap, "spill arrays alias the position buffer");
@@ -810,7 +811,8 @@ __device__ __forceinline__ void tile_scatter(const DevTable& t, const uint8_t* s
     if (state_out) *state_out = pid;
 }
 
-template <bool kSeedsSmem, int kR0, bool kGeneral>
+// kSplit3: type window 3 with the split tables in shared memory (compile-time type window: the common model shape)
+template <bool kSeedsSmem, int kR0, bool kGeneral, bool kSplit3>
 __global__ void __launch_bounds__(kTileThreads, 1) k_tile_fast(DevModel m, BatchArgs a, int gap) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* s_seeds = smem + kOffSeeds;
@@ -832,7 +834,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_fast(DevModel m, Batch
     const uint8_t* __restrict__ text = a.text;
 
     // ---- CTA-shared tables ----------------------------------------------------------------------------
-    const bool tsplit = m.type_a != nullptr && m.type_cache_window == 3;
+    const bool tsplit = kSplit3;
     if (kSeedsSmem) {
         const uint32_t nwords = (m.ct.nbuckets + 3) / 4;
         const uint32_t* src = reinterpret_cast<const uint32_t*>(m.ct.seeds);
@@ -843,6 +845,20 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_fast(DevModel m, Batch
             s_type_a[i] = __ldg(m.type_a + i);
             s_type_b[i] = __ldg(m.type_b + i);
         }
+    }
+    // character types by table: page table over c >> 8 (entries >= 0x80 select a 256-entry sub-table)
+    uint8_t* s_tytab = smem + kOffTyTab;
+    {
+        const int i = threadIdx.x;  // 1024 threads fill 1024 bytes
+        uint32_t v;
+        if (i < 256) {
+            v = i == 0x00 ? 0x80u : i == 0x30 ? 0x81u : i == 0xFF ? 0x82u : char_type(uint32_t(i) << 8);
+            // a page maps to one class only if its first and last code point agree (true for all other BMP pages)
+        } else {
+            const uint32_t page = i < 512 ? 0x00u : i < 768 ? 0x30u : 0xFFu;
+            v = char_type((page << 8) | uint32_t(i & 255));
+        }
+        s_tytab[i] = uint8_t(v);
     }
     if (tid == 0) mbar_init(s_bar, 1);
     if (tid < 8) reinterpret_cast<uint32_t*>(sb + kOffTy)[tid] = 0;  // front guard of s_ty
@@ -870,7 +886,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_fast(DevModel m, Batch
             const uint64_t ob = a.group_bound[grp] + lb, cb = a.group_char[grp] + lc;
             T.nch[tid] = n;
             T.lc[tid] = lc;
-            T.st[tid] = a.status[s];
+            T.st[tid] = int8_t(a.status[s]);
             T.obase[tid] = ob;
             T.cbase[tid] = cb;
             a.bound_offsets[s] = a.bound_base + ob;
@@ -945,12 +961,14 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_fast(DevModel m, Batch
                 for (uint32_t w = rb0 & ~3u; w < rb1; w += 128) {
                     const uint32_t addr = w + 4u * uint32_t(lane);
                     const uint32_t lo = addr < rb1 ? *reinterpret_cast<const uint32_t*>(s_text + addr) : 0u;
-                    // start-of-character bytes of this word that lie inside the sentence
+                    // start-of-character bytes of this word that lie inside the sentence (SWAR: bit 7 of byte j)
                     uint32_t smask = 0;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const uint32_t p = addr + j;
-                        if (p >= rb0 && p < rb1 && ((lo >> (8 * j)) & 0xC0) != 0x80) smask |= 1u << j;
+                    if (addr < rb1) {
+                        const uint32_t from = rb0 > addr ? rb0 - addr : 0u;
+                        const uint32_t to = rb1 - addr < 4u ? rb1 - addr : 4u;
+                        const uint32_t im80 = (from >= 4u ? 0u : 0x80808080u << (8 * from)) & (0x80808080u >> (8 * (4 - to)));
+                        const uint32_t st80 = ~(lo & ~(lo << 1)) & im80;       // not 10xxxxxx
+                        smask = ((st80 >> 7) | (st80 >> 14) | (st80 >> 21) | (st80 >> 28)) & 15u;
                     }
                     const uint32_t cnt = __popc(smask);
                     const uint32_t incl = warp_incl_scan(cnt, lane);
@@ -977,7 +995,12 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_fast(DevModel m, Batch
                     const uint32_t lo = *reinterpret_cast<const uint32_t*>(s_text + al);
                     const uint32_t hi = *reinterpret_cast<const uint32_t*>(s_text + al + 4);
                     c = decode_cp(__funnelshift_r(lo, hi, 8 * (pos & 3u)));
-                    ty = char_type(c);
+                    if (c < 0x10000u) {
+                        ty = s_tytab[c >> 8];
+                        if (ty & 0x80u) ty = s_tytab[256u + ((ty & 3u) << 8) + (c & 255u)];
+                    } else {
+                        ty = char_type(c);
+                    }
                 }
                 s_cp[p] = c;
                 s_ty[p] = uint8_t(ty);
@@ -1089,10 +1112,14 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_fast(DevModel m, Batch
                     if (ln >= 24 && wc + 1 < nwc) v += s_spill_prev[(wc + 1) * 8 + ln - 24];
                     if (ln < 8 && wc > 0) v += s_spill_next[(wc - 1) * 8 + ln];
                 }
-                if (tw > 0) {
+                if (kSplit3) {
+                    const uint32_t ia = (uint32_t(s_ty[p - 2]) << 9) | (uint32_t(s_ty[p - 1]) << 6) | (uint32_t(s_ty[p]) << 3) | s_ty[p + 1];
+                    const uint32_t ib = ((ia & 63u) << 6) | (uint32_t(s_ty[p + 2]) << 3) | s_ty[p + 3];
+                    v += s_type_a[ia] + s_type_b[ib];
+                } else if (tw > 0) {
                     uint32_t idx = 0;
                     for (int q = p - tw + 1; q <= p + tw; ++q) idx = (idx << 3) | s_ty[q];
-                    v += tsplit ? s_type_a[idx >> 6] + s_type_b[idx & 4095u] : __ldg(m.type_cache + idx);
+                    v += __ldg(m.type_cache + idx);
                 }
                 const int64_t o = int64_t(p) + T.odelta[k];
                 a.scores[o] = v;
@@ -1146,18 +1173,25 @@ static bool tile_fast_ok(const DevModel& m) {
 
 constexpr int kMaxDevices = 64;
 
-template <bool kSeeds, int kR0, bool kGeneral>
-static cudaError_t launch_tile(const DevModel& m, const BatchArgs& a, cudaStream_t stream, int dev, int n_sm) {
+template <bool kSeeds, int kR0, bool kGeneral, bool kSplit3>
+static cudaError_t launch_tile_t(const DevModel& m, const BatchArgs& a, cudaStream_t stream, int dev, int n_sm) {
     static bool attr_set[kMaxDevices] = {};  // the opt-in shared memory size is a per-device function attribute
     if (!attr_set[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(k_tile_fast<kSeeds, kR0, kGeneral>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem);
+        cudaError_t e = cudaFuncSetAttribute(k_tile_fast<kSeeds, kR0, kGeneral, kSplit3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem);
         if (e != cudaSuccess) return e;
         attr_set[dev] = true;
     }
     const uint64_t ngroups = (a.n_sent + kGroup - 1) / kGroup;
     const unsigned grid = unsigned(std::min<uint64_t>(uint64_t(n_sm), (ngroups + kSubBlocks - 1) / kSubBlocks));
-    k_tile_fast<kSeeds, kR0, kGeneral><<<grid, kTileThreads, kTileSmem, stream>>>(m, a, tile_gap(m));
+    k_tile_fast<kSeeds, kR0, kGeneral, kSplit3><<<grid, kTileThreads, kTileSmem, stream>>>(m, a, tile_gap(m));
     return cudaGetLastError();
+}
+
+template <bool kSeeds, int kR0, bool kGeneral>
+static cudaError_t launch_tile(const DevModel& m, const BatchArgs& a, cudaStream_t stream, int dev, int n_sm) {
+    const bool split3 = m.type_a != nullptr && m.type_cache_window == 3;
+    return split3 ? launch_tile_t<kSeeds, kR0, kGeneral, true>(m, a, stream, dev, n_sm)
+                  : launch_tile_t<kSeeds, kR0, kGeneral, false>(m, a, stream, dev, n_sm);
 }
 
 cudaError_t launch_score(const DevModel& m, const BatchArgs& a, cudaStream_t stream) {

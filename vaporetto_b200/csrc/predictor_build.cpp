@@ -80,7 +80,7 @@ HostPredictor build_host_predictor(const Model& m, bool predict_tags) {
     NodeTable ctab, ttab;
     std::vector<int32_t> tcache;
     std::vector<uint32_t> tstate3;
-    constexpr uint32_t kSeedBudget = 37888;  // seed bytes the tile kernel keeps in shared memory (kernels.cu kSeedCap)
+    constexpr uint32_t kSeedBudget = 37632;  // seed bytes the tile kernel keeps in shared memory (kernels.cu kSeedCap)
     // Type scorer.  The boundary scores of the automaton variants equal the cached table's whenever the window is
     // <= 3 (sum of all boundary n-gram occurrences either way), so tag predictors with short type patterns use the
     // table for scores and a 512-entry direct table for the pattern-id states; only windows > 3 or long tag type
