@@ -344,6 +344,21 @@ def test_blob_roundtrip_and_device_api(synth_model):
     assert int(d_status.abs().sum().item()) == 0
 
 
+def test_many_tiny_sentences_offsets():
+    """2.2 M two-character sentences: exercises the carry loop of the group scan (> 32768 groups), the
+    chunked host path and tiny tiles.  Every sentence is the same text, so every score must be the same."""
+    mb = read("model.bin")
+    p, o = make(mb), OraclePredictor(mb)
+    n = 2_200_000
+    unit = "火星".encode()
+    text = np.frombuffer(unit * n, np.uint8)
+    offs = (np.arange(n + 1, dtype=np.uint64) * len(unit))
+    r = p.predict_batch(text, offs)
+    assert r.n_boundaries == n and np.array_equal(r.bound_offsets, np.arange(n + 1, dtype=np.uint64))
+    want = o.predict("火星")[0]
+    assert np.all(r.scores == want[0]) and int(r.status.sum()) == 0
+
+
 def test_full_size_properties():
     """BASELINE config-2 size (1M x 40 chars) is checked through size-independent properties:
     (1) a batch equals the concatenation of its halves (sentences are independent);
