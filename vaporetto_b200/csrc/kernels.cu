@@ -233,22 +233,24 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_count(BatchArgs a) {
         {
             // lanes of a quad beyond the group's last sentence run an empty range (all 32 lanes must reach
             // the shuffles below)
-            const uint64_t b0 = i < ns ? s_off[i] : 0, b1 = i < ns ? s_off[i + 1] : 0;
+            // 32-bit byte offsets relative to a0 (a group's text is far below 4 GB)
+            const uint32_t b0 = i < ns ? uint32_t(s_off[i] - a0) : 0u, b1 = i < ns ? uint32_t(s_off[i + 1] - a0) : 0u;
+            const uint8_t* __restrict__ gtext = text + a0;
             uint32_t starts = 0, conts = 0, expect = 0, flags = 0;  // flags: 1 NUL, 2 malformed
-            for (uint64_t wpos = b0 & ~3ull; wpos < b1; wpos += 32) {
-                const uint64_t addr = wpos + 4u * uint32_t(l8);
+            for (uint32_t wpos = b0 & ~3u; wpos < b1; wpos += 32) {
+                const uint32_t addr = wpos + 4u * uint32_t(l8);
                 if (addr < b1) {
                     uint32_t lo, hi = 0;
                     if (staged) {
-                        lo = *reinterpret_cast<const uint32_t*>(s_text + (addr - a0));
-                        if (addr + 4 < b1) hi = *reinterpret_cast<const uint32_t*>(s_text + (addr + 4 - a0));
+                        lo = *reinterpret_cast<const uint32_t*>(s_text + addr);
+                        if (addr + 4 < b1) hi = *reinterpret_cast<const uint32_t*>(s_text + addr + 4);
                     } else {
-                        lo = __ldg(reinterpret_cast<const uint32_t*>(text + addr));
-                        if (addr + 4 < b1) hi = __ldg(reinterpret_cast<const uint32_t*>(text + addr + 4));
+                        lo = __ldg(reinterpret_cast<const uint32_t*>(gtext + addr));
+                        if (addr + 4 < b1) hi = __ldg(reinterpret_cast<const uint32_t*>(gtext + addr + 4));
                     }
                     // ---- SWAR fast path over the 4 bytes of this word (V = the word and the 4 bytes after it) ----
-                    const uint32_t from = b0 > addr ? uint32_t(b0 - addr) : 0u;           // first byte inside
-                    const uint32_t to = b1 - addr < 4 ? uint32_t(b1 - addr) : 4u;         // one past the last
+                    const uint32_t from = b0 > addr ? b0 - addr : 0u;                     // first byte inside
+                    const uint32_t to = b1 - addr < 4u ? b1 - addr : 4u;                  // one past the last
                     const uint32_t im = (from >= 4 ? 0u : 0xFFFFFFFFu << (8 * from)) & (0xFFFFFFFFu >> (8 * (4 - to)));
                     const uint32_t im80 = im & 0x80808080u;
                     const uint32_t top2 = lo & (lo << 1);                                  // bit7 = b7&b6
@@ -275,7 +277,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_count(BatchArgs a) {
                     } else {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const uint64_t p = addr + j;
+                        const uint32_t p = addr + j;
                         if (p < b0 || p >= b1) continue;
                         const uint32_t x = __funnelshift_r(lo, hi, 8 * j);
                         const uint32_t b = x & 0xFF;
