@@ -17,7 +17,7 @@ namespace {
 struct Tab {
     const BlobTable* bt;
     const uint8_t* base;
-    TableGeom geom() const { return TableGeom{bt->nslots, bt->nbuckets, bt->salt}; }
+    TableGeom geom() const { TableGeom g; g.nslots = bt->nslots; g.nbuckets = bt->nbuckets; g.salt = bt->salt; g.seed_bits = bt->seed_bits; return g; }
     const uint8_t* seeds() const { return base + bt->seeds_off; }
     const uint32_t* rec(uint32_t slot) const { return reinterpret_cast<const uint32_t*>(base + bt->rec_off + size_t(slot) * 32); }
     const uint32_t* slot_node() const { return reinterpret_cast<const uint32_t*>(base + bt->node_off); }

@@ -299,6 +299,20 @@ def test_synthetic_config2_shape(synth_model):
     check_batch(p, o, text, offs)
 
 
+@pytest.mark.parametrize("budget", ["3", "300"])
+def test_table_layout_variants_gpu(budget, monkeypatch):
+    """dense 16-bit-seed tables (large dictionaries) and fat buckets, forced on a small model"""
+    monkeypatch.setenv("VPT_SEED_BUDGET", budget)
+    mb = synth.gen_model_bccwj_shaped(n_patterns=6000, sample_sentences=10000, dict_words=3000)
+    p, o = make(mb), OraclePredictor(mb)
+    text, offs, _ = synth.gen_text(3000, ragged=True)
+    check_batch(p, o, text, offs)
+    mb2 = synth.gen_model_bccwj_shaped(n_patterns=6000, sample_sentences=10000)
+    p2, o2 = make(mb2), OraclePredictor(mb2)
+    assert p2.info["fast_path"] == 1
+    check_batch(p2, o2, text, offs)
+
+
 def test_synthetic_config4_shape():
     # KyTea-shaped: + dictionary with words up to 16 chars (Variable-length rows, general kernel)
     mb = synth.gen_model_bccwj_shaped(n_patterns=20000, sample_sentences=40000, dict_words=20000)

@@ -138,3 +138,18 @@ def test_tables_equal_oracle(emul, model, text, tags):
             assert ts == ots.tolist()
         if model["char_window"] and (model["char_ngrams"] or model["dict"]):
             assert cs == ocs.tolist()
+
+
+@pytest.mark.parametrize("budget", ["3", "40", "300"])
+def test_table_layout_variants(emul, budget, monkeypatch):
+    """VPT_SEED_BUDGET shrinks the shared-memory seed budget so that small models exercise the fat-bucket layout
+    and the dense 16-bit-seed layout of large dictionaries."""
+    from vpt_testlib import synth
+    monkeypatch.setenv("VPT_SEED_BUDGET", budget)
+    mb = synth.gen_model_bccwj_shaped(n_patterns=3000, sample_sentences=5000, dict_words=800)
+    o = OraclePredictor(mb)
+    text, offs, _ = synth.gen_text(60, ragged=True)
+    for i in range(60):
+        s = bytes(text[int(offs[i]):int(offs[i + 1])]).decode()
+        sc, _, _, _ = run(emul, mb, s)
+        assert sc == o.predict(s)[0].tolist()

@@ -285,7 +285,9 @@ bool build_type_state3(const PatternSet& tps, std::vector<uint32_t>& table) {
 uint32_t table_slot(const TableGeom& g, const uint8_t* seeds, uint64_t key) {
     uint32_t ha, hb;
     key_hashes(key, g.salt, ha, hb);
-    return slot_with_seed(ha, hb, seeds[bucket_of(ha, g.nbuckets)], g.nslots);
+    const uint32_t bk = bucket_of(ha, g.nbuckets);
+    const uint32_t seed = g.seed_bits == 16 ? uint32_t(seeds[2 * size_t(bk)]) | (uint32_t(seeds[2 * size_t(bk) + 1]) << 8) : seeds[bk];
+    return slot_with_seed(ha, hb, seed, g.nslots);
 }
 
 namespace {
@@ -304,6 +306,8 @@ struct TrieNode {
 // distinct free slots.  Buckets are placed largest first.
 bool place_keys(const std::vector<uint64_t>& keys, TableGeom& g, std::vector<uint8_t>& seeds,
                 std::vector<uint32_t>& slot_of_key) {
+    const uint32_t max_seed = g.seed_bits == 16 ? 65536u : 256u;
+    const size_t seed_bytes = g.seed_bits == 16 ? 2 : 1;
     const size_t n = keys.size();
     std::vector<uint32_t> ha(n), hb(n);
     std::vector<std::vector<uint32_t>> buckets(g.nbuckets);
@@ -316,14 +320,14 @@ bool place_keys(const std::vector<uint64_t>& keys, TableGeom& g, std::vector<uin
     std::stable_sort(order.begin(), order.end(),
                      [&](uint32_t a, uint32_t b) { return buckets[a].size() > buckets[b].size(); });
     std::vector<uint8_t> used(g.nslots, 0);
-    seeds.assign(g.nbuckets, 0);
+    seeds.assign(size_t(g.nbuckets) * seed_bytes, 0);
     slot_of_key.assign(n, 0);
     std::vector<uint32_t> tmp;
     for (uint32_t b : order) {
         const auto& ks = buckets[b];
         if (ks.empty()) break;
         bool placed = false;
-        for (uint32_t seed = 0; seed < 256 && !placed; ++seed) {
+        for (uint32_t seed = 0; seed < max_seed && !placed; ++seed) {
             tmp.clear();
             bool ok = true;
             for (uint32_t ki : ks) {
@@ -335,7 +339,8 @@ bool place_keys(const std::vector<uint64_t>& keys, TableGeom& g, std::vector<uin
             }
             if (ok) {
                 for (size_t k = 0; k < ks.size(); ++k) { used[tmp[k]] = 1; slot_of_key[ks[k]] = tmp[k]; }
-                seeds[b] = uint8_t(seed);
+                if (seed_bytes == 2) { seeds[2 * size_t(b)] = uint8_t(seed); seeds[2 * size_t(b) + 1] = uint8_t(seed >> 8); }
+                else seeds[b] = uint8_t(seed);
                 placed = true;
             }
         }
@@ -421,6 +426,19 @@ NodeTable build_node_table(const PatternSet& ps, bool force_general, uint32_t bu
             t.geom.salt = 0x7f4a7c159e3779b9ULL * uint64_t(attempt + 1);
             ok = place_keys(keys, t.geom, t.seeds, slot_of_key);
         }
+    }
+    // Tables far beyond the shared-memory seed budget are built dense instead (16-bit seeds, load factor 0.85):
+    // what matters for them is staying resident in L2.
+    if (bucket_cap && double(n) / 12.0 >= double(bucket_cap)) {
+        static const double kDenseAlpha[] = {0.85, 0.80, 0.70};
+        for (int attempt = 0; attempt < 3 && !ok; ++attempt) {
+            t.geom.seed_bits = 16;
+            t.geom.nslots = uint32_t(double(n) / kDenseAlpha[attempt] + 1.0);
+            t.geom.nbuckets = uint32_t(double(n) / 5.0 + 1.0);
+            t.geom.salt = 0x2545f4914f6cdd1dULL * uint64_t(attempt + 1);
+            ok = place_keys(keys, t.geom, t.seeds, slot_of_key);
+        }
+        if (!ok) t.geom.seed_bits = 8;
     }
     for (int attempt = 0; attempt < 10 && !ok; ++attempt) {
         t.geom.nslots = uint32_t(std::max<double>(16.0, double(n) / kAlpha[attempt] + 1.0));

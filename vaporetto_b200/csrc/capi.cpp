@@ -109,6 +109,7 @@ DevTable dev_table(const BlobTable& bt, const uint8_t* base) {
     d.nslots = bt.nslots;
     d.nbuckets = bt.nbuckets;
     d.salt = bt.salt;
+    d.seed16 = bt.seed_bits == 16;
     d.records = base + bt.rec_off;
     d.seeds = base + bt.seeds_off;
     d.slot_node = reinterpret_cast<const uint32_t*>(base + bt.node_off);

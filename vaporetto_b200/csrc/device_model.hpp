@@ -20,6 +20,7 @@ struct DevTable {
     uint32_t max_depth = 0;
     int32_t present = 0;
     int32_t fast = 0;
+    int32_t seed16 = 0;                // seeds are 16-bit (dense tables; never staged in shared memory)
 };
 
 struct DevModel {

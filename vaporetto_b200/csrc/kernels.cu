@@ -54,7 +54,8 @@ __device__ __forceinline__ Rec32 load_record(const void* base, uint32_t slot) {
 __device__ __forceinline__ uint32_t slot_of(const DevTable& t, uint64_t key) {
     uint32_t ha, hb;
     key_hashes(key, t.salt, ha, hb);
-    const uint32_t seed = __ldg(t.seeds + bucket_of(ha, t.nbuckets));
+    const uint32_t b = bucket_of(ha, t.nbuckets);
+    const uint32_t seed = t.seed16 ? uint32_t(__ldg(reinterpret_cast<const uint16_t*>(t.seeds) + b)) : uint32_t(__ldg(t.seeds + b));
     return slot_with_seed(ha, hb, seed, t.nslots);
 }
 
@@ -716,7 +717,9 @@ __device__ __forceinline__ uint32_t slot_of_t(const DevTable& t, const uint8_t* 
     uint32_t ha, hb;
     key_hashes(key, t.salt, ha, hb);
     const uint32_t b = bucket_of(ha, t.nbuckets);
-    const uint32_t seed = kSeedsSmem ? uint32_t(s_seeds[b]) : uint32_t(__ldg(t.seeds + b));
+    const uint32_t seed = kSeedsSmem ? uint32_t(s_seeds[b])
+                                     : t.seed16 ? uint32_t(__ldg(reinterpret_cast<const uint16_t*>(t.seeds) + b))
+                                                : uint32_t(__ldg(t.seeds + b));
     return slot_with_seed(ha, hb, seed, t.nslots);
 }
 
@@ -1210,7 +1213,7 @@ cudaError_t launch_score(const DevModel& m, const BatchArgs& a, cudaStream_t str
         sm_count[dev] = v;
     }
     const int n_sm = sm_count[dev];
-    const bool seeds_smem = m.ct.present && m.ct.nbuckets <= uint32_t(kSeedCap);
+    const bool seeds_smem = m.ct.present && !m.ct.seed16 && m.ct.nbuckets <= uint32_t(kSeedCap);
     if (tile_fast_ok(m)) {
         const bool r3 = m.ct.present && m.ct.r0 == -3;
         if (seeds_smem && r3) return launch_tile<true, -3, false>(m, a, stream, dev, n_sm);

@@ -14,6 +14,7 @@ struct TableGeom {
     uint32_t nslots = 0;
     uint32_t nbuckets = 0;
     uint64_t salt = 0;
+    uint32_t seed_bits = 8;  // 8: one byte per bucket (fits shared memory); 16: dense tables that live in L2
 };
 
 // 32-byte records.  `key` bit 63 = node has longer extensions (a deeper node exists).

@@ -1,6 +1,7 @@
 #include "predictor_build.hpp"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.hpp"
@@ -29,6 +30,7 @@ void write_table(BlobWriter& w, const NodeTable& t, size_t n_patterns, BlobTable
     bt.nslots = t.geom.nslots;
     bt.nbuckets = t.geom.nbuckets;
     bt.salt = t.geom.salt;
+    bt.seed_bits = t.geom.seed_bits;
     bt.n_nodes = t.n_nodes;
     bt.n_patterns = uint32_t(n_patterns);
     bt.rec_off = w.add(t.records.data(), t.records.size());
@@ -80,7 +82,13 @@ HostPredictor build_host_predictor(const Model& m, bool predict_tags) {
     NodeTable ctab, ttab;
     std::vector<int32_t> tcache;
     std::vector<uint32_t> tstate3;
-    constexpr uint32_t kSeedBudget = 37632;  // seed bytes the tile kernel keeps in shared memory (kernels.cu kSeedCap)
+    // seed bytes the tile kernel keeps in shared memory (kernels.cu kSeedCap); VPT_SEED_BUDGET overrides it so that
+    // tests can drive small models through the fat-bucket and dense 16-bit-seed table layouts
+    uint32_t kSeedBudget = 37632;
+    if (const char* e = getenv("VPT_SEED_BUDGET")) {
+        const long v = atol(e);
+        if (v > 0 && v < 37632) kSeedBudget = uint32_t(v);
+    }
     // Type scorer.  The boundary scores of the automaton variants equal the cached table's whenever the window is
     // <= 3 (sum of all boundary n-gram occurrences either way), so tag predictors with short type patterns use the
     // table for scores and a 512-entry direct table for the pattern-id states; only windows > 3 or long tag type
@@ -105,7 +113,7 @@ HostPredictor build_host_predictor(const Model& m, bool predict_tags) {
             }
         }
         if (!light) {
-            ttab = build_node_table(tps, true);
+            ttab = build_node_table(tps, true, kSeedBudget);
             type_table_on_device = true;
         }
     }
