@@ -23,11 +23,12 @@ struct Tab {
     const uint32_t* slot_node() const { return reinterpret_cast<const uint32_t*>(base + bt->node_off); }
     const int32_t* pool() const { return reinterpret_cast<const int32_t*>(base + bt->pool_off); }
     const uint32_t* slot_pid() const { return reinterpret_cast<const uint32_t*>(base + bt->pid_off); }
-    bool probe(uint64_t key, const uint32_t*& r, uint32_t& slot) const {
+    const uint64_t* slot_ovf() const { return reinterpret_cast<const uint64_t*>(base + bt->ovf_off); }
+    bool probe(uint64_t key, const uint32_t*& r, uint32_t& slot, bool deep = false) const {
         slot = table_slot(geom(), seeds(), key);
         r = rec(slot);
         uint64_t k = (uint64_t(r[1]) << 32) | r[0];
-        return (k & ~kExtFlag) == key;
+        return (k & ~(deep ? (kExtFlag | kOvfFlag) : kExtFlag)) == key;
     }
 };
 
@@ -41,7 +42,8 @@ uint8_t ctype(uint32_t c) {
     return 6;
 }
 
-bool find_node(const Tab& t, const std::vector<uint32_t>& sym, size_t g, const uint32_t*& rec, uint32_t& slot) {
+bool find_node(const Tab& t, const std::vector<uint32_t>& sym, size_t g, const uint32_t*& rec, uint32_t& slot, bool& deep_hit) {
+    deep_hit = false;
     uint32_t c3 = sym[g], c2 = g >= 1 ? sym[g - 1] : 0, c1 = g >= 2 ? sym[g - 2] : 0;
     bool found = t.probe(shallow_key(c1, c2, c3), rec, slot);
     bool depth3 = found && c1 != 0;
@@ -53,8 +55,8 @@ bool find_node(const Tab& t, const std::vector<uint32_t>& sym, size_t g, const u
         while (i > 0) {
             --i;
             const uint32_t* nrec; uint32_t nslot;
-            if (!t.probe(deep_key(node, sym[i]), nrec, nslot)) break;
-            rec = nrec; slot = nslot;
+            if (!t.probe(deep_key(node, sym[i]), nrec, nslot, true)) break;
+            rec = nrec; slot = nslot; deep_hit = true;
             if (!(rec[1] >> 31)) break;
             node = t.slot_node()[slot];
         }
@@ -118,13 +120,24 @@ long emul_predict(const uint8_t* model, size_t model_len, int predict_tags, cons
             if (!t.bt->present) continue;
             const std::vector<uint32_t>& sym = which ? tys : cps;
             for (size_t g = 0; g < n; ++g) {
-                const uint32_t* rec; uint32_t slot;
-                if (!find_node(t, sym, g, rec, slot)) continue;
+                const uint32_t* rec; uint32_t slot; bool deep_hit;
+                if (!find_node(t, sym, g, rec, slot, deep_hit)) continue;
                 if (t.bt->fast) {
                     if (h.emit_states && which == 0 && cstates) cstates[g] = t.slot_pid()[slot];
                     for (int j = 0; j < kInlineWidth; ++j) {
                         long i = long(g) + t.bt->r0 + j;
                         if (i >= 0 && i < nout) scores[i] = wrapping_add(scores[i], int32_t(rec[2 + j]));
+                    }
+                    if (deep_hit && ((uint64_t(rec[1]) << 32) & kOvfFlag)) {
+                        if (!t.bt->has_overflow) throw Error(kInternal, "overflow flag on a table without overflow rows");
+                        const uint64_t dsc = t.slot_ovf()[slot];
+                        const uint32_t ptr = uint32_t(dsc);
+                        const int off = int(int16_t(uint16_t(dsc >> 32)));
+                        const int len = int(uint16_t(dsc >> 48));
+                        for (int k = 0; k < len; ++k) {
+                            long i = long(g) + off + k;
+                            if (i >= 0 && i < nout) scores[i] = wrapping_add(scores[i], t.pool()[ptr + k]);
+                        }
                     }
                 } else {
                     if (h.emit_states) { if (which == 0 && cstates) cstates[g] = rec[2]; if (which == 1 && tstates) tstates[g] = rec[2]; }

@@ -314,10 +314,11 @@ def test_table_layout_variants_gpu(budget, monkeypatch):
 
 
 def test_synthetic_config4_shape():
-    # KyTea-shaped: + dictionary with words up to 16 chars (Variable-length rows, general kernel)
+    # KyTea-shaped: + dictionary with words up to 16 chars (Variable-length rows in the reference; here inline
+    # window + overflow rows on the deep records, tile kernel)
     mb = synth.gen_model_bccwj_shaped(n_patterns=20000, sample_sentences=40000, dict_words=20000)
     p, o = make(mb), OraclePredictor(mb)
-    assert p.info["fast_path"] == 0 and p.info["max_char_pattern_len"] > 8
+    assert p.info["fast_path"] == 1 and p.info["max_char_pattern_len"] > 8
     text, offs, _ = synth.gen_text(10000, 40)
     check_batch(p, o, text, offs)
     text, offs, _ = synth.gen_text(3000, ragged=True)

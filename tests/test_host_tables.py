@@ -71,7 +71,10 @@ def test_fast_path_selected(emul):
     _, _, _, info = run(emul, encode_model(kat.PREDICTOR_TEST_MODEL), "この人は地球人だ")
     assert info[0] == 1
     _, _, _, info = run(emul, encode_model(kat.CHAR_ADD_SCORES_3["model"]), "我らは全世界の国民")
-    assert info[0] == 0  # 5-char dictionary word: rows wider than the inline window
+    assert info[0] == 1  # 5-char dictionary words: inline window + overflow rows on the deep records
+    wide = dict(char_ngrams=[("界", list(range(1, 11)))], bias=0, char_window=5, type_window=0)  # 10-wide n-gram row
+    _, _, _, info = run(emul, encode_model(wide), "我らは全世界の国民")
+    assert info[0] == 0
     _, _, _, info = run(emul, encode_model(kat.TYPE_ADD_SCORES["model"]), "我らは全世界の国民")
     assert info[0] == 0 and info[2] == 1  # type window 4: automaton variant
 

@@ -400,9 +400,23 @@ NodeTable build_node_table(const PatternSet& ps, bool force_general, uint32_t bu
         if (!any) { t.rel_min = lo; t.rel_max = hi; any = true; }
         else { t.rel_min = std::min(t.rel_min, lo); t.rel_max = std::max(t.rel_max, hi); }
     }
-    t.fast = !force_general && (!any || t.rel_max - t.rel_min <= kInlineWidth);
-    t.r0 = any ? t.rel_min : 0;
+    // Inline format: the window is placed on the rows of the patterns of at most 3 symbols (n-grams, short words),
+    // which must all fit; rows of longer patterns (dictionary words) may stick out: their records live at depth >= 4,
+    // where the key has room for an overflow flag, and the outside part goes to the overflow pool.
+    bool any_short = false;
+    int smin = 0, smax = 0;
+    for (size_t p = 0; p < ps.rows.size(); ++p) {
+        const Row& r = ps.rows[p];
+        if (!r.present || r.w.empty() || ps.syms[p].size() > 3) continue;
+        const int lo = r.off, hi = r.off + int(r.w.size());
+        if (!any_short) { smin = lo; smax = hi; any_short = true; }
+        else { smin = std::min(smin, lo); smax = std::max(smax, hi); }
+    }
+    t.fast = !force_general && (!any_short || smax - smin <= kInlineWidth);
+    t.r0 = any_short ? smin : (any ? std::max(t.rel_min, t.rel_max - kInlineWidth) : 0);
     if (t.r0 < -24 || t.r0 > 18) t.fast = false;  // shuffle gather reaches at most one warp left/right
+    if (t.fast && any && (t.rel_min < -32000 || t.rel_max > 32000)) t.fast = false;  // overflow offsets are 16-bit
+    t.has_overflow = t.fast && any && (t.rel_min < t.r0 || t.rel_max > t.r0 + kInlineWidth);
 
     // 3. keys and perfect hash
     std::vector<uint64_t> keys(n);
@@ -452,6 +466,13 @@ NodeTable build_node_table(const PatternSet& ps, bool force_general, uint32_t bu
     t.records.assign(size_t(t.geom.nslots) * 32, 0);
     t.slot_node.assign(t.geom.nslots, 0);
     t.slot_pid.assign(t.geom.nslots, kNoPattern);
+    std::vector<uint32_t> ovf_ptr;
+    if (t.has_overflow) {
+        t.slot_ovf.assign(t.geom.nslots, 0);
+        ovf_ptr.assign(ps.rows.size(), kNoPattern);
+        for (const auto& r : ps.rows)
+            if (r.w.size() > 65535) throw Error(kInvalidModel, "InvalidModelError: weight row too long");
+    }
     std::vector<uint32_t> row_ptr;
     if (!t.fast) {
         row_ptr.assign(ps.rows.size(), kNoPattern);
@@ -475,7 +496,26 @@ NodeTable build_node_table(const PatternSet& ps, bool force_general, uint32_t bu
             rec.key = key;
             if (nd.best != kNoPattern) {
                 const Row& r = ps.rows[nd.best];
-                for (size_t k = 0; r.present && k < r.w.size(); ++k) rec.w[r.off - t.r0 + int(k)] = r.w[k];
+                bool outside = false;
+                for (size_t k = 0; r.present && k < r.w.size(); ++k) {
+                    const int rel = r.off + int(k) - t.r0;
+                    if (rel >= 0 && rel < kInlineWidth) rec.w[rel] = r.w[k];
+                    else if (r.w[k] != 0) outside = true;
+                }
+                if (outside) {
+                    // only reachable for depth >= 4 (the window covers every pattern of <= 3 symbols)
+                    if (nd.depth <= 3) throw Error(kInternal, "internal error: overflow row on a shallow node");
+                    if (ovf_ptr[nd.best] == kNoPattern) {
+                        ovf_ptr[nd.best] = uint32_t(t.pool.size());
+                        for (size_t k = 0; k < r.w.size(); ++k) {
+                            const int rel = r.off + int(k) - t.r0;
+                            t.pool.push_back((rel >= 0 && rel < kInlineWidth) ? 0 : r.w[k]);
+                        }
+                    }
+                    rec.key |= kOvfFlag;
+                    t.slot_ovf[slot] = uint64_t(ovf_ptr[nd.best]) | (uint64_t(uint16_t(int16_t(r.off))) << 32) |
+                                       (uint64_t(uint16_t(r.w.size())) << 48);
+                }
             }
             memcpy(dst, &rec, 32);
         } else {

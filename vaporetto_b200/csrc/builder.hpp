@@ -56,7 +56,9 @@ struct NodeTable {
     std::vector<uint8_t> seeds;         // nbuckets
     std::vector<uint32_t> slot_node;    // nslots: node id of the record in the slot (deep keys)
     std::vector<uint32_t> slot_pid;     // nslots: best pattern id (tag states); fast tables only
-    std::vector<int32_t> pool;          // general rows
+    std::vector<int32_t> pool;          // general rows / overflow rows (full row with the inline part zeroed)
+    std::vector<uint64_t> slot_ovf;     // fast tables with overflow: ptr | (off & 0xFFFF) << 32 | len << 48 per slot
+    bool has_overflow = false;
     int rel_min = 0, rel_max = 0;       // union extent of all rows: [rel_min, rel_max)
 };
 

@@ -110,6 +110,8 @@ DevTable dev_table(const BlobTable& bt, const uint8_t* base) {
     d.nbuckets = bt.nbuckets;
     d.salt = bt.salt;
     d.seed16 = bt.seed_bits == 16;
+    d.has_overflow = bt.has_overflow;
+    d.slot_ovf = bt.has_overflow ? reinterpret_cast<const uint64_t*>(base + bt.ovf_off) : nullptr;
     d.records = base + bt.rec_off;
     d.seeds = base + bt.seeds_off;
     d.slot_node = reinterpret_cast<const uint32_t*>(base + bt.node_off);

@@ -12,7 +12,8 @@ struct DevTable {
     const uint8_t* seeds = nullptr;    // nbuckets
     const uint32_t* slot_node = nullptr;
     const uint32_t* slot_pid = nullptr;
-    const int32_t* pool = nullptr;     // general rows
+    const int32_t* pool = nullptr;     // general rows / overflow rows
+    const uint64_t* slot_ovf = nullptr; // fast tables with overflow rows: ptr | off16 << 32 | len16 << 48
     uint64_t salt = 0;
     uint32_t nslots = 0;
     uint32_t nbuckets = 0;
@@ -21,6 +22,7 @@ struct DevTable {
     int32_t present = 0;
     int32_t fast = 0;
     int32_t seed16 = 0;                // seeds are 16-bit (dense tables; never staged in shared memory)
+    int32_t has_overflow = 0;          // fast table whose deep records may carry kOvfFlag
 };
 
 struct DevModel {

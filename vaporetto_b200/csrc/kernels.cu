@@ -60,11 +60,11 @@ __device__ __forceinline__ uint32_t slot_of(const DevTable& t, uint64_t key) {
 }
 
 // One probe: returns true when the node with `key` exists; rec/slot are valid then.
-__device__ __forceinline__ bool probe(const DevTable& t, uint64_t key, Rec32& rec, uint32_t& slot) {
+__device__ __forceinline__ bool probe(const DevTable& t, uint64_t key, Rec32& rec, uint32_t& slot, bool deep = false) {
     slot = slot_of(t, key);
     rec = load_record(t.records, slot);
     const uint64_t k = (uint64_t(rec.v[1]) << 32) | rec.v[0];
-    return (k & ~kExtFlag) == key;
+    return (k & ~(deep ? (kExtFlag | kOvfFlag) : kExtFlag)) == key;
 }
 
 // CharacterType::get_type (reference sentence.rs:50-67)
@@ -420,7 +420,8 @@ __device__ __forceinline__ uint32_t type_index(const Rings& r, int64_t g, uint32
 // or character types (types=true).  Returns true and the record of the deepest existing node.
 template <bool kTypes>
 __device__ __forceinline__ bool find_node(const DevTable& t, const Rings& r, const uint8_t* __restrict__ text,
-                                          uint64_t b0, uint32_t g, Rec32& rec, uint32_t& slot) {
+                                          uint64_t b0, uint32_t g, Rec32& rec, uint32_t& slot, bool* deep_hit = nullptr) {
+    if (deep_hit) *deep_hit = false;
     uint32_t c3, c2 = 0, c1 = 0;
     if (kTypes) {
         c3 = r.ty[g & kRingMask];
@@ -444,9 +445,10 @@ __device__ __forceinline__ bool find_node(const DevTable& t, const Rings& r, con
             if (kTypes) sym = char_type(sym);
             Rec32 nrec;
             uint32_t nslot;
-            if (!probe(t, deep_key(node, sym), nrec, nslot)) break;
+            if (!probe(t, deep_key(node, sym), nrec, nslot, true)) break;
             rec = nrec;
             slot = nslot;
+            if (deep_hit) *deep_hit = true;
             if (!(rec.v[1] >> 31)) break;
             node = __ldg(t.slot_node + slot);
         }
@@ -535,6 +537,41 @@ __device__ __forceinline__ void fast_sentence_warp(const DevModel& m, const Batc
     if (have_prev && prev_g + 1 < n) {
         a.scores[si.obase + prev_g] = prev_main;
         a.boundaries[si.obase + prev_g] = prev_main > 0 ? 1 : 0;
+    }
+    if (m.ct.present && m.ct.has_overflow) {
+        // rows of long dictionary words stick out of the inline window: add the outside parts with atomics in a
+        // second sweep and redo the thresholds (only sentences larger than a tile come through here)
+        __threadfence();
+        __syncwarp();
+        uint64_t wpos2 = si.b0 & ~3ull;
+        uint32_t nd2 = 0;
+        for (uint32_t cb = 0; cb < n; cb += 32) {
+            const uint32_t need = min(n, cb + 32u);
+            while (nd2 < need && wpos2 < si.b1) {
+                nd2 += decode_window(text, wpos2, si.b0, si.b1, nd2, r, lane);
+                wpos2 += 128;
+            }
+            __syncwarp();
+            const uint32_t g = cb + lane;
+            if (g < n) {
+                Rec32 rec;
+                uint32_t slot;
+                bool deep_hit;
+                if (find_node<false>(m.ct, r, text, si.b0, g, rec, slot, &deep_hit) && deep_hit && (rec.v[1] & (1u << 29))) {
+                    const uint64_t dsc = __ldg(m.ct.slot_ovf + slot);
+                    const uint32_t ptr = uint32_t(dsc);
+                    const int off = int(int16_t(uint16_t(dsc >> 32))), len = int(uint16_t(dsc >> 48));
+                    for (int k = 0; k < len; ++k) {
+                        const int64_t i = int64_t(g) + off + k;
+                        if (i >= 0 && i < int64_t(si.nout)) atomicAdd(a.scores + si.obase + i, __ldg(m.ct.pool + ptr + k));
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        __threadfence();
+        __syncwarp();
+        for (uint32_t i = lane; i < si.nout; i += 32) a.boundaries[si.obase + i] = __ldcg(a.scores + si.obase + i) > 0 ? 1 : 0;
     }
 }
 
@@ -730,25 +767,44 @@ __device__ __forceinline__ bool rec_matches(const Rec32& rec, uint64_t key) {
 
 // Continues a depth-3 hit backwards through the text for patterns longer than three characters (rare).
 template <bool kSeedsSmem>
-__device__ __forceinline__ void deep_walk(const DevTable& t, const uint8_t* s_seeds, const uint32_t* __restrict__ cp, int p,
+__device__ __forceinline__ bool deep_walk(const DevTable& t, const uint8_t* s_seeds, const uint32_t* __restrict__ cp, int p,
                                           uint32_t& slot, Rec32& rec) {
+    bool deep_hit = false;
     uint32_t node = __ldg(t.slot_node + slot);
     for (int i = p - 3; cp[i] != 0; --i) {
         const uint64_t key = deep_key(node, cp[i]);
         const uint32_t nslot = slot_of_t<kSeedsSmem>(t, s_seeds, key);
         const Rec32 nrec = load_record(t.records, nslot);
-        if (!rec_matches(nrec, key)) break;
+        const uint64_t k = (uint64_t(nrec.v[1]) << 32) | nrec.v[0];
+        if ((k & ~(kExtFlag | kOvfFlag)) != key) break;
         rec = nrec;
         slot = nslot;
+        deep_hit = true;
         if (!(rec.v[1] >> 31)) break;
         node = __ldg(t.slot_node + nslot);
+    }
+    return deep_hit;
+}
+
+// Adds the part of a long row that lies outside the inline window (record flagged kOvfFlag) to the per-slot sums,
+// clipped to the boundary slots [lo_slot, hi_slot) of the character's sentence.
+__device__ __forceinline__ void apply_overflow(const DevTable& t, uint32_t slot, int p, int lo_slot, int hi_slot, int32_t* s_sc) {
+    const uint64_t dsc = __ldg(t.slot_ovf + slot);
+    const uint32_t ptr = uint32_t(dsc);
+    const int off = int(int16_t(uint16_t(dsc >> 32))), len = int(uint16_t(dsc >> 48));
+    int k_lo = lo_slot - (p + off), k_hi = hi_slot - (p + off);
+    if (k_lo < 0) k_lo = 0;
+    if (k_hi > len) k_hi = len;
+    for (int k = k_lo; k < k_hi; ++k) {
+        const int32_t w = __ldg(t.pool + ptr + k);
+        if (w != 0) atomicAdd(s_sc + p + off + k, w);
     }
 }
 
 // gather of the 6-wide rows of one 32-slot warp chunk: boundary (lane) <- row entry j of lane - r0 - j
 // (kR0 = compile-time window start for the common char-window-3 model, kRuntimeR0 = use the argument)
 constexpr int kRuntimeR0 = 99;
-template <int kR0>
+template <int kR0, bool kAtomic = false>
 __device__ __forceinline__ void gather_store(const int32_t (&d)[kInlineWidth], int r0_arg, int lane, int p, int32_t* s_sc,
                                              int32_t* s_spill_prev, int32_t* s_spill_next) {
     const int r0 = kR0 == kRuntimeR0 ? r0_arg : kR0;
@@ -761,7 +817,8 @@ __device__ __forceinline__ void gather_store(const int32_t (&d)[kInlineWidth], i
         else if (src >= 32) to_prev += v;
         else mainv += v;
     }
-    s_sc[p] = mainv;
+    if (kAtomic) atomicAdd(s_sc + p, mainv);  // overflow rows of other characters may target this slot concurrently
+    else s_sc[p] = mainv;
     const int wc = p >> 5;
     if (lane >= 24) s_spill_prev[wc * 8 + lane - 24] = to_prev;
     if (lane < 8) s_spill_next[wc * 8 + lane] = to_next;
@@ -817,7 +874,8 @@ __device__ __forceinline__ void tile_scatter(const DevTable& t, const uint8_t* s
 }
 
 // kSplit3: type window 3 with the split tables in shared memory (compile-time type window: the common model shape)
-template <bool kSeedsSmem, int kR0, bool kGeneral, bool kSplit3>
+// kOverflow: inline-format table whose deep records may carry rows wider than the window (dictionary words)
+template <bool kSeedsSmem, int kR0, bool kGeneral, bool kSplit3, bool kOverflow>
 __global__ void __launch_bounds__(kTileThreads, 1) k_tile_fast(DevModel m, BatchArgs a, int gap) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* s_seeds = smem + kOffSeeds;
@@ -1032,7 +1090,11 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_fast(DevModel m, Batch
                                                   tst ? tst + (int64_t(p) + T.cdelta[k]) : nullptr);
                 }
             } else {
-            // ---- pass C: node lookup + warp-shuffle gather, two slots per thread in flight --------------------
+                if constexpr (kOverflow) {
+                    for (int p = tid; p < Sround; p += kSubThreads) s_sc[p] = 0;
+                    sub_sync(sub);
+                }
+                // ---- pass C: node lookup + warp-shuffle gather, two slots per thread in flight ----------------
                 for (int base = 0; base < Sround; base += 2 * kSubThreads) {
                     const int pA = base + tid, pB = pA + kSubThreads;
                     const bool hasB = pB < Sround;  // uniform: Sround is a multiple of 256
@@ -1077,8 +1139,19 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_fast(DevModel m, Batch
                         if (nA) fA = rec_matches(rA, kA);
                         if (nB) fB = rec_matches(rB, kB);
                     }
-                    if (deepA) deep_walk<kSeedsSmem>(m.ct, s_seeds, s_cp, pA, slA, rA);
-                    if (deepB) deep_walk<kSeedsSmem>(m.ct, s_seeds, s_cp, pB, slB, rB);
+                    bool dhA = false, dhB = false;
+                    if (deepA) dhA = deep_walk<kSeedsSmem>(m.ct, s_seeds, s_cp, pA, slA, rA);
+                    if (deepB) dhB = deep_walk<kSeedsSmem>(m.ct, s_seeds, s_cp, pB, slB, rB);
+                    if constexpr (kOverflow) {
+                        if (dhA && (rA.v[1] & (1u << 29))) {
+                            const int k = s_kk[pA], lo_slot = int(int64_t(T.obase[k]) - T.odelta[k]);
+                            apply_overflow(m.ct, slA, pA, lo_slot, lo_slot + int(T.nch[k]) - 1, s_sc);
+                        }
+                        if (dhB && (rB.v[1] & (1u << 29))) {
+                            const int k = s_kk[pB], lo_slot = int(int64_t(T.obase[k]) - T.odelta[k]);
+                            apply_overflow(m.ct, slB, pB, lo_slot, lo_slot + int(T.nch[k]) - 1, s_sc);
+                        }
+                    }
                     if (m.emit_states && a.char_states) {
                         // pattern id of the longest match (tag prediction input): side array indexed by the final slot
                         if (a3) a.char_states[int64_t(pA) + T.cdelta[s_kk[pA]]] = fA ? __ldg(m.ct.slot_pid + slA) : kNoPattern;
@@ -1089,8 +1162,8 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_fast(DevModel m, Batch
                         dA[j] = fA ? int32_t(rA.v[2 + j]) : 0;
                         dB[j] = fB ? int32_t(rB.v[2 + j]) : 0;
                     }
-                    gather_store<kR0>(dA, r0, lane, pA, s_sc, s_spill_prev, s_spill_next);
-                    if (hasB) gather_store<kR0>(dB, r0, lane, pB, s_sc, s_spill_prev, s_spill_next);
+                    gather_store<kR0, kOverflow>(dA, r0, lane, pA, s_sc, s_spill_prev, s_spill_next);
+                    if (hasB) gather_store<kR0, kOverflow>(dB, r0, lane, pB, s_sc, s_spill_prev, s_spill_next);
                 }
             }
             sub_sync(sub);
@@ -1178,25 +1251,28 @@ static bool tile_fast_ok(const DevModel& m) {
 
 constexpr int kMaxDevices = 64;
 
-template <bool kSeeds, int kR0, bool kGeneral, bool kSplit3>
+template <bool kSeeds, int kR0, bool kGeneral, bool kSplit3, bool kOverflow>
 static cudaError_t launch_tile_t(const DevModel& m, const BatchArgs& a, cudaStream_t stream, int dev, int n_sm) {
     static bool attr_set[kMaxDevices] = {};  // the opt-in shared memory size is a per-device function attribute
     if (!attr_set[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(k_tile_fast<kSeeds, kR0, kGeneral, kSplit3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem);
+        cudaError_t e = cudaFuncSetAttribute(k_tile_fast<kSeeds, kR0, kGeneral, kSplit3, kOverflow>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem);
         if (e != cudaSuccess) return e;
         attr_set[dev] = true;
     }
     const uint64_t ngroups = (a.n_sent + kGroup - 1) / kGroup;
     const unsigned grid = unsigned(std::min<uint64_t>(uint64_t(n_sm), (ngroups + kSubBlocks - 1) / kSubBlocks));
-    k_tile_fast<kSeeds, kR0, kGeneral, kSplit3><<<grid, kTileThreads, kTileSmem, stream>>>(m, a, tile_gap(m));
+    k_tile_fast<kSeeds, kR0, kGeneral, kSplit3, kOverflow><<<grid, kTileThreads, kTileSmem, stream>>>(m, a, tile_gap(m));
     return cudaGetLastError();
 }
 
 template <bool kSeeds, int kR0, bool kGeneral>
 static cudaError_t launch_tile(const DevModel& m, const BatchArgs& a, cudaStream_t stream, int dev, int n_sm) {
     const bool split3 = m.type_a != nullptr && m.type_cache_window == 3;
-    return split3 ? launch_tile_t<kSeeds, kR0, kGeneral, true>(m, a, stream, dev, n_sm)
-                  : launch_tile_t<kSeeds, kR0, kGeneral, false>(m, a, stream, dev, n_sm);
+    if (!kGeneral && m.ct.present && m.ct.has_overflow)
+        return split3 ? launch_tile_t<kSeeds, kR0, false, true, true>(m, a, stream, dev, n_sm)
+                      : launch_tile_t<kSeeds, kR0, false, false, true>(m, a, stream, dev, n_sm);
+    return split3 ? launch_tile_t<kSeeds, kR0, kGeneral, true, false>(m, a, stream, dev, n_sm)
+                  : launch_tile_t<kSeeds, kR0, kGeneral, false, false>(m, a, stream, dev, n_sm);
 }
 
 cudaError_t launch_score(const DevModel& m, const BatchArgs& a, cudaStream_t stream) {

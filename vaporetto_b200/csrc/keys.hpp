@@ -34,6 +34,11 @@ struct alignas(32) GeneralRecord {
 static_assert(sizeof(FastRecord) == 32 && sizeof(GeneralRecord) == 32, "record size");
 
 constexpr uint64_t kExtFlag = 1ull << 63;
+// Deep keys (depth >= 4) leave bits 59..61 of the key free (their top field is kDeepMarker + a 10-bit value):
+// bit 61 marks a record whose merged row does not fit the inline window; the part outside the window lives in
+// the overflow pool (slot_ovf side array).  Only deep records can carry it: rows of patterns of <= 3 symbols
+// must fit the window for a table to use the inline format at all.
+constexpr uint64_t kOvfFlag = 1ull << 61;
 constexpr uint64_t kDeepMarker = 0x110000ull;  // first invalid code point: marks (parent node, symbol) keys
 
 // key of a node at depth <= 3: c3 is the last symbol of the suffix, c1 the first (0 if absent).

@@ -38,6 +38,8 @@ void write_table(BlobWriter& w, const NodeTable& t, size_t n_patterns, BlobTable
     bt.node_off = w.add(t.slot_node.data(), t.slot_node.size() * 4);
     bt.pid_off = w.add(t.slot_pid.data(), t.slot_pid.size() * 4);
     bt.pool_off = w.add(t.pool.data(), t.pool.size() * 4);
+    bt.has_overflow = t.has_overflow;
+    if (t.has_overflow) bt.ovf_off = w.add(t.slot_ovf.data(), t.slot_ovf.size() * 8);
 }
 
 

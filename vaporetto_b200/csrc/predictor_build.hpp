@@ -11,7 +11,7 @@
 
 namespace vpt {
 
-constexpr char kBlobMagic[8] = {'V', 'P', 'T', 'B', '2', '0', '0', '\4'};
+constexpr char kBlobMagic[8] = {'V', 'P', 'T', 'B', '2', '0', '0', '\5'};
 
 struct BlobTable {
     uint64_t rec_off, seeds_off, node_off, pid_off, pool_off;
@@ -21,7 +21,8 @@ struct BlobTable {
     uint32_t max_depth;
     int32_t present, fast;
     uint32_t n_nodes, n_patterns;
-    uint32_t seed_bits, pad;
+    uint32_t seed_bits, has_overflow;
+    uint64_t ovf_off;
 };
 struct BlobHeader {
     char magic[8];
