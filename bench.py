@@ -355,6 +355,23 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = total_bytes * args.e2e_steps / float(te.item()) / 1e6
+    # same call without the i32 scores in the D2H copy (boundaries + offsets only): what a tokenizer front-end needs
+    def step_e2e_nb():
+        rc = L.vpt_predict_batch(pred._h, h_text.data_ptr(), h_off.data_ptr(), n, None, h_bounds.data_ptr(), n_bound,
+                                 h_boff.data_ptr(), h_status.data_ptr(), None, None, 0, None, C.byref(nb_out), C.byref(nc_out))
+        if rc:
+            raise RuntimeError(L.vpt_last_error().decode())
+
+    step_e2e_nb()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        step_e2e_nb()
+    torch.cuda.synchronize()
+    tnb = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tnb, op=dist.ReduceOp.MAX)
+    e2e_nb_value = total_bytes * args.e2e_steps / float(tnb.item()) / 1e6
     h2d = nbytes + 8 * (n + 1)
     d2h = 4 * n_bound + n_bound + 8 * (n + 1) + 4 * n + 16 + (8 * n_chars_total + 8 * (n + 1) if want_states else 0)
 
@@ -389,7 +406,8 @@ def main():
                          "read_only_GBps": round((nbytes + 8 * n) / (score_ms / 1e3) / 1e9, 1),
                          "whole_step_frac": round(alg_bytes / (ms_all / args.steps / 1e3) / 1e9 / peak, 4)},
             "e2e": {"value": round(e2e_value, 1), "unit": "MB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": args.e2e_steps, "api": "vpt_predict_batch (pinned host buffers; scores+boundaries returned)"},
+                    "steps": args.e2e_steps, "api": "vpt_predict_batch (pinned host buffers; scores+boundaries returned)",
+                    "boundaries_only_value": round(e2e_nb_value, 1)},
             "gpu_launches": args.steps * pred.info["kernel_launches_per_batch"],
             "clocks": clocks,
             "bit_exact_checked": True,
