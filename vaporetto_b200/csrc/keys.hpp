@@ -54,23 +54,19 @@ VPT_HD uint64_t deep_key(uint32_t parent_id, uint32_t sym) {
 // 32-bit hashes; the first picks the bucket, the bucket's 16-bit seed displaces the second into the slot.
 VPT_HD void key_hashes(uint64_t key, uint64_t salt, uint32_t& ha, uint32_t& hb) {
     const uint32_t lo = uint32_t(key) ^ uint32_t(salt), hi = uint32_t(key >> 32) ^ uint32_t(salt >> 32);
-    // multiplication only carries differences upwards, so each half is folded (>> 16) into the other before
-    // the second multiply: keys that differ only in high bits (deep vs shallow keys) still separate
+    // Multiplication carries differences upwards only, so each half is multiplied, folded down (>> 16) and mixed
+    // into the other half before the second multiply; every consumer below reads the HIGH bits of these products
+    // (mulhi32), which depend on all input bits.
     const uint32_t t = hi * 0x85EBCA77u;
-    uint32_t a = (lo ^ t ^ (t >> 16)) * 0x9E3779B1u;
-    a ^= a >> 15;
-    ha = a * 0xC2B2AE3Du;
+    ha = (lo ^ t ^ (t >> 16)) * 0x9E3779B1u;
     const uint32_t u = lo * 0x27D4EB2Fu;
-    uint32_t b = (hi ^ u ^ (u >> 15)) * 0x165667B1u;
-    hb = b ^ (b >> 16);
+    hb = (hi ^ u ^ (u >> 15)) * 0x165667B1u;
 }
 VPT_HD uint32_t mulhi32(uint32_t a, uint32_t b) { return uint32_t((uint64_t(a) * b) >> 32); }
 VPT_HD uint32_t bucket_of(uint32_t ha, uint32_t nbuckets) { return mulhi32(ha, nbuckets); }
 VPT_HD uint32_t slot_with_seed(uint32_t ha, uint32_t hb, uint32_t seed, uint32_t nslots) {
-    uint32_t v = hb + seed * (ha | 1u);
-    v ^= v >> 15;
-    v *= 0x85EBCA6Bu;
-    return mulhi32(v, nslots);
+    const uint32_t v = (hb + seed * (ha | 1u)) * 0x85EBCA6Bu;
+    return mulhi32(v ^ (v >> 15), nslots);
 }
 
 }  // namespace vpt
