@@ -185,6 +185,22 @@ int vpt_write_tokenized_text(const vpt_predictor* predictor, const uint8_t* utf8
                              const uint8_t* boundaries, const int32_t* tag_token, const int32_t* tag_cand,
                              char* buf, size_t capacity, uint64_t* len_out);
 
+/* ---- Whole-buffer tokenisation: the reference CLI's loop on the device ----------------------------- */
+
+/* The `predict --no-norm` loop (predict/src/main.rs:126-150) over a whole buffer of raw file bytes:
+ *   for line in stdin.lines():  if s.update_raw(line).is_ok() { predict; write_tokenized_text }  write "\n"
+ * Lines are split ON THE DEVICE with `BufRead::lines` semantics ('\n' or "\r\n" terminated; the last line may
+ * be unterminated; a trailing '\n' adds no empty line), scored by the same kernels as vpt_predict_batch, and
+ * the tokenised text (' ' between tokens; '\\' before ' ', '\\', '/': sentence.rs:850-886) is materialised on the
+ * device, so the only transfers are the input bytes in and the output bytes out.  Lines that update_raw
+ * rejects (empty, or containing U+0000) produce an empty line as in the CLI; so do lines that are not valid
+ * UTF-8 (the CLI stops with an I/O error on those).  Tags are not predicted on this path.
+ * `out` receives the output lines, each terminated by '\n' (at most 3 * n_bytes + n_lines bytes); *out_len
+ * the number of bytes produced (also when `out_capacity` was too small, which returns InvalidArgument);
+ * *n_lines the number of input lines.  Chunk size of the internal pipeline: env VPT_CHUNK_BYTES (8 MiB). */
+int vpt_tokenize_lines(const vpt_predictor* predictor, const uint8_t* utf8, size_t n_bytes, uint8_t* out,
+                       size_t out_capacity, uint64_t* out_len, uint64_t* n_lines);
+
 /* library build info, e.g. "vaporetto_b200 0.1.0 sm_100a" */
 const char* vpt_version(void);
 

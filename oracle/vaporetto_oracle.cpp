@@ -908,6 +908,43 @@ long ora_tokenize(const void* p, const char* utf8, size_t nbytes, int fill_tags,
     ORA_CATCH(neg)
 }
 
+// The `predict --no-norm` loop of the reference CLI (predict/src/main.rs:126-150) over a buffer:
+//   for line in stdin.lines() { if s.update_raw(line).is_ok() { predict; write_tokenized_text }; out "\n" }
+// `BufRead::lines` (std): a line ends at '\n'; a '\r' directly before that '\n' is dropped; the last line may be
+// unterminated; a trailing '\n' adds no empty line.  Lines update_raw rejects (empty / NUL) print an empty
+// line.  A line that is not valid UTF-8 makes `lines()` fail and the CLI stop; the batch interface this
+// checks prints an empty line for it instead (documented difference).  Returns the output size (or
+// -(1000000 + needed) when cap is too small); *n_lines receives the number of lines.
+long ora_tokenize_lines(const void* p, const char* utf8, size_t nbytes, char* buf, size_t cap, uint64_t* n_lines) {
+    auto neg = [](int c) { return -long(c); };
+    ORA_TRY
+    auto* pr = static_cast<const Predictor*>(p);
+    string out;
+    uint64_t nl = 0;
+    size_t lo = 0;
+    Sentence s;
+    while (lo < nbytes) {
+        const void* q = memchr(utf8 + lo, '\n', nbytes - lo);
+        size_t end = q ? size_t(static_cast<const char*>(q) - utf8) : nbytes;
+        const size_t next = q ? end + 1 : nbytes;
+        if (q && end > lo && utf8[end - 1] == '\r') --end;
+        ++nl;
+        bool ok = true;
+        try { s.parse_raw(utf8 + lo, end - lo); } catch (const Error&) { ok = false; }
+        if (ok) {
+            pr->predict(s);
+            out += write_tokenized(*pr, s, nullptr, nullptr);
+        }
+        out.push_back('\n');
+        lo = next;
+    }
+    if (n_lines) *n_lines = nl;
+    if (out.size() > cap) return -long(1000000 + out.size());
+    memcpy(buf, out.data(), out.size());
+    return long(out.size());
+    ORA_CATCH(neg)
+}
+
 // predict + fill_tags: tag_token[n_chars], tag_idx[n_chars*n_tags]. Returns n_chars.
 long ora_predict_tags(const void* p, const char* utf8, size_t nbytes, int32_t* tag_token, int32_t* tag_idx) {
     auto neg = [](int c) { return -long(c); };

@@ -1,0 +1,120 @@
+"""GPU parity tests of vpt_tokenize_lines (device-side line splitting + tokenised output)
+against the oracle's restatement of the reference CLI loop (predict/src/main.rs:126-150).  Byte-exact."""
+import os
+
+import numpy as np
+import pytest
+
+import vaporetto_b200 as vb
+from vpt_testlib import synth
+from vpt_testlib.bincode_model import encode_model
+from vpt_testlib.oracle import OraclePredictor
+from test_gpu_parity import _random_model, make, read
+
+pytestmark = pytest.mark.gpu
+
+
+def check(p, o, data: bytes):
+    got, nl = p.tokenize_lines(data)
+    want, wl = o.tokenize_lines(data)
+    assert nl == wl
+    assert got.tobytes() == want
+
+
+@pytest.fixture(scope="module")
+def kat_pair():
+    mb = read("model.bin")
+    return make(mb), OraclePredictor(mb)
+
+
+def test_lines_semantics(kat_pair, monkeypatch):
+    p, o = kat_pair
+    cases = [
+        b"",
+        b"\n",
+        b"\n\n\n",
+        b"\r\n",
+        b"\r",
+        b"a",
+        b"a\n",
+        b"a\r\n",
+        b"a\r\r\n",
+        b"a\rb\n",
+        "まぁ社長は火星猫だ".encode(),
+        "まぁ社長は火星猫だ\n".encode(),
+        "まぁ社長は火星猫だ\r\nまぁ社長は火星猫だ".encode(),
+        "火星 猫/です\\ね\n\n 火星\n/\n\\\n".encode(),                 # escapes of ' ', '/', '\\'
+        "まぁ\x00社長\n火星猫\n".encode(),                                # NUL line -> empty line
+        b"\xe3\x81\n" + "火星猫\n".encode() + b"\xff\xfe\n\xc0\x80\n",      # invalid UTF-8 lines -> empty lines
+        ("火星猫だ" * 3000 + "\n" + "まぁ社長は" * 7 + "\n").encode(),     # a line larger than a tile
+        "\n".join("まぁ社長は火星猫だ"[: 1 + i % 9] for i in range(500)).encode(),
+        "\U00020000\U0002a6df火星été ab12 ｶﾀｶﾅ\n".encode(),       # 4-, 2-byte characters
+    ]
+    for chunk in ("", "64", "200"):
+        if chunk:
+            monkeypatch.setenv("VPT_CHUNK_BYTES", chunk)
+        for data in cases:
+            check(p, o, data)
+
+
+def test_lines_out_capacity(kat_pair):
+    p, o = kat_pair
+    data = "まぁ社長は火星猫だ\n".encode() * 10
+    want, _ = o.tokenize_lines(data)
+    out = np.empty(len(want), np.uint8)
+    got, nl = p.tokenize_lines(data, out=out)
+    assert got.tobytes() == want and nl == 10
+    with pytest.raises(vb.VaporettoError):
+        p.tokenize_lines(data, out=np.empty(len(want) - 1, np.uint8))
+
+
+def _random_lines(rng, n_lines, alphabet, maxlen):
+    parts = []
+    for _ in range(n_lines):
+        r = rng.random()
+        if r < 0.05:
+            line = b""
+        elif r < 0.08:
+            line = bytes(rng.integers(0, 256, rng.integers(1, 12)).astype(np.uint8))  # mostly malformed
+        else:
+            n = int(rng.integers(1, maxlen))
+            line = "".join(alphabet[int(i)] for i in rng.integers(0, len(alphabet), n)).encode()
+        line = line.replace(b"\n", b"")
+        parts.append(line + (b"\r\n" if rng.random() < 0.2 else b"\n"))
+    data = b"".join(parts)
+    if rng.random() < 0.5:
+        data = data[:-1] if not data.endswith(b"\r\n") else data[:-2]
+    return data
+
+
+@pytest.mark.parametrize("cw,tw,maxdict", [(3, 3, 3), (3, 3, 9), (2, 4, 6)])
+def test_random_lines_vs_oracle(cw, tw, maxdict, monkeypatch):
+    rng = np.random.default_rng(cw * 100 + tw * 10 + maxdict)
+    for it in range(6):
+        m, alpha = _random_model(rng, cw, tw, maxdict=maxdict)
+        alphabet = list(alpha) + list(" /\\é\U00020000")
+        mb = encode_model(m)
+        p, o = make(mb), OraclePredictor(mb)
+        monkeypatch.setenv("VPT_CHUNK_BYTES", str(int(rng.choice([64, 1000, 1 << 16, 8 << 20]))))
+        check(p, o, _random_lines(rng, int(rng.integers(1, 400)), alphabet, 80))
+        check(p, o, _random_lines(rng, 5, alphabet, 3000))
+
+
+def test_lines_full_size():
+    """BASELINE config-2 shape (300 K-pattern model, 200 K lines): byte-exact against the oracle, and the
+    size-independent properties: removing the inserted bytes gives the input back; line count is kept."""
+    mb = synth.gen_model_bccwj_shaped(n_patterns=300_000, sample_sentences=200_000)
+    p, o = make(mb), OraclePredictor(mb)
+    text, offs, _ = synth.gen_text(200_000, 40, seed=99)
+    lines = [text[int(offs[i]):int(offs[i + 1])].tobytes() for i in range(len(offs) - 1)]
+    data = b"\n".join(lines) + b"\n"
+    got, nl = p.tokenize_lines(data)
+    assert nl == len(lines)
+    want, _ = o.tokenize_lines(data)
+    assert got.tobytes() == want
+    g = got.tobytes()
+    assert g.count(b"\n") == len(lines)
+    # the synthetic text has ' ' but no '/', '\\' or NUL: undoing the escapes and dropping the separators
+    # restores the input
+    assert b"/" not in data and b"\\" not in data
+    assert g.replace(b"\\ ", b"\x00").replace(b" ", b"").replace(b"\x00", b" ") == data

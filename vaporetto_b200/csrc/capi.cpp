@@ -45,9 +45,17 @@ struct Scratch {
     void* d_bounds = nullptr; size_t bounds_cap = 0;
     void* d_cst = nullptr; size_t cst_cap = 0;
     void* d_tst = nullptr; size_t tst_cap = 0;
-    uint64_t* h_totals = nullptr;  // pinned, 2 x u64
+    // line splitting / tokenised output (vpt_tokenize_lines)
+    void* d_trims = nullptr; size_t trims_cap = 0;
+    void* d_blk = nullptr; size_t blk_cap = 0;
+    void* d_blkbase = nullptr; size_t blkbase_cap = 0;
+    void* d_tokl = nullptr; size_t tokl_cap = 0;
+    void* d_tokg = nullptr; size_t tokg_cap = 0;
+    void* d_out = nullptr; size_t out_cap = 0;
+    uint64_t* h_totals = nullptr;  // pinned, 4 x u64: boundaries, chars, lines, output bytes
     ~Scratch() {
-        for (void* p : {d_text, d_off, d_ws, d_status, d_boff, d_coff, d_scores, d_bounds, d_cst, d_tst})
+        for (void* p : {d_text, d_off, d_ws, d_status, d_boff, d_coff, d_scores, d_bounds, d_cst, d_tst, d_trims, d_blk,
+                        d_blkbase, d_tokl, d_tokg, d_out})
             if (p) cudaFree(p);
         if (h_totals) cudaFreeHost(h_totals);
         if (stream) cudaStreamDestroy(stream);
@@ -158,7 +166,7 @@ struct ScratchLease {
         if (!s) {
             s.reset(new Scratch());
             cuda_check(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking), "cudaStreamCreate");
-            cuda_check(cudaMallocHost(reinterpret_cast<void**>(&s->h_totals), 16), "cudaMallocHost");
+            cuda_check(cudaMallocHost(reinterpret_cast<void**>(&s->h_totals), 32), "cudaMallocHost");
         }
     }
     ~ScratchLease() {
@@ -596,6 +604,169 @@ int vpt_predict_batch(const vpt_predictor* p, const uint8_t* utf8, const uint64_
     if (n_boundaries_out) *n_boundaries_out = nb_total;
     if (n_chars_out) *n_chars_out = nc_total;
     if (overflow) throw Error(kInvalidArgument, "InvalidArgumentError: out_capacity/states_capacity: too small for the batch");
+    return kOk;
+    VPT_API_END
+}
+
+namespace {
+
+// bytes per pipelined chunk of vpt_tokenize_lines (tuning knob: env VPT_CHUNK_BYTES)
+size_t chunk_bytes() {
+    const char* e = getenv("VPT_CHUNK_BYTES");
+    const long long x = e ? atoll(e) : 0;
+    return x >= 64 ? size_t(x) : size_t(8) << 20;
+}
+
+constexpr uint64_t kMaxLineChunk = uint64_t(1) << 30;  // 32-bit group-local output offsets (3 bytes out per byte in)
+
+struct LineChunk {
+    uint64_t byte_lo = 0, nbytes = 0;
+    uint64_t n_lines = 0;
+    cudaEvent_t split = nullptr, done = nullptr;
+    SplitArgs sp;
+};
+
+// stage 0 of a chunk: H2D of the text, newline counts, the number of lines to pinned host memory
+void lines_stage0(Scratch& s, LineChunk& ch, const uint8_t* utf8) {
+    cudaStream_t st = s.stream;
+    const size_t nblk = (ch.nbytes + kSplitBlockBytes - 1) / kSplitBlockBytes;
+    Scratch::ensure(s.d_text, s.text_cap, ch.nbytes + 64);
+    Scratch::ensure(s.d_blk, s.blk_cap, 4 * nblk + 4);
+    Scratch::ensure(s.d_blkbase, s.blkbase_cap, 8 * nblk + 16);
+    cuda_check(cudaMemcpyAsync(s.d_text, utf8 + ch.byte_lo, ch.nbytes, cudaMemcpyHostToDevice, st), "H2D(text)");
+    SplitArgs& sp = ch.sp;
+    sp = SplitArgs();
+    sp.text = static_cast<const uint8_t*>(s.d_text);
+    sp.n_bytes = ch.nbytes;
+    sp.blk = static_cast<uint32_t*>(s.d_blk);
+    sp.blk_base = static_cast<uint64_t*>(s.d_blkbase);
+    sp.n_lines = sp.blk_base + nblk;  // the element after the per-block bases
+    cuda_check(launch_split_count(sp, st), "launch(split)");
+    cuda_check(cudaMemcpyAsync(&s.h_totals[2], sp.n_lines, 8, cudaMemcpyDeviceToHost, st), "D2H(lines)");
+    if (!ch.split) cuda_check(cudaEventCreateWithFlags(&ch.split, cudaEventDisableTiming), "cudaEventCreate");
+    cuda_check(cudaEventRecord(ch.split, st), "cudaEventRecord");
+}
+
+// stage 1: line offsets, count + score, tokenised bytes; the output size to pinned host memory
+void lines_stage1(const vpt_predictor& p, Scratch& s, LineChunk& ch) {
+    cudaStream_t st = s.stream;
+    cuda_check(cudaEventSynchronize(ch.split), "sync(split)");
+    const size_t n = size_t(s.h_totals[2]);
+    ch.n_lines = n;
+    if (!ch.done) cuda_check(cudaEventCreateWithFlags(&ch.done, cudaEventDisableTiming), "cudaEventCreate");
+    s.h_totals[3] = 0;
+    if (n == 0) { cuda_check(cudaEventRecord(ch.done, st), "cudaEventRecord"); return; }
+    const WorkspaceLayout wl = workspace_layout(n);
+    const size_t ng = (n + kGroup - 1) / kGroup;
+    Scratch::ensure(s.d_off, s.off_cap, 8 * (n + 1));
+    Scratch::ensure(s.d_trims, s.trims_cap, n + 4);
+    Scratch::ensure(s.d_ws, s.ws_cap, wl.total);
+    Scratch::ensure(s.d_status, s.status_cap, 4 * n);
+    Scratch::ensure(s.d_boff, s.boff_cap, 8 * (n + 1));
+    // every character is at least one byte: the chunk's bytes bound its boundaries
+    Scratch::ensure(s.d_scores, s.scores_cap, 4 * ch.nbytes + 4);
+    Scratch::ensure(s.d_bounds, s.bounds_cap, ch.nbytes + 4);
+    Scratch::ensure(s.d_tokl, s.tokl_cap, 4 * n);
+    Scratch::ensure(s.d_tokg, s.tokg_cap, 8 * (ng + 1));
+    // surface bytes + at most one '\\' per byte + at most one ' ' per character + one '\n' per line
+    Scratch::ensure(s.d_out, s.out_cap, 3 * ch.nbytes + n + 4);
+    ch.sp.offsets = static_cast<uint64_t*>(s.d_off);
+    ch.sp.trims = static_cast<uint8_t*>(s.d_trims);
+    cuda_check(launch_split_write(ch.sp, st), "launch(split)");
+    BatchArgs a;
+    a.text = ch.sp.text;
+    a.offsets = ch.sp.offsets;
+    a.trims = ch.sp.trims;
+    a.n_sent = n;
+    bind_workspace(a, s.d_ws, n);
+    a.status = static_cast<int32_t*>(s.d_status);
+    a.bound_offsets = static_cast<uint64_t*>(s.d_boff);
+    a.scores = static_cast<int32_t*>(s.d_scores);
+    a.boundaries = static_cast<uint8_t*>(s.d_bounds);
+    cuda_check(launch_count(a, st), "launch(count)");
+    cuda_check(launch_score(p.dm, a, st), "launch(score)");
+    TokArgs t;
+    t.text = a.text;
+    t.offsets = a.offsets;
+    t.trims = a.trims;
+    t.n_sent = n;
+    t.status = a.status;
+    t.n_chars = a.n_chars;
+    t.boundaries = a.boundaries;
+    t.bound_offsets = a.bound_offsets;
+    t.tok_local = static_cast<uint32_t*>(s.d_tokl);
+    t.tok_group = static_cast<uint64_t*>(s.d_tokg);
+    t.out = static_cast<uint8_t*>(s.d_out);
+    cuda_check(launch_tok_count(t, st), "launch(tok)");
+    cuda_check(launch_tok_write(t, st), "launch(tok)");
+    cuda_check(cudaMemcpyAsync(&s.h_totals[3], t.tok_group + ng, 8, cudaMemcpyDeviceToHost, st), "D2H(total)");
+    cuda_check(cudaEventRecord(ch.done, st), "cudaEventRecord");
+}
+
+}  // namespace
+
+int vpt_tokenize_lines(const vpt_predictor* p, const uint8_t* utf8, size_t n_bytes, uint8_t* out, size_t out_capacity,
+                       uint64_t* out_len, uint64_t* n_lines_out) {
+    VPT_API_BEGIN
+    require_device(p);
+    if (out_len) *out_len = 0;
+    if (n_lines_out) *n_lines_out = 0;
+    if (n_bytes && !utf8) throw Error(kInvalidArgument, "InvalidArgumentError: utf8: must not be NULL");
+    if (n_bytes == 0) return kOk;
+    cuda_check(cudaSetDevice(p->device), "cudaSetDevice");
+
+    // cut the buffer into chunks that end after a '\n' (memrchr from the nominal cut; a line longer than a
+    // chunk extends it to the line's end)
+    const size_t target = chunk_bytes();
+    std::vector<LineChunk> chunks;
+    for (size_t lo = 0; lo < n_bytes;) {
+        size_t hi = std::min(n_bytes, lo + target);
+        if (hi < n_bytes) {
+            const void* q = memrchr(utf8 + lo, 0x0A, hi - lo);
+            if (q) hi = size_t(static_cast<const uint8_t*>(q) - utf8) + 1;
+            else {
+                const void* f = memchr(utf8 + hi, 0x0A, n_bytes - hi);
+                hi = f ? size_t(static_cast<const uint8_t*>(f) - utf8) + 1 : n_bytes;
+            }
+        }
+        if (hi - lo > kMaxLineChunk) throw Error(kInvalidArgument, "InvalidArgumentError: utf8: a line is longer than 1 GiB");
+        LineChunk ch;
+        ch.byte_lo = lo;
+        ch.nbytes = hi - lo;
+        chunks.push_back(ch);
+        lo = hi;
+    }
+    const size_t nchunks = chunks.size();
+    constexpr int kDepth = 3;
+    std::unique_ptr<ScratchLease> lease[kDepth];
+    for (int i = 0; i < kDepth && size_t(i) < nchunks; ++i) lease[i].reset(new ScratchLease(*p));
+    struct EventGuard {
+        std::vector<LineChunk>& c;
+        ~EventGuard() { for (auto& x : c) { if (x.split) cudaEventDestroy(x.split); if (x.done) cudaEventDestroy(x.done); } }
+    } guard{chunks};
+
+    // chunk c+2 is copied in and split while chunk c+1 is scored and chunk c is copied out
+    uint64_t total = 0, lines = 0;
+    bool overflow = false;
+    for (size_t c = 0; c < std::min<size_t>(2, nchunks); ++c) lines_stage0(*lease[c % kDepth]->s, chunks[c], utf8);
+    lines_stage1(*p, *lease[0]->s, chunks[0]);
+    for (size_t c = 0; c < nchunks; ++c) {
+        if (c + 2 < nchunks) lines_stage0(*lease[(c + 2) % kDepth]->s, chunks[c + 2], utf8);
+        if (c + 1 < nchunks) lines_stage1(*p, *lease[(c + 1) % kDepth]->s, chunks[c + 1]);
+        Scratch& s = *lease[c % kDepth]->s;
+        cuda_check(cudaEventSynchronize(chunks[c].done), "sync(tokenize)");
+        const uint64_t nb = s.h_totals[3];
+        if (total + nb > out_capacity || (nb && !out)) overflow = true;
+        if (!overflow && nb)
+            cuda_check(cudaMemcpyAsync(out + total, s.d_out, nb, cudaMemcpyDeviceToHost, s.stream), "D2H(text)");
+        total += nb;
+        lines += chunks[c].n_lines;
+    }
+    for (int i = 0; i < kDepth; ++i)
+        if (lease[i]) cuda_check(cudaStreamSynchronize(lease[i]->s->stream), "sync(tokenize)");
+    if (out_len) *out_len = total;
+    if (n_lines_out) *n_lines_out = lines;
+    if (overflow) throw Error(kInvalidArgument, "InvalidArgumentError: out_capacity: too small for the tokenized text");
     return kOk;
     VPT_API_END
 }

@@ -43,6 +43,8 @@ struct DevModel {
 struct BatchArgs {
     const uint8_t* text = nullptr;        // concatenated UTF-8, 16-byte aligned, readable up to a multiple of 16
     const uint64_t* offsets = nullptr;    // [n_sent + 1] byte offsets into text
+    const uint8_t* trims = nullptr;       // nullable [n_sent]: separator bytes at the end of [offsets[i], offsets[i+1])
+                                          // that are not part of sentence i (line terminators, see lines.cu)
     uint64_t n_sent = 0;
     // scratch written by the count pass
     uint32_t* n_chars = nullptr;          // [n_sent]
@@ -72,5 +74,36 @@ cudaError_t launch_scan_only(const BatchArgs& a, cudaStream_t stream);
 cudaError_t launch_score(const DevModel& m, const BatchArgs& a, cudaStream_t stream);
 // number of kernel launches issued by launch_count + launch_score for this model
 int launches_per_batch(const DevModel& m);
+
+// ---- lines.cu: device-side line splitting and tokenised output -------------------------------------
+constexpr int kSplitBlockBytes = 8192;  // bytes of text per CTA of the line splitter
+
+struct SplitArgs {
+    const uint8_t* text = nullptr;   // 16-byte aligned, readable up to a multiple of 16
+    uint64_t n_bytes = 0;
+    uint32_t* blk = nullptr;         // [n_blocks] newline count per block (scratch)
+    uint64_t* blk_base = nullptr;    // [n_blocks] lines before each block (scratch)
+    uint64_t* n_lines = nullptr;     // device scalar: number of lines
+    uint64_t* offsets = nullptr;     // [n_lines + 1] out: line starts (+ n_bytes)
+    uint8_t* trims = nullptr;        // [n_lines] out: terminator bytes of each line (0, 1 or 2)
+};
+cudaError_t launch_split_count(const SplitArgs& s, cudaStream_t stream);  // fills *n_lines (and the scratch)
+cudaError_t launch_split_write(const SplitArgs& s, cudaStream_t stream);  // fills offsets / trims
+
+struct TokArgs {
+    const uint8_t* text = nullptr;          // as BatchArgs (4-byte aligned is enough)
+    const uint64_t* offsets = nullptr;
+    const uint8_t* trims = nullptr;         // nullable
+    uint64_t n_sent = 0;
+    const int32_t* status = nullptr;        // from the count pass
+    const uint32_t* n_chars = nullptr;
+    const uint8_t* boundaries = nullptr;    // 4-byte aligned; from the scoring pass
+    const uint64_t* bound_offsets = nullptr;  // index of a sentence's first boundary in `boundaries`
+    uint32_t* tok_local = nullptr;          // [n_sent] scratch: output offset inside the 64-sentence group
+    uint64_t* tok_group = nullptr;          // [n_groups + 1] scratch; [n_groups] = total output bytes
+    uint8_t* out = nullptr;                 // tokenised lines, each terminated by '\n'
+};
+cudaError_t launch_tok_count(const TokArgs& t, cudaStream_t stream);  // lengths + offsets (tok_local / tok_group)
+cudaError_t launch_tok_write(const TokArgs& t, cudaStream_t stream);
 
 }  // namespace vpt

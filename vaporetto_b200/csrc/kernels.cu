@@ -208,12 +208,14 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_count(BatchArgs a) {
     __shared__ __align__(128) uint8_t s_text[kCountTextCap];
     __shared__ uint64_t s_off[kGroup + 1];
     __shared__ uint32_t s_nout[kGroup], s_nch[kGroup];
+    __shared__ uint8_t s_trim[kGroup];
     __shared__ __align__(8) uint64_t s_bar;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint64_t gbase = uint64_t(blockIdx.x) * kGroup;
     const int ns = int(min(uint64_t(kGroup), a.n_sent - gbase));
     const uint8_t* __restrict__ text = a.text;
     if (threadIdx.x <= ns) s_off[threadIdx.x] = a.offsets[gbase + threadIdx.x];
+    if (threadIdx.x < kGroup) s_trim[threadIdx.x] = (a.trims && threadIdx.x < ns) ? a.trims[gbase + threadIdx.x] : uint8_t(0);
     if (threadIdx.x == 0) mbar_init(&s_bar, 1);
     __syncthreads();
     const uint64_t a0 = s_off[0] & ~15ull;
@@ -235,7 +237,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_count(BatchArgs a) {
             // lanes of a quad beyond the group's last sentence run an empty range (all 32 lanes must reach
             // the shuffles below)
             // 32-bit byte offsets relative to a0 (a group's text is far below 4 GB)
-            const uint32_t b0 = i < ns ? uint32_t(s_off[i] - a0) : 0u, b1 = i < ns ? uint32_t(s_off[i + 1] - a0) : 0u;
+            const uint32_t b0 = i < ns ? uint32_t(s_off[i] - a0) : 0u, b1 = i < ns ? uint32_t(s_off[i + 1] - a0) - s_trim[i] : 0u;
             const uint8_t* __restrict__ gtext = text + a0;
             uint32_t starts = 0, conts = 0, expect = 0, flags = 0;  // flags: 1 NUL, 2 malformed
             for (uint32_t wpos = b0 & ~3u; wpos < b1; wpos += 32) {
@@ -386,7 +388,7 @@ struct SentInfo {
 __device__ __forceinline__ SentInfo sentence_info(const BatchArgs& a, uint64_t s, int lane) {
     SentInfo si;
     si.b0 = a.offsets[s];
-    si.b1 = a.offsets[s + 1];
+    si.b1 = a.offsets[s + 1] - (a.trims ? a.trims[s] : 0);
     si.n = a.n_chars[s];
     si.status = a.status[s];
     si.nout = si.n > 0 ? si.n - 1 : 0;
@@ -719,6 +721,7 @@ struct TileTables {
     int64_t cdelta[kGroup];   // state index of a character = its slot + cdelta[sentence]
     uint32_t nch[kGroup];
     int8_t st[kGroup];
+    uint8_t trim[kGroup];     // separator bytes after sentence k (BatchArgs::trims)
     uint32_t ticket;
     int32_t k1;               // end of the current sentence range
     uint32_t pad[2];
@@ -950,6 +953,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_fast(DevModel m, Batch
             T.nch[tid] = n;
             T.lc[tid] = lc;
             T.st[tid] = int8_t(a.status[s]);
+            T.trim[tid] = a.trims ? a.trims[s] : uint8_t(0);
             T.obase[tid] = ob;
             T.cbase[tid] = cb;
             a.bound_offsets[s] = a.bound_base + ob;
@@ -1019,7 +1023,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_fast(DevModel m, Batch
                     if (a.type_states) for (uint32_t i = lane; i < T.nch[k]; i += 32) a.type_states[T.cbase[k] + i] = kNoPattern;
                     continue;
                 }
-                const uint32_t rb0 = uint32_t(T.off[k] - a0), rb1 = uint32_t(T.off[k + 1] - a0);
+                const uint32_t rb0 = uint32_t(T.off[k] - a0), rb1 = uint32_t(T.off[k + 1] - a0) - T.trim[k];
                 uint32_t idx = uint32_t(gap) + (T.lc[k] - lc0) + uint32_t(gap) * uint32_t(k - k0);
                 for (uint32_t w = rb0 & ~3u; w < rb1; w += 128) {
                     const uint32_t addr = w + 4u * uint32_t(lane);
