@@ -372,6 +372,41 @@ def main():
     if world > 1:
         dist.all_reduce(tnb, op=dist.ReduceOp.MAX)
     e2e_nb_value = total_bytes * args.e2e_steps / float(tnb.item()) / 1e6
+    # the reference CLI loop on the device (vpt_tokenize_lines): raw lines in, space-separated tokens out; line
+    # splitting and output materialisation run on the GPU, so no offsets / scores cross PCIe
+    starts = offs[:-1].astype(np.int64) + np.arange(n, dtype=np.int64)
+    lines_np = np.full(nbytes + n, 10, np.uint8)
+    keep = np.ones(nbytes + n, bool)
+    keep[starts[1:] - 1] = False
+    keep[-1] = False
+    lines_np[keep] = text[:nbytes]
+    h_lines = torch.from_numpy(lines_np).pin_memory()
+    h_tok = torch.empty(3 * (nbytes + n), dtype=torch.uint8).pin_memory()
+    tok_len, tok_lines = C.c_uint64(), C.c_uint64()
+
+    def step_lines():
+        rc = L.vpt_tokenize_lines(pred._h, h_lines.data_ptr(), nbytes + n, h_tok.data_ptr(), h_tok.numel(),
+                                  C.byref(tok_len), C.byref(tok_lines))
+        if rc:
+            raise RuntimeError(L.vpt_last_error().decode())
+
+    step_lines()
+    step_lines()
+    assert tok_lines.value == n
+    # spaces in the output = word boundaries + escaped spaces of the input (the synthetic text has no '/' or '\\')
+    tok_np = h_tok.numpy()[: tok_len.value]
+    n_wb = int(np.count_nonzero(h_bounds.numpy() == 1))
+    assert tok_len.value == nbytes + n + n_wb + int(np.count_nonzero(text[:nbytes] == 0x20)), "tokenize_lines size"
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        step_lines()
+    torch.cuda.synchronize()
+    tl = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tl, op=dist.ReduceOp.MAX)
+    e2e_lines_value = total_bytes * args.e2e_steps / float(tl.item()) / 1e6
+    lines_d2h = int(tok_len.value)
     h2d = nbytes + 8 * (n + 1)
     d2h = 4 * n_bound + n_bound + 8 * (n + 1) + 4 * n + 16 + (8 * n_chars_total + 8 * (n + 1) if want_states else 0)
 
@@ -407,7 +442,11 @@ def main():
                          "whole_step_frac": round(alg_bytes / (ms_all / args.steps / 1e3) / 1e9 / peak, 4)},
             "e2e": {"value": round(e2e_value, 1), "unit": "MB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": args.e2e_steps, "api": "vpt_predict_batch (pinned host buffers; scores+boundaries returned)",
-                    "boundaries_only_value": round(e2e_nb_value, 1)},
+                    "boundaries_only_value": round(e2e_nb_value, 1),
+                    "tokenize_lines": {"value": round(e2e_lines_value, 1), "unit": "MB/s",
+                                       "api": "vpt_tokenize_lines (raw lines in, tokenised text out; split + "
+                                              "materialisation on the device)",
+                                       "h2d_bytes_per_step": nbytes + n, "d2h_bytes_per_step": lines_d2h}},
             "gpu_launches": args.steps * pred.info["kernel_launches_per_batch"],
             "clocks": clocks,
             "bit_exact_checked": True,

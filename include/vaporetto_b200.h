@@ -197,7 +197,7 @@ int vpt_write_tokenized_text(const vpt_predictor* predictor, const uint8_t* utf8
  * UTF-8 (the CLI stops with an I/O error on those).  Tags are not predicted on this path.
  * `out` receives the output lines, each terminated by '\n' (at most 3 * n_bytes + n_lines bytes); *out_len
  * the number of bytes produced (also when `out_capacity` was too small, which returns InvalidArgument);
- * *n_lines the number of input lines.  Chunk size of the internal pipeline: env VPT_CHUNK_BYTES (8 MiB). */
+ * *n_lines the number of input lines.  Chunk size of the internal pipeline: env VPT_CHUNK_BYTES (16 MiB, with smaller chunks at both ends). */
 int vpt_tokenize_lines(const vpt_predictor* predictor, const uint8_t* utf8, size_t n_bytes, uint8_t* out,
                        size_t out_capacity, uint64_t* out_len, uint64_t* n_lines);
 

@@ -3,6 +3,7 @@
 #include "../../include/vaporetto_b200.h"
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
@@ -34,7 +35,10 @@ void cuda_check(cudaError_t e, const char* what) {
 
 // Per-call scratch: a stream plus grow-only device buffers.
 struct Scratch {
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;      // copy-in + kernels
+    cudaStream_t stream_out = nullptr;  // copy-out: a chunk's D2H never delays the next chunk's H2D on `stream`
+    cudaEvent_t ev_kernels = nullptr;   // recorded on `stream` after a chunk's last kernel
+    cudaEvent_t ev_out = nullptr;       // recorded on `stream_out` after a chunk's last D2H copy
     void* d_text = nullptr; size_t text_cap = 0;
     void* d_off = nullptr; size_t off_cap = 0;
     void* d_ws = nullptr; size_t ws_cap = 0;
@@ -49,15 +53,17 @@ struct Scratch {
     void* d_trims = nullptr; size_t trims_cap = 0;
     void* d_blk = nullptr; size_t blk_cap = 0;
     void* d_blkbase = nullptr; size_t blkbase_cap = 0;
-    void* d_tokl = nullptr; size_t tokl_cap = 0;
     void* d_tokg = nullptr; size_t tokg_cap = 0;
     void* d_out = nullptr; size_t out_cap = 0;
     uint64_t* h_totals = nullptr;  // pinned, 4 x u64: boundaries, chars, lines, output bytes
     ~Scratch() {
         for (void* p : {d_text, d_off, d_ws, d_status, d_boff, d_coff, d_scores, d_bounds, d_cst, d_tst, d_trims, d_blk,
-                        d_blkbase, d_tokl, d_tokg, d_out})
+                        d_blkbase, d_tokg, d_out})
             if (p) cudaFree(p);
         if (h_totals) cudaFreeHost(h_totals);
+        if (ev_kernels) cudaEventDestroy(ev_kernels);
+        if (ev_out) cudaEventDestroy(ev_out);
+        if (stream_out) cudaStreamDestroy(stream_out);
         if (stream) cudaStreamDestroy(stream);
     }
     static void ensure(void*& p, size_t& cap, size_t need) {
@@ -166,6 +172,9 @@ struct ScratchLease {
         if (!s) {
             s.reset(new Scratch());
             cuda_check(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking), "cudaStreamCreate");
+            cuda_check(cudaStreamCreateWithFlags(&s->stream_out, cudaStreamNonBlocking), "cudaStreamCreate");
+            cuda_check(cudaEventCreateWithFlags(&s->ev_kernels, cudaEventDisableTiming), "cudaEventCreate");
+            cuda_check(cudaEventCreateWithFlags(&s->ev_out, cudaEventDisableTiming), "cudaEventCreate");
             cuda_check(cudaMallocHost(reinterpret_cast<void**>(&s->h_totals), 32), "cudaMallocHost");
         }
     }
@@ -477,10 +486,70 @@ size_t chunk_sentences() {
     return v;
 }
 
+// Chunk sizes of a copy/compute/copy pipeline over `total` units: small chunks first (the first copy-in and
+// kernels are not overlapped with anything) growing by doubling to `big`, equal chunks of at most `big` in the
+// middle, halving again to `small_down` at the end (the last copy-out is not overlapped either).
+std::vector<size_t> ramp_schedule(size_t total, size_t big, size_t small_up, size_t small_down) {
+    std::vector<size_t> up, down, out;
+    size_t sum = 0;
+    for (size_t v = std::max<size_t>(small_up, 1); v < big; v *= 2) { up.push_back(v); sum += v; }
+    for (size_t v = std::max<size_t>(small_down, 1); v < big; v *= 2) { down.push_back(v); sum += v; }
+    if (total <= sum + big) {
+        // too small for the full ramps: equal chunks of about a quarter
+        const size_t c = std::max<size_t>(std::min(big, (total + 3) / 4), std::min(small_up, big));
+        for (size_t lo = 0; lo < total; lo += c) out.push_back(std::min(c, total - lo));
+        return out;
+    }
+    const size_t middle = total - sum;
+    const size_t nmid = (middle + big - 1) / big;
+    out = up;
+    for (size_t i = 0; i < nmid; ++i) out.push_back(middle / nmid + (i < middle % nmid ? 1 : 0));
+    out.insert(out.end(), down.rbegin(), down.rend());
+    return out;
+}
+
+// Pipeline trace (env VPT_TRACE=1): per chunk, CUDA-event times of copy-in end, kernels start / end and copy-out
+// end are printed to stderr when the call returns.
+bool pipeline_trace() {
+    const char* e = getenv("VPT_TRACE");
+    return e && *e == '1';
+}
+struct TraceEvents {
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t sub[4] = {nullptr, nullptr, nullptr, nullptr};  // optional marks between the kernels of a chunk
+    void mark_sub(int i, cudaStream_t st) {
+        if (!sub[i]) cuda_check(cudaEventCreate(&sub[i]), "cudaEventCreate");
+        cuda_check(cudaEventRecord(sub[i], st), "cudaEventRecord");
+    }
+    void mark(int i, cudaStream_t st) {
+        if (!ev[i]) cuda_check(cudaEventCreate(&ev[i]), "cudaEventCreate");
+        cuda_check(cudaEventRecord(ev[i], st), "cudaEventRecord");
+    }
+    void destroy() {
+        for (cudaEvent_t& e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
+        for (cudaEvent_t& e : sub) if (e) { cudaEventDestroy(e); e = nullptr; }
+    }
+    void print(const char* what, size_t c, unsigned long long units, const TraceEvents& first) const {
+        float t[4] = {0, 0, 0, 0};
+        for (int i = 0; i < 4; ++i)
+            if (ev[i] && first.ev[0]) cudaEventElapsedTime(&t[i], first.ev[0], ev[i]);
+        fprintf(stderr, "[vpt %s] chunk %zu (%llu): copy-in end %.3f  kernels %.3f..%.3f  copy-out end %.3f ms", what, c,
+                units, t[0], t[1], t[2], t[3]);
+        for (int i = 0; i < 4; ++i)
+            if (sub[i] && first.ev[0]) {
+                float x = 0;
+                cudaEventElapsedTime(&x, first.ev[0], sub[i]);
+                fprintf(stderr, "%s%.3f", i ? " " : "  marks ", x);
+            }
+        fprintf(stderr, "\n");
+    }
+};
+
 struct ChunkState {
     size_t s_lo = 0, n = 0;       // sentence range
     uint64_t byte_lo = 0, nbytes = 0;
     cudaEvent_t counted = nullptr;
+    TraceEvents tr;
     BatchArgs a;
 };
 
@@ -499,6 +568,9 @@ void chunk_count(Scratch& s, ChunkState& ch, const uint8_t* utf8, const uint64_t
         cuda_check(cudaMemcpyAsync(static_cast<uint8_t*>(s.d_text) + shift, utf8 + ch.byte_lo, ch.nbytes,
                                    cudaMemcpyHostToDevice, st), "H2D(text)");
     cuda_check(cudaMemcpyAsync(s.d_off, byte_offsets + ch.s_lo, 8 * (ch.n + 1), cudaMemcpyHostToDevice, st), "H2D(offsets)");
+    // the kernels overwrite buffers the previous chunk of this scratch may still be copying out
+    cuda_check(cudaStreamWaitEvent(st, s.ev_out, 0), "cudaStreamWaitEvent");
+    if (pipeline_trace()) ch.tr.mark(0, st);
     BatchArgs& a = ch.a;
     a = BatchArgs();
     // offsets are absolute in the caller's buffer: bias the text pointer so that text[offset] is right
@@ -541,19 +613,20 @@ int vpt_predict_batch(const vpt_predictor* p, const uint8_t* utf8, const uint64_
     // kernels of chunk c+1 and the D2H copy of chunk c overlap.  Each chunk is an independent batch on the
     // device; its output offsets are rebased with the running totals (known on the host after its count pass).
     const size_t kChunkSentences = chunk_sentences();
-    const size_t nchunks = (n_sent + kChunkSentences - 1) / kChunkSentences;
-    constexpr int kDepth = 3;
+    const std::vector<size_t> sizes = ramp_schedule(n_sent, kChunkSentences, kChunkSentences / 8, kChunkSentences / 4);
+    const size_t nchunks = sizes.size();
+    constexpr int kDepth = 4;
     std::unique_ptr<ScratchLease> lease[kDepth];
     for (int i = 0; i < kDepth && size_t(i) < nchunks; ++i) lease[i].reset(new ScratchLease(*p));
     std::vector<ChunkState> chunks(nchunks);
     struct EventGuard {
         std::vector<ChunkState>& c;
-        ~EventGuard() { for (auto& x : c) if (x.counted) cudaEventDestroy(x.counted); }
+        ~EventGuard() { for (auto& x : c) { if (x.counted) cudaEventDestroy(x.counted); x.tr.destroy(); } }
     } guard{chunks};
-    for (size_t c = 0; c < nchunks; ++c) {
+    for (size_t c = 0, lo = 0; c < nchunks; lo += sizes[c], ++c) {
         ChunkState& ch = chunks[c];
-        ch.s_lo = c * kChunkSentences;
-        ch.n = std::min(kChunkSentences, n_sent - ch.s_lo);
+        ch.s_lo = lo;
+        ch.n = sizes[c];
         ch.byte_lo = byte_offsets[ch.s_lo];
         if (byte_offsets[ch.s_lo + ch.n] < ch.byte_lo)
             throw Error(kInvalidArgument, "InvalidArgumentError: byte_offsets: must be non-decreasing");
@@ -562,7 +635,8 @@ int vpt_predict_batch(const vpt_predictor* p, const uint8_t* utf8, const uint64_
     const bool want_states = char_states_out || type_states_out;
     uint64_t nb_total = 0, nc_total = 0;
     bool overflow = false;
-    for (size_t c = 0; c < std::min<size_t>(2, nchunks); ++c) chunk_count(*lease[c % kDepth]->s, chunks[c], utf8, byte_offsets);
+    constexpr size_t kAhead = kDepth - 1;  // chunks whose copy-in + count pass are issued ahead of the scoring
+    for (size_t c = 0; c < std::min<size_t>(kAhead, nchunks); ++c) chunk_count(*lease[c % kDepth]->s, chunks[c], utf8, byte_offsets);
     for (size_t c = 0; c < nchunks; ++c) {
         ChunkState& ch = chunks[c];
         Scratch& s = *lease[c % kDepth]->s;
@@ -573,34 +647,49 @@ int vpt_predict_batch(const vpt_predictor* p, const uint8_t* utf8, const uint64_
             overflow = true;
         if (!overflow) {
             BatchArgs& a = ch.a;
-            Scratch::ensure(s.d_scores, s.scores_cap, 4 * nb + 4);
             Scratch::ensure(s.d_bounds, s.bounds_cap, nb + 4);
-            a.scores = static_cast<int32_t*>(s.d_scores);
+            a.scores = nullptr;  // boundaries only, when the caller wants no scores and the kernel can skip them
+            if (scores_out || !scores_optional(p->dm)) {
+                Scratch::ensure(s.d_scores, s.scores_cap, 4 * nb + 4);
+                a.scores = static_cast<int32_t*>(s.d_scores);
+            }
             a.boundaries = static_cast<uint8_t*>(s.d_bounds);
             if (char_states_out) { Scratch::ensure(s.d_cst, s.cst_cap, 4 * nc + 4); a.char_states = static_cast<uint32_t*>(s.d_cst); }
             if (type_states_out) { Scratch::ensure(s.d_tst, s.tst_cap, 4 * nc + 4); a.type_states = static_cast<uint32_t*>(s.d_tst); }
             a.bound_base = nb_total;
             a.char_base = nc_total;
+            if (pipeline_trace()) ch.tr.mark(1, st);
             cuda_check(launch_score(p->dm, a, st), "launch(score)");
+            if (pipeline_trace()) ch.tr.mark(2, st);
+            cuda_check(cudaEventRecord(s.ev_kernels, st), "cudaEventRecord");
+            cudaStream_t so = s.stream_out;
+            cuda_check(cudaStreamWaitEvent(so, s.ev_kernels, 0), "cudaStreamWaitEvent");
             if (nb) {
-                if (scores_out) cuda_check(cudaMemcpyAsync(scores_out + nb_total, s.d_scores, 4 * nb, cudaMemcpyDeviceToHost, st), "D2H(scores)");
-                cuda_check(cudaMemcpyAsync(boundaries_out + nb_total, s.d_bounds, nb, cudaMemcpyDeviceToHost, st), "D2H(boundaries)");
+                if (scores_out) cuda_check(cudaMemcpyAsync(scores_out + nb_total, s.d_scores, 4 * nb, cudaMemcpyDeviceToHost, so), "D2H(scores)");
+                cuda_check(cudaMemcpyAsync(boundaries_out + nb_total, s.d_bounds, nb, cudaMemcpyDeviceToHost, so), "D2H(boundaries)");
             }
             // the last element of a chunk's offsets is the first of the next chunk's: copy n (+1 for the last chunk)
             const size_t noff = ch.n + (c + 1 == nchunks ? 1 : 0);
-            cuda_check(cudaMemcpyAsync(bound_offsets_out + ch.s_lo, s.d_boff, 8 * noff, cudaMemcpyDeviceToHost, st), "D2H(offsets)");
+            cuda_check(cudaMemcpyAsync(bound_offsets_out + ch.s_lo, s.d_boff, 8 * noff, cudaMemcpyDeviceToHost, so), "D2H(offsets)");
             if (char_offsets_out)
-                cuda_check(cudaMemcpyAsync(char_offsets_out + ch.s_lo, s.d_coff, 8 * noff, cudaMemcpyDeviceToHost, st), "D2H(offsets)");
-            if (status_out) cuda_check(cudaMemcpyAsync(status_out + ch.s_lo, s.d_status, 4 * ch.n, cudaMemcpyDeviceToHost, st), "D2H(status)");
-            if (nc && char_states_out) cuda_check(cudaMemcpyAsync(char_states_out + nc_total, s.d_cst, 4 * nc, cudaMemcpyDeviceToHost, st), "D2H(states)");
-            if (nc && type_states_out) cuda_check(cudaMemcpyAsync(type_states_out + nc_total, s.d_tst, 4 * nc, cudaMemcpyDeviceToHost, st), "D2H(states)");
+                cuda_check(cudaMemcpyAsync(char_offsets_out + ch.s_lo, s.d_coff, 8 * noff, cudaMemcpyDeviceToHost, so), "D2H(offsets)");
+            if (status_out) cuda_check(cudaMemcpyAsync(status_out + ch.s_lo, s.d_status, 4 * ch.n, cudaMemcpyDeviceToHost, so), "D2H(status)");
+            if (nc && char_states_out) cuda_check(cudaMemcpyAsync(char_states_out + nc_total, s.d_cst, 4 * nc, cudaMemcpyDeviceToHost, so), "D2H(states)");
+            if (nc && type_states_out) cuda_check(cudaMemcpyAsync(type_states_out + nc_total, s.d_tst, 4 * nc, cudaMemcpyDeviceToHost, so), "D2H(states)");
+            cuda_check(cudaEventRecord(s.ev_out, so), "cudaEventRecord");
+            if (pipeline_trace()) ch.tr.mark(3, so);
         }
         nb_total += nb;
         nc_total += nc;
-        if (c + 2 < nchunks) chunk_count(*lease[(c + 2) % kDepth]->s, chunks[c + 2], utf8, byte_offsets);
+        if (c + kAhead < nchunks) chunk_count(*lease[(c + kAhead) % kDepth]->s, chunks[c + kAhead], utf8, byte_offsets);
     }
     for (int i = 0; i < kDepth; ++i)
-        if (lease[i]) cuda_check(cudaStreamSynchronize(lease[i]->s->stream), "sync(score)");
+        if (lease[i]) {
+            cuda_check(cudaStreamSynchronize(lease[i]->s->stream), "sync(score)");
+            cuda_check(cudaStreamSynchronize(lease[i]->s->stream_out), "sync(copy-out)");
+        }
+    if (pipeline_trace())
+        for (size_t c = 0; c < nchunks; ++c) chunks[c].tr.print("batch", c, chunks[c].n, chunks[0].tr);
     if (n_boundaries_out) *n_boundaries_out = nb_total;
     if (n_chars_out) *n_chars_out = nc_total;
     if (overflow) throw Error(kInvalidArgument, "InvalidArgumentError: out_capacity/states_capacity: too small for the batch");
@@ -614,7 +703,7 @@ namespace {
 size_t chunk_bytes() {
     const char* e = getenv("VPT_CHUNK_BYTES");
     const long long x = e ? atoll(e) : 0;
-    return x >= 64 ? size_t(x) : size_t(8) << 20;
+    return x >= 64 ? size_t(x) : size_t(16) << 20;
 }
 
 constexpr uint64_t kMaxLineChunk = uint64_t(1) << 30;  // 32-bit group-local output offsets (3 bytes out per byte in)
@@ -623,6 +712,7 @@ struct LineChunk {
     uint64_t byte_lo = 0, nbytes = 0;
     uint64_t n_lines = 0;
     cudaEvent_t split = nullptr, done = nullptr;
+    TraceEvents tr;
     SplitArgs sp;
 };
 
@@ -634,6 +724,7 @@ void lines_stage0(Scratch& s, LineChunk& ch, const uint8_t* utf8) {
     Scratch::ensure(s.d_blk, s.blk_cap, 4 * nblk + 4);
     Scratch::ensure(s.d_blkbase, s.blkbase_cap, 8 * nblk + 16);
     cuda_check(cudaMemcpyAsync(s.d_text, utf8 + ch.byte_lo, ch.nbytes, cudaMemcpyHostToDevice, st), "H2D(text)");
+    if (pipeline_trace()) ch.tr.mark(0, st);
     SplitArgs& sp = ch.sp;
     sp = SplitArgs();
     sp.text = static_cast<const uint8_t*>(s.d_text);
@@ -663,15 +754,15 @@ void lines_stage1(const vpt_predictor& p, Scratch& s, LineChunk& ch) {
     Scratch::ensure(s.d_ws, s.ws_cap, wl.total);
     Scratch::ensure(s.d_status, s.status_cap, 4 * n);
     Scratch::ensure(s.d_boff, s.boff_cap, 8 * (n + 1));
-    // every character is at least one byte: the chunk's bytes bound its boundaries
-    Scratch::ensure(s.d_scores, s.scores_cap, 4 * ch.nbytes + 4);
     Scratch::ensure(s.d_bounds, s.bounds_cap, ch.nbytes + 4);
-    Scratch::ensure(s.d_tokl, s.tokl_cap, 4 * n);
-    Scratch::ensure(s.d_tokg, s.tokg_cap, 8 * (ng + 1));
+    Scratch::ensure(s.d_tokg, s.tokg_cap, 8 * (ng + 2));
     // surface bytes + at most one '\\' per byte + at most one ' ' per character + one '\n' per line
     Scratch::ensure(s.d_out, s.out_cap, 3 * ch.nbytes + n + 4);
     ch.sp.offsets = static_cast<uint64_t*>(s.d_off);
     ch.sp.trims = static_cast<uint8_t*>(s.d_trims);
+    // the kernels overwrite d_out, which the previous chunk of this scratch may still be copying out
+    cuda_check(cudaStreamWaitEvent(st, s.ev_out, 0), "cudaStreamWaitEvent");
+    if (pipeline_trace()) ch.tr.mark(1, st);
     cuda_check(launch_split_write(ch.sp, st), "launch(split)");
     BatchArgs a;
     a.text = ch.sp.text;
@@ -681,10 +772,19 @@ void lines_stage1(const vpt_predictor& p, Scratch& s, LineChunk& ch) {
     bind_workspace(a, s.d_ws, n);
     a.status = static_cast<int32_t*>(s.d_status);
     a.bound_offsets = static_cast<uint64_t*>(s.d_boff);
-    a.scores = static_cast<int32_t*>(s.d_scores);
+    // the tokenised text needs the boundaries only (every character is at least one byte: the chunk's bytes
+    // bound its boundaries)
+    a.scores = nullptr;
+    if (!scores_optional(p.dm)) {
+        Scratch::ensure(s.d_scores, s.scores_cap, 4 * ch.nbytes + 4);
+        a.scores = static_cast<int32_t*>(s.d_scores);
+    }
     a.boundaries = static_cast<uint8_t*>(s.d_bounds);
+    if (pipeline_trace()) ch.tr.mark_sub(0, st);  // after the line offsets
     cuda_check(launch_count(a, st), "launch(count)");
+    if (pipeline_trace()) ch.tr.mark_sub(1, st);  // after count + scan
     cuda_check(launch_score(p.dm, a, st), "launch(score)");
+    if (pipeline_trace()) ch.tr.mark_sub(2, st);  // after the scoring kernel
     TokArgs t;
     t.text = a.text;
     t.offsets = a.offsets;
@@ -694,12 +794,13 @@ void lines_stage1(const vpt_predictor& p, Scratch& s, LineChunk& ch) {
     t.n_chars = a.n_chars;
     t.boundaries = a.boundaries;
     t.bound_offsets = a.bound_offsets;
-    t.tok_local = static_cast<uint32_t*>(s.d_tokl);
-    t.tok_group = static_cast<uint64_t*>(s.d_tokg);
+    t.tok_state = static_cast<uint64_t*>(s.d_tokg);
+    t.ticket = reinterpret_cast<uint32_t*>(t.tok_state + ng);
+    t.total = t.tok_state + ng + 1;
     t.out = static_cast<uint8_t*>(s.d_out);
-    cuda_check(launch_tok_count(t, st), "launch(tok)");
-    cuda_check(launch_tok_write(t, st), "launch(tok)");
-    cuda_check(cudaMemcpyAsync(&s.h_totals[3], t.tok_group + ng, 8, cudaMemcpyDeviceToHost, st), "D2H(total)");
+    cuda_check(launch_tokenize(t, st), "launch(tok)");
+    if (pipeline_trace()) ch.tr.mark(2, st);
+    cuda_check(cudaMemcpyAsync(&s.h_totals[3], t.total, 8, cudaMemcpyDeviceToHost, st), "D2H(total)");
     cuda_check(cudaEventRecord(ch.done, st), "cudaEventRecord");
 }
 
@@ -717,10 +818,14 @@ int vpt_tokenize_lines(const vpt_predictor* p, const uint8_t* utf8, size_t n_byt
 
     // cut the buffer into chunks that end after a '\n' (memrchr from the nominal cut; a line longer than a
     // chunk extends it to the line's end)
-    const size_t target = chunk_bytes();
+    const size_t big = chunk_bytes();
+    const std::vector<size_t> sizes = ramp_schedule(n_bytes, big, big / 8, big / 8);
     std::vector<LineChunk> chunks;
+    size_t cum = 0, k = 0;
     for (size_t lo = 0; lo < n_bytes;) {
-        size_t hi = std::min(n_bytes, lo + target);
+        // every chunk ends at the next nominal cut of the schedule (a line that ran past cuts skips them)
+        do { cum = k < sizes.size() ? cum + sizes[k++] : n_bytes; } while (cum <= lo);
+        size_t hi = std::min(n_bytes, cum);
         if (hi < n_bytes) {
             const void* q = memrchr(utf8 + lo, 0x0A, hi - lo);
             if (q) hi = size_t(static_cast<const uint8_t*>(q) - utf8) + 1;
@@ -737,33 +842,47 @@ int vpt_tokenize_lines(const vpt_predictor* p, const uint8_t* utf8, size_t n_byt
         lo = hi;
     }
     const size_t nchunks = chunks.size();
-    constexpr int kDepth = 3;
+    constexpr int kDepth = 4;
     std::unique_ptr<ScratchLease> lease[kDepth];
     for (int i = 0; i < kDepth && size_t(i) < nchunks; ++i) lease[i].reset(new ScratchLease(*p));
     struct EventGuard {
         std::vector<LineChunk>& c;
-        ~EventGuard() { for (auto& x : c) { if (x.split) cudaEventDestroy(x.split); if (x.done) cudaEventDestroy(x.done); } }
+        ~EventGuard() {
+            for (auto& x : c) {
+                if (x.split) cudaEventDestroy(x.split);
+                if (x.done) cudaEventDestroy(x.done);
+                x.tr.destroy();
+            }
+        }
     } guard{chunks};
 
-    // chunk c+2 is copied in and split while chunk c+1 is scored and chunk c is copied out
+    // chunks c+2, c+3 are copied in and split while chunk c+1 is scored and chunk c is copied out
     uint64_t total = 0, lines = 0;
     bool overflow = false;
-    for (size_t c = 0; c < std::min<size_t>(2, nchunks); ++c) lines_stage0(*lease[c % kDepth]->s, chunks[c], utf8);
+    for (size_t c = 0; c < std::min<size_t>(3, nchunks); ++c) lines_stage0(*lease[c % kDepth]->s, chunks[c], utf8);
     lines_stage1(*p, *lease[0]->s, chunks[0]);
     for (size_t c = 0; c < nchunks; ++c) {
-        if (c + 2 < nchunks) lines_stage0(*lease[(c + 2) % kDepth]->s, chunks[c + 2], utf8);
+        if (c + 3 < nchunks) lines_stage0(*lease[(c + 3) % kDepth]->s, chunks[c + 3], utf8);
         if (c + 1 < nchunks) lines_stage1(*p, *lease[(c + 1) % kDepth]->s, chunks[c + 1]);
         Scratch& s = *lease[c % kDepth]->s;
         cuda_check(cudaEventSynchronize(chunks[c].done), "sync(tokenize)");
         const uint64_t nb = s.h_totals[3];
         if (total + nb > out_capacity || (nb && !out)) overflow = true;
-        if (!overflow && nb)
-            cuda_check(cudaMemcpyAsync(out + total, s.d_out, nb, cudaMemcpyDeviceToHost, s.stream), "D2H(text)");
+        if (!overflow && nb) {
+            cuda_check(cudaMemcpyAsync(out + total, s.d_out, nb, cudaMemcpyDeviceToHost, s.stream_out), "D2H(text)");
+            cuda_check(cudaEventRecord(s.ev_out, s.stream_out), "cudaEventRecord");
+        }
+        if (pipeline_trace()) chunks[c].tr.mark(3, s.stream_out);
         total += nb;
         lines += chunks[c].n_lines;
     }
     for (int i = 0; i < kDepth; ++i)
-        if (lease[i]) cuda_check(cudaStreamSynchronize(lease[i]->s->stream), "sync(tokenize)");
+        if (lease[i]) {
+            cuda_check(cudaStreamSynchronize(lease[i]->s->stream), "sync(tokenize)");
+            cuda_check(cudaStreamSynchronize(lease[i]->s->stream_out), "sync(copy-out)");
+        }
+    if (pipeline_trace())
+        for (size_t c = 0; c < nchunks; ++c) chunks[c].tr.print("lines", c, chunks[c].nbytes, chunks[0].tr);
     if (out_len) *out_len = total;
     if (n_lines_out) *n_lines_out = lines;
     if (overflow) throw Error(kInvalidArgument, "InvalidArgumentError: out_capacity: too small for the tokenized text");

@@ -55,7 +55,7 @@ struct BatchArgs {
     uint64_t* group_char = nullptr;       // [n_groups + 1]
     uint32_t* ticket = nullptr;           // work counter of the persistent tile kernel (zeroed by the scan)
     // outputs
-    int32_t* scores = nullptr;            // [sum(max(chars_i - 1, 0))]
+    int32_t* scores = nullptr;            // [sum(max(chars_i - 1, 0))] (nullable: boundaries only)
     uint8_t* boundaries = nullptr;        // same length
     uint64_t* bound_offsets = nullptr;    // [n_sent + 1]; values are chunk-local offsets + bound_base
     uint64_t bound_base = 0;              // added to the bound_offsets / char_offsets written out
@@ -74,6 +74,8 @@ cudaError_t launch_scan_only(const BatchArgs& a, cudaStream_t stream);
 cudaError_t launch_score(const DevModel& m, const BatchArgs& a, cudaStream_t stream);
 // number of kernel launches issued by launch_count + launch_score for this model
 int launches_per_batch(const DevModel& m);
+// true when launch_score accepts BatchArgs::scores == nullptr (boundaries only) for this model
+bool scores_optional(const DevModel& m);
 
 // ---- lines.cu: device-side line splitting and tokenised output -------------------------------------
 constexpr int kSplitBlockBytes = 8192;  // bytes of text per CTA of the line splitter
@@ -99,11 +101,12 @@ struct TokArgs {
     const uint32_t* n_chars = nullptr;
     const uint8_t* boundaries = nullptr;    // 4-byte aligned; from the scoring pass
     const uint64_t* bound_offsets = nullptr;  // index of a sentence's first boundary in `boundaries`
-    uint32_t* tok_local = nullptr;          // [n_sent] scratch: output offset inside the 64-sentence group
-    uint64_t* tok_group = nullptr;          // [n_groups + 1] scratch; [n_groups] = total output bytes
+    uint64_t* tok_state = nullptr;          // [n_groups] scratch: look-back state of every 64-sentence group
+    uint32_t* ticket = nullptr;             // scratch: group ticket (the 8 bytes after tok_state)
+    uint64_t* total = nullptr;              // device scalar out: total output bytes
     uint8_t* out = nullptr;                 // tokenised lines, each terminated by '\n'
 };
-cudaError_t launch_tok_count(const TokArgs& t, cudaStream_t stream);  // lengths + offsets (tok_local / tok_group)
-cudaError_t launch_tok_write(const TokArgs& t, cudaStream_t stream);
+// zeroes tok_state[0 .. n_groups] (ticket included), then one pass: lengths, offsets (look-back), output bytes
+cudaError_t launch_tokenize(const TokArgs& t, cudaStream_t stream);
 
 }  // namespace vpt

@@ -468,7 +468,7 @@ __device__ __forceinline__ void fast_sentence_warp(const DevModel& m, const Batc
     const uint8_t* __restrict__ text = a.text;
     const uint32_t n = si.n;
     if (si.status != 0) {
-        for (uint32_t i = lane; i < si.nout; i += 32) { a.scores[si.obase + i] = 0; a.boundaries[si.obase + i] = 0; }
+        for (uint32_t i = lane; i < si.nout; i += 32) { if (a.scores) a.scores[si.obase + i] = 0; a.boundaries[si.obase + i] = 0; }
         if (a.char_states) for (uint32_t i = lane; i < n; i += 32) a.char_states[si.cbase + i] = kNoPattern;
         if (a.type_states) for (uint32_t i = lane; i < n; i += 32) a.type_states[si.cbase + i] = kNoPattern;
         return;
@@ -518,7 +518,7 @@ __device__ __forceinline__ void fast_sentence_warp(const DevModel& m, const Batc
         mainv += m.bias + tsc + carry_r;
         if (have_prev && prev_g + 1 < n) {
             const int32_t fin = prev_main + to_prev;
-            a.scores[si.obase + prev_g] = fin;
+            if (a.scores) a.scores[si.obase + prev_g] = fin;
             a.boundaries[si.obase + prev_g] = fin > 0 ? 1 : 0;
         }
         if (a.char_states && active) a.char_states[si.cbase + g] = cstate;
@@ -537,7 +537,7 @@ __device__ __forceinline__ void fast_sentence_warp(const DevModel& m, const Batc
         __syncwarp();
     }
     if (have_prev && prev_g + 1 < n) {
-        a.scores[si.obase + prev_g] = prev_main;
+        if (a.scores) a.scores[si.obase + prev_g] = prev_main;
         a.boundaries[si.obase + prev_g] = prev_main > 0 ? 1 : 0;
     }
     if (m.ct.present && m.ct.has_overflow) {
@@ -620,7 +620,7 @@ __device__ __forceinline__ void general_sentence_warp(const DevModel& m, const B
     uint32_t* cstates = a.char_states;
     uint32_t* tstates = a.type_states;
     if (si.status != 0) {
-        for (uint32_t i = lane; i < si.nout; i += 32) { a.scores[si.obase + i] = 0; a.boundaries[si.obase + i] = 0; }
+        for (uint32_t i = lane; i < si.nout; i += 32) { if (a.scores) a.scores[si.obase + i] = 0; a.boundaries[si.obase + i] = 0; }
         if (cstates) for (uint32_t i = lane; i < n; i += 32) cstates[si.cbase + i] = kNoPattern;
         if (tstates) for (uint32_t i = lane; i < n; i += 32) tstates[si.cbase + i] = kNoPattern;
         return;
@@ -641,7 +641,7 @@ __device__ __forceinline__ void general_sentence_warp(const DevModel& m, const B
             if (g + 1 < n) {
                 int32_t v = m.bias;
                 if (tw > 0) v += __ldg(m.type_cache + type_index(r, int64_t(g), n, tw));
-                a.scores[si.obase + g] = v;
+                if (a.scores) a.scores[si.obase + g] = v;
             }
             if (g < n) {
                 if (cstates) cstates[si.cbase + g] = kNoPattern;
@@ -1018,7 +1018,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_fast(DevModel m, Batch
             for (int k = k0 + warp; k < k1; k += kSubThreads / 32) {
                 if (T.st[k] != 0) {
                     const uint32_t nout = T.nch[k] > 0 ? T.nch[k] - 1 : 0;
-                    for (uint32_t i = lane; i < nout; i += 32) { a.scores[T.obase[k] + i] = 0; a.boundaries[T.obase[k] + i] = 0; }
+                    for (uint32_t i = lane; i < nout; i += 32) { if (a.scores) a.scores[T.obase[k] + i] = 0; a.boundaries[T.obase[k] + i] = 0; }
                     if (a.char_states) for (uint32_t i = lane; i < T.nch[k]; i += 32) a.char_states[T.cbase[k] + i] = kNoPattern;
                     if (a.type_states) for (uint32_t i = lane; i < T.nch[k]; i += 32) a.type_states[T.cbase[k] + i] = kNoPattern;
                     continue;
@@ -1204,7 +1204,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_fast(DevModel m, Batch
                     v += __ldg(m.type_cache + idx);
                 }
                 const int64_t o = int64_t(p) + T.odelta[k];
-                a.scores[o] = v;
+                if (a.scores) a.scores[o] = v;
                 a.boundaries[o] = v > 0 ? 1 : 0;
             }
             sub_sync(sub);
@@ -1319,5 +1319,9 @@ cudaError_t launch_score(const DevModel& m, const BatchArgs& a, cudaStream_t str
 }
 
 int launches_per_batch(const DevModel&) { return 3; }
+
+// The paths that accumulate into the score array itself (general rows, overflow rows of long sentences) need
+// it; the inline-row tile kernel keeps the sums in shared memory and can skip the score stores.
+bool scores_optional(const DevModel& m) { return tile_fast_ok(m) && !m.ct.has_overflow; }
 
 }  // namespace vpt

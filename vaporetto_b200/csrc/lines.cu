@@ -155,112 +155,174 @@ __global__ void __launch_bounds__(kSplitThreads) k_nl_write(SplitArgs s) {
 // ------------------------------------------------------------------------------------------------
 constexpr int kTokThreads = 256;
 
-// Output bytes of every sentence of a 64-sentence group (one warp per sentence, 8 sentences per warp), their
-// exclusive prefix inside the group, and the group total.
-__global__ void __launch_bounds__(kTokThreads) k_tok_count(TokArgs t) {
-    __shared__ uint32_t s_len[kGroup];
+// Tokenised output in one pass.  One CTA per 64-sentence group (groups handed out by an atomic ticket, so a
+// group's predecessors are always resident or done):
+//   1. one warp per sentence counts its output bytes: surface + escapes + word boundaries + the '\n';
+//   2. the group's total is published and the output offset of the group is found by a decoupled look-back
+//      over the predecessors' published totals (state word = 2 flag bits | 62 value bits);
+//   3. one warp per sentence writes: every byte of the surface goes to  base + index + (escapes and spaces
+//      before it), preceded by its own ' ' (word boundary before this character) and '\' (escape).
+constexpr uint64_t kStAgg = 1ull << 62, kStIncl = 2ull << 62, kStMask = (1ull << 62) - 1;
+
+__global__ void __launch_bounds__(kTokThreads) k_tok_write(TokArgs t, uint64_t ngroups) {
+    __shared__ uint64_t s_off[kGroup + 1], s_bo[kGroup];
+    __shared__ uint32_t s_nch[kGroup], s_len[kGroup], s_excl[kGroup];
+    __shared__ uint8_t s_trim[kGroup], s_bad[kGroup];
+    __shared__ uint64_t s_base;
+    __shared__ uint32_t s_grp;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint64_t gbase = uint64_t(blockIdx.x) * kGroup;
+    if (threadIdx.x == 0) s_grp = atomicAdd(t.ticket, 1u);
+    __syncthreads();
+    const uint64_t grp = s_grp;
+    const uint64_t gbase = grp * kGroup;
     const int ns = int(min(uint64_t(kGroup), t.n_sent - gbase));
-    for (int i = warp; i < kGroup; i += kTokThreads / 32) {
+    if (threadIdx.x <= ns) s_off[threadIdx.x] = t.offsets[gbase + threadIdx.x];
+    if (threadIdx.x < ns) {
+        const uint64_t s = gbase + threadIdx.x;
+        s_bo[threadIdx.x] = t.bound_offsets[s];
+        s_nch[threadIdx.x] = t.n_chars[s];
+        s_trim[threadIdx.x] = t.trims ? t.trims[s] : uint8_t(0);
+        s_bad[threadIdx.x] = t.status[s] != 0;
+    }
+    __syncthreads();
+
+    // ---- 1. output bytes per sentence -------------------------------------------------------------------
+    // A sentence that fits one 128-byte window (the common case) is analysed once: its word, flag masks and
+    // per-lane output index stay in registers for step 3.  Longer sentences are only counted here.
+    constexpr int kPerWarp = kGroup / (kTokThreads / 32);
+    uint32_t r_lo[kPerWarp], r_fl[kPerWarp], r_at[kPerWarp];
+#pragma unroll
+    for (int it = 0; it < kPerWarp; ++it) {
+        const int i = warp + it * (kTokThreads / 32);
         uint32_t len = 0;
+        r_lo[it] = 0; r_fl[it] = 0; r_at[it] = 0;
         if (i < ns) {
-            const uint64_t s = gbase + i;
             len = 1;  // the '\n'
-            if (t.status[s] == 0) {
-                const uint64_t o0 = t.offsets[s];
+            if (!s_bad[i]) {
+                const uint64_t o0 = s_off[i];
                 const uint64_t a0 = o0 & ~3ull;
-                const uint32_t b0 = uint32_t(o0 - a0), b1 = uint32_t(t.offsets[s + 1] - a0) - (t.trims ? t.trims[s] : 0);
+                const uint32_t b0 = uint32_t(o0 - a0), b1 = uint32_t(s_off[i + 1] - a0) - s_trim[i];
                 const uint8_t* __restrict__ base = t.text + a0;
-                uint32_t cnt = 0;
-                for (uint32_t addr = 4u * uint32_t(lane); addr < b1; addr += 128) {
-                    const uint32_t lo = __ldg(reinterpret_cast<const uint32_t*>(base + addr));
-                    const uint32_t in80 = inside80(addr, b0, b1);
-                    cnt += __popc((eq_bytes(lo, 0x20u) | eq_bytes(lo, 0x2Fu) | eq_bytes(lo, 0x5Cu)) & in80);
-                }
-                // word boundaries of the sentence
-                const uint32_t nch = t.n_chars[s];
-                if (nch > 1) {
-                    const uint64_t q0 = t.bound_offsets[s];
-                    const uint64_t qa = q0 & ~3ull;
-                    const uint32_t c0 = uint32_t(q0 - qa), c1 = c0 + nch - 1;
-                    const uint8_t* __restrict__ bb = t.boundaries + qa;
-                    for (uint32_t addr = 4u * uint32_t(lane); addr < c1; addr += 128) {
-                        const uint32_t w = *reinterpret_cast<const uint32_t*>(bb + addr);
-                        cnt += __popc(eq_bytes(w, 1u) & inside80(addr, c0, c1));
+                if (b1 <= 128u) {
+                    const uint32_t addr = 4u * uint32_t(lane);
+                    uint32_t lo = 0, in80 = 0;
+                    if (addr < b1) {
+                        lo = __ldg(reinterpret_cast<const uint32_t*>(base + addr));
+                        in80 = inside80(addr, b0, b1);
                     }
+                    const uint32_t st80 = ~(lo & ~(lo << 1)) & in80;  // character starts (not 10xxxxxx)
+                    const uint32_t nst = __popc(st80);
+                    const uint32_t st_incl = warp_incl_scan_u32(nst, lane);
+                    const uint8_t* __restrict__ bnd = t.boundaries + s_bo[i];
+                    uint32_t sp80 = 0, k = st_incl - nst;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (st80 & (0x80u << (8 * j))) {
+                            if (k >= 1 && bnd[k - 1] == 1) sp80 |= 0x80u << (8 * j);
+                            ++k;
+                        }
+                    }
+                    const uint32_t esc80 = (eq_bytes(lo, 0x20u) | eq_bytes(lo, 0x2Fu) | eq_bytes(lo, 0x5Cu)) & in80;
+                    const uint32_t nex = __popc(sp80) + __popc(esc80);
+                    const uint32_t ex_incl = warp_incl_scan_u32(nex, lane);
+                    r_lo[it] = lo;
+                    r_fl[it] = in80 | (sp80 >> 1) | (esc80 >> 2);
+                    r_at[it] = (addr - b0) + ex_incl - nex;
+                    len += (b1 - b0) + __shfl_sync(kFull, ex_incl, 31);
+                } else {
+                    uint32_t cnt = 0;
+                    for (uint32_t addr = 4u * uint32_t(lane); addr < b1; addr += 128) {
+                        const uint32_t lo = __ldg(reinterpret_cast<const uint32_t*>(base + addr));
+                        cnt += __popc((eq_bytes(lo, 0x20u) | eq_bytes(lo, 0x2Fu) | eq_bytes(lo, 0x5Cu)) & inside80(addr, b0, b1));
+                    }
+                    const uint32_t nch = s_nch[i];
+                    if (nch > 1) {
+                        const uint64_t q0 = s_bo[i];
+                        const uint64_t qa = q0 & ~3ull;
+                        const uint32_t c0 = uint32_t(q0 - qa), c1 = c0 + nch - 1;
+                        const uint8_t* __restrict__ bb = t.boundaries + qa;
+                        for (uint32_t addr = 4u * uint32_t(lane); addr < c1; addr += 128) {
+                            const uint32_t w = *reinterpret_cast<const uint32_t*>(bb + addr);
+                            cnt += __popc(eq_bytes(w, 1u) & inside80(addr, c0, c1));
+                        }
+                    }
+                    len += (b1 - b0) + __reduce_add_sync(kFull, cnt);
                 }
-                len += (b1 - b0) + __reduce_add_sync(kFull, cnt);
             }
         }
         if (lane == 0) s_len[i] = len;
     }
     __syncthreads();
+
+    // ---- 2. offsets: scan inside the group, look-back across groups -----------------------------------------
     if (warp == 0) {
         const uint32_t v0 = s_len[2 * lane], v1 = s_len[2 * lane + 1];
         const uint32_t iv = warp_incl_scan_u32(v0 + v1, lane);
-        const uint64_t s0 = gbase + 2 * lane;
-        if (s0 < t.n_sent) t.tok_local[s0] = iv - v0 - v1;
-        if (s0 + 1 < t.n_sent) t.tok_local[s0 + 1] = iv - v1;
-        if (lane == 31) t.tok_group[blockIdx.x] = iv;
-    }
-}
-
-// Exclusive scan of the group totals in place; element [ngroups] receives the grand total.
-__global__ void __launch_bounds__(1024) k_tok_scan(uint64_t* g, uint64_t ngroups) {
-    __shared__ uint64_t s_w[32];
-    __shared__ uint64_t s_carry;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) s_carry = 0;
-    __syncthreads();
-    for (uint64_t base = 0; base < ngroups; base += 1024) {
-        const uint64_t i = base + threadIdx.x;
-        const uint64_t v = i < ngroups ? g[i] : 0;
-        uint64_t incl = v;
+        s_excl[2 * lane] = iv - v0 - v1;
+        s_excl[2 * lane + 1] = iv - v1;
+        const uint64_t total = __shfl_sync(kFull, iv, 31);
+        volatile uint64_t* state = t.tok_state;
+        if (lane == 0) state[grp] = (grp == 0 ? kStIncl : kStAgg) | total;
+        uint64_t prefix = 0;
+        if (grp > 0) {
+            int64_t idx = int64_t(grp) - 1;
+            for (;;) {
+                const int64_t j = idx - lane;
+                uint64_t v = kStIncl;  // groups before the first: inclusive prefix 0
+                if (j >= 0) {
+                    do { v = state[j]; } while ((v >> 62) == 0);
+                }
+                // nearest predecessor (lowest lane) that already knows its inclusive prefix
+                const unsigned incl = __ballot_sync(kFull, (v >> 62) == 2);
+                const int stop = incl ? __ffs(incl) - 1 : 32;
+                uint64_t add = lane <= stop ? (v & kStMask) : 0;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint64_t o = __shfl_up_sync(kFull, incl, d);
-            if (lane >= d) incl += o;
-        }
-        if (lane == 31) s_w[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            uint64_t w = s_w[lane];
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint64_t o = __shfl_up_sync(kFull, w, d);
-                if (lane >= d) w += o;
+                for (int d = 16; d > 0; d >>= 1) add += __shfl_xor_sync(kFull, add, d);
+                prefix += add;
+                if (incl) break;
+                idx -= 32;
             }
-            s_w[lane] = w;
+            if (lane == 0) state[grp] = kStIncl | (prefix + total);
         }
-        __syncthreads();
-        if (i < ngroups) g[i] = s_carry + (warp ? s_w[warp - 1] : 0) + incl - v;
-        __syncthreads();
-        if (threadIdx.x == 0) s_carry += s_w[31];
-        __syncthreads();
+        if (lane == 0) {
+            s_base = prefix;
+            if (grp + 1 == ngroups) *t.total = prefix + total;
+        }
     }
-    if (threadIdx.x == 0) g[ngroups] = s_carry;
-}
+    __syncthreads();
 
-// One warp per sentence: every byte of the surface goes to  base + index + (escapes and spaces before it),
-// preceded by its own ' ' (a word boundary before this character) and '\' (escape).
-__global__ void __launch_bounds__(kTokThreads) k_tok_write(TokArgs t) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint64_t gbase = uint64_t(blockIdx.x) * kGroup;
-    const int ns = int(min(uint64_t(kGroup), t.n_sent - gbase));
-    const uint64_t gout = t.tok_group[blockIdx.x];
-    for (int i = warp; i < ns; i += kTokThreads / 32) {
-        const uint64_t s = gbase + i;
-        uint8_t* __restrict__ out = t.out + gout + t.tok_local[s];
-        if (t.status[s] != 0) {
+    // ---- 3. write ---------------------------------------------------------------------------------------------
+    const uint64_t gout = s_base;
+#pragma unroll
+    for (int it = 0; it < kPerWarp; ++it) {
+        const int i = warp + it * (kTokThreads / 32);
+        if (i >= ns) continue;
+        uint8_t* __restrict__ out = t.out + gout + s_excl[i];
+        if (s_bad[i]) {
             if (lane == 0) out[0] = 0x0A;
             continue;
         }
-        const uint64_t o0 = t.offsets[s];
+        if (lane == 0) out[s_len[i] - 1] = 0x0A;
+        const uint64_t o0 = s_off[i];
         const uint64_t a0 = o0 & ~3ull;
-        const uint32_t b0 = uint32_t(o0 - a0), b1 = uint32_t(t.offsets[s + 1] - a0) - (t.trims ? t.trims[s] : 0);
+        const uint32_t b0 = uint32_t(o0 - a0), b1 = uint32_t(s_off[i + 1] - a0) - s_trim[i];
+        if (b1 <= 128u) {
+            const uint32_t lo = r_lo[it], fl = r_fl[it];
+            uint32_t at = r_at[it];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t bit = 0x80u << (8 * j);
+                if (fl & bit) {
+                    if (fl & (bit >> 1)) out[at++] = 0x20;
+                    if (fl & (bit >> 2)) out[at++] = 0x5C;
+                    out[at] = uint8_t(lo >> (8 * j));
+                }
+                ++at;
+            }
+            continue;
+        }
         const uint8_t* __restrict__ base = t.text + a0;
-        const uint8_t* __restrict__ bnd = t.boundaries + t.bound_offsets[s];
+        const uint8_t* __restrict__ bnd = t.boundaries + s_bo[i];
         uint32_t chars = 0, extra = 0;  // characters / inserted bytes before this window
         for (uint32_t w0 = 0; w0 < b1; w0 += 128) {
             const uint32_t addr = w0 + 4u * uint32_t(lane);
@@ -269,7 +331,7 @@ __global__ void __launch_bounds__(kTokThreads) k_tok_write(TokArgs t) {
                 lo = __ldg(reinterpret_cast<const uint32_t*>(base + addr));
                 in80 = inside80(addr, b0, b1);
             }
-            const uint32_t st80 = ~(lo & ~(lo << 1)) & in80;  // character starts (not 10xxxxxx)
+            const uint32_t st80 = ~(lo & ~(lo << 1)) & in80;
             const uint32_t nst = __popc(st80);
             const uint32_t st_incl = warp_incl_scan_u32(nst, lane);
             // a ' ' goes before character k >= 1 when boundary k-1 is a word boundary
@@ -301,7 +363,6 @@ __global__ void __launch_bounds__(kTokThreads) k_tok_write(TokArgs t) {
             chars += __shfl_sync(kFull, st_incl, 31);
             extra += __shfl_sync(kFull, ex_incl, 31);
         }
-        if (lane == 0) out[(b1 - b0) + extra] = 0x0A;
     }
 }
 
@@ -321,18 +382,13 @@ cudaError_t launch_split_write(const SplitArgs& s, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
-cudaError_t launch_tok_count(const TokArgs& t, cudaStream_t stream) {
-    if (t.n_sent == 0) return cudaSuccess;
+cudaError_t launch_tokenize(const TokArgs& t, cudaStream_t stream) {
+    if (t.n_sent == 0) return cudaMemsetAsync(t.total, 0, 8, stream);
     const uint64_t ngroups = (t.n_sent + kGroup - 1) / kGroup;
-    k_tok_count<<<unsigned(ngroups), kTokThreads, 0, stream>>>(t);
-    k_tok_scan<<<1, 1024, 0, stream>>>(t.tok_group, ngroups);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_tok_write(const TokArgs& t, cudaStream_t stream) {
-    if (t.n_sent == 0) return cudaSuccess;
-    const uint64_t ngroups = (t.n_sent + kGroup - 1) / kGroup;
-    k_tok_write<<<unsigned(ngroups), kTokThreads, 0, stream>>>(t);
+    // look-back state words + the ticket that follows them
+    cudaError_t e = cudaMemsetAsync(t.tok_state, 0, 8 * (ngroups + 1), stream);
+    if (e != cudaSuccess) return e;
+    k_tok_write<<<unsigned(ngroups), kTokThreads, 0, stream>>>(t, ngroups);
     return cudaGetLastError();
 }
 
