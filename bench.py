@@ -385,7 +385,7 @@ def main():
     tok_len, tok_lines = C.c_uint64(), C.c_uint64()
 
     def step_lines():
-        rc = L.vpt_tokenize_lines(pred._h, h_lines.data_ptr(), nbytes + n, h_tok.data_ptr(), h_tok.numel(),
+        rc = L.vpt_tokenize_lines(pred._h, h_lines.data_ptr(), nbytes + n, 1, h_tok.data_ptr(), h_tok.numel(),
                                   C.byref(tok_len), C.byref(tok_lines))
         if rc:
             raise RuntimeError(L.vpt_last_error().decode())
@@ -444,7 +444,7 @@ def main():
                     "steps": args.e2e_steps, "api": "vpt_predict_batch (pinned host buffers; scores+boundaries returned)",
                     "boundaries_only_value": round(e2e_nb_value, 1),
                     "tokenize_lines": {"value": round(e2e_lines_value, 1), "unit": "MB/s",
-                                       "api": "vpt_tokenize_lines (raw lines in, tokenised text out; split + "
+                                       "api": "vpt_tokenize_lines, no_norm = 1 (raw lines in, tokenised text out; split + "
                                               "materialisation on the device)",
                                        "h2d_bytes_per_step": nbytes + n, "d2h_bytes_per_step": lines_d2h}},
             "gpu_launches": args.steps * pred.info["kernel_launches_per_batch"],

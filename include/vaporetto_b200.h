@@ -187,19 +187,30 @@ int vpt_write_tokenized_text(const vpt_predictor* predictor, const uint8_t* utf8
 
 /* ---- Whole-buffer tokenisation: the reference CLI's loop on the device ----------------------------- */
 
-/* The `predict --no-norm` loop (predict/src/main.rs:126-150) over a whole buffer of raw file bytes:
- *   for line in stdin.lines():  if s.update_raw(line).is_ok() { predict; write_tokenized_text }  write "\n"
+/* The loop of the reference's `predict` CLI (predict/src/main.rs:126-181) over a whole buffer of raw file bytes:
+ *   for line in stdin.lines():
+ *       s = KyteaFullwidthFilter(line) unless --no-norm          (main.rs:98,154; vaporetto_rules kytea_fullwidth.rs)
+ *       if s.update_raw(..).is_ok() { predict(s); copy the boundaries to the original line; write_tokenized_text }
+ *       write "\n"
  * Lines are split ON THE DEVICE with `BufRead::lines` semantics ('\n' or "\r\n" terminated; the last line may
- * be unterminated; a trailing '\n' adds no empty line), scored by the same kernels as vpt_predict_batch, and
- * the tokenised text (' ' between tokens; '\\' before ' ', '\\', '/': sentence.rs:850-886) is materialised on the
- * device, so the only transfers are the input bytes in and the output bytes out.  Lines that update_raw
- * rejects (empty, or containing U+0000) produce an empty line as in the CLI; so do lines that are not valid
- * UTF-8 (the CLI stops with an I/O error on those).  Tags are not predicted on this path.
+ * be unterminated; a trailing '\n' adds no empty line), scored by the same kernels as vpt_predict_batch (with the
+ * full-width character map applied to the code points the kernels look up when no_norm == 0; the map is one
+ * character to one character, so the boundaries apply to the original text), and the tokenised ORIGINAL text
+ * (' ' between tokens; '\\' before ' ', '\\', '/': sentence.rs:850-886) is materialised on the device: the only
+ * transfers are the input bytes in and the output bytes out.  Lines that update_raw rejects (empty, or
+ * containing U+0000) produce an empty line as in the CLI; so do lines that are not valid UTF-8 (the CLI stops
+ * with an I/O error on those).  Tags, --wsconst post-filters and score printing are not part of this path.
+ * `no_norm`: the CLI flag of the same name (0 = apply KyteaFullwidthFilter, the CLI default).
  * `out` receives the output lines, each terminated by '\n' (at most 3 * n_bytes + n_lines bytes); *out_len
  * the number of bytes produced (also when `out_capacity` was too small, which returns InvalidArgument);
- * *n_lines the number of input lines.  Chunk size of the internal pipeline: env VPT_CHUNK_BYTES (16 MiB, with smaller chunks at both ends). */
-int vpt_tokenize_lines(const vpt_predictor* predictor, const uint8_t* utf8, size_t n_bytes, uint8_t* out,
+ * *n_lines the number of input lines.  Chunk size of the internal pipeline: env VPT_CHUNK_BYTES (16 MiB, with
+ * smaller chunks at both ends); VPT_TRACE=1 prints the pipeline's per-chunk timeline to stderr. */
+int vpt_tokenize_lines(const vpt_predictor* predictor, const uint8_t* utf8, size_t n_bytes, int no_norm, uint8_t* out,
                        size_t out_capacity, uint64_t* out_len, uint64_t* n_lines);
+
+/* `KyteaFullwidthFilter` for one character (vaporetto_rules/src/string_filters/kytea_fullwidth.rs:13-118): the
+ * same function the kernels apply (csrc/textnorm.hpp). */
+uint32_t vpt_kytea_fullwidth(uint32_t code_point);
 
 /* library build info, e.g. "vaporetto_b200 0.1.0 sm_100a" */
 const char* vpt_version(void);

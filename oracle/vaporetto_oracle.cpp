@@ -908,21 +908,62 @@ long ora_tokenize(const void* p, const char* utf8, size_t nbytes, int fill_tags,
     ORA_CATCH(neg)
 }
 
-// The `predict --no-norm` loop of the reference CLI (predict/src/main.rs:126-150) over a buffer:
-//   for line in stdin.lines() { if s.update_raw(line).is_ok() { predict; write_tokenized_text }; out "\n" }
+// KyteaFullwidthFilter (vaporetto_rules/src/string_filters/kytea_fullwidth.rs:13-118): the match arms as a table,
+// in the order of the source.  Checked against tests/golden/kytea_fullwidth_map.json.
+static uint32_t kytea_fullwidth_cp(uint32_t c) {
+    static const uint32_t kMap[][2] = {
+        {'a', 0xFF41}, {'b', 0xFF42}, {'c', 0xFF43}, {'d', 0xFF44}, {'e', 0xFF45}, {'f', 0xFF46}, {'g', 0xFF47},
+        {'h', 0xFF48}, {'i', 0xFF49}, {'j', 0xFF4A}, {'k', 0xFF4B}, {'l', 0xFF4C}, {'m', 0xFF4D}, {'n', 0xFF4E},
+        {'o', 0xFF4F}, {'p', 0xFF50}, {'q', 0xFF51}, {'r', 0xFF52}, {'s', 0xFF53}, {'t', 0xFF54}, {'u', 0xFF55},
+        {'v', 0xFF56}, {'w', 0xFF57}, {'x', 0xFF58}, {'y', 0xFF59}, {'z', 0xFF5A},
+        {'A', 0xFF21}, {'B', 0xFF22}, {'C', 0xFF23}, {'D', 0xFF24}, {'E', 0xFF25}, {'F', 0xFF26}, {'G', 0xFF27},
+        {'H', 0xFF28}, {'I', 0xFF29}, {'J', 0xFF2A}, {'K', 0xFF2B}, {'L', 0xFF2C}, {'M', 0xFF2D}, {'N', 0xFF2E},
+        {'O', 0xFF2F}, {'P', 0xFF30}, {'Q', 0xFF31}, {'R', 0xFF32}, {'S', 0xFF33}, {'T', 0xFF34}, {'U', 0xFF35},
+        {'V', 0xFF36}, {'W', 0xFF37}, {'X', 0xFF38}, {'Y', 0xFF39}, {'Z', 0xFF3A},
+        {'0', 0xFF10}, {'1', 0xFF11}, {'2', 0xFF12}, {'3', 0xFF13}, {'4', 0xFF14}, {'5', 0xFF15}, {'6', 0xFF16},
+        {'7', 0xFF17}, {'8', 0xFF18}, {'9', 0xFF19},
+        {'(', 0xFF08}, {')', 0xFF09}, {'{', 0xFF5B}, {'}', 0xFF5D}, {'<', 0xFF1C}, {'>', 0xFF1E},
+        {0xFF62, 0x300C}, {0xFF63, 0x300D}, {'[', 0xFF3B}, {']', 0xFF3D}, {'-', 0x2212}, {0xFF5E, 0x301C},
+        {'.', 0x3002}, {0xFF0D, 0x30FC}, {'/', 0xFF0F}, {'_', 0xFF3F}, {',', 0xFF0C}, {'%', 0xFF05}, {'?', 0xFF1F},
+        {0xFF64, 0x3001}, {0x2015, 0x30FC}, {'"', 0x201D}, {0x27, 0x2019}, {0xFF65, 0x30FB}, {0x2500, 0x30FC},
+        {'+', 0xFF0B}, {':', 0xFF1A}, {0x2013, 0x30FC}, {'!', 0xFF01}, {0xFF61, 0x3002}, {'&', 0xFF06},
+        {'*', 0xFF0A}, {'@', 0xFF20}, {'=', 0xFF1D},
+    };
+    for (const auto& e : kMap) if (e[0] == c) return e[1];
+    return c;
+}
+
+static void append_utf8(string& out, uint32_t c) {
+    if (c < 0x80) out.push_back(char(c));
+    else if (c < 0x800) { out.push_back(char(0xC0 | (c >> 6))); out.push_back(char(0x80 | (c & 0x3F))); }
+    else if (c < 0x10000) {
+        out.push_back(char(0xE0 | (c >> 12))); out.push_back(char(0x80 | ((c >> 6) & 0x3F))); out.push_back(char(0x80 | (c & 0x3F)));
+    } else {
+        out.push_back(char(0xF0 | (c >> 18))); out.push_back(char(0x80 | ((c >> 12) & 0x3F)));
+        out.push_back(char(0x80 | ((c >> 6) & 0x3F))); out.push_back(char(0x80 | (c & 0x3F)));
+    }
+}
+
+uint32_t ora_kytea_fullwidth(uint32_t c) { return kytea_fullwidth_cp(c); }
+
+// The loop of the reference CLI (predict/src/main.rs:126-181) over a buffer:
+//   --no-norm:  for line in stdin.lines() { if s.update_raw(line).is_ok() { predict; write_tokenized_text }; out "\n" }
+//   default:    line_preproc = KyteaFullwidthFilter(line); if s.update_raw(line_preproc).is_ok() { predict(s);
+//               s_orig.update_raw(line); s_orig.boundaries = s.boundaries; write_tokenized_text(s_orig); } out "\n"
 // `BufRead::lines` (std): a line ends at '\n'; a '\r' directly before that '\n' is dropped; the last line may be
 // unterminated; a trailing '\n' adds no empty line.  Lines update_raw rejects (empty / NUL) print an empty
 // line.  A line that is not valid UTF-8 makes `lines()` fail and the CLI stop; the batch interface this
 // checks prints an empty line for it instead (documented difference).  Returns the output size (or
 // -(1000000 + needed) when cap is too small); *n_lines receives the number of lines.
-long ora_tokenize_lines(const void* p, const char* utf8, size_t nbytes, char* buf, size_t cap, uint64_t* n_lines) {
+long ora_tokenize_lines(const void* p, const char* utf8, size_t nbytes, int no_norm, char* buf, size_t cap,
+                        uint64_t* n_lines) {
     auto neg = [](int c) { return -long(c); };
     ORA_TRY
     auto* pr = static_cast<const Predictor*>(p);
     string out;
     uint64_t nl = 0;
     size_t lo = 0;
-    Sentence s;
+    Sentence s, s_orig;
     while (lo < nbytes) {
         const void* q = memchr(utf8 + lo, '\n', nbytes - lo);
         size_t end = q ? size_t(static_cast<const char*>(q) - utf8) : nbytes;
@@ -930,10 +971,18 @@ long ora_tokenize_lines(const void* p, const char* utf8, size_t nbytes, char* bu
         if (q && end > lo && utf8[end - 1] == '\r') --end;
         ++nl;
         bool ok = true;
-        try { s.parse_raw(utf8 + lo, end - lo); } catch (const Error&) { ok = false; }
+        try { s_orig.parse_raw(utf8 + lo, end - lo); } catch (const Error&) { ok = false; }
         if (ok) {
-            pr->predict(s);
-            out += write_tokenized(*pr, s, nullptr, nullptr);
+            if (no_norm) {
+                pr->predict(s_orig);
+            } else {
+                string pre;
+                for (uint32_t c : s_orig.chars) append_utf8(pre, kytea_fullwidth_cp(c));
+                s.parse_raw(pre.data(), pre.size());
+                pr->predict(s);
+                s_orig.boundaries = s.boundaries;
+            }
+            out += write_tokenized(*pr, s_orig, nullptr, nullptr);
         }
         out.push_back('\n');
         lo = next;

@@ -15,10 +15,11 @@ pytestmark = pytest.mark.gpu
 
 
 def check(p, o, data: bytes):
-    got, nl = p.tokenize_lines(data)
-    want, wl = o.tokenize_lines(data)
-    assert nl == wl
-    assert got.tobytes() == want
+    for no_norm in (True, False):
+        got, nl = p.tokenize_lines(data, no_norm=no_norm)
+        want, wl = o.tokenize_lines(data, no_norm=no_norm)
+        assert nl == wl
+        assert got.tobytes() == want, (no_norm, data[:200])
 
 
 @pytest.fixture(scope="module")
@@ -49,6 +50,9 @@ def test_lines_semantics(kat_pair, monkeypatch):
         ("火星猫だ" * 3000 + "\n" + "まぁ社長は" * 7 + "\n").encode(),     # a line larger than a tile
         "\n".join("まぁ社長は火星猫だ"[: 1 + i % 9] for i in range(500)).encode(),
         "\U00020000\U0002a6df火星été ab12 ｶﾀｶﾅ\n".encode(),       # 4-, 2-byte characters
+        "Vaporetto is a tokenizer. (v0.6.5) - 100% [test]\n".encode(),                 # KyteaFullwidthFilter sources
+        "ｶﾞｰﾃﾞﾝ－ハウス―A–B─C ｢x｣ ～ ､ ･ ｡\n".encode(),
+        "a/b c\\d 1.5 -3 \"q\" 'r' #$;^`|~\n".encode(),
     ]
     for chunk in ("", "64", "200"):
         if chunk:
@@ -60,9 +64,9 @@ def test_lines_semantics(kat_pair, monkeypatch):
 def test_lines_out_capacity(kat_pair):
     p, o = kat_pair
     data = "まぁ社長は火星猫だ\n".encode() * 10
-    want, _ = o.tokenize_lines(data)
+    want, _ = o.tokenize_lines(data, no_norm=True)
     out = np.empty(len(want), np.uint8)
-    got, nl = p.tokenize_lines(data, out=out)
+    got, nl = p.tokenize_lines(data, out=out, no_norm=True)
     assert got.tobytes() == want and nl == 10
     with pytest.raises(vb.VaporettoError):
         p.tokenize_lines(data, out=np.empty(len(want) - 1, np.uint8))
@@ -92,7 +96,7 @@ def test_random_lines_vs_oracle(cw, tw, maxdict, monkeypatch):
     rng = np.random.default_rng(cw * 100 + tw * 10 + maxdict)
     for it in range(6):
         m, alpha = _random_model(rng, cw, tw, maxdict=maxdict)
-        alphabet = list(alpha) + list(" /\\é\U00020000")
+        alphabet = list(alpha) + list(" /\\é\U00020000") + list("ab.-ｱ－―｢､")
         mb = encode_model(m)
         p, o = make(mb), OraclePredictor(mb)
         monkeypatch.setenv("VPT_CHUNK_BYTES", str(int(rng.choice([64, 1000, 1 << 16, 8 << 20]))))
@@ -108,10 +112,13 @@ def test_lines_full_size():
     text, offs, _ = synth.gen_text(200_000, 40, seed=99)
     lines = [text[int(offs[i]):int(offs[i + 1])].tobytes() for i in range(len(offs) - 1)]
     data = b"\n".join(lines) + b"\n"
-    got, nl = p.tokenize_lines(data)
+    got, nl = p.tokenize_lines(data, no_norm=True)
     assert nl == len(lines)
-    want, _ = o.tokenize_lines(data)
+    want, _ = o.tokenize_lines(data, no_norm=True)
     assert got.tobytes() == want
+    got_n, _ = p.tokenize_lines(data)                      # CLI default: full-width normalisation before scoring
+    want_n, _ = o.tokenize_lines(data)
+    assert got_n.tobytes() == want_n
     g = got.tobytes()
     assert g.count(b"\n") == len(lines)
     # the synthetic text has ' ' but no '/', '\\' or NUL: undoing the escapes and dropping the separators

@@ -1,9 +1,11 @@
 """The oracle's restatement of the reference CLI loop (`predict --no-norm`, predict/src/main.rs:126-150) against
 the per-sentence oracle (itself pinned to the reference's vectors) and Rust's `BufRead::lines` rules as Python's
 own line handling states them."""
+import json
 import os
 
-from vpt_testlib.oracle import OraclePredictor
+import vaporetto_b200 as vb
+from vpt_testlib.oracle import OraclePredictor, lib as oracle_lib
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -20,7 +22,17 @@ def rust_lines(data: bytes):
     return out
 
 
-def expected(o, data: bytes) -> bytes:
+def fullwidth_map():
+    with open(os.path.join(GOLDEN, "kytea_fullwidth_map.json")) as f:
+        return {int(k): v for k, v in json.load(f).items()}
+
+
+def escape(tok: str) -> str:
+    return tok.replace("\\", "\\\\").replace(" ", "\\ ").replace("/", "\\/")
+
+
+def expected(o, data: bytes, no_norm: bool = True) -> bytes:
+    fw = fullwidth_map()
     out = []
     for line in rust_lines(data):
         try:
@@ -28,8 +40,34 @@ def expected(o, data: bytes) -> bytes:
             ok = len(s) > 0 and "\x00" not in s
         except UnicodeDecodeError:
             ok = False
-        out.append(o.tokenize(s).encode() if ok else b"")
+        if not ok:
+            out.append(b"")
+        elif no_norm:
+            out.append(o.tokenize(s).encode())
+        else:
+            # predict on the filtered line, put its boundaries on the original line (predict/src/main.rs:154-166)
+            pre = "".join(chr(fw.get(ord(c), ord(c))) for c in s)
+            _, bounds = o.predict(pre)
+            toks, start = [], 0
+            for i, b in enumerate(bounds.tolist()):
+                if b == 1:
+                    toks.append(s[start:i + 1])
+                    start = i + 1
+            toks.append(s[start:])
+            out.append(" ".join(escape(t) for t in toks).encode())
     return b"".join(x + b"\n" for x in out)
+
+
+def test_fullwidth_map_matches_reference_fixture():
+    """Every code point up to U+FFFF (and a few beyond): the oracle's table and the library's arithmetic form
+    (csrc/textnorm.hpp, the function the kernels apply) against the map extracted from the reference source."""
+    fw = fullwidth_map()
+    assert len(fw) == 96
+    L, O = vb.lib(), oracle_lib()
+    for c in list(range(0, 0x10000)) + [0x10000, 0x1F600, 0x2A6DF, 0x10FFFF]:
+        want = fw.get(c, c)
+        assert O.ora_kytea_fullwidth(c) == want, hex(c)
+        assert L.vpt_kytea_fullwidth(c) == want, hex(c)
 
 
 def test_cli_loop_matches_per_line_oracle():
@@ -43,16 +81,22 @@ def test_cli_loop_matches_per_line_oracle():
         "まぁ\x00社長\n火星猫\n".encode(),
         b"\xe3\x81\n" + "火星猫\n".encode() + b"\xff\n",
     ]
+    cases += [
+        "Vaporetto is a tokenizer. (v0.6.5) - 100% [test]\n".encode(),
+        "ｶﾞｰﾃﾞﾝ－ハウス―A–B─C ｢x｣ ～ ､ ･ ｡\n".encode(),
+        "a/b c\\d 1.5 -3 \"q\" 'r' #$;^`|~\n".encode(),
+    ]
     for data in cases:
-        got, nl = o.tokenize_lines(data)
-        assert nl == len(rust_lines(data))
-        assert got == expected(o, data), data
+        for no_norm in (True, False):
+            got, nl = o.tokenize_lines(data, no_norm=no_norm)
+            assert nl == len(rust_lines(data))
+            assert got == expected(o, data, no_norm), (data, no_norm)
 
 
 def test_docs_tok_through_cli_loop():
     """The reference's documented tokenisation (tests/golden/docs.tok) through the whole-buffer loop."""
     with open(os.path.join(GOLDEN, "model.bin"), "rb") as f:
         o = OraclePredictor(f.read())
-    got, nl = o.tokenize_lines("まぁ社長は火星猫だ\nまぁ社長は火星猫だ\n".encode())
+    got, nl = o.tokenize_lines("まぁ社長は火星猫だ\nまぁ社長は火星猫だ\n".encode(), no_norm=True)
     assert nl == 2
     assert got.decode() == "まぁ 社長 は 火星 猫 だ\n" * 2

@@ -19,6 +19,7 @@
 #include "device_model.hpp"
 #include "model.hpp"
 #include "predictor_build.hpp"
+#include "textnorm.hpp"
 
 using namespace vpt;
 
@@ -739,7 +740,7 @@ void lines_stage0(Scratch& s, LineChunk& ch, const uint8_t* utf8) {
 }
 
 // stage 1: line offsets, count + score, tokenised bytes; the output size to pinned host memory
-void lines_stage1(const vpt_predictor& p, Scratch& s, LineChunk& ch) {
+void lines_stage1(const vpt_predictor& p, Scratch& s, LineChunk& ch, bool normalize) {
     cudaStream_t st = s.stream;
     cuda_check(cudaEventSynchronize(ch.split), "sync(split)");
     const size_t n = size_t(s.h_totals[2]);
@@ -775,7 +776,9 @@ void lines_stage1(const vpt_predictor& p, Scratch& s, LineChunk& ch) {
     // the tokenised text needs the boundaries only (every character is at least one byte: the chunk's bytes
     // bound its boundaries)
     a.scores = nullptr;
-    if (!scores_optional(p.dm)) {
+    DevModel dm = p.dm;
+    dm.kytea_norm = normalize ? 1 : 0;
+    if (!scores_optional(dm)) {
         Scratch::ensure(s.d_scores, s.scores_cap, 4 * ch.nbytes + 4);
         a.scores = static_cast<int32_t*>(s.d_scores);
     }
@@ -783,7 +786,7 @@ void lines_stage1(const vpt_predictor& p, Scratch& s, LineChunk& ch) {
     if (pipeline_trace()) ch.tr.mark_sub(0, st);  // after the line offsets
     cuda_check(launch_count(a, st), "launch(count)");
     if (pipeline_trace()) ch.tr.mark_sub(1, st);  // after count + scan
-    cuda_check(launch_score(p.dm, a, st), "launch(score)");
+    cuda_check(launch_score(dm, a, st), "launch(score)");
     if (pipeline_trace()) ch.tr.mark_sub(2, st);  // after the scoring kernel
     TokArgs t;
     t.text = a.text;
@@ -806,8 +809,10 @@ void lines_stage1(const vpt_predictor& p, Scratch& s, LineChunk& ch) {
 
 }  // namespace
 
-int vpt_tokenize_lines(const vpt_predictor* p, const uint8_t* utf8, size_t n_bytes, uint8_t* out, size_t out_capacity,
-                       uint64_t* out_len, uint64_t* n_lines_out) {
+uint32_t vpt_kytea_fullwidth(uint32_t code_point) { return kytea_fullwidth(code_point); }
+
+int vpt_tokenize_lines(const vpt_predictor* p, const uint8_t* utf8, size_t n_bytes, int no_norm, uint8_t* out,
+                       size_t out_capacity, uint64_t* out_len, uint64_t* n_lines_out) {
     VPT_API_BEGIN
     require_device(p);
     if (out_len) *out_len = 0;
@@ -860,10 +865,10 @@ int vpt_tokenize_lines(const vpt_predictor* p, const uint8_t* utf8, size_t n_byt
     uint64_t total = 0, lines = 0;
     bool overflow = false;
     for (size_t c = 0; c < std::min<size_t>(3, nchunks); ++c) lines_stage0(*lease[c % kDepth]->s, chunks[c], utf8);
-    lines_stage1(*p, *lease[0]->s, chunks[0]);
+    lines_stage1(*p, *lease[0]->s, chunks[0], no_norm == 0);
     for (size_t c = 0; c < nchunks; ++c) {
         if (c + 3 < nchunks) lines_stage0(*lease[(c + 3) % kDepth]->s, chunks[c + 3], utf8);
-        if (c + 1 < nchunks) lines_stage1(*p, *lease[(c + 1) % kDepth]->s, chunks[c + 1]);
+        if (c + 1 < nchunks) lines_stage1(*p, *lease[(c + 1) % kDepth]->s, chunks[c + 1], no_norm == 0);
         Scratch& s = *lease[c % kDepth]->s;
         cuda_check(cudaEventSynchronize(chunks[c].done), "sync(tokenize)");
         const uint64_t nb = s.h_totals[3];

@@ -37,6 +37,7 @@ struct DevModel {
     int32_t char_window = 0;
     int32_t type_window = 0;
     int32_t emit_states = 0;             // tag variant: pattern-id states are meaningful
+    int32_t kytea_norm = 0;              // per call: score KyteaFullwidthFilter(text) (textnorm.hpp) instead of text
 };
 
 // Per-batch device buffers (all device pointers).

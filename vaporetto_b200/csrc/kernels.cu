@@ -27,6 +27,7 @@
 
 #include "device_model.hpp"
 #include "keys.hpp"
+#include "textnorm.hpp"
 
 namespace vpt {
 
@@ -119,7 +120,7 @@ struct Rings {
 // Decodes the 128-byte window starting at the 4-byte aligned position `wpos`, appends its characters
 // (those whose lead byte lies in [b0, b1)) to the ring at index nd.., returns how many were appended.
 __device__ __forceinline__ uint32_t decode_window(const uint8_t* __restrict__ text, uint64_t wpos, uint64_t b0,
-                                                  uint64_t b1, uint32_t nd, Rings& r, int lane) {
+                                                  uint64_t b1, uint32_t nd, Rings& r, int lane, bool norm) {
     const uint64_t addr = wpos + 4u * uint32_t(lane);
     uint32_t lo = 0, hi = 0;
     if (addr < b1) {
@@ -140,7 +141,8 @@ __device__ __forceinline__ uint32_t decode_window(const uint8_t* __restrict__ te
     for (int j = 0; j < 4; ++j) {
         if (smask & (1u << j)) {
             const uint32_t x = __funnelshift_r(lo, hi, 8 * j);
-            const uint32_t c = decode_cp(x);
+            uint32_t c = decode_cp(x);
+            if (norm) c = kytea_fullwidth(c);
             r.cp[idx & kRingMask] = c;
             r.bp[idx & kRingMask] = uint32_t(addr + j - b0);
             r.ty[idx & kRingMask] = uint8_t(char_type(c));
@@ -152,7 +154,7 @@ __device__ __forceinline__ uint32_t decode_window(const uint8_t* __restrict__ te
 
 // Steps back from byte position `pos` (a character start, > b0) to the previous character; returns its
 // code point and updates pos.
-__device__ __forceinline__ uint32_t prev_char(const uint8_t* __restrict__ text, uint64_t b0, uint64_t& pos) {
+__device__ __forceinline__ uint32_t prev_char(const uint8_t* __restrict__ text, uint64_t b0, uint64_t& pos, bool norm) {
     uint64_t q = pos - 1;
     uint32_t x = __ldg(text + q);
     uint32_t bytes = x;
@@ -162,7 +164,8 @@ __device__ __forceinline__ uint32_t prev_char(const uint8_t* __restrict__ text, 
         bytes = (bytes << 8) | x;
     }
     pos = q;
-    return decode_cp(bytes);
+    const uint32_t c = decode_cp(bytes);
+    return norm ? kytea_fullwidth(c) : c;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -422,7 +425,8 @@ __device__ __forceinline__ uint32_t type_index(const Rings& r, int64_t g, uint32
 // or character types (types=true).  Returns true and the record of the deepest existing node.
 template <bool kTypes>
 __device__ __forceinline__ bool find_node(const DevTable& t, const Rings& r, const uint8_t* __restrict__ text,
-                                          uint64_t b0, uint32_t g, Rec32& rec, uint32_t& slot, bool* deep_hit = nullptr) {
+                                          uint64_t b0, uint32_t g, Rec32& rec, uint32_t& slot, bool norm,
+                                          bool* deep_hit = nullptr) {
     if (deep_hit) *deep_hit = false;
     uint32_t c3, c2 = 0, c1 = 0;
     if (kTypes) {
@@ -443,7 +447,7 @@ __device__ __forceinline__ bool find_node(const DevTable& t, const Rings& r, con
         uint64_t pos = b0 + r.bp[(g - 2) & kRingMask];
         uint32_t node = __ldg(t.slot_node + slot);
         while (pos > b0) {
-            uint32_t sym = prev_char(text, b0, pos);
+            uint32_t sym = prev_char(text, b0, pos, norm);
             if (kTypes) sym = char_type(sym);
             Rec32 nrec;
             uint32_t nslot;
@@ -483,7 +487,7 @@ __device__ __forceinline__ void fast_sentence_warp(const DevModel& m, const Batc
     for (uint32_t cb = 0; cb < n; cb += 32) {
         const uint32_t need = min(n, cb + 32u + uint32_t(tw));
         while (nd < need && wpos < si.b1) {
-            nd += decode_window(text, wpos, si.b0, si.b1, nd, r, lane);
+            nd += decode_window(text, wpos, si.b0, si.b1, nd, r, lane, m.kytea_norm != 0);
             wpos += 128;
         }
         __syncwarp();
@@ -496,7 +500,7 @@ __device__ __forceinline__ void fast_sentence_warp(const DevModel& m, const Batc
         if (active && m.ct.present) {
             Rec32 rec;
             uint32_t slot;
-            if (find_node<false>(m.ct, r, text, si.b0, g, rec, slot)) {
+            if (find_node<false>(m.ct, r, text, si.b0, g, rec, slot, m.kytea_norm != 0)) {
 #pragma unroll
                 for (int j = 0; j < kInlineWidth; ++j) d[j] = int32_t(rec.v[2 + j]);
                 if (m.emit_states && a.char_states) cstate = __ldg(m.ct.slot_pid + slot);
@@ -550,7 +554,7 @@ __device__ __forceinline__ void fast_sentence_warp(const DevModel& m, const Batc
         for (uint32_t cb = 0; cb < n; cb += 32) {
             const uint32_t need = min(n, cb + 32u);
             while (nd2 < need && wpos2 < si.b1) {
-                nd2 += decode_window(text, wpos2, si.b0, si.b1, nd2, r, lane);
+                nd2 += decode_window(text, wpos2, si.b0, si.b1, nd2, r, lane, m.kytea_norm != 0);
                 wpos2 += 128;
             }
             __syncwarp();
@@ -559,7 +563,7 @@ __device__ __forceinline__ void fast_sentence_warp(const DevModel& m, const Batc
                 Rec32 rec;
                 uint32_t slot;
                 bool deep_hit;
-                if (find_node<false>(m.ct, r, text, si.b0, g, rec, slot, &deep_hit) && deep_hit && (rec.v[1] & (1u << 29))) {
+                if (find_node<false>(m.ct, r, text, si.b0, g, rec, slot, m.kytea_norm != 0, &deep_hit) && deep_hit && (rec.v[1] & (1u << 29))) {
                     const uint64_t dsc = __ldg(m.ct.slot_ovf + slot);
                     const uint32_t ptr = uint32_t(dsc);
                     const int off = int(int16_t(uint16_t(dsc >> 32))), len = int(uint16_t(dsc >> 48));
@@ -591,11 +595,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_score_fast(DevModel m, 
 // ------------------------------------------------------------------------------------------------
 template <bool kTypes>
 __device__ __forceinline__ void scatter_general(const DevTable& t, const Rings& r, const uint8_t* __restrict__ text,
-                                                const SentInfo& si, uint32_t g, int32_t* scores, uint32_t* states) {
+                                                const SentInfo& si, uint32_t g, int32_t* scores, uint32_t* states,
+                                                bool norm) {
     Rec32 rec;
     uint32_t slot;
     uint32_t pid = kNoPattern;
-    if (find_node<kTypes>(t, r, text, si.b0, g, rec, slot)) {
+    if (find_node<kTypes>(t, r, text, si.b0, g, rec, slot, norm)) {
         pid = rec.v[2];
         const uint32_t row = rec.v[3];
         if (row != kNoPattern) {
@@ -633,7 +638,7 @@ __device__ __forceinline__ void general_sentence_warp(const DevModel& m, const B
         for (uint32_t cb = 0; cb < n; cb += 32) {
             const uint32_t need = min(n, cb + 32u + uint32_t(tw));
             while (nd < need && wpos < si.b1) {
-                nd += decode_window(text, wpos, si.b0, si.b1, nd, r, lane);
+                nd += decode_window(text, wpos, si.b0, si.b1, nd, r, lane, m.kytea_norm != 0);
                 wpos += 128;
             }
             __syncwarp();
@@ -667,16 +672,16 @@ __device__ __forceinline__ void general_sentence_warp(const DevModel& m, const B
         for (uint32_t cb = 0; cb < n; cb += 32) {
             const uint32_t need = min(n, cb + 32u);
             while (nd < need && wpos < si.b1) {
-                nd += decode_window(text, wpos, si.b0, si.b1, nd, r, lane);
+                nd += decode_window(text, wpos, si.b0, si.b1, nd, r, lane, m.kytea_norm != 0);
                 wpos += 128;
             }
             __syncwarp();
             const uint32_t g = cb + lane;
             if (g < n) {
                 if (m.ct.present)
-                    scatter_general<false>(m.ct, r, text, si, g, a.scores, m.emit_states ? cstates : nullptr);
+                    scatter_general<false>(m.ct, r, text, si, g, a.scores, m.emit_states ? cstates : nullptr, m.kytea_norm != 0);
                 if (m.tt.present)
-                    scatter_general<true>(m.tt, r, text, si, g, a.scores, m.emit_states ? tstates : nullptr);
+                    scatter_general<true>(m.tt, r, text, si, g, a.scores, m.emit_states ? tstates : nullptr, m.kytea_norm != 0);
             }
             __syncwarp();
         }
@@ -1062,6 +1067,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_fast(DevModel m, Batch
                     const uint32_t lo = *reinterpret_cast<const uint32_t*>(s_text + al);
                     const uint32_t hi = *reinterpret_cast<const uint32_t*>(s_text + al + 4);
                     c = decode_cp(__funnelshift_r(lo, hi, 8 * (pos & 3u)));
+                    if (m.kytea_norm) c = kytea_fullwidth(c);
                     if (c < 0x10000u) {
                         ty = s_tytab[c >> 8];
                         if (ty & 0x80u) ty = s_tytab[256u + ((ty & 3u) << 8) + (c & 255u)];
