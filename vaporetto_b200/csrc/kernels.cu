@@ -1067,7 +1067,6 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_fast(DevModel m, Batch
                     const uint32_t lo = *reinterpret_cast<const uint32_t*>(s_text + al);
                     const uint32_t hi = *reinterpret_cast<const uint32_t*>(s_text + al + 4);
                     c = decode_cp(__funnelshift_r(lo, hi, 8 * (pos & 3u)));
-                    if (m.kytea_norm) c = kytea_fullwidth(c);
                     if (c < 0x10000u) {
                         ty = s_tytab[c >> 8];
                         if (ty & 0x80u) ty = s_tytab[256u + ((ty & 3u) << 8) + (c & 255u)];
@@ -1079,6 +1078,19 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_fast(DevModel m, Batch
                 s_ty[p] = uint8_t(ty);
             }
             sub_sync(sub);
+            if (m.kytea_norm) {
+                // KyteaFullwidthFilter (textnorm.hpp) as its own pass, so that the common path above stays as it is:
+                // the few characters the filter changes get their code point and type rewritten in place
+                for (int p = tid; p < Sround; p += kSubThreads) {
+                    const uint32_t c = s_cp[p];
+                    const uint32_t f = kytea_fullwidth(c);
+                    if (f != c) {
+                        s_cp[p] = f;
+                        s_ty[p] = uint8_t(char_type(f));
+                    }
+                }
+                sub_sync(sub);
+            }
 
             if constexpr (kGeneral) {
                 // ---- pass C (general tables): rows of any offset/length scatter into the per-slot sums with
