@@ -3,6 +3,7 @@
 #include "../../include/vaporetto_b200.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -582,10 +583,10 @@ void chunk_count(Scratch& s, ChunkState& ch, const uint8_t* utf8, const uint64_t
     a.status = static_cast<int32_t*>(s.d_status);
     a.bound_offsets = static_cast<uint64_t*>(s.d_boff);
     a.char_offsets = static_cast<uint64_t*>(s.d_coff);
+    // the totals come back through pinned host memory the scan kernel writes itself: an 8-byte D2H copy would
+    // queue behind the bulk copy-out of earlier chunks on the copy engine
+    a.totals_host = &s.h_totals[0];
     cuda_check(launch_count(a, st), "launch(count)");
-    const size_t ng = (ch.n + kGroup - 1) / kGroup;
-    cuda_check(cudaMemcpyAsync(&s.h_totals[0], a.group_bound + ng, 8, cudaMemcpyDeviceToHost, st), "D2H(total)");
-    cuda_check(cudaMemcpyAsync(&s.h_totals[1], a.group_char + ng, 8, cudaMemcpyDeviceToHost, st), "D2H(total)");
     if (!ch.counted) cuda_check(cudaEventCreateWithFlags(&ch.counted, cudaEventDisableTiming), "cudaEventCreate");
     cuda_check(cudaEventRecord(ch.counted, st), "cudaEventRecord");
 }
@@ -733,8 +734,8 @@ void lines_stage0(Scratch& s, LineChunk& ch, const uint8_t* utf8) {
     sp.blk = static_cast<uint32_t*>(s.d_blk);
     sp.blk_base = static_cast<uint64_t*>(s.d_blkbase);
     sp.n_lines = sp.blk_base + nblk;  // the element after the per-block bases
+    sp.n_lines_host = &s.h_totals[2];  // read back through pinned host memory written by the kernel (see chunk_count)
     cuda_check(launch_split_count(sp, st), "launch(split)");
-    cuda_check(cudaMemcpyAsync(&s.h_totals[2], sp.n_lines, 8, cudaMemcpyDeviceToHost, st), "D2H(lines)");
     if (!ch.split) cuda_check(cudaEventCreateWithFlags(&ch.split, cudaEventDisableTiming), "cudaEventCreate");
     cuda_check(cudaEventRecord(ch.split, st), "cudaEventRecord");
 }
@@ -800,10 +801,10 @@ void lines_stage1(const vpt_predictor& p, Scratch& s, LineChunk& ch, bool normal
     t.tok_state = static_cast<uint64_t*>(s.d_tokg);
     t.ticket = reinterpret_cast<uint32_t*>(t.tok_state + ng);
     t.total = t.tok_state + ng + 1;
+    t.total_host = &s.h_totals[3];
     t.out = static_cast<uint8_t*>(s.d_out);
     cuda_check(launch_tokenize(t, st), "launch(tok)");
     if (pipeline_trace()) ch.tr.mark(2, st);
-    cuda_check(cudaMemcpyAsync(&s.h_totals[3], t.total, 8, cudaMemcpyDeviceToHost, st), "D2H(total)");
     cuda_check(cudaEventRecord(ch.done, st), "cudaEventRecord");
 }
 
@@ -864,13 +865,22 @@ int vpt_tokenize_lines(const vpt_predictor* p, const uint8_t* utf8, size_t n_byt
     // chunks c+2, c+3 are copied in and split while chunk c+1 is scored and chunk c is copied out
     uint64_t total = 0, lines = 0;
     bool overflow = false;
+    const bool trace = pipeline_trace();
+    const auto host_t0 = std::chrono::steady_clock::now();
+    auto host_ms = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count(); };
     for (size_t c = 0; c < std::min<size_t>(3, nchunks); ++c) lines_stage0(*lease[c % kDepth]->s, chunks[c], utf8);
     lines_stage1(*p, *lease[0]->s, chunks[0], no_norm == 0);
     for (size_t c = 0; c < nchunks; ++c) {
+        const double h0 = host_ms();
         if (c + 3 < nchunks) lines_stage0(*lease[(c + 3) % kDepth]->s, chunks[c + 3], utf8);
+        const double h1 = host_ms();
         if (c + 1 < nchunks) lines_stage1(*p, *lease[(c + 1) % kDepth]->s, chunks[c + 1], no_norm == 0);
+        const double h2 = host_ms();
         Scratch& s = *lease[c % kDepth]->s;
         cuda_check(cudaEventSynchronize(chunks[c].done), "sync(tokenize)");
+        if (trace)
+            fprintf(stderr, "[vpt lines host] iteration %zu: begins %.3f  copy-in+split issued %.3f  kernels issued %.3f  "
+                            "chunk done seen %.3f ms\n", c, h0, h1, h2, host_ms());
         const uint64_t nb = s.h_totals[3];
         if (total + nb > out_capacity || (nb && !out)) overflow = true;
         if (!overflow && nb) {

@@ -55,6 +55,8 @@ struct BatchArgs {
     uint64_t* group_bound = nullptr;      // [n_groups + 1]
     uint64_t* group_char = nullptr;       // [n_groups + 1]
     uint32_t* ticket = nullptr;           // work counter of the persistent tile kernel (zeroed by the scan)
+    uint64_t* totals_host = nullptr;      // nullable: pinned host memory [2]; the scan also stores the batch's boundary
+                                          // and character totals there (no D2H copy queued behind bulk copies)
     // outputs
     int32_t* scores = nullptr;            // [sum(max(chars_i - 1, 0))] (nullable: boundaries only)
     uint8_t* boundaries = nullptr;        // same length
@@ -87,6 +89,7 @@ struct SplitArgs {
     uint32_t* blk = nullptr;         // [n_blocks] newline count per block (scratch)
     uint64_t* blk_base = nullptr;    // [n_blocks] lines before each block (scratch)
     uint64_t* n_lines = nullptr;     // device scalar: number of lines
+    uint64_t* n_lines_host = nullptr;  // nullable: pinned host memory, receives the same number
     uint64_t* offsets = nullptr;     // [n_lines + 1] out: line starts (+ n_bytes)
     uint8_t* trims = nullptr;        // [n_lines] out: terminator bytes of each line (0, 1 or 2)
 };
@@ -105,6 +108,7 @@ struct TokArgs {
     uint64_t* tok_state = nullptr;          // [n_groups] scratch: look-back state of every 64-sentence group
     uint32_t* ticket = nullptr;             // scratch: group ticket (the 8 bytes after tok_state)
     uint64_t* total = nullptr;              // device scalar out: total output bytes
+    uint64_t* total_host = nullptr;         // nullable: pinned host memory, receives the same number
     uint8_t* out = nullptr;                 // tokenised lines, each terminated by '\n'
 };
 // zeroes tok_state[0 .. n_groups] (ticket included), then one pass: lengths, offsets (look-back), output bytes

@@ -342,7 +342,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_count(BatchArgs a) {
 }
 
 // Exclusive scan of the per-group totals (in place); element [ngroups] receives the grand total.
-__global__ void __launch_bounds__(1024) k_scan_groups(uint64_t* gb, uint64_t* gc, uint64_t ngroups, uint32_t* ticket) {
+__global__ void __launch_bounds__(1024) k_scan_groups(uint64_t* gb, uint64_t* gc, uint64_t ngroups, uint32_t* ticket,
+                                                     uint64_t* totals_host) {
     __shared__ uint64_t s_wb[32], s_wc[32];
     __shared__ uint64_t s_carry[2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -376,7 +377,12 @@ __global__ void __launch_bounds__(1024) k_scan_groups(uint64_t* gb, uint64_t* gc
         if (threadIdx.x == 0) { s_carry[0] += s_wb[31]; s_carry[1] += s_wc[31]; }
         __syncthreads();
     }
-    if (threadIdx.x == 0) { gb[ngroups] = s_carry[0]; gc[ngroups] = s_carry[1]; *ticket = 0; }
+    if (threadIdx.x == 0) {
+        gb[ngroups] = s_carry[0];
+        gc[ngroups] = s_carry[1];
+        *ticket = 0;
+        if (totals_host) { totals_host[0] = s_carry[0]; totals_host[1] = s_carry[1]; }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1243,7 +1249,7 @@ cudaError_t launch_count_only(const BatchArgs& a, cudaStream_t stream) {
 cudaError_t launch_scan_only(const BatchArgs& a, cudaStream_t stream) {
     if (a.n_sent == 0) return cudaSuccess;
     const uint64_t ngroups = (a.n_sent + kGroup - 1) / kGroup;
-    k_scan_groups<<<1, 1024, 0, stream>>>(a.group_bound, a.group_char, ngroups, a.ticket);
+    k_scan_groups<<<1, 1024, 0, stream>>>(a.group_bound, a.group_char, ngroups, a.ticket, a.totals_host);
     return cudaGetLastError();
 }
 

@@ -115,7 +115,9 @@ __global__ void __launch_bounds__(1024) k_nl_scan(SplitArgs s, uint64_t nblk) {
     }
     if (threadIdx.x == 0) {
         const bool open_tail = s.n_bytes > 0 && s.text[s.n_bytes - 1] != 0x0A;
-        *s.n_lines = s_carry + (open_tail ? 1 : 0);
+        const uint64_t nl = s_carry + (open_tail ? 1 : 0);
+        *s.n_lines = nl;
+        if (s.n_lines_host) *s.n_lines_host = nl;
     }
 }
 
@@ -286,7 +288,10 @@ __global__ void __launch_bounds__(kTokThreads) k_tok_write(TokArgs t, uint64_t n
         }
         if (lane == 0) {
             s_base = prefix;
-            if (grp + 1 == ngroups) *t.total = prefix + total;
+            if (grp + 1 == ngroups) {
+                *t.total = prefix + total;
+                if (t.total_host) *t.total_host = prefix + total;
+            }
         }
     }
     __syncthreads();
