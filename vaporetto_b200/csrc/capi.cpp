@@ -483,7 +483,7 @@ size_t chunk_sentences() {
     static const size_t v = [] {
         const char* e = getenv("VPT_CHUNK_SENTENCES");
         const long long x = e ? atoll(e) : 0;
-        return x >= 1024 ? size_t(x) : size_t(65536);
+        return x >= 1024 ? size_t(x) : size_t(262144);
     }();
     return v;
 }
