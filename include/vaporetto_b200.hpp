@@ -2,7 +2,8 @@
 //
 // Same names, argument meaning and error behaviour as the crate (vaporetto/src/lib.rs:82-91):
 //   vaporetto::Model      model.rs:58   (read / read_slice)
-//   vaporetto::Predictor  predictor.rs:434   (new(model, predict_tags), predict(&mut Sentence))
+//   vaporetto::Predictor  predictor.rs:434   (new(model, predict_tags), predict(&mut Sentence);
+//                                             tokenize_lines = the `predict` CLI loop, predict/src/main.rs:126-181)
 //   vaporetto::Sentence   sentence.rs:85   (from_raw, update_raw, as_raw_text, char_types, boundaries,
 //                                           boundaries_mut, boundary_scores, fill_tags, tags, n_tags,
 //                                           iter_tokens, write_tokenized_text)
@@ -93,6 +94,20 @@ public:
 
     /// `Predictor::predict(&self, &mut Sentence)` (predictor.rs:518-543).
     inline void predict(Sentence& s) const;
+
+    /// The loop of the reference's `predict` CLI over a buffer of raw lines (predict/src/main.rs:126-181;
+    /// `vpt_tokenize_lines`): line splitting, the KyteaFullwidthFilter pre-filter (unless `no_norm`), prediction and
+    /// `write_tokenized_text` + '\n' all run on the device.  Returns the output text.
+    std::string tokenize_lines(const std::string& text, bool no_norm = false) const {
+        size_t n_lines = 0;
+        for (char c : text) n_lines += c == '\n';
+        std::string out(3 * text.size() + n_lines + 1, '\0');
+        uint64_t n_out = 0, nl = 0;
+        detail::check(vpt_tokenize_lines(h_, reinterpret_cast<const uint8_t*>(text.data()), text.size(), no_norm ? 1 : 0,
+                                         reinterpret_cast<uint8_t*>(&out[0]), out.size(), &n_out, &nl));
+        out.resize(size_t(n_out));
+        return out;
+    }
 
     const vpt_predictor_info& info() const { return info_; }
     const vpt_predictor* handle() const { return h_; }

@@ -42,6 +42,8 @@ int main(int argc, char** argv) {
         Predictor host(std::move(model), true, -1);
         Sentence t = Sentence::from_raw("まぁ社長は火星猫だ");
         try { host.predict(t); CHECK(false); } catch (const VaporettoError& e) { CHECK(e.code() == VPT_CUDA_ERROR); }
+        try { host.tokenize_lines("まぁ社長は火星猫だ\n"); CHECK(false); } catch (const VaporettoError& e) { CHECK(e.code() == VPT_CUDA_ERROR); }
+        CHECK(vpt_kytea_fullwidth('a') == 0xFF41 && vpt_kytea_fullwidth('.') == 0x3002 && vpt_kytea_fullwidth('#') == '#');
         std::printf("cpp mirror (host) ok\n");
         return 0;
     }
@@ -72,6 +74,9 @@ int main(int argc, char** argv) {
     try { u.fill_tags(); CHECK(false); } catch (const VaporettoError& e) {
         CHECK(std::string(e.what()).find("predict_tags = false") != std::string::npos);
     }
+    // the CLI loop (predict/src/main.rs:126-181): CRLF, an empty line, an unterminated last line
+    CHECK(plain.tokenize_lines("まぁ社長は火星猫だ\r\n\nまぁ良いだろう") == "まぁ 社長 は 火星 猫 だ\n\nまぁ 良い だろう\n");
+    CHECK(plain.tokenize_lines("") == "");
     std::printf("cpp mirror (gpu) ok\n");
     return 0;
 }
