@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """Randomised GPU-vs-oracle parity fuzzer (run manually on the GPU box: python tests/fuzz_gpu.py [seconds]).
 Random models (windows 0-5, n-grams 1-4 chars, dictionary words up to 20 chars, optional tag models, duplicate
-entries, short/over-long weight vectors) x random batches (lengths 1-600, mixed scripts, 4-byte characters)."""
+entries, short/over-long weight vectors) x random batches (lengths 1-600, mixed scripts, 4-byte characters).
+Every model also goes through vpt_tokenize_lines (both with and without the full-width pre-filter) on the same
+sentences joined by random line terminators, with empty / malformed lines mixed in and a random chunk size."""
 import os
 import sys
 import time
@@ -16,6 +18,7 @@ from vpt_testlib.bincode_model import encode_model  # noqa: E402
 from vpt_testlib.oracle import OraclePredictor  # noqa: E402
 
 ALPHA = list("あいうえおかきアイウエ人火星地球猫社長漢字aBc1 9。、🤌𠀋é")
+LINE_EXTRA = list("/\\.-ａ１。－―｢")  # escapes and sources / targets of the full-width filter
 
 
 def rand_model(rng):
@@ -80,6 +83,30 @@ def main():
         if not (np.array_equal(r.scores, sc) and np.array_equal(r.boundaries, bd) and np.array_equal(r.bound_offsets, boff)):
             np.save("/tmp/fuzz_fail_model.npy", np.frombuffer(mb, np.uint8))
             raise SystemExit(f"iteration {it}: MISMATCH (model saved to /tmp/fuzz_fail_model.npy), path {key}")
+        # the CLI loop on the device (untagged output): the same sentences as lines
+        parts = []
+        for sline in sents[: 120]:
+            r2 = rng.random()
+            if r2 < 0.05:
+                body = b""
+            elif r2 < 0.08:
+                body = bytes(rng.integers(0, 256, rng.integers(1, 9)).astype(np.uint8)).replace(b"\n", b"")
+            elif r2 < 0.4:
+                body = (sline[: 1 + len(sline) // 2] + "".join(rng.choice(LINE_EXTRA, size=rng.integers(1, 6)))).encode()
+            else:
+                body = sline.encode()
+            parts.append(body + (b"\r\n" if rng.random() < 0.15 else b"\n"))
+        data = b"".join(parts)
+        if rng.random() < 0.5 and data.endswith(b"\n") and not data.endswith(b"\r\n"):
+            data = data[:-1]
+        os.environ["VPT_CHUNK_BYTES"] = str(int(rng.choice([64, 777, 1 << 14, 16 << 20])))
+        for no_norm in (True, False):
+            got, nl = p.tokenize_lines(data, no_norm=no_norm)
+            want, wl = o.tokenize_lines(data, no_norm=no_norm)
+            if nl != wl or got.tobytes() != want:
+                np.save("/tmp/fuzz_fail_model.npy", np.frombuffer(mb, np.uint8))
+                open("/tmp/fuzz_fail_lines.bin", "wb").write(data)
+                raise SystemExit(f"iteration {it}: tokenize_lines MISMATCH (no_norm={no_norm}), path {key}")
         if tags:
             for i in rng.integers(0, len(sents), size=3):
                 _, _, ocs, ots = o.predict(sents[i], states=True)
