@@ -17,6 +17,15 @@ for kw, tags in ((dict(), False), (dict(dict_words=2000), False), (dict(tag_mode
     r = p.predict_batch(text, offs, want_states=tags)
     sc, bd, boff, st = o.predict_batch(text, offs, nthreads=2)
     assert np.array_equal(r.scores, sc) and np.array_equal(r.boundaries, bd), kw
+    # the lines path: splitter, trims through every scoring kernel, look-back output kernel; tiny and default chunks
+    lines = [text[int(offs[i]):int(offs[i + 1])].tobytes() for i in range(len(lens))]
+    data = b"\r\n".join(lines[:7]) + b"\n\n\xff\xfe\na/b c\\d.\n" + b"\n".join(lines[7:])
+    for chunk in ("64", "4096", ""):
+        os.environ["VPT_CHUNK_BYTES"] = chunk
+        for no_norm in (True, False):
+            got, nl = p.tokenize_lines(data, no_norm=no_norm)
+            want, wl = o.tokenize_lines(data, no_norm=no_norm)
+            assert nl == wl and got.tobytes() == want, (kw, chunk, no_norm)
 print("sanitizer workload ok")
 PY
 for tool in memcheck racecheck; do
