@@ -117,8 +117,11 @@ int vpt_predictor_from_blob(const void* blob, uint64_t len, int device, vpt_pred
  *
  * out_capacity / states_capacity are the element capacities of the output arrays; if too small the call
  * fails with VPT_INVALID_ARGUMENT and the required sizes are in *n_boundaries_out / *n_chars_out.
- * scores_out, char_states_out, type_states_out, char_offsets_out, status_out may be NULL.
- * For full PCIe bandwidth pass page-locked (pinned) host buffers. */
+ * scores_out, char_states_out, type_states_out, char_offsets_out, status_out may be NULL (without scores_out the
+ * inline-row kernel skips the score stores and only boundaries cross PCIe).
+ * For full PCIe bandwidth pass page-locked (pinned) host buffers.  The batch flows through an internal pipeline
+ * (copy-in + kernels and copy-out on separate streams, four chunks in flight, chunk sizes ramping up from 1/8 of
+ * env VPT_CHUNK_SENTENCES, default 262144); VPT_TRACE=1 prints its per-chunk timeline to stderr. */
 int vpt_predict_batch(const vpt_predictor* predictor, const uint8_t* utf8, const uint64_t* byte_offsets, size_t n_sent,
                       int32_t* scores_out, uint8_t* boundaries_out, size_t out_capacity, uint64_t* bound_offsets_out,
                       int32_t* status_out, uint32_t* char_states_out, uint32_t* type_states_out,
