@@ -385,7 +385,7 @@ def main():
     tok_len, tok_lines = C.c_uint64(), C.c_uint64()
 
     def step_lines():
-        rc = L.vpt_tokenize_lines(pred._h, h_lines.data_ptr(), nbytes + n, 1, h_tok.data_ptr(), h_tok.numel(),
+        rc = L.vpt_tokenize_lines(pred._h, h_lines.data_ptr(), nbytes + n, 1, 0, h_tok.data_ptr(), h_tok.numel(),
                                   C.byref(tok_len), C.byref(tok_lines))
         if rc:
             raise RuntimeError(L.vpt_last_error().decode())

@@ -202,14 +202,23 @@ int vpt_write_tokenized_text(const vpt_predictor* predictor, const uint8_t* utf8
  * (' ' between tokens; '\\' before ' ', '\\', '/': sentence.rs:850-886) is materialised on the device: the only
  * transfers are the input bytes in and the output bytes out.  Lines that update_raw rejects (empty, or
  * containing U+0000) produce an empty line as in the CLI; so do lines that are not valid UTF-8 (the CLI stops
- * with an I/O error on those).  Tags, --wsconst post-filters and score printing are not part of this path.
+ * with an I/O error on those).  Tags, `--wsconst G` (grapheme clusters) and score printing are not part of this path.
  * `no_norm`: the CLI flag of the same name (0 = apply KyteaFullwidthFilter, the CLI default).
+ * `wsconst_types`: the CLI's `--wsconst D/R/H/T/K/O` options as a bit set, bit t for CharacterType t (VPT_WSCONST_*):
+ * `KyteaWsConstFilter` (vaporetto_rules/src/sentence_filters/kytea_wsconst.rs:27-44) clears the boundary between two
+ * characters of such a type after prediction (types of the filtered text when no_norm == 0, main.rs:157).
  * `out` receives the output lines, each terminated by '\n' (at most 3 * n_bytes + n_lines bytes); *out_len
  * the number of bytes produced (also when `out_capacity` was too small, which returns InvalidArgument);
  * *n_lines the number of input lines.  Chunk size of the internal pipeline: env VPT_CHUNK_BYTES (16 MiB, with
  * smaller chunks at both ends); VPT_TRACE=1 prints the pipeline's per-chunk timeline to stderr. */
-int vpt_tokenize_lines(const vpt_predictor* predictor, const uint8_t* utf8, size_t n_bytes, int no_norm, uint8_t* out,
-                       size_t out_capacity, uint64_t* out_len, uint64_t* n_lines);
+#define VPT_WSCONST_DIGIT (1u << 1)    /* --wsconst D */
+#define VPT_WSCONST_ROMAN (1u << 2)    /* --wsconst R */
+#define VPT_WSCONST_HIRAGANA (1u << 3) /* --wsconst H */
+#define VPT_WSCONST_KATAKANA (1u << 4) /* --wsconst T */
+#define VPT_WSCONST_KANJI (1u << 5)    /* --wsconst K */
+#define VPT_WSCONST_OTHER (1u << 6)    /* --wsconst O */
+int vpt_tokenize_lines(const vpt_predictor* predictor, const uint8_t* utf8, size_t n_bytes, int no_norm,
+                       uint32_t wsconst_types, uint8_t* out, size_t out_capacity, uint64_t* out_len, uint64_t* n_lines);
 
 /* `KyteaFullwidthFilter` for one character (vaporetto_rules/src/string_filters/kytea_fullwidth.rs:13-118): the
  * same function the kernels apply (csrc/textnorm.hpp). */

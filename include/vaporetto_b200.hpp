@@ -98,13 +98,13 @@ public:
     /// The loop of the reference's `predict` CLI over a buffer of raw lines (predict/src/main.rs:126-181;
     /// `vpt_tokenize_lines`): line splitting, the KyteaFullwidthFilter pre-filter (unless `no_norm`), prediction and
     /// `write_tokenized_text` + '\n' all run on the device.  Returns the output text.
-    std::string tokenize_lines(const std::string& text, bool no_norm = false) const {
+    std::string tokenize_lines(const std::string& text, bool no_norm = false, uint32_t wsconst_types = 0) const {
         size_t n_lines = 0;
         for (char c : text) n_lines += c == '\n';
         std::string out(3 * text.size() + n_lines + 1, '\0');
         uint64_t n_out = 0, nl = 0;
         detail::check(vpt_tokenize_lines(h_, reinterpret_cast<const uint8_t*>(text.data()), text.size(), no_norm ? 1 : 0,
-                                         reinterpret_cast<uint8_t*>(&out[0]), out.size(), &n_out, &nl));
+                                         wsconst_types, reinterpret_cast<uint8_t*>(&out[0]), out.size(), &n_out, &nl));
         out.resize(size_t(n_out));
         return out;
     }

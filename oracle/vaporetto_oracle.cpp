@@ -955,8 +955,16 @@ uint32_t ora_kytea_fullwidth(uint32_t c) { return kytea_fullwidth_cp(c); }
 // line.  A line that is not valid UTF-8 makes `lines()` fail and the CLI stop; the batch interface this
 // checks prints an empty line for it instead (documented difference).  Returns the output size (or
 // -(1000000 + needed) when cap is too small); *n_lines receives the number of lines.
-long ora_tokenize_lines(const void* p, const char* utf8, size_t nbytes, int no_norm, char* buf, size_t cap,
-                        uint64_t* n_lines) {
+// KyteaWsConstFilter::filter (vaporetto_rules/src/sentence_filters/kytea_wsconst.rs:27-44)
+static void wsconst_filter(Sentence& s, uint8_t char_type) {
+    for (size_t i = 0; i + 1 < s.char_types.size(); ++i)
+        if (s.char_types[i] == char_type && s.char_types[i + 1] == char_type) s.boundaries[i] = 0;
+}
+
+// `wsconst_types`: bit t set = a `--wsconst` option for CharacterType t (post_filters, main.rs:100-106; applied to
+// the sentence that was predicted, main.rs:138,157).
+long ora_tokenize_lines(const void* p, const char* utf8, size_t nbytes, int no_norm, uint32_t wsconst_types, char* buf,
+                        size_t cap, uint64_t* n_lines) {
     auto neg = [](int c) { return -long(c); };
     ORA_TRY
     auto* pr = static_cast<const Predictor*>(p);
@@ -975,11 +983,13 @@ long ora_tokenize_lines(const void* p, const char* utf8, size_t nbytes, int no_n
         if (ok) {
             if (no_norm) {
                 pr->predict(s_orig);
+                for (uint8_t t = 1; t <= 6; ++t) if (wsconst_types & (1u << t)) wsconst_filter(s_orig, t);
             } else {
                 string pre;
                 for (uint32_t c : s_orig.chars) append_utf8(pre, kytea_fullwidth_cp(c));
                 s.parse_raw(pre.data(), pre.size());
                 pr->predict(s);
+                for (uint8_t t = 1; t <= 6; ++t) if (wsconst_types & (1u << t)) wsconst_filter(s, t);
                 s_orig.boundaries = s.boundaries;
             }
             out += write_tokenized(*pr, s_orig, nullptr, nullptr);

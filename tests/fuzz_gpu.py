@@ -101,8 +101,9 @@ def main():
             data = data[:-1]
         os.environ["VPT_CHUNK_BYTES"] = str(int(rng.choice([64, 777, 1 << 14, 16 << 20])))
         for no_norm in (True, False):
-            got, nl = p.tokenize_lines(data, no_norm=no_norm)
-            want, wl = o.tokenize_lines(data, no_norm=no_norm)
+            ws = "".join(rng.choice(list("DRHTKO"), size=rng.integers(0, 3)))  # --wsconst options
+            got, nl = p.tokenize_lines(data, no_norm=no_norm, wsconst=ws)
+            want, wl = o.tokenize_lines(data, no_norm=no_norm, wsconst=ws)
             if nl != wl or got.tobytes() != want:
                 np.save("/tmp/fuzz_fail_model.npy", np.frombuffer(mb, np.uint8))
                 open("/tmp/fuzz_fail_lines.bin", "wb").write(data)

@@ -14,12 +14,13 @@ from test_gpu_parity import _random_model, make, read
 pytestmark = pytest.mark.gpu
 
 
-def check(p, o, data: bytes):
+def check(p, o, data: bytes, wsconsts=("", "D", "HK", "DRHTKO")):
     for no_norm in (True, False):
-        got, nl = p.tokenize_lines(data, no_norm=no_norm)
-        want, wl = o.tokenize_lines(data, no_norm=no_norm)
-        assert nl == wl
-        assert got.tobytes() == want, (no_norm, data[:200])
+        for ws in wsconsts:
+            got, nl = p.tokenize_lines(data, no_norm=no_norm, wsconst=ws)
+            want, wl = o.tokenize_lines(data, no_norm=no_norm, wsconst=ws)
+            assert nl == wl
+            assert got.tobytes() == want, (no_norm, ws, data[:200])
 
 
 @pytest.fixture(scope="module")
@@ -59,6 +60,16 @@ def test_lines_semantics(kat_pair, monkeypatch):
             monkeypatch.setenv("VPT_CHUNK_BYTES", chunk)
         for data in cases:
             check(p, o, data)
+
+
+def test_wsconst_reference_vectors():
+    # kytea_wsconst.rs:57-80 through a model that cuts everywhere (bias > 0, no features)
+    mb = encode_model(dict(char_ngrams=[], type_ngrams=[], dict=[], bias=1, char_window=1, type_window=1, tag_models=[]))
+    p = make(mb)
+    got, _ = p.tokenize_lines("5\n5000\n2021年8月24日\n".encode(), no_norm=True, wsconst="D")
+    assert got.tobytes().decode() == "5\n5000\n2021 年 8 月 24 日\n"
+    with pytest.raises(vb.VaporettoError):
+        p.tokenize_lines(b"a\n", wsconst="G")
 
 
 def test_lines_out_capacity(kat_pair):
@@ -116,8 +127,8 @@ def test_lines_full_size():
     assert nl == len(lines)
     want, _ = o.tokenize_lines(data, no_norm=True)
     assert got.tobytes() == want
-    got_n, _ = p.tokenize_lines(data)                      # CLI default: full-width normalisation before scoring
-    want_n, _ = o.tokenize_lines(data)
+    got_n, _ = p.tokenize_lines(data, wsconst="DK")        # CLI default (full-width normalisation) + --wsconst D K
+    want_n, _ = o.tokenize_lines(data, wsconst="DK")
     assert got_n.tobytes() == want_n
     g = got.tobytes()
     assert g.count(b"\n") == len(lines)

@@ -31,7 +31,11 @@ def escape(tok: str) -> str:
     return tok.replace("\\", "\\\\").replace(" ", "\\ ").replace("/", "\\/")
 
 
-def expected(o, data: bytes, no_norm: bool = True) -> bytes:
+def char_type(c: str) -> int:
+    return int(vb.Sentence.from_raw(c).char_types()[0])
+
+
+def expected(o, data: bytes, no_norm: bool = True, wsconst: str = "") -> bytes:
     fw = fullwidth_map()
     out = []
     for line in rust_lines(data):
@@ -42,14 +46,22 @@ def expected(o, data: bytes, no_norm: bool = True) -> bytes:
             ok = False
         if not ok:
             out.append(b"")
-        elif no_norm:
+        elif no_norm and not wsconst:
             out.append(o.tokenize(s).encode())
         else:
-            # predict on the filtered line, put its boundaries on the original line (predict/src/main.rs:154-166)
-            pre = "".join(chr(fw.get(ord(c), ord(c))) for c in s)
+            # predict on the filtered line, put its boundaries on the original line (predict/src/main.rs:154-166);
+            # --wsconst filters run on the predicted sentence (kytea_wsconst.rs:27-44)
+            pre = s if no_norm else "".join(chr(fw.get(ord(c), ord(c))) for c in s)
             _, bounds = o.predict(pre)
+            bounds = bounds.tolist()
+            types = [char_type(c) for c in pre]
+            for letter in wsconst:
+                t = "DRHTKO".index(letter) + 1
+                for i in range(len(types) - 1):
+                    if types[i] == t and types[i + 1] == t:
+                        bounds[i] = 0
             toks, start = [], 0
-            for i, b in enumerate(bounds.tolist()):
+            for i, b in enumerate(bounds):
                 if b == 1:
                     toks.append(s[start:i + 1])
                     start = i + 1
@@ -88,9 +100,22 @@ def test_cli_loop_matches_per_line_oracle():
     ]
     for data in cases:
         for no_norm in (True, False):
-            got, nl = o.tokenize_lines(data, no_norm=no_norm)
-            assert nl == len(rust_lines(data))
-            assert got == expected(o, data, no_norm), (data, no_norm)
+            for ws in ("", "D", "RK", "DRHTKO"):
+                got, nl = o.tokenize_lines(data, no_norm=no_norm, wsconst=ws)
+                assert nl == len(rust_lines(data))
+                assert got == expected(o, data, no_norm, ws), (data, no_norm, ws)
+
+
+def test_wsconst_reference_vectors():
+    """kytea_wsconst.rs:57-80: the filter on given boundaries ("5 00 0" -> "5000", "20 21 年 8 月 2 4 日" ->
+    "2021 年 8 月 24 日"), through a model that cuts everywhere (bias > 0, no features)."""
+    from vpt_testlib.bincode_model import encode_model
+    o = OraclePredictor(encode_model(dict(char_ngrams=[], type_ngrams=[], dict=[], bias=1, char_window=1, type_window=1,
+                                          tag_models=[])))
+    got, _ = o.tokenize_lines("5\n5000\n2021年8月24日\n".encode(), no_norm=True, wsconst="D")
+    assert got.decode() == "5\n5000\n2021 年 8 月 24 日\n"
+    got, _ = o.tokenize_lines("2021年8月24日\n".encode(), no_norm=True)
+    assert got.decode() == "2 0 2 1 年 8 月 2 4 日\n"
 
 
 def test_docs_tok_through_cli_loop():

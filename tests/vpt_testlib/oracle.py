@@ -45,8 +45,8 @@ def lib():
         L.ora_char_types.restype = C.c_long
         L.ora_tokenize.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_int, C.c_char_p, C.c_size_t]
         L.ora_tokenize.restype = C.c_long
-        L.ora_tokenize_lines.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_int, C.c_char_p, C.c_size_t,
-                                         C.POINTER(C.c_uint64)]
+        L.ora_tokenize_lines.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_int, C.c_uint32, C.c_char_p,
+                                         C.c_size_t, C.POINTER(C.c_uint64)]
         L.ora_tokenize_lines.restype = C.c_long
         L.ora_kytea_fullwidth.argtypes = [C.c_uint32]
         L.ora_kytea_fullwidth.restype = C.c_uint32
@@ -120,12 +120,13 @@ class OraclePredictor:
             raise _err(-n)
         return buf.raw[:n].decode("utf-8")
 
-    def tokenize_lines(self, data: bytes, no_norm: bool = False):
+    def tokenize_lines(self, data: bytes, no_norm: bool = False, wsconst: str = ""):
         """The reference CLI's loop over a buffer of raw bytes -> (output bytes, n_lines)."""
         cap = 3 * len(data) + data.count(b"\n") + 16
         buf = C.create_string_buffer(cap)
         nl = C.c_uint64(0)
-        n = lib().ora_tokenize_lines(self._p, data, len(data), int(no_norm), buf, cap, C.byref(nl))
+        mask = sum(1 << ("DRHTKO".index(ch) + 1) for ch in set(wsconst))
+        n = lib().ora_tokenize_lines(self._p, data, len(data), int(no_norm), mask, buf, cap, C.byref(nl))
         if n < 0:
             raise _err(-n)
         return buf.raw[:n], int(nl.value)

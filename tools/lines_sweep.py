@@ -34,15 +34,15 @@ def main():
     for mbs in chunks:
         os.environ["VPT_CHUNK_BYTES"] = str(mbs << 20)
         for _ in range(2):
-            assert L.vpt_tokenize_lines(pred._h, h_in.data_ptr(), nbytes + n, 1, h_out.data_ptr(), h_out.numel(), C.byref(ln), C.byref(nl)) == 0
+            assert L.vpt_tokenize_lines(pred._h, h_in.data_ptr(), nbytes + n, 1, 0, h_out.data_ptr(), h_out.numel(), C.byref(ln), C.byref(nl)) == 0
         t0 = time.perf_counter()
         k = 5
         for _ in range(k):
-            L.vpt_tokenize_lines(pred._h, h_in.data_ptr(), nbytes + n, 1, h_out.data_ptr(), h_out.numel(), C.byref(ln), C.byref(nl))
+            L.vpt_tokenize_lines(pred._h, h_in.data_ptr(), nbytes + n, 1, 0, h_out.data_ptr(), h_out.numel(), C.byref(ln), C.byref(nl))
         dt = (time.perf_counter() - t0) / k
         if os.environ.get("TRACE_ONE"):
             os.environ["VPT_TRACE"] = "1"
-            L.vpt_tokenize_lines(pred._h, h_in.data_ptr(), nbytes + n, 1, h_out.data_ptr(), h_out.numel(), C.byref(ln), C.byref(nl))
+            L.vpt_tokenize_lines(pred._h, h_in.data_ptr(), nbytes + n, 1, 0, h_out.data_ptr(), h_out.numel(), C.byref(ln), C.byref(nl))
             os.environ["VPT_TRACE"] = "0"
         print(f"chunk {mbs:3d} MiB: {dt * 1e3:7.3f} ms  {nbytes / dt / 1e9:6.2f} GB/s  out {ln.value} bytes, {nl.value} lines", flush=True)
 

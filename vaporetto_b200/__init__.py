@@ -89,7 +89,7 @@ ABI = [
     ("vpt_char_types", C.c_int, [C.c_char_p, C.c_size_t, _P, C.c_size_t, C.POINTER(C.c_uint64)]),
     ("vpt_write_tokenized_text", C.c_int, [_P, C.c_char_p, C.c_size_t, _P, _P, _P, _P, C.c_size_t,
                                            C.POINTER(C.c_uint64)]),
-    ("vpt_tokenize_lines", C.c_int, [_P, _P, C.c_size_t, C.c_int, _P, C.c_size_t, C.POINTER(C.c_uint64),
+    ("vpt_tokenize_lines", C.c_int, [_P, _P, C.c_size_t, C.c_int, C.c_uint32, _P, C.c_size_t, C.POINTER(C.c_uint64),
                                      C.POINTER(C.c_uint64)]),
     ("vpt_kytea_fullwidth", C.c_uint32, [C.c_uint32]),
 ]
@@ -290,16 +290,22 @@ class Predictor:
         res.n_chars = nc.value
         return res
 
-    def tokenize_lines(self, data, out: Optional[np.ndarray] = None, no_norm: bool = False):
+    def tokenize_lines(self, data, out: Optional[np.ndarray] = None, no_norm: bool = False, wsconst: str = ""):
         """The reference CLI's `predict` loop (predict/src/main.rs:126-181) over a whole buffer of raw bytes
         (vpt_tokenize_lines): lines are split, scored (on KyteaFullwidthFilter(line) unless no_norm) and written
-        out as space-separated tokens on the device.  Returns (uint8 view of the output lines, number of lines)."""
+        out as space-separated tokens on the device; `wsconst`: letters of the CLI's --wsconst options ("D", "DR", ...;
+        KyteaWsConstFilter).  Returns (uint8 view of the output lines, number of lines)."""
+        mask = 0
+        for ch in wsconst:
+            if ch not in "DRHTKO":
+                raise VaporettoError(2, "InvalidArgumentError: wsconst: one of D, R, H, T, K, O")
+            mask |= 1 << ("DRHTKO".index(ch) + 1)
         t = np.frombuffer(data, np.uint8) if isinstance(data, (bytes, bytearray)) else np.ascontiguousarray(data, np.uint8)
         if out is None:
             out = np.empty(3 * t.size + int(np.count_nonzero(t == 10)) + 16, np.uint8)
         n = C.c_uint64()
         nl = C.c_uint64()
-        _check(lib().vpt_tokenize_lines(self._h, t.ctypes.data, t.size, int(no_norm), out.ctypes.data, out.size,
+        _check(lib().vpt_tokenize_lines(self._h, t.ctypes.data, t.size, int(no_norm), mask, out.ctypes.data, out.size,
                                         C.byref(n), C.byref(nl)))
         return out[: n.value], int(nl.value)
 

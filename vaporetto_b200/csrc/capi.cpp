@@ -741,7 +741,7 @@ void lines_stage0(Scratch& s, LineChunk& ch, const uint8_t* utf8) {
 }
 
 // stage 1: line offsets, count + score, tokenised bytes; the output size to pinned host memory
-void lines_stage1(const vpt_predictor& p, Scratch& s, LineChunk& ch, bool normalize) {
+void lines_stage1(const vpt_predictor& p, Scratch& s, LineChunk& ch, bool normalize, uint32_t wsconst) {
     cudaStream_t st = s.stream;
     cuda_check(cudaEventSynchronize(ch.split), "sync(split)");
     const size_t n = size_t(s.h_totals[2]);
@@ -803,6 +803,7 @@ void lines_stage1(const vpt_predictor& p, Scratch& s, LineChunk& ch, bool normal
     t.total = t.tok_state + ng + 1;
     t.total_host = &s.h_totals[3];
     t.out = static_cast<uint8_t*>(s.d_out);
+    cuda_check(launch_wsconst(t, a.boundaries, wsconst, normalize, st), "launch(wsconst)");
     cuda_check(launch_tokenize(t, st), "launch(tok)");
     if (pipeline_trace()) ch.tr.mark(2, st);
     cuda_check(cudaEventRecord(ch.done, st), "cudaEventRecord");
@@ -812,12 +813,14 @@ void lines_stage1(const vpt_predictor& p, Scratch& s, LineChunk& ch, bool normal
 
 uint32_t vpt_kytea_fullwidth(uint32_t code_point) { return kytea_fullwidth(code_point); }
 
-int vpt_tokenize_lines(const vpt_predictor* p, const uint8_t* utf8, size_t n_bytes, int no_norm, uint8_t* out,
-                       size_t out_capacity, uint64_t* out_len, uint64_t* n_lines_out) {
+int vpt_tokenize_lines(const vpt_predictor* p, const uint8_t* utf8, size_t n_bytes, int no_norm, uint32_t wsconst_types,
+                       uint8_t* out, size_t out_capacity, uint64_t* out_len, uint64_t* n_lines_out) {
     VPT_API_BEGIN
     require_device(p);
     if (out_len) *out_len = 0;
     if (n_lines_out) *n_lines_out = 0;
+    if (wsconst_types & ~0x7Eu)
+        throw Error(kInvalidArgument, "InvalidArgumentError: wsconst_types: bits 1..6 (Digit .. Other) only");
     if (n_bytes && !utf8) throw Error(kInvalidArgument, "InvalidArgumentError: utf8: must not be NULL");
     if (n_bytes == 0) return kOk;
     cuda_check(cudaSetDevice(p->device), "cudaSetDevice");
@@ -869,12 +872,12 @@ int vpt_tokenize_lines(const vpt_predictor* p, const uint8_t* utf8, size_t n_byt
     const auto host_t0 = std::chrono::steady_clock::now();
     auto host_ms = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count(); };
     for (size_t c = 0; c < std::min<size_t>(3, nchunks); ++c) lines_stage0(*lease[c % kDepth]->s, chunks[c], utf8);
-    lines_stage1(*p, *lease[0]->s, chunks[0], no_norm == 0);
+    lines_stage1(*p, *lease[0]->s, chunks[0], no_norm == 0, wsconst_types);
     for (size_t c = 0; c < nchunks; ++c) {
         const double h0 = host_ms();
         if (c + 3 < nchunks) lines_stage0(*lease[(c + 3) % kDepth]->s, chunks[c + 3], utf8);
         const double h1 = host_ms();
-        if (c + 1 < nchunks) lines_stage1(*p, *lease[(c + 1) % kDepth]->s, chunks[c + 1], no_norm == 0);
+        if (c + 1 < nchunks) lines_stage1(*p, *lease[(c + 1) % kDepth]->s, chunks[c + 1], no_norm == 0, wsconst_types);
         const double h2 = host_ms();
         Scratch& s = *lease[c % kDepth]->s;
         cuda_check(cudaEventSynchronize(chunks[c].done), "sync(tokenize)");

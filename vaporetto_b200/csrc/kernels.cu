@@ -68,40 +68,6 @@ __device__ __forceinline__ bool probe(const DevTable& t, uint64_t key, Rec32& re
     return (k & ~(deep ? (kExtFlag | kOvfFlag) : kExtFlag)) == key;
 }
 
-// CharacterType::get_type (reference sentence.rs:50-67)
-__device__ __forceinline__ uint32_t char_type(uint32_t c) {
-    if (c < 0x80) {
-        if (c - 0x30u <= 9u) return 1;
-        if ((c | 0x20u) - 0x61u <= 25u) return 2;
-        return 6;
-    }
-    if (c - 0x3040u <= 0x56u) return 3;                                  // 3040..3096
-    if (c - 0x30A0u <= 0x5Au || c - 0x30FCu <= 3u) return 4;             // 30A0..30FA, 30FC..30FF
-    if (c - 0x4E00u <= 0x51FFu || c - 0x3400u <= 0x19BFu) return 5;      // 4E00..9FFF, 3400..4DBF
-    if (c < 0xF900u) return 6;
-    if (c <= 0xFAFFu) return 5;                                          // F900..FAFF
-    if (c - 0xFF10u <= 9u) return 1;
-    if (c - 0xFF21u <= 25u || c - 0xFF41u <= 25u) return 2;
-    if (c - 0xFF66u <= 0x39u) return 4;                                  // FF66..FF9F
-    if (c < 0x20000u) return 6;
-    if (c <= 0x2A6DFu || c - 0x2A700u <= 0x103Fu || c - 0x2B740u <= 0xDFu || c - 0x2B820u <= 0x168Fu ||
-        c - 0x2F800u <= 0x21Fu)
-        return 5;
-    return 6;
-}
-
-// Decodes the code point whose lead byte is the low byte of x (valid UTF-8 assumed).
-__device__ __forceinline__ uint32_t decode_cp(uint32_t x) {
-    const uint32_t b0 = x & 0xFF;
-    if (b0 < 0x80) return b0;
-    const uint32_t b1 = (x >> 8) & 0x3F;
-    if (b0 < 0xE0) return ((b0 & 0x1F) << 6) | b1;
-    const uint32_t b2 = (x >> 16) & 0x3F;
-    if (b0 < 0xF0) return ((b0 & 0x0F) << 12) | (b1 << 6) | b2;
-    const uint32_t b3 = (x >> 24) & 0x3F;
-    return ((b0 & 0x07) << 18) | (b1 << 12) | (b2 << 6) | b3;
-}
-
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {

@@ -14,6 +14,7 @@
 #include <cstdint>
 
 #include "device_model.hpp"
+#include "textnorm.hpp"
 
 namespace vpt {
 
@@ -371,7 +372,86 @@ __global__ void __launch_bounds__(kTokThreads) k_tok_write(TokArgs t, uint64_t n
     }
 }
 
+// KyteaWsConstFilter (vaporetto_rules/src/sentence_filters/kytea_wsconst.rs:27-44) for a set of character types —
+// the CLI's --wsconst D/R/H/T/K/O options, applied after prediction (predict/src/main.rs:100-106,157): boundary i
+// becomes NotWordBoundary when characters i and i+1 have the same type and that type is in `mask` (bit t = type t).
+// The types are those of the text the predictor saw, i.e. of the full-width filtered characters when norm != 0.
+// One warp per sentence, 128 bytes per step; only zeros are written, the scores stay as they are.
+__global__ void __launch_bounds__(kTokThreads) k_wsconst(TokArgs t, uint8_t* __restrict__ boundaries, uint32_t mask, int norm) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t gbase = uint64_t(blockIdx.x) * kGroup;
+    const int ns = int(min(uint64_t(kGroup), t.n_sent - gbase));
+    for (int i = warp; i < ns; i += kTokThreads / 32) {
+        const uint64_t s = gbase + i;
+        if (t.status[s] != 0 || t.n_chars[s] < 2) continue;
+        const uint64_t o0 = t.offsets[s];
+        const uint64_t a0 = o0 & ~3ull;
+        const uint32_t b0 = uint32_t(o0 - a0), b1 = uint32_t(t.offsets[s + 1] - a0) - (t.trims ? t.trims[s] : 0);
+        const uint8_t* __restrict__ base = t.text + a0;
+        uint8_t* __restrict__ bnd = boundaries + t.bound_offsets[s];
+        uint32_t chars = 0;    // characters before this window
+        uint32_t prev_ty = 0;  // type of the last character before this window (0: none yet)
+        for (uint32_t w0 = 0; w0 < b1; w0 += 128) {
+            const uint32_t addr = w0 + 4u * uint32_t(lane);
+            uint32_t lo = 0, hi = 0, in80 = 0;
+            if (addr < b1) {
+                lo = __ldg(reinterpret_cast<const uint32_t*>(base + addr));
+                if (addr + 4 < b1) hi = __ldg(reinterpret_cast<const uint32_t*>(base + addr + 4));
+                in80 = inside80(addr, b0, b1);
+            }
+            const uint32_t st80 = ~(lo & ~(lo << 1)) & in80;  // character starts (not 10xxxxxx)
+            const uint32_t nst = __popc(st80);
+            const uint32_t st_incl = warp_incl_scan_u32(nst, lane);
+            // types of this lane's characters in order, 3 bits each
+            uint32_t tys = 0, cnt = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (st80 & (0x80u << (8 * j))) {
+                    uint32_t c = decode_cp(__funnelshift_r(lo, hi, 8 * j));
+                    if (norm) c = kytea_fullwidth(c);
+                    tys |= char_type(c) << (3 * cnt);
+                    ++cnt;
+                }
+            }
+            // f = type of the first character at or after this lane inside the window (0: none)
+            uint32_t f = cnt ? (tys & 7u) : 0u;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t v = __shfl_down_sync(kFull, f, d);
+                if (f == 0 && lane + d < 32) f = v;
+            }
+            uint32_t next_first = __shfl_down_sync(kFull, f, 1);
+            if (lane == 31) next_first = 0;
+            const uint32_t k = chars + st_incl - nst;  // index of this lane's first character
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (uint32_t(q) < cnt) {
+                    const uint32_t ta = (tys >> (3 * q)) & 7u;
+                    const uint32_t tb = uint32_t(q) + 1 < cnt ? (tys >> (3 * (q + 1))) & 7u : next_first;
+                    if (tb != 0 && ta == tb && ((mask >> ta) & 1u)) bnd[k + q] = 0;
+                }
+            }
+            // the pair across the window edge: last character before this window / first character of it
+            const uint32_t f0 = __shfl_sync(kFull, f, 0);
+            if (lane == 0 && prev_ty != 0 && f0 == prev_ty && ((mask >> f0) & 1u)) bnd[chars - 1] = 0;
+            const unsigned has = __ballot_sync(kFull, cnt > 0);
+            if (has) {
+                const uint32_t last = cnt ? (tys >> (3 * (cnt - 1))) & 7u : 0u;
+                prev_ty = __shfl_sync(kFull, last, 31 - __clz(has));
+            }
+            chars += __shfl_sync(kFull, st_incl, 31);
+        }
+    }
+}
+
 }  // namespace
+
+cudaError_t launch_wsconst(const TokArgs& t, uint8_t* boundaries, uint32_t mask, bool norm, cudaStream_t stream) {
+    if (t.n_sent == 0 || (mask & 0x7Eu) == 0) return cudaSuccess;
+    const uint64_t ngroups = (t.n_sent + kGroup - 1) / kGroup;
+    k_wsconst<<<unsigned(ngroups), kTokThreads, 0, stream>>>(t, boundaries, mask, norm ? 1 : 0);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_split_count(const SplitArgs& s, cudaStream_t stream) {
     const uint64_t nblk = (s.n_bytes + kSplitBlockBytes - 1) / kSplitBlockBytes;
