@@ -207,3 +207,24 @@ TANTIVY_TOKENIZE = [
     ("東京特許許可局", "東京 特許 許可 局"),
     ("123456円🤌🏿", "1 2 3 4 5 6 円 🤌 🏿"),
 ]
+
+# #18 vaporetto_tantivy/src/lib.rs:160-199 token_stream = KyteaFullwidthFilter -> predict -> --wsconst post-filters ->
+# tokens of the ORIGINAL text; tests lib.rs:255-260 (empty), :263-295, :298-365, :368-399 (wsconst "D") with
+# test_model/model.zst (tests/golden/tantivy_model.bin).  (text, wsconst, tokens joined by ' ')
+TANTIVY_PIPELINE = [
+    ("東京特許許可局", "", "東京 特許 許可 局"),
+    ("123456円🤌🏿", "", "1 2 3 4 5 6 円 🤌 🏿"),
+    ("123456円🤌🏿", "D", "123456 円 🤌 🏿"),
+]
+
+# #19 sentence.rs:2695-2701 test_sentence_to_tokenized_string_escape: from_partial_annotation("火-星-猫|の| |生-態|\\-n")
+# -> write_tokenized_text == "火星猫 の \\  生態 \\\\n" (Rust literals): ' ' and '\\' of a surface are escaped with '\\'.
+TOKENIZED_ESCAPE = dict(
+    text="火星猫の 生態\\n",
+    boundaries=[0, 0, 1, 1, 1, 0, 1, 0],
+    tokenized="火星猫 の \\  生態 \\\\n",
+    # a model that produces exactly these boundaries: bias -1, +2 on the boundary after 猫, の, ' ', 態 (window 1:
+    # a unigram's two weights land on the boundaries before and after the character)
+    model=dict(char_ngrams=[("猫", [0, 2]), ("の", [0, 2]), (" ", [0, 2]), ("態", [0, 2])], type_ngrams=[], dict=[], bias=-1,
+               char_window=1, type_window=1, tag_models=[]),
+)

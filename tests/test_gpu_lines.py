@@ -8,6 +8,7 @@ import pytest
 import vaporetto_b200 as vb
 from vpt_testlib import synth
 from vpt_testlib.bincode_model import encode_model
+from golden import reference_kat as kat
 from vpt_testlib.oracle import OraclePredictor
 from test_gpu_parity import _random_model, make, read
 
@@ -70,6 +71,25 @@ def test_wsconst_reference_vectors():
     assert got.tobytes().decode() == "5\n5000\n2021 年 8 月 24 日\n"
     with pytest.raises(vb.VaporettoError):
         p.tokenize_lines(b"a\n", wsconst="G")
+
+
+def test_tantivy_pipeline_vectors():
+    # vaporetto_tantivy/src/lib.rs:160-199 + its tests (:263-399): pre-filter -> predict -> wsconst -> original text
+    p = make(read("tantivy_model.bin"))
+    for text, ws, want in kat.TANTIVY_PIPELINE:
+        got, nl = p.tokenize_lines((text + "\n").encode(), wsconst=ws)
+        assert nl == 1 and got.tobytes().decode() == want + "\n", (text, ws)
+
+
+def test_tokenized_escape_vector():
+    # sentence.rs:2695-2701 on the device: boundaries from a model built to give the annotation, escapes of ' ' and '\\'
+    case = kat.TOKENIZED_ESCAPE
+    p = make(encode_model(case["model"]))
+    s = vb.Sentence.from_raw(case["text"])
+    p.predict(s)
+    assert s.boundaries().tolist() == case["boundaries"]
+    got, _ = p.tokenize_lines((case["text"] + "\n").encode(), no_norm=True)
+    assert got.tobytes().decode() == case["tokenized"] + "\n"
 
 
 def test_lines_out_capacity(kat_pair):

@@ -125,3 +125,32 @@ def test_docs_tok_through_cli_loop():
     got, nl = o.tokenize_lines("まぁ社長は火星猫だ\nまぁ社長は火星猫だ\n".encode(), no_norm=True)
     assert nl == 2
     assert got.decode() == "まぁ 社長 は 火星 猫 だ\n" * 2
+
+
+def test_tantivy_pipeline_vectors():
+    """vaporetto_tantivy's token_stream (lib.rs:160-199: pre-filter -> predict -> wsconst post-filters -> tokens of the
+    original text) is the same pipeline as the CLI loop: its unit tests pin the oracle's restatement."""
+    from golden import reference_kat as kat
+    with open(os.path.join(GOLDEN, "tantivy_model.bin"), "rb") as f:
+        o = OraclePredictor(f.read())
+    for text, ws, want in kat.TANTIVY_PIPELINE:
+        got, nl = o.tokenize_lines((text + "\n").encode(), no_norm=False, wsconst=ws)
+        assert nl == 1 and got.decode() == want + "\n", (text, ws)
+    assert o.tokenize_lines(b"", no_norm=False) == (b"", 0)          # lib.rs:255-260: no tokens for ""
+
+
+def test_tokenized_escape_vector():
+    """sentence.rs:2695-2701 through the oracle (a model built to give the annotated boundaries) and through the
+    library's host-side `Sentence::write_tokenized_text` with the boundaries set by hand."""
+    from golden import reference_kat as kat
+    from vpt_testlib.bincode_model import encode_model
+    case = kat.TOKENIZED_ESCAPE
+    o = OraclePredictor(encode_model(case["model"]))
+    _, bounds = o.predict(case["text"])
+    assert bounds.tolist() == case["boundaries"]
+    assert o.tokenize(case["text"]) == case["tokenized"]
+    got, _ = o.tokenize_lines((case["text"] + "\n").encode(), no_norm=True)
+    assert got.decode() == case["tokenized"] + "\n"
+    s = vb.Sentence.from_raw(case["text"])
+    s.boundaries_mut()[:] = case["boundaries"]
+    assert s.write_tokenized_text() == case["tokenized"]
