@@ -61,6 +61,16 @@ const char* vpt_last_error(void);
 /* `Model::read_slice(&[u8]) -> Result<(Model, &[u8])>` (model.rs:127-134) and `Model::read` (model.rs:142-153).
  * `data` is the raw (already un-zstd'd) model image; `*consumed` (nullable) receives the bytes used. */
 int vpt_model_read(const uint8_t* data, size_t len, vpt_model** out, size_t* consumed);
+
+/* `KyteaModel::read` + `Model::try_from(KyteaModel)` (kytea_model.rs:423-450, :453-550; the reference's
+ * `convert_kytea_model` tool): a KyTea binary model becomes a vaporetto model — the word-segmentation linear model's
+ * character / type n-gram weights (i16 -> i32, truncated to the window), bias, and the dictionary words with their
+ * left / inside / right weights by word-length bucket; KyTea's tag models are not converted (as in the reference). */
+int vpt_model_read_kytea(const uint8_t* data, size_t len, vpt_model** model_out);
+
+/* `Model::to_vec` / `Model::write` (model.rs:99-120): the model file image (magic + bincode standard encoding);
+ * byte-identical to what the reference writes for the same model.  Release the buffer with vpt_blob_free. */
+int vpt_model_to_vec(const vpt_model* model, uint8_t** bytes_out, uint64_t* len_out);
 void vpt_model_free(vpt_model* model);
 
 /* ---- Predictor ----------------------------------------------------------------------------------- */

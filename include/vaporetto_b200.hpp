@@ -1,7 +1,8 @@
 // vaporetto_b200.hpp — header-only C++ mirror of the reference's Rust API over the C ABI (vaporetto_b200.h).
 //
 // Same names, argument meaning and error behaviour as the crate (vaporetto/src/lib.rs:82-91):
-//   vaporetto::Model      model.rs:58   (read / read_slice)
+//   vaporetto::Model      model.rs:58   (read / read_slice / to_vec; read_kytea = KyteaModel::read + try_from,
+//                                         kytea_model.rs:423-550)
 //   vaporetto::Predictor  predictor.rs:434   (new(model, predict_tags), predict(&mut Sentence);
 //                                             tokenize_lines = the `predict` CLI loop, predict/src/main.rs:126-181)
 //   vaporetto::Sentence   sentence.rs:85   (from_raw, update_raw, as_raw_text, char_types, boundaries,
@@ -54,6 +55,22 @@ public:
     }
     /// `Model::read(R: Read)`: the whole buffer is the model.
     static Model read(const std::vector<uint8_t>& bytes) { return read_slice(bytes.data(), bytes.size()).first; }
+
+    /// `KyteaModel::read` + `Model::try_from(KyteaModel)` (kytea_model.rs:423-550): converts a KyTea binary model.
+    static Model read_kytea(const std::vector<uint8_t>& bytes) {
+        vpt_model* h = nullptr;
+        detail::check(vpt_model_read_kytea(bytes.data(), bytes.size(), &h));
+        return Model(h);
+    }
+    /// `Model::to_vec` (model.rs:99-104): the model file image.
+    std::vector<uint8_t> to_vec() const {
+        uint8_t* p = nullptr;
+        uint64_t n = 0;
+        detail::check(vpt_model_to_vec(h_, &p, &n));
+        std::vector<uint8_t> out(p, p + n);
+        vpt_blob_free(p);
+        return out;
+    }
 
     Model(Model&& o) noexcept : h_(o.h_) { o.h_ = nullptr; }
     Model& operator=(Model&& o) noexcept { std::swap(h_, o.h_); return *this; }

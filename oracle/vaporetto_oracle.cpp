@@ -46,7 +46,7 @@ struct Error : std::runtime_error {
     int code;
     Error(int c, const string& m) : std::runtime_error(m), code(c) {}
 };
-enum { OK = 0, INVALID_MODEL = 1, INVALID_ARGUMENT = 2, DECODE_ERROR = 3 };
+enum { OK = 0, INVALID_MODEL = 1, INVALID_ARGUMENT = 2, DECODE_ERROR = 3, IO_ERROR = 5 };
 
 // ---------------------------------------------------------------------------
 // bincode standard-config decoder (bincode 2.0.1 varint spec).
@@ -212,6 +212,310 @@ static Model model_read(const uint8_t* data, size_t n, size_t* consumed) {
     if (consumed) *consumed = ml + r.pos;
     return m;
 }
+
+// Model::to_vec (model.rs:99-104): MODEL_MAGIC + bincode `config::standard()` encoding of ModelData
+// (varint: < 251 one byte, else marker 251/252/253 + u16/u32/u64 little endian; zigzag for signed).
+namespace kw {
+static void uvar(string& o, uint64_t v) {
+    if (v < 251) { o.push_back(char(v)); return; }
+    int w = v <= 0xFFFF ? 2 : v <= 0xFFFFFFFFull ? 4 : 8;
+    o.push_back(char(w == 2 ? 251 : w == 4 ? 252 : 253));
+    for (int k = 0; k < w; ++k) o.push_back(char((v >> (8 * k)) & 0xFF));
+}
+static void zz(string& o, int64_t v) { uvar(o, v < 0 ? (uint64_t(~v) << 1) | 1 : uint64_t(v) << 1); }
+static void bytes(string& o, const string& b) { uvar(o, b.size()); o += b; }
+static void vec_i32(string& o, const vector<int32_t>& v) { uvar(o, v.size()); for (int32_t x : v) zz(o, x); }
+}  // namespace kw
+static string model_to_vec(const Model& m) {
+    string o(MODEL_MAGIC, sizeof(MODEL_MAGIC) - 1);
+    for (const auto* ng : {&m.char_ngram_model, &m.type_ngram_model}) {
+        kw::uvar(o, ng->size());
+        for (const NgramData& d : *ng) { kw::bytes(o, d.ngram); kw::vec_i32(o, d.weights); }
+    }
+    kw::uvar(o, m.dict_model.size());
+    for (const WordWeightRecord& w : m.dict_model) { kw::bytes(o, w.word); kw::vec_i32(o, w.weights); kw::bytes(o, w.comment); }
+    kw::zz(o, m.bias);
+    o.push_back(char(m.char_window_size));
+    o.push_back(char(m.type_window_size));
+    kw::uvar(o, m.tag_models.size());
+    for (const TagModel& t : m.tag_models) {
+        kw::bytes(o, t.token);
+        kw::uvar(o, t.tags.size());
+        for (const auto& c : t.tags) { kw::uvar(o, c.size()); for (const string& x : c) kw::bytes(o, x); }
+        for (const auto* ng : {&t.char_ngram_model, &t.type_ngram_model}) {
+            kw::uvar(o, ng->size());
+            for (const TagNgramData& d : *ng) {
+                kw::bytes(o, d.ngram);
+                kw::uvar(o, d.weights.size());
+                for (const auto& w : d.weights) { o.push_back(char(w.rel_position)); kw::vec_i32(o, w.weights); }
+            }
+        }
+        kw::vec_i32(o, t.bias);
+    }
+    return o;
+}
+
+// ---------------------------------------------------------------------------
+// KyTea model reader and converter (kytea_model.rs), restated struct by struct
+// ---------------------------------------------------------------------------
+namespace kytea {
+
+struct In {
+    const uint8_t* p; size_t n; size_t i = 0;
+    void need(size_t k) { if (n - i < k) throw Error(IO_ERROR, "failed to fill whole buffer"); }
+    uint8_t u8() { need(1); return p[i++]; }
+    template <class T> T le() { need(sizeof(T)); T v; memcpy(&v, p + i, sizeof(T)); i += sizeof(T); return v; }
+    // BufRead::read_until / read_line: up to and including the delimiter
+    string until(uint8_t d) {
+        size_t s = i;
+        while (i < n && p[i] != d) ++i;
+        if (i < n) ++i;
+        return string(reinterpret_cast<const char*>(p + s), i - s);
+    }
+};
+
+// KyteaConfig (kytea_model.rs:11-63)
+struct Config { uint32_t n_tags; uint8_t char_w, type_w, dict_n; vector<uint32_t> char_map; };
+
+static vector<uint32_t> decode_chars(const string& s) {
+    vector<uint32_t> out;
+    for (size_t i = 0; i < s.size();) {
+        uint8_t b = uint8_t(s[i]);
+        int l = b < 0x80 ? 1 : b < 0xE0 ? 2 : b < 0xF0 ? 3 : 4;
+        uint32_t c = l == 1 ? b : b & (0xFF >> (l + 1));
+        for (int k = 1; k < l; ++k) c = (c << 6) | (uint8_t(s[i + k]) & 0x3F);
+        out.push_back(c);
+        i += size_t(l);
+    }
+    return out;
+}
+static Config read_config(In& r) {
+    Config c;
+    r.until('\n');                       // model_tag
+    r.u8(); r.u8();                       // do_ws, do_tags
+    c.n_tags = r.le<uint32_t>();
+    c.char_w = r.u8(); r.u8();            // char_w, char_n
+    c.type_w = r.u8(); r.u8();            // type_w, type_n
+    c.dict_n = r.u8();
+    r.u8();                               // bias
+    r.le<double>();                       // epsilon
+    r.u8();                               // solver_type
+    string cm = r.until(0);
+    if (!valid_utf8(cm)) throw Error(DECODE_ERROR, "invalid utf-8 sequence");
+    c.char_map = decode_chars(cm);
+    return c;
+}
+// Readable for char / String (kytea_model.rs:90-130)
+static uint32_t read_char(const Config& c, In& r) {
+    size_t idx = r.le<uint16_t>();
+    if (idx == 0 || idx > c.char_map.size()) throw Error(INVALID_MODEL, "character index out of range");  // (panics)
+    return c.char_map[idx - 1];
+}
+static vector<uint32_t> read_string(const Config& c, In& r) {
+    uint32_t size = r.le<uint32_t>();
+    vector<uint32_t> s;
+    for (uint32_t k = 0; k < size; ++k) s.push_back(read_char(c, r));
+    return s;
+}
+static vector<int16_t> read_vec_i16(const Config&, In& r) {
+    uint32_t size = r.le<uint32_t>();
+    vector<int16_t> v;
+    for (uint32_t k = 0; k < size; ++k) v.push_back(r.le<int16_t>());
+    return v;
+}
+
+// State / Dictionary<T> (kytea_model.rs:132-217)
+struct State { vector<std::pair<uint32_t, uint32_t>> gotos; vector<uint32_t> outputs; bool is_branch; };
+template <class T> struct Dictionary {
+    bool some = false;
+    uint8_t n_dicts = 0;
+    vector<State> states;
+    vector<T> entries;
+    // dump_items (:152-167): explicit stack, gotos pushed in reverse
+    vector<std::pair<vector<uint32_t>, const T*>> dump_items() const {
+        vector<std::pair<vector<uint32_t>, const T*>> result;
+        vector<std::pair<size_t, vector<uint32_t>>> stack{{0, {}}};
+        size_t guard = 0;
+        while (!stack.empty()) {
+            auto [idx, word] = stack.back();
+            stack.pop_back();
+            if (idx >= states.size() || ++guard > 4 * states.size() + 4) throw Error(INVALID_MODEL, "bad dictionary");
+            const State& st = states[idx];
+            if (st.is_branch) {
+                if (st.outputs.empty() || st.outputs[0] >= entries.size()) throw Error(INVALID_MODEL, "bad dictionary output");
+                result.push_back({word, &entries[st.outputs[0]]});
+            }
+            for (auto it = st.gotos.rbegin(); it != st.gotos.rend(); ++it) {
+                vector<uint32_t> w = word;
+                w.push_back(it->first);
+                stack.push_back({it->second, w});
+            }
+        }
+        return result;
+    }
+};
+template <class T, class F> static Dictionary<T> read_dictionary(const Config& c, In& r, F read_entry) {
+    Dictionary<T> d;
+    d.n_dicts = r.u8();
+    uint32_t n_states = r.le<uint32_t>();
+    if (n_states == 0) return d;
+    d.some = true;
+    for (uint32_t s = 0; s < n_states; ++s) {
+        State st;
+        r.le<uint32_t>();  // failure
+        uint32_t n_gotos = r.le<uint32_t>();
+        for (uint32_t g = 0; g < n_gotos; ++g) {
+            uint32_t k = read_char(c, r);
+            uint32_t v = r.le<uint32_t>();
+            st.gotos.push_back({k, v});
+        }
+        std::sort(st.gotos.begin(), st.gotos.end());
+        uint32_t n_outputs = r.le<uint32_t>();
+        for (uint32_t o = 0; o < n_outputs; ++o) st.outputs.push_back(r.le<uint32_t>());
+        st.is_branch = r.u8() != 0;
+        d.states.push_back(std::move(st));
+    }
+    uint32_t n_entries = r.le<uint32_t>();
+    for (uint32_t e = 0; e < n_entries; ++e) d.entries.push_back(read_entry(c, r));
+    return d;
+}
+
+// FeatureLookup<i16> (:220-262), Option<LinearModel> (:264-300)
+struct FeatureLookup {
+    Dictionary<vector<int16_t>> char_dict, type_dict, self_dict;
+    vector<int16_t> dict_vec, biases, tag_dict_vec, tag_unk_vec;
+};
+struct LinearModel { bool some = false; bool has_lookup = false; FeatureLookup fl; };
+static LinearModel read_linear_model(const Config& c, In& r) {
+    LinearModel m;
+    uint32_t n_classes = r.le<uint32_t>();
+    if (n_classes == 0) return m;
+    m.some = true;
+    r.u8();                                                   // solver_type
+    for (uint32_t k = 0; k < n_classes; ++k) r.le<int32_t>();  // labels
+    r.u8();                                                   // bias
+    r.le<double>();                                           // multiplier
+    if (r.u8() == 0) return m;                                // FeatureLookup::read: active
+    m.has_lookup = true;
+    m.fl.char_dict = read_dictionary<vector<int16_t>>(c, r, read_vec_i16);
+    m.fl.type_dict = read_dictionary<vector<int16_t>>(c, r, read_vec_i16);
+    m.fl.self_dict = read_dictionary<vector<int16_t>>(c, r, read_vec_i16);
+    m.fl.dict_vec = read_vec_i16(c, r);
+    m.fl.biases = read_vec_i16(c, r);
+    m.fl.tag_dict_vec = read_vec_i16(c, r);
+    m.fl.tag_unk_vec = read_vec_i16(c, r);
+    return m;
+}
+
+// ModelTagEntry (:302-342), ProbTagEntry (:344-377)
+struct ModelTagEntry { uint8_t in_dict; };
+static ModelTagEntry read_model_tag_entry(const Config& c, In& r) {
+    read_string(c, r);  // word
+    for (uint32_t t = 0; t < c.n_tags; ++t) {
+        uint32_t size = r.le<uint32_t>();
+        for (uint32_t k = 0; k < size; ++k) { read_string(c, r); r.u8(); }
+    }
+    ModelTagEntry e{r.u8()};
+    for (uint32_t t = 0; t < c.n_tags; ++t) read_linear_model(c, r);
+    return e;
+}
+struct ProbTagEntry {};
+static ProbTagEntry read_prob_tag_entry(const Config& c, In& r) {
+    read_string(c, r);
+    for (uint32_t t = 0; t < c.n_tags; ++t) {
+        uint32_t size = r.le<uint32_t>();
+        for (uint32_t k = 0; k < size; ++k) { read_string(c, r); r.le<double>(); }
+    }
+    return {};
+}
+
+static string to_utf8(const vector<uint32_t>& w) {  // chars -> String
+    string s;
+    for (uint32_t c : w) {
+        if (c < 0x80) s.push_back(char(c));
+        else if (c < 0x800) { s.push_back(char(0xC0 | (c >> 6))); s.push_back(char(0x80 | (c & 0x3F))); }
+        else if (c < 0x10000) {
+            s.push_back(char(0xE0 | (c >> 12))); s.push_back(char(0x80 | ((c >> 6) & 0x3F))); s.push_back(char(0x80 | (c & 0x3F)));
+        } else {
+            s.push_back(char(0xF0 | (c >> 18))); s.push_back(char(0x80 | ((c >> 12) & 0x3F)));
+            s.push_back(char(0x80 | ((c >> 6) & 0x3F))); s.push_back(char(0x80 | (c & 0x3F)));
+        }
+    }
+    return s;
+}
+
+// KyteaModel::read (:423-450) followed by TryFrom<KyteaModel> for Model (:453-550)
+static Model convert(const uint8_t* data, size_t n) {
+    In r{data, n};
+    Config config = read_config(r);
+    LinearModel wordseg_model = read_linear_model(config, r);
+    for (uint32_t t = 0; t < config.n_tags; ++t) {
+        uint32_t size = r.le<uint32_t>();                       // global_tags: Vec<String>
+        for (uint32_t k = 0; k < size; ++k) read_string(config, r);
+        read_linear_model(config, r);                           // global_models
+    }
+    auto dict = read_dictionary<ModelTagEntry>(config, r, read_model_tag_entry);
+    read_dictionary<ProbTagEntry>(config, r, read_prob_tag_entry);
+
+    if (!wordseg_model.some) throw Error(INVALID_MODEL, "no word segmentation model.");
+    if (!wordseg_model.has_lookup) throw Error(INVALID_MODEL, "no lookup data.");
+    const FeatureLookup& fl = wordseg_model.fl;
+    if (fl.biases.empty()) throw Error(INVALID_MODEL, "no bias.");  // (index panic in the reference)
+    Model m;
+    m.bias = fl.biases[0];
+    if (!fl.char_dict.some) throw Error(INVALID_MODEL, "no character dictionary.");
+    if (!fl.type_dict.some) throw Error(INVALID_MODEL, "no type dictionary.");
+    auto slice = [](const vector<int16_t>& v, size_t window, size_t len) {
+        if (len > 2 * window + 1 || 2 * window + 1 - len > v.size()) throw Error(INVALID_MODEL, "weight slice out of range");
+        return vector<int32_t>(v.begin(), v.begin() + long(2 * window + 1 - len));
+    };
+    for (auto& [ngram, v] : fl.char_dict.dump_items())
+        m.char_ngram_model.push_back(NgramData{to_utf8(ngram), slice(*v, config.char_w, ngram.size())});
+    for (auto& [ngram, v] : fl.type_dict.dump_items()) {
+        string bytes = to_utf8(ngram);
+        bool skip = false;
+        for (char& t : bytes) {
+            switch (uint8_t(t)) {
+                case 'D': t = 1; break;
+                case 'R': t = 2; break;
+                case 'H': t = 3; break;
+                case 'T': t = 4; break;
+                case 'K': t = 5; break;
+                case 'O': t = 6; break;
+                case 4: skip = true; break;  // vaporetto issue #110
+                default: throw Error(INVALID_MODEL, "unsupported character type: " + std::to_string(int(uint8_t(t))));
+            }
+            if (skip) break;
+        }
+        if (skip) continue;
+        m.type_ngram_model.push_back(NgramData{bytes, slice(*v, config.type_w, ngram.size())});
+    }
+    if (dict.some) {
+        for (auto& [w, data] : dict.dump_items()) {
+            if (w.empty() || config.dict_n == 0) throw Error(INVALID_MODEL, "empty dictionary word");
+            size_t idx = std::min<size_t>(w.size(), config.dict_n) - 1;
+            int32_t left = 0, inside = 0, right = 0;
+            for (size_t j = 0; j < dict.n_dicts; ++j) {
+                if (j < 8 && ((data->in_dict >> j) & 1) == 1) {
+                    size_t offset = 3 * size_t(config.dict_n) * j + 3 * idx;
+                    if (offset + 2 >= fl.dict_vec.size()) throw Error(INVALID_MODEL, "dict_vec index out of range");
+                    left += fl.dict_vec[offset];
+                    inside += fl.dict_vec[offset + 1];
+                    right += fl.dict_vec[offset + 2];
+                }
+            }
+            vector<int32_t> weights(w.size() + 1, inside);
+            weights.front() = left;
+            weights.back() = right;
+            m.dict_model.push_back(WordWeightRecord{to_utf8(w), weights, ""});
+        }
+    }
+    m.char_window_size = config.char_w;
+    m.type_window_size = config.type_w;
+    return m;
+}
+
+}  // namespace kytea
 
 // ---------------------------------------------------------------------------
 // PositionalWeight (predictor.rs:138-165) and the tag variant (:217-262)
@@ -816,6 +1120,22 @@ int ora_model_read(const uint8_t* data, size_t n, void** out, size_t* consumed) 
     ORA_CATCH(idret)
 }
 void ora_model_free(void* m) { delete static_cast<Model*>(m); }
+
+// KyteaModel::read + Model::try_from (kytea_model.rs:423-550)
+int ora_model_from_kytea(const uint8_t* data, size_t n, void** out) {
+    ORA_TRY
+    *out = new Model(kytea::convert(data, n));
+    return 0;
+    ORA_CATCH(idret)
+}
+
+// Model::to_vec (model.rs:99-104); returns the size, or -(needed) when cap is too small
+long ora_model_to_vec(const void* m, uint8_t* buf, size_t cap) {
+    const string v = model_to_vec(*static_cast<const Model*>(m));
+    if (v.size() > cap) return -long(v.size());
+    memcpy(buf, v.data(), v.size());
+    return long(v.size());
+}
 
 int ora_predictor_new(const void* model, int predict_tags, void** out) {
     ORA_TRY

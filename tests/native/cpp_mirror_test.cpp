@@ -35,6 +35,8 @@ int main(int argc, char** argv) {
     }
     auto [model, used] = Model::read_slice(bytes.data(), bytes.size());
     CHECK(used == bytes.size());
+    CHECK(model.to_vec() == bytes);  // Model::to_vec writes what Model::read read (model.rs:99-134)
+    try { Model::read_kytea(bytes); CHECK(false); } catch (const VaporettoError&) {}  // not a KyTea model
 
     if (!gpu) {
         // no CUDA device: Predictor::new must fail loudly, a host-only handle cannot score

@@ -33,6 +33,9 @@ def lib():
         L.ora_last_error.restype = C.c_char_p
         L.ora_model_read.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
         L.ora_model_free.argtypes = [C.c_void_p]
+        L.ora_model_from_kytea.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_void_p)]
+        L.ora_model_to_vec.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
+        L.ora_model_to_vec.restype = C.c_long
         L.ora_predictor_new.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
         L.ora_predictor_free.argtypes = [C.c_void_p]
         L.ora_predictor_n_tags.argtypes = [C.c_void_p]
@@ -209,3 +212,22 @@ def char_types(text: str) -> np.ndarray:
     if n < 0:
         raise _err(-n)
     return out[:n].copy()
+
+
+def kytea_to_model_bytes(data: bytes) -> bytes:
+    """KyteaModel::read + Model::try_from + Model::to_vec through the oracle's restatement (kytea_model.rs, model.rs)."""
+    L = lib()
+    m = C.c_void_p()
+    rc = L.ora_model_from_kytea(data, len(data), C.byref(m))
+    if rc:
+        raise _err(rc)
+    try:
+        cap = 1 << 16
+        while True:
+            buf = C.create_string_buffer(cap)
+            n = L.ora_model_to_vec(m, buf, cap)
+            if n >= 0:
+                return buf.raw[:n]
+            cap = -n
+    finally:
+        L.ora_model_free(m)

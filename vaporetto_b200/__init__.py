@@ -66,6 +66,8 @@ ABI = [
     ("vpt_version", C.c_char_p, []),
     ("vpt_model_read", C.c_int, [C.c_char_p, C.c_size_t, C.POINTER(_P), C.POINTER(C.c_size_t)]),
     ("vpt_model_free", None, [_P]),
+    ("vpt_model_read_kytea", C.c_int, [C.c_char_p, C.c_size_t, C.POINTER(_P)]),
+    ("vpt_model_to_vec", C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_uint64)]),
     ("vpt_predictor_new", C.c_int, [_P, C.c_int, C.c_int, C.POINTER(_P)]),
     ("vpt_predictor_free", None, [_P]),
     ("vpt_predictor_get_info", C.c_int, [_P, C.POINTER(_Info)]),
@@ -142,6 +144,27 @@ class Model:
         used = C.c_size_t()
         _check(lib().vpt_model_read(data, len(data), C.byref(h), C.byref(used)))
         return cls(h, used.value), data[used.value:]
+
+    @classmethod
+    def read_kytea(cls, src) -> "Model":
+        """`KyteaModel::read` + `Model::try_from` (kytea_model.rs:423-550): converts a KyTea binary model."""
+        data = src if isinstance(src, (bytes, bytearray, memoryview)) else src.read()
+        data = bytes(data)
+        h = _P()
+        _check(lib().vpt_model_read_kytea(data, len(data), C.byref(h)))
+        return cls(h, len(data))
+
+    def to_vec(self) -> bytes:
+        """`Model::to_vec` (model.rs:99-104): the model file image."""
+        if self._h is None:
+            raise VaporettoError(2, "InvalidArgumentError: model: already consumed by Predictor::new")
+        out = _P()
+        n = C.c_uint64()
+        _check(lib().vpt_model_to_vec(self._h, C.byref(out), C.byref(n)))
+        try:
+            return C.string_at(out, n.value)
+        finally:
+            lib().vpt_blob_free(out)
 
     def _take(self):
         h, self._h = self._h, None

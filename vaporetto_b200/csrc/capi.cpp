@@ -308,6 +308,31 @@ int vpt_model_read(const uint8_t* data, size_t len, vpt_model** out, size_t* con
     VPT_API_END
 }
 
+int vpt_model_read_kytea(const uint8_t* data, size_t len, vpt_model** out) {
+    VPT_API_BEGIN
+    if (!out) throw Error(kInvalidArgument, "InvalidArgumentError: out: must not be NULL");
+    *out = nullptr;
+    std::unique_ptr<vpt_model> m(new vpt_model());
+    m->m = Model::from_kytea(data, len);
+    *out = m.release();
+    return kOk;
+    VPT_API_END
+}
+
+int vpt_model_to_vec(const vpt_model* model, uint8_t** bytes_out, uint64_t* len_out) {
+    VPT_API_BEGIN
+    if (!model || !bytes_out || !len_out) throw Error(kInvalidArgument, "InvalidArgumentError: model/out: must not be NULL");
+    *bytes_out = nullptr;
+    const std::vector<uint8_t> v = model->m.to_vec();
+    uint8_t* buf = static_cast<uint8_t*>(malloc(v.size() ? v.size() : 1));
+    if (!buf) throw Error(kInternal, "internal error: out of memory");
+    memcpy(buf, v.data(), v.size());
+    *bytes_out = buf;
+    *len_out = v.size();
+    return kOk;
+    VPT_API_END
+}
+
 void vpt_model_free(vpt_model* model) { delete model; }
 
 int vpt_predictor_new(vpt_model* model, int predict_tags, int device, vpt_predictor** out) {

@@ -149,6 +149,70 @@ const char kMagic[] = "VaporettoTokenizer 0.5.0\n";  // reference model.rs:15
 
 }  // namespace
 
+namespace {
+
+// bincode 2.0.1 `config::standard()` encoder (the inverse of Cursor)
+class Sink {
+public:
+    std::vector<uint8_t> out;
+    void byte(uint8_t b) { out.push_back(b); }
+    void uvar(uint64_t v) {
+        if (v < 251) { byte(uint8_t(v)); return; }
+        int width;
+        if (v <= 0xFFFFu) { byte(251); width = 2; }
+        else if (v <= 0xFFFFFFFFull) { byte(252); width = 4; }
+        else { byte(253); width = 8; }
+        for (int k = 0; k < width; ++k) byte(uint8_t(v >> (8 * k)));
+    }
+    void i32(int32_t v) { uvar(v < 0 ? (uint64_t(~int64_t(v)) << 1) | 1u : uint64_t(v) << 1); }
+    void blob(const std::string& s) {
+        uvar(s.size());
+        out.insert(out.end(), s.begin(), s.end());
+    }
+    void ints(const std::vector<int32_t>& v) {
+        uvar(v.size());
+        for (int32_t x : v) i32(x);
+    }
+};
+
+void write_tag_ngram_list(Sink& k, const std::vector<TagNgramEntry>& list) {
+    k.uvar(list.size());
+    for (const TagNgramEntry& e : list) {
+        k.blob(e.ngram);
+        k.uvar(e.weights.size());
+        for (const TagWeightEntry& w : e.weights) { k.byte(w.rel_position); k.ints(w.weights); }
+    }
+}
+
+}  // namespace
+
+std::vector<uint8_t> Model::to_vec() const {
+    Sink k;
+    k.out.assign(kMagic, kMagic + sizeof(kMagic) - 1);
+    for (const auto* list : {&char_ngrams, &type_ngrams}) {
+        k.uvar(list->size());
+        for (const NgramEntry& e : *list) { k.blob(e.ngram); k.ints(e.weights); }
+    }
+    k.uvar(dict.size());
+    for (const DictEntry& e : dict) { k.blob(e.word); k.ints(e.weights); k.blob(e.comment); }
+    k.i32(bias);
+    k.byte(char_window);
+    k.byte(type_window);
+    k.uvar(tag_models.size());
+    for (const TagModelEntry& t : tag_models) {
+        k.blob(t.token);
+        k.uvar(t.tags.size());
+        for (const auto& cands : t.tags) {
+            k.uvar(cands.size());
+            for (const std::string& c : cands) k.blob(c);
+        }
+        write_tag_ngram_list(k, t.char_ngrams);
+        write_tag_ngram_list(k, t.type_ngrams);
+        k.ints(t.bias);
+    }
+    return std::move(k.out);
+}
+
 Model Model::read(const uint8_t* data, size_t len, size_t* consumed) {
     const size_t ml = sizeof(kMagic) - 1;
     if (data == nullptr || len < ml || memcmp(data, kMagic, ml) != 0)

@@ -42,6 +42,10 @@ struct Model {
 
     // Parses a model image; returns the number of bytes consumed (read_slice semantics).
     static Model read(const uint8_t* data, size_t len, size_t* consumed);
+    // `Model::to_vec` / `Model::write` (model.rs:99-120): magic + bincode standard encoding of the fields.
+    std::vector<uint8_t> to_vec() const;
+    // `KyteaModel::read` + `Model::try_from(KyteaModel)` (kytea_model.rs:423-550), see kytea_model.cpp.
+    static Model from_kytea(const uint8_t* data, size_t len);
 };
 
 // Decodes a UTF-8 string known to be valid into code points.
