@@ -74,6 +74,52 @@ def test_two_rank_shard_and_broadcast(tmp_path):
     assert abs(b0 - int(offs[-1]) / 2) < 600
 
 
+def _lines_worker(rank, world, port, model_bytes, data, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lo, hi = vb.shard_lines(data, rank, world)
+        out, nl = OraclePredictor(model_bytes).tokenize_lines(data[lo:hi], wsconst="D")
+        with open(os.path.join(out_dir, f"l{rank}.bin"), "wb") as f:
+            f.write(out)
+        n = torch.tensor([nl], dtype=torch.int64)
+        dist.all_reduce(n)  # total line count over the ranks
+        with open(os.path.join(out_dir, f"n{rank}.txt"), "w") as f:
+            f.write(str(int(n.item())))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_line_sharding(tmp_path):
+    """The lines path (vpt_tokenize_lines) shards by bytes at line ends; per-rank outputs concatenate to the
+    single-process output.  The per-shard worker here is the CPU oracle (no GPU in this test)."""
+    model_bytes = open(os.path.join(GOLDEN, "model.bin"), "rb").read()
+    text, offs, _ = synth.gen_text(300, ragged=True)
+    lines = [text[int(offs[i]):int(offs[i + 1])].tobytes() for i in range(len(offs) - 1)]
+    data = b"\r\n".join(lines[:100]) + b"\n\n" + b"\n".join(lines[100:])  # unterminated last line
+    world = 2
+    mp.spawn(_lines_worker, args=(world, _free_port(), model_bytes, data, str(tmp_path)), nprocs=world, join=True)
+    want, nl = OraclePredictor(model_bytes).tokenize_lines(data, wsconst="D")
+    got = b"".join(open(os.path.join(tmp_path, f"l{r}.bin"), "rb").read() for r in range(world))
+    assert got == want
+    assert int(open(os.path.join(tmp_path, "n0.txt")).read()) == nl
+
+
+def test_shard_lines_properties():
+    rng = np.random.default_rng(5)
+    for _ in range(200):
+        n = int(rng.integers(0, 200))
+        data = bytes(rng.choice(np.frombuffer(b"ab\n\r", np.uint8), size=n, p=[0.4, 0.35, 0.2, 0.05]))
+        world = int(rng.integers(1, 6))
+        cuts = [vb.shard_lines(data, r, world) for r in range(world)]
+        assert cuts[0][0] == 0 and cuts[-1][1] == n
+        for (a, b), (c, d) in zip(cuts, cuts[1:]):
+            assert b == c and a <= b
+        for lo, hi in cuts[:-1]:
+            assert hi == lo or hi == n or data[hi - 1:hi] == b"\n"   # a cut sits right after a line end
+
+
 def test_shard_by_bytes_properties():
     rng = np.random.default_rng(3)
     for _ in range(50):

@@ -204,6 +204,21 @@ def shard_by_bytes(offsets, rank: int, world: int):
     return cuts[rank], cuts[rank + 1]
 
 
+def shard_lines(data, rank: int, world: int):
+    """Byte range [lo, hi) of `rank` when a buffer of lines (the input of Predictor.tokenize_lines) is split over
+    `world` ranks: cuts are placed after the first '\n' at or after every r/world-th byte, so every line belongs to
+    exactly one rank and the concatenation of the ranks' outputs equals the single-process output."""
+    t = np.frombuffer(data, np.uint8) if isinstance(data, (bytes, bytearray)) else np.ascontiguousarray(data, np.uint8)
+    n = t.size
+    cuts = [0]
+    for r in range(1, world):
+        p = max(n * r // world, cuts[-1])
+        nl = np.flatnonzero(t[p:] == 10)
+        cuts.append(p + int(nl[0]) + 1 if p < n and nl.size else n)
+    cuts.append(n)
+    return cuts[rank], cuts[rank + 1]
+
+
 class BatchResult:
     """Outputs of a batched predict: flat arrays + per-sentence offsets."""
 
