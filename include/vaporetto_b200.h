@@ -68,6 +68,19 @@ int vpt_model_read(const uint8_t* data, size_t len, vpt_model** out, size_t* con
  * left / inside / right weights by word-length bucket; KyTea's tag models are not converted (as in the reference). */
 int vpt_model_read_kytea(const uint8_t* data, size_t len, vpt_model** model_out);
 
+/* `Model::dictionary` (model.rs:155-158) / `WordWeightRecord::get_word, get_weights, get_comment` (dict_model.rs:53-66):
+ * record `index` of the model's word dictionary; the pointers stay valid until the model is freed or its dictionary
+ * replaced. */
+uint64_t vpt_model_dictionary_len(const vpt_model* model);
+int vpt_model_dictionary_get(const vpt_model* model, uint64_t index, const char** word, const int32_t** weights,
+                             uint64_t* n_weights, const char** comment);
+
+/* `Model::replace_dictionary` (model.rs:160-163) with the check of `WordWeightRecord::new` (dict_model.rs:39-50):
+ * every record needs chars(word) + 1 weights, else VPT_INVALID_ARGUMENT and the model is unchanged.  `comments` (and
+ * its elements) may be NULL.  With vpt_model_to_vec this is the reference's `manipulate_model` tool. */
+int vpt_model_replace_dictionary(vpt_model* model, const char* const* words, const int32_t* const* weights,
+                                 const uint64_t* n_weights, const char* const* comments, uint64_t n_records);
+
 /* `Model::to_vec` / `Model::write` (model.rs:99-120): the model file image (magic + bincode standard encoding);
  * byte-identical to what the reference writes for the same model.  Release the buffer with vpt_blob_free. */
 int vpt_model_to_vec(const vpt_model* model, uint8_t** bytes_out, uint64_t* len_out);

@@ -87,3 +87,28 @@ def test_kytea_errors():
             vb.Model.read_kytea(ok[:cut])
         with pytest.raises(Exception):
             kytea_to_model_bytes(ok[:cut])
+
+
+def test_dictionary_access_and_replacement():
+    """Model::dictionary / replace_dictionary (model.rs:155-163) + WordWeightRecord::new's check (dict_model.rs:39-50):
+    with Model::to_vec this is the reference's manipulate_model tool; bytes compared with the test-side bincode encoder."""
+    from vpt_testlib.bincode_model import encode_model
+    spec = dict(char_ngrams=[("火星", [1, 2, 3])], type_ngrams=[(bytes([5, 5]), [4, 5, 6])],
+                dict=[("火星猫", [1, -2, 3, 4], "comment"), ("é", [5, 6], "")], bias=7, char_window=2, type_window=2,
+                tag_models=[])
+    m = vb.Model.read(encode_model(spec))
+    assert m.dictionary() == [("火星猫", [1, -2, 3, 4], "comment"), ("é", [5, 6], "")]
+    new = [("社長", [10, 20, -30], "x"), ("\U00020000", [1, 2], "")]
+    m.replace_dictionary(new)
+    assert m.dictionary() == new
+    assert m.to_vec() == encode_model(dict(spec, dict=new))
+    with pytest.raises(vb.VaporettoError) as e:
+        m.replace_dictionary([("社長", [1, 2], "")])   # needs 3 weights
+    assert "does not match the length of the `word`" in str(e.value)
+    assert m.dictionary() == new                        # unchanged after the failed call
+    m.replace_dictionary([])
+    assert m.dictionary() == [] and m.to_vec() == encode_model(dict(spec, dict=[]))
+    # the converted KyTea fixture exposes its dictionary: [left, inside.., right] per word
+    km = vb.Model.read_kytea(read("kytea-model.bin"))
+    for word, weights, _ in km.dictionary():
+        assert len(weights) == len(word) + 1

@@ -68,6 +68,10 @@ ABI = [
     ("vpt_model_free", None, [_P]),
     ("vpt_model_read_kytea", C.c_int, [C.c_char_p, C.c_size_t, C.POINTER(_P)]),
     ("vpt_model_to_vec", C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_uint64)]),
+    ("vpt_model_dictionary_len", C.c_uint64, [_P]),
+    ("vpt_model_dictionary_get", C.c_int, [_P, C.c_uint64, C.POINTER(C.c_char_p), C.POINTER(_P), C.POINTER(C.c_uint64),
+                                          C.POINTER(C.c_char_p)]),
+    ("vpt_model_replace_dictionary", C.c_int, [_P, _P, _P, _P, _P, C.c_uint64]),
     ("vpt_predictor_new", C.c_int, [_P, C.c_int, C.c_int, C.POINTER(_P)]),
     ("vpt_predictor_free", None, [_P]),
     ("vpt_predictor_get_info", C.c_int, [_P, C.POINTER(_Info)]),
@@ -165,6 +169,28 @@ class Model:
             return C.string_at(out, n.value)
         finally:
             lib().vpt_blob_free(out)
+
+    def dictionary(self):
+        """`Model::dictionary` (model.rs:155-158): [(word, weights, comment)]."""
+        out = []
+        for i in range(lib().vpt_model_dictionary_len(self._h)):
+            w, c = C.c_char_p(), C.c_char_p()
+            p, n = _P(), C.c_uint64()
+            _check(lib().vpt_model_dictionary_get(self._h, i, C.byref(w), C.byref(p), C.byref(n), C.byref(c)))
+            weights = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_int32)), shape=(n.value,)).tolist() if n.value else []
+            out.append((w.value.decode("utf-8"), weights, c.value.decode("utf-8")))
+        return out
+
+    def replace_dictionary(self, records) -> None:
+        """`Model::replace_dictionary` (model.rs:160-163); records: [(word, weights, comment)] checked like
+        `WordWeightRecord::new` (dict_model.rs:39-50)."""
+        n = len(records)
+        words = (C.c_char_p * max(n, 1))(*[r[0].encode("utf-8") for r in records])
+        comments = (C.c_char_p * max(n, 1))(*[r[2].encode("utf-8") for r in records])
+        arrays = [np.ascontiguousarray(r[1], np.int32) for r in records]
+        wptr = (_P * max(n, 1))(*[a.ctypes.data for a in arrays])
+        lens = (C.c_uint64 * max(n, 1))(*[a.size for a in arrays])
+        _check(lib().vpt_model_replace_dictionary(self._h, words, wptr, lens, comments, n))
 
     def _take(self):
         h, self._h = self._h, None

@@ -333,6 +333,48 @@ int vpt_model_to_vec(const vpt_model* model, uint8_t** bytes_out, uint64_t* len_
     VPT_API_END
 }
 
+uint64_t vpt_model_dictionary_len(const vpt_model* model) { return model ? model->m.dict.size() : 0; }
+
+int vpt_model_dictionary_get(const vpt_model* model, uint64_t index, const char** word, const int32_t** weights,
+                             uint64_t* n_weights, const char** comment) {
+    VPT_API_BEGIN
+    if (!model) throw Error(kInvalidArgument, "InvalidArgumentError: model: must not be NULL");
+    if (index >= model->m.dict.size()) throw Error(kInvalidArgument, "InvalidArgumentError: index: out of range");
+    const DictEntry& e = model->m.dict[index];
+    if (word) *word = e.word.c_str();
+    if (weights) *weights = e.weights.data();
+    if (n_weights) *n_weights = e.weights.size();
+    if (comment) *comment = e.comment.c_str();
+    return kOk;
+    VPT_API_END
+}
+
+int vpt_model_replace_dictionary(vpt_model* model, const char* const* words, const int32_t* const* weights,
+                                 const uint64_t* n_weights, const char* const* comments, uint64_t n_records) {
+    VPT_API_BEGIN
+    if (!model) throw Error(kInvalidArgument, "InvalidArgumentError: model: must not be NULL");
+    if (n_records && (!words || !weights || !n_weights))
+        throw Error(kInvalidArgument, "InvalidArgumentError: words/weights/n_weights: must not be NULL");
+    std::vector<DictEntry> dict;
+    dict.reserve(n_records);
+    for (uint64_t i = 0; i < n_records; ++i) {
+        DictEntry e;
+        e.word = words[i] ? words[i] : "";
+        if (!is_valid_utf8(reinterpret_cast<const uint8_t*>(e.word.data()), e.word.size()))
+            throw Error(kInvalidArgument, "InvalidArgumentError: word: must be valid UTF-8");
+        // WordWeightRecord::new (dict_model.rs:39-50)
+        if (n_weights[i] != utf8_to_codepoints(e.word).size() + 1)
+            throw Error(kInvalidArgument, "InvalidArgumentError: weights: does not match the length of the `word`");
+        if (n_weights[i] && !weights[i]) throw Error(kInvalidArgument, "InvalidArgumentError: weights: must not be NULL");
+        e.weights.assign(weights[i], weights[i] + n_weights[i]);
+        e.comment = (comments && comments[i]) ? comments[i] : "";
+        dict.push_back(std::move(e));
+    }
+    model->m.dict = std::move(dict);
+    return kOk;
+    VPT_API_END
+}
+
 void vpt_model_free(vpt_model* model) { delete model; }
 
 int vpt_predictor_new(vpt_model* model, int predict_tags, int device, vpt_predictor** out) {
