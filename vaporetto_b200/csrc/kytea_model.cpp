@@ -135,6 +135,7 @@ struct Trie {
         std::vector<uint32_t> word;
         struct Frame { uint32_t node; size_t child; };
         std::vector<Frame> stack{{0, 0}};
+        size_t visits = 1;
         auto visit = [&](uint32_t node) {
             const Node& nd = at(node);
             if (nd.is_branch) {
@@ -153,7 +154,8 @@ struct Trie {
                 continue;
             }
             const auto& e = nd.next[fr.child++];
-            if (stack.size() > nodes.size()) throw Error(kInvalidModel, "InvalidModelError: dictionary is not a tree");
+            // a trie reaches every state once; shared or cyclic states would make the enumeration explode or never end
+            if (++visits > nodes.size()) throw Error(kInvalidModel, "InvalidModelError: dictionary is not a tree");
             word.push_back(e.first);
             stack.push_back({e.second, 0});
             visit(e.second);
