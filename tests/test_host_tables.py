@@ -156,3 +156,23 @@ def test_table_layout_variants(emul, budget, monkeypatch):
         s = bytes(text[int(offs[i]):int(offs[i + 1])]).decode()
         sc, _, _, _ = run(emul, mb, s)
         assert sc == o.predict(s)[0].tolist()
+
+
+def test_builder_survives_mutated_models(tmp_path):
+    """ASan + UBSan build of the model reader + host predictor builder against mutated model files (random bytes, bit
+    flips, small values in length / window positions): built or rejected with an error, never a crash."""
+    import struct
+    exe = str(tmp_path / "build_fuzz")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined",
+                           "-I" + CSRC, os.path.join(HERE, "native", "build_fuzz.cpp")] +
+                          [os.path.join(CSRC, f) for f in ("model.cpp", "builder.cpp", "predictor_build.cpp")] + ["-o", exe])
+    samples = [open(os.path.join(GOLDEN, fn), "rb").read() for fn in ("model.bin", "tantivy_model.bin")]
+    samples += [encode_model(m) for m in (kat.PREDICTOR_TEST_MODEL, kat.CHAR_ADD_SCORES_WITH_TAGS["model"],
+                                          kat.CHAR_ADD_SCORES_3["model"], kat.TYPE_ADD_SCORES["model"],
+                                          kat.TYPE_ADD_SCORES_WITH_TAGS["model"])]
+    with open(tmp_path / "samples.bin", "wb") as f:
+        for b in samples:
+            f.write(struct.pack("<I", len(b)) + b)
+    out = subprocess.run([exe, str(tmp_path / "samples.bin"), "3000"], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "build fuzz done" in out.stdout
