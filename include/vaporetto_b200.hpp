@@ -201,12 +201,19 @@ public:
 
     /// `Sentence::write_tokenized_text(&self, buf: &mut String)` (sentence.rs:850-886).
     void write_tokenized_text(std::string& buf) const {
+        // the C call reports the full length even when it had to truncate: size the buffer from a first guess and
+        // retry once with the exact length (tag strings come from the model file and can be arbitrarily long)
         uint64_t need = 0;
-        std::vector<char> tmp(16 * text_.size() + 256 + 64 * types_.size() * (tags_filled_ ? n_tags_ + 1 : 1));
-        detail::check(vpt_write_tokenized_text(predictor_ ? predictor_->handle() : nullptr,
-                                               reinterpret_cast<const uint8_t*>(text_.data()), text_.size(),
-                                               boundaries_.data(), tags_filled_ ? tag_token_.data() : nullptr,
-                                               tags_filled_ ? tag_cand_.data() : nullptr, tmp.data(), tmp.size(), &need));
+        std::vector<char> tmp(2 * text_.size() + 64);
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            detail::check(vpt_write_tokenized_text(predictor_ ? predictor_->handle() : nullptr,
+                                                   reinterpret_cast<const uint8_t*>(text_.data()), text_.size(),
+                                                   boundaries_.data(), tags_filled_ ? tag_token_.data() : nullptr,
+                                                   tags_filled_ ? tag_cand_.data() : nullptr, tmp.data(), tmp.size(), &need));
+            if (need < tmp.size()) break;
+            tmp.resize(size_t(need) + 1);
+        }
+        if (need >= tmp.size()) throw std::runtime_error("write_tokenized_text: length changed between calls");
         buf.assign(tmp.data(), size_t(need));
     }
 

@@ -11,4 +11,4 @@ for i,name in enumerate(h):
     if name.startswith('smsp__average_warps_issue_stalled') and name.endswith('per_issue_active.ratio') and float(v[i] or 0) > 0.3: print(f'{name[34:-24]} = {v[i]}')
 "
 rm -rf /tmp/vpt_cubin && mkdir -p /tmp/vpt_cubin && (cd /tmp/vpt_cubin && cuobjdump -xelf all /root/repo/vaporetto_b200/libvaporetto_b200.so > /dev/null 2>&1)
-python /root/repo/profiles/line_profile.py $1 $2 /tmp/vpt_cubin/kernels.sm_100a.cubin ${3:-30}
+python /root/repo/profiles/line_profile.py $1 $2 /tmp/vpt_cubin/$(ls /tmp/vpt_cubin/*${4:-kernels}*.cubin | head -1 | xargs basename) ${3:-30}

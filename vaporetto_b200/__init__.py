@@ -494,15 +494,19 @@ class Sentence:
     def write_tokenized_text(self) -> str:
         """`Sentence::write_tokenized_text` (sentence.rs:850-886)."""
         p = self._predictor
-        cap = 8 * len(self._bytes) + 64
-        if self._tags is not None:
-            cap += 64 * self._n * max(p.n_tags, 1)
-        buf = C.create_string_buffer(cap)
+        cap = 2 * len(self._bytes) + 64
         ln = C.c_uint64()
         have = self._tags is not None
-        _check(lib().vpt_write_tokenized_text(p._h if p else None, self._bytes, len(self._bytes),
-                                              self._boundaries.ctypes.data,
-                                              self._tag_token.ctypes.data if have else None,
-                                              self._tag_cand.ctypes.data if have else None, buf, cap, C.byref(ln)))
-        assert ln.value < cap
+        for _ in range(2):
+            # the call reports the full length even when it truncated: retry once with the exact size
+            buf = C.create_string_buffer(cap)
+            _check(lib().vpt_write_tokenized_text(p._h if p else None, self._bytes, len(self._bytes),
+                                                  self._boundaries.ctypes.data,
+                                                  self._tag_token.ctypes.data if have else None,
+                                                  self._tag_cand.ctypes.data if have else None, buf, cap, C.byref(ln)))
+            if ln.value < cap:
+                break
+            cap = ln.value + 1
+        if ln.value >= cap:
+            raise VaporettoError(18, "write_tokenized_text: length changed between calls")
         return buf.raw[: ln.value].decode("utf-8")

@@ -284,7 +284,7 @@ bool build_type_state3(const PatternSet& tps, std::vector<uint32_t>& table) {
 
 uint32_t table_slot(const TableGeom& g, const uint8_t* seeds, uint64_t key) {
     uint32_t ha, hb;
-    key_hashes(key, g.salt, ha, hb);
+    key_hashes(key, hash_consts(g.salt), ha, hb);
     const uint32_t bk = bucket_of(ha, g.nbuckets);
     const uint32_t seed = g.seed_bits == 16 ? uint32_t(seeds[2 * size_t(bk)]) | (uint32_t(seeds[2 * size_t(bk) + 1]) << 8) : seeds[bk];
     return slot_with_seed(ha, hb, seed, g.nslots);
@@ -311,9 +311,16 @@ bool place_keys(const std::vector<uint64_t>& keys, TableGeom& g, std::vector<uin
     const size_t n = keys.size();
     std::vector<uint32_t> ha(n), hb(n);
     std::vector<std::vector<uint32_t>> buckets(g.nbuckets);
+    const HashK hk = hash_consts(g.salt);
     for (size_t i = 0; i < n; ++i) {
-        key_hashes(keys[i], g.salt, ha[i], hb[i]);
+        key_hashes(keys[i], hk, ha[i], hb[i]);
         buckets[bucket_of(ha[i], g.nbuckets)].push_back(uint32_t(i));
+    }
+    {   // two keys with the same pair of hashes can never be separated by a seed: re-salt
+        std::vector<uint64_t> pairs(n);
+        for (size_t i = 0; i < n; ++i) pairs[i] = (uint64_t(ha[i]) << 32) | hb[i];
+        std::sort(pairs.begin(), pairs.end());
+        if (std::adjacent_find(pairs.begin(), pairs.end()) != pairs.end()) return false;
     }
     std::vector<uint32_t> order(g.nbuckets);
     std::iota(order.begin(), order.end(), 0u);

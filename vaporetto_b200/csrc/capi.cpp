@@ -125,6 +125,7 @@ DevTable dev_table(const BlobTable& bt, const uint8_t* base) {
     d.nslots = bt.nslots;
     d.nbuckets = bt.nbuckets;
     d.salt = bt.salt;
+    d.hk = hash_consts(bt.salt);
     d.seed16 = bt.seed_bits == 16;
     d.has_overflow = bt.has_overflow;
     d.slot_ovf = bt.has_overflow ? reinterpret_cast<const uint64_t*>(base + bt.ovf_off) : nullptr;
@@ -134,6 +135,29 @@ DevTable dev_table(const BlobTable& bt, const uint8_t* base) {
     d.slot_pid = reinterpret_cast<const uint32_t*>(base + bt.pid_off);
     d.pool = reinterpret_cast<const int32_t*>(base + bt.pool_off);
     return d;
+}
+
+// Every section a blob header points at must lie inside the blob, and the geometry must be what the kernels were
+// built for: a truncated or corrupted blob is an InvalidModel error, not an out-of-bounds read on the device.
+void validate_blob_header(const BlobHeader& h, uint64_t len) {
+    auto inside = [&](uint64_t off, uint64_t bytes) { return off >= sizeof(BlobHeader) && off <= len && bytes <= len - off; };
+    auto bad = [](const char* what) { return Error(kInvalidModel, std::string("InvalidModelError: model blob: bad ") + what); };
+    auto table = [&](const BlobTable& t, const char* name) {
+        if (!t.present) return;
+        if (t.nslots == 0 || t.nbuckets == 0 || (t.seed_bits != 8 && t.seed_bits != 16)) throw bad(name);
+        if (!inside(t.rec_off, uint64_t(t.nslots) * 32) || !inside(t.seeds_off, uint64_t(t.nbuckets) * (t.seed_bits / 8)) ||
+            !inside(t.node_off, uint64_t(t.nslots) * 4) || !inside(t.pid_off, uint64_t(t.nslots) * 4) || !inside(t.pool_off, 4))
+            throw bad(name);
+        if (t.has_overflow && !inside(t.ovf_off, uint64_t(t.nslots) * 8)) throw bad(name);
+        if (t.r0 < -64 || t.r0 > 64) throw bad(name);
+    };
+    table(h.ct, "char table");
+    table(h.tt, "type table");
+    if (h.char_window < 0 || h.char_window > 255 || h.type_window < 0 || h.type_window > 255) throw bad("window");
+    if (h.type_cache_window < 0 || h.type_cache_window > 3) throw bad("type table window");
+    if (h.type_cache_window && !inside(h.type_cache_off, (uint64_t(4) << (6 * h.type_cache_window)))) throw bad("type table");
+    if (h.type_a_off && (!inside(h.type_a_off, 4 * 4096) || !inside(h.type_b_off, 4 * 4096))) throw bad("split type tables");
+    if (h.type_state3_off && !inside(h.type_state3_off, 4 * 512)) throw bad("type state table");
 }
 
 void upload(vpt_predictor& p) {
@@ -181,6 +205,12 @@ struct ScratchLease {
         }
     }
     ~ScratchLease() {
+        // a lease can end on an exception path while copies into the caller's buffers or kernels are still queued:
+        // drain both streams before the scratch becomes reusable and control returns to the caller
+        if (s) {
+            if (s->stream) cudaStreamSynchronize(s->stream);
+            if (s->stream_out) cudaStreamSynchronize(s->stream_out);
+        }
         std::lock_guard<std::mutex> g(p.mu);
         p.pool.push_back(std::move(s));
     }
@@ -258,15 +288,12 @@ void add_truncated(const std::vector<int32_t>& w, std::vector<int32_t>& ys) {  /
 bool merged_tag_weight(const std::unordered_map<uint32_t, std::vector<int32_t>>& table,
                        const std::vector<uint32_t>& suffix_link, uint32_t pid, std::vector<int32_t>& out) {
     // collect the chain entries (longest pattern first)
-    const std::vector<int32_t>* chain[64];
-    int n = 0;
+    std::vector<const std::vector<int32_t>*> chain;
     for (uint32_t q = pid; q != kNoPattern; q = suffix_link[q]) {
         auto it = table.find(q);
-        if (it != table.end()) {
-            if (n == 64) break;  // patterns are far shorter than 64 symbols per chain in practice
-            chain[n++] = &it->second;
-        }
+        if (it != table.end()) chain.push_back(&it->second);
     }
+    const int n = int(chain.size());
     if (n == 0) return false;
     // evaluate from the shortest suffix outwards
     out = *chain[n - 1];
@@ -454,6 +481,7 @@ int vpt_predictor_from_blob(const void* blob, uint64_t len, int device, vpt_pred
     memcpy(&h, blob, sizeof h);
     if (memcmp(h.magic, kBlobMagic, 8) != 0 || h.total_bytes != len)
         throw Error(kInvalidModel, "InvalidModelError: not a vaporetto_b200 model blob");
+    validate_blob_header(h, len);
     std::unique_ptr<vpt_predictor> p(new vpt_predictor());
     p->device = device;
     p->from_blob = true;
@@ -501,16 +529,16 @@ static void run_batch_dev(const vpt_predictor* p, const uint8_t* d_utf8, const u
     a.char_states = d_char_states;
     a.type_states = d_type_states;
     if (!stage_ms) {
-        cuda_check(launch_count(a, st), "launch(count)");
-        cuda_check(launch_score(p->dm, a, st), "launch(score)");
+        cuda_check(launch_batch(p->dm, a, st), "launch(batch)");
         return;
     }
     cudaEvent_t ev[4];
     for (auto& e : ev) cuda_check(cudaEventCreate(&e), "cudaEventCreate");
+    const bool fused = fused_ok(p->dm);  // one launch: the count and scan stages do not exist
     cuda_check(cudaEventRecord(ev[0], st), "record");
-    cuda_check(launch_count_only(a, st), "launch(count)");
+    if (!fused) cuda_check(launch_count_only(a, st), "launch(count)");
     cuda_check(cudaEventRecord(ev[1], st), "record");
-    cuda_check(launch_scan_only(a, st), "launch(scan)");
+    if (!fused) cuda_check(launch_scan_only(a, st), "launch(scan)");
     cuda_check(cudaEventRecord(ev[2], st), "record");
     cuda_check(launch_score(p->dm, a, st), "launch(score)");
     cuda_check(cudaEventRecord(ev[3], st), "record");
@@ -852,8 +880,8 @@ void lines_stage1(const vpt_predictor& p, Scratch& s, LineChunk& ch, bool normal
     }
     a.boundaries = static_cast<uint8_t*>(s.d_bounds);
     if (pipeline_trace()) ch.tr.mark_sub(0, st);  // after the line offsets
-    cuda_check(launch_count(a, st), "launch(count)");
-    if (pipeline_trace()) ch.tr.mark_sub(1, st);  // after count + scan
+    if (!fused_ok(dm)) cuda_check(launch_count(a, st), "launch(count)");
+    if (pipeline_trace()) ch.tr.mark_sub(1, st);  // after count + scan (none when the scoring launch is fused)
     cuda_check(launch_score(dm, a, st), "launch(score)");
     if (pipeline_trace()) ch.tr.mark_sub(2, st);  // after the scoring kernel
     TokArgs t;
@@ -1034,6 +1062,8 @@ int vpt_fill_tags(const vpt_predictor* p, const uint8_t* utf8, size_t n_bytes, c
     if (!p) throw Error(kInvalidArgument, "InvalidArgumentError: predictor: must not be NULL");
     if (!p->predict_tags || p->from_blob)
         throw Error(kInvalidArgument, "InvalidArgumentError: this predictor is created with predict_tags = false");
+    if (!utf8 || !boundaries || !tag_token_out || !tag_cand_out)
+        throw Error(kInvalidArgument, "InvalidArgumentError: utf8/boundaries/tag_token_out/tag_cand_out: must not be NULL");
     check_raw_text(utf8, n_bytes);
     const std::vector<uint32_t> pos = char_starts(utf8, n_bytes);
     const size_t n = pos.size() - 1;
@@ -1097,6 +1127,7 @@ int vpt_write_tokenized_text(const vpt_predictor* p, const uint8_t* utf8, size_t
                              const int32_t* tag_token, const int32_t* tag_cand, char* buf, size_t capacity,
                              uint64_t* len_out) {
     VPT_API_BEGIN
+    if (!utf8 || !boundaries) throw Error(kInvalidArgument, "InvalidArgumentError: utf8/boundaries: must not be NULL");
     check_raw_text(utf8, n_bytes);
     const std::vector<uint32_t> pos = char_starts(utf8, n_bytes);
     const size_t n = pos.size() - 1;

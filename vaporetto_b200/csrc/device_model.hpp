@@ -5,6 +5,8 @@
 
 #include <cuda_runtime.h>
 
+#include "keys.hpp"
+
 namespace vpt {
 
 struct DevTable {
@@ -15,6 +17,7 @@ struct DevTable {
     const int32_t* pool = nullptr;     // general rows / overflow rows
     const uint64_t* slot_ovf = nullptr; // fast tables with overflow rows: ptr | off16 << 32 | len16 << 48
     uint64_t salt = 0;
+    HashK hk{};                        // hash multipliers derived from the salt (keys.hpp)
     uint32_t nslots = 0;
     uint32_t nbuckets = 0;
     int32_t r0 = 0;
@@ -75,7 +78,14 @@ cudaError_t launch_count(const BatchArgs& a, cudaStream_t stream);  // count + s
 cudaError_t launch_count_only(const BatchArgs& a, cudaStream_t stream);
 cudaError_t launch_scan_only(const BatchArgs& a, cudaStream_t stream);
 cudaError_t launch_score(const DevModel& m, const BatchArgs& a, cudaStream_t stream);
-// number of kernel launches issued by launch_count + launch_score for this model
+// fused.cu: validation, counts, output offsets (decoupled look-back) and scoring of a batch in one launch, for the
+// inline-row model shapes fused_ok() accepts; needs neither launch_count nor the count pass's scratch arrays
+// (group_bound / group_char / ticket are used as look-back descriptors and cleared by a memset node)
+bool fused_ok(const DevModel& m);
+cudaError_t launch_fused(const DevModel& m, const BatchArgs& a, cudaStream_t stream);
+// count (+ scan) + score, or the fused launch when the model qualifies
+cudaError_t launch_batch(const DevModel& m, const BatchArgs& a, cudaStream_t stream);
+// number of kernel launches issued by launch_batch for this model
 int launches_per_batch(const DevModel& m);
 // true when launch_score accepts BatchArgs::scores == nullptr (boundaries only) for this model
 bool scores_optional(const DevModel& m);

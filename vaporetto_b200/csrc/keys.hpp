@@ -50,23 +50,36 @@ VPT_HD uint64_t deep_key(uint32_t parent_id, uint32_t sym) {
     return ((kDeepMarker + (uint64_t(parent_id) >> 21)) << 42) | ((uint64_t(parent_id) & 0x1FFFFF) << 21) | uint64_t(sym);
 }
 
-// Hash-and-displace perfect hash (32-bit arithmetic: cheap on the GPU).  A key is reduced to two mixed
-// 32-bit hashes; the first picks the bucket, the bucket's 16-bit seed displaces the second into the slot.
-VPT_HD void key_hashes(uint64_t key, uint64_t salt, uint32_t& ha, uint32_t& hb) {
-    const uint32_t lo = uint32_t(key) ^ uint32_t(salt), hi = uint32_t(key >> 32) ^ uint32_t(salt >> 32);
-    // Multiplication carries differences upwards only, so each half is multiplied, folded down (>> 16) and mixed
-    // into the other half before the second multiply; every consumer below reads the HIGH bits of these products
-    // (mulhi32), which depend on all input bits.
-    const uint32_t t = hi * 0x85EBCA77u;
-    ha = (lo ^ t ^ (t >> 16)) * 0x9E3779B1u;
-    const uint32_t u = lo * 0x27D4EB2Fu;
-    hb = (hi ^ u ^ (u >> 15)) * 0x165667B1u;
+// Hash-and-displace perfect hash (32-bit arithmetic: cheap on the GPU).  A key is reduced to two 32-bit hashes
+// that are LINEAR in its three 21-bit fields (c1, c2, c3): h = c3*k[0] + c2*k[1] + c1*k[2] (mod 2^32), with odd
+// multipliers derived from the table's salt.  Linearity is what the streaming kernel (fused.cu) exploits: the
+// hashes of the three suffix levels of one text position share their partial sums (h1 = c3*k0, h2 = h1 + c2*k1,
+// h3 = h2 + c1*k2), so a fallback probe costs one multiply-add per hash instead of a full mix.  Every consumer
+// reads the HIGH bits of these sums or of a product of them (mulhi32), which depend on all input bits.  The
+// builder checks that no two keys of a table share both hashes (it re-salts otherwise).
+struct HashK {
+    uint32_t a[3];  // bucket hash multipliers for c3, c2, c1
+    uint32_t b[3];  // displacement hash multipliers
+};
+VPT_HD HashK hash_consts(uint64_t salt) {
+    HashK k;
+    for (int i = 0; i < 3; ++i) {
+        const uint64_t m = mix64(salt + 0x9E3779B97F4A7C15ull * uint64_t(i + 1));
+        k.a[i] = uint32_t(m) | 1u;
+        k.b[i] = uint32_t(m >> 32) | 1u;
+    }
+    return k;
+}
+VPT_HD void key_hashes(uint64_t key, const HashK& k, uint32_t& ha, uint32_t& hb) {
+    const uint32_t c3 = uint32_t(key) & 0x1FFFFFu, c2 = uint32_t(key >> 21) & 0x1FFFFFu, c1 = uint32_t(key >> 42) & 0x1FFFFFu;
+    ha = c3 * k.a[0] + c2 * k.a[1] + c1 * k.a[2];
+    hb = c3 * k.b[0] + c2 * k.b[1] + c1 * k.b[2];
 }
 VPT_HD uint32_t mulhi32(uint32_t a, uint32_t b) { return uint32_t((uint64_t(a) * b) >> 32); }
 VPT_HD uint32_t bucket_of(uint32_t ha, uint32_t nbuckets) { return mulhi32(ha, nbuckets); }
 VPT_HD uint32_t slot_with_seed(uint32_t ha, uint32_t hb, uint32_t seed, uint32_t nslots) {
     const uint32_t v = (hb + seed * (ha | 1u)) * 0x85EBCA6Bu;
-    return mulhi32(v ^ (v >> 15), nslots);
+    return mulhi32(v, nslots);
 }
 
 }  // namespace vpt
