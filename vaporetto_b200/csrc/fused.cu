@@ -26,6 +26,8 @@
 // Groups the fast path cannot take (text or slots beyond the tile buffers, NUL / malformed UTF-8, zero-width
 // sentences) run the same stream stage behind an exact per-sentence count (slow_*), a range at a time.
 // No tensor cores: integer indexing + gather-add.
+#include <type_traits>
+
 #include "kernels_common.cuh"
 
 namespace vpt {
@@ -108,26 +110,40 @@ __device__ __forceinline__ uint64_t warp_sum64(uint64_t v) {
     return v;
 }
 
-// Exclusive prefix of group `grp` over one descriptor array (called by a full warp).  Every predecessor has at
-// least published its aggregate or is being processed by a resident sub-block (tickets are handed out in order).
-__device__ __forceinline__ uint64_t lookback(const uint64_t* desc, uint64_t grp, int lane) {
-    uint64_t sum = 0;
-    for (int64_t j = int64_t(grp) - 1; j >= 0; j -= 32) {
+// Exclusive prefixes of group `grp` over the two descriptor arrays at once (called by a full warp).  Every
+// predecessor has at least published its aggregate or is being processed by a resident sub-block (tickets are handed
+// out in order).  The two arrays are written independently (each word carries its own state), so the two scans may
+// stop at different predecessors.
+__device__ __forceinline__ void lookback2(const uint64_t* desc_b, const uint64_t* desc_c, uint64_t grp, int lane, uint64_t& sum_b,
+                                          uint64_t& sum_c) {
+    sum_b = 0;
+    sum_c = 0;
+    bool done_b = false, done_c = false;
+    for (int64_t j = int64_t(grp) - 1; j >= 0 && !(done_b && done_c); j -= 32) {
         const int64_t idx = j - lane;
-        uint64_t v = kDescIncl;  // before the first group: an inclusive prefix of zero
+        uint64_t vb = kDescIncl, vc = kDescIncl;  // before the first group: an inclusive prefix of zero
         if (idx >= 0) {
-            v = ld_relaxed(desc + idx);
-            while ((v >> 62) == 0) {
-                __nanosleep(32);
-                v = ld_relaxed(desc + idx);
+            vb = ld_relaxed(desc_b + idx);
+            vc = ld_relaxed(desc_c + idx);
+            while ((vb >> 62) == 0 || (vc >> 62) == 0) {
+                __nanosleep(20);
+                vb = ld_relaxed(desc_b + idx);
+                vc = ld_relaxed(desc_c + idx);
             }
         }
-        const unsigned incl = __ballot_sync(kFull, (v >> 62) == 2);
-        const int first = incl ? __ffs(incl) - 1 : 32;
-        sum += warp_sum64(lane <= first ? (v & kDescVal) : 0ull);
-        if (incl) break;
+        if (!done_b) {
+            const unsigned incl = __ballot_sync(kFull, (vb >> 62) == 2);
+            const int first = incl ? __ffs(incl) - 1 : 32;
+            sum_b += warp_sum64(lane <= first ? (vb & kDescVal) : 0ull);
+            done_b = incl != 0;
+        }
+        if (!done_c) {
+            const unsigned incl = __ballot_sync(kFull, (vc >> 62) == 2);
+            const int first = incl ? __ffs(incl) - 1 : 32;
+            sum_c += warp_sum64(lane <= first ? (vc & kDescVal) : 0ull);
+            done_c = incl != 0;
+        }
     }
-    return sum;
 }
 
 // value of lane (lane - d) of the 64-lane sequence [prev chunk | this chunk] (shfl takes the source lane modulo 32)
@@ -339,7 +355,7 @@ __device__ __forceinline__ void stream_stage(const DevModel& m, const BatchArgs&
     uint32_t cA = 0, c2A = 0, c1A = 0, HA = 0, slA = 0;
     Rec32 rA;
     //   state B: chunk it-2 after stage 2 (second probe issued)
-    uint32_t kloB = 0, khiB = 0, HB = 0, flB = 0, slB = 0;  // flB: 1 first probe hit, 2 second probe issued, 4 .. for 3 characters
+    uint32_t kloB = 0, khiB = 0, HB = 0, flB = 0, slB = 0, sl1B = 0;  // slB / sl1B: slots of the second / first probe  // flB: 1 first probe hit, 2 second probe issued, 4 .. for 3 characters
     int32_t dB[kInlineWidth];
     Rec32 rB;
     //   carried from chunk to chunk
@@ -351,10 +367,10 @@ __device__ __forceinline__ void stream_stage(const DevModel& m, const BatchArgs&
 #pragma unroll
     for (int j = 0; j < 8; ++j) { rA.v[j] = 0; rB.v[j] = 0; }
 
-#pragma unroll 2
-    for (int it = 0; it < nchunk + 2; ++it) {
+    // one pipeline step; d3 / d2 / d1 select the stages at compile time (prologue, steady state, epilogue)
+    auto step = [&](const int it, auto d3, auto d2, auto d1) {
         // ================= stage 3: chunk it-2 — second probe result, gather, type table, output ========================
-        if (it >= 2) {
+        if constexpr (decltype(d3)::value) {
             const int p = p0 + ((it - 2) << 5) + lane;
             bool f2 = (flB & 2u) && rB.v[0] == kloB && (rB.v[1] & 0x7FFFFFFFu) == khiB;
             if (kDeep > 0) {
@@ -371,7 +387,7 @@ __device__ __forceinline__ void stream_stage(const DevModel& m, const BatchArgs&
             if (kStates) {
                 if ((want_cst || want_tst) && (HB & 7u) != 0 && p >= ra && p < rb) {
                     const uint64_t ci = cbase + (uint32_t(s_meta[p]) >> 12);
-                    if (want_cst) a.char_states[ci] = (emit_c && (f2 || (flB & 1u))) ? __ldg(ct.slot_pid + slB) : kNoPattern;
+                    if (want_cst) a.char_states[ci] = (emit_c && (f2 || (flB & 1u))) ? __ldg(ct.slot_pid + (f2 ? slB : sl1B)) : kNoPattern;
                     if (want_tst) a.type_states[ci] = (m.emit_states && m.type_state3) ? __ldg(m.type_state3 + (HB & 0x1FFu)) : kNoPattern;
                 }
             }
@@ -404,13 +420,14 @@ __device__ __forceinline__ void stream_stage(const DevModel& m, const BatchArgs&
             }
         }
         // ================= stage 2: chunk it-1 — first probe result, second probe =====================================
-        if (it >= 1 && it <= nchunk) {
+        if constexpr (decltype(d2)::value) {
             const uint32_t klo = cA | (c2A << 21), khi = c2A >> 11;
             const bool act = cA != 0 && have_ct;
             const bool f1 = act && rA.v[0] == klo && (rA.v[1] & 0x7FFFFFFFu) == khi;
             // the 3-character node if the 2-character node has extensions, the 1-character node if it does not exist
             const bool w3 = f1 && (rA.v[1] >> 31) && c1A != 0, w1 = act && !f1 && c2A != 0;
             slB = slA;
+            if (kStates) sl1B = slA;
             if (w3 || w1) {
                 const uint32_t h2 = cA * ka0 + c2A * ka1, g2 = cA * kb0 + c2A * kb1;
                 rB = probe_load<kSeedsSmem>(ct, s_seeds, w3 ? h2 + c1A * ka2 : cA * ka0, w3 ? g2 + c1A * kb2 : cA * kb0, slB);
@@ -423,7 +440,7 @@ __device__ __forceinline__ void stream_stage(const DevModel& m, const BatchArgs&
             HB = HA;
         }
         // ================= stage 1: chunk it — decode, type, neighbours, first probe ====================================
-        if (it < nchunk) {
+        if constexpr (decltype(d1)::value) {
             const int p = p0 + (it << 5) + lane;
             bool bad;
             uint32_t len;
@@ -446,6 +463,19 @@ __device__ __forceinline__ void stream_stage(const DevModel& m, const BatchArgs&
             // first probe: the node of the last two characters (one character at a sentence start)
             if (c != 0 && have_ct) rA = probe_load<kSeedsSmem>(ct, s_seeds, c * ka0 + c2A * ka1, c * kb0 + c2A * kb1, slA);
         }
+    };
+    using Yes = std::true_type;
+    using No = std::false_type;
+    step(0, No{}, No{}, Yes{});
+    if (nchunk >= 2) {
+        step(1, No{}, Yes{}, Yes{});
+#pragma unroll 2
+        for (int it = 2; it < nchunk; ++it) step(it, Yes{}, Yes{}, Yes{});
+        step(nchunk, Yes{}, Yes{}, No{});
+        step(nchunk + 1, Yes{}, No{}, No{});
+    } else {
+        step(1, No{}, Yes{}, No{});
+        step(2, Yes{}, No{}, No{});
     }
 #pragma unroll
     for (int dd = 16; dd > 0; dd >>= 1) nbytes += __shfl_xor_sync(kFull, nbytes, dd);
@@ -553,9 +583,13 @@ k_fused(DevModel m, BatchArgs a, StreamCfg cfg) {
                 mbar_expect_tx(s_bar, span);
                 tma_bulk_g2s(s_text, text + a0, span, s_bar);
             }
-            for (int i = tid; i < kFSlotAlloc / 4; i += kFSubThreads) reinterpret_cast<uint4*>(s_raw_alloc)[i] = make_uint4(0, 0, 0, 0);
+            // (the separator slots of the slot stream are cleared by the scatter step itself; the front padding here)
+            if (tid < kFPadFront) s_raw_alloc[tid] = 0;
             if (kOverflow)
                 for (int i = tid; i < kFSlotAlloc / 4; i += kFSubThreads) reinterpret_cast<uint4*>(s_acc - kFPadFront)[i] = make_uint4(0, 0, 0, 0);
+            // (the finishing pass of the overflow variant trusts the per-slot "valid boundary" flags: none may be stale)
+            if (kOverflow)
+                for (int i = tid; i < kFSlotAlloc; i += kFSubThreads) (s_meta - kFPadFront)[i] = MetaT(0);
             for (int i = tid; i < kFTextCap / 32 + 4; i += kFSubThreads) { s_sbits[i] = 0; s_xbits[i] = 0; }
             fsub_sync(sub);
             if (tid < ns) {
@@ -659,6 +693,8 @@ k_fused(DevModel m, BatchArgs a, StreamCfg cfg) {
                     // bytes the characters of the group must add up to (stream stage: structural check)
                     T.bytes_want = hi_byte - lo_byte - T.bytes_want;
                 }
+                // the separator slots behind the last sentence and the padding the lagging outputs read
+                if (tid < gap + kFPadBack) s_raw[S - gap + tid] = 0;
 #pragma unroll
                 for (int pass = 0; pass < 2; ++pass) {
                     uint32_t mset = u_starts[pass] | u_sbits[pass];
@@ -677,6 +713,7 @@ k_fused(DevModel m, BatchArgs a, StreamCfg cfg) {
                             T.first[K] = G;
                             T.lb[K] = G - NE;
                             ++K;
+                            for (int g = 0; g < gap; ++g) s_raw[slot + uint32_t(g)] = 0;  // the separator slots in front of it
                             slot += uint32_t(gap);
                             if (is_start) { ++NE; --ol; }
                         }
@@ -691,7 +728,8 @@ k_fused(DevModel m, BatchArgs a, StreamCfg cfg) {
                 fsub_sync(sub);
                 // ---- output offsets of the group (look-back), per-sentence outputs -----------------------------------
                 if (warp == 0) {
-                    const uint64_t pb = lookback(desc_b, grp, lane), pcv = lookback(desc_c, grp, lane);
+                    uint64_t pb, pcv;
+                    lookback2(desc_b, desc_c, grp, lane, pb, pcv);
                     if (lane == 0) {
                         st_relaxed(desc_c + grp, kDescIncl | (pcv + g_tot));
                         st_relaxed(desc_b + grp, kDescIncl | (pb + (g_tot - ne_tot)));
@@ -761,7 +799,8 @@ k_fused(DevModel m, BatchArgs a, StreamCfg cfg) {
                 st_relaxed(desc_c + grp, kDescAgg | uint64_t(gc));
                 st_relaxed(desc_b + grp, kDescAgg | uint64_t(go));
             }
-            const uint64_t pb = lookback(desc_b, grp, lane), pcv = lookback(desc_c, grp, lane);
+            uint64_t pb, pcv;
+            lookback2(desc_b, desc_c, grp, lane, pb, pcv);
             if (lane == 0) {
                 st_relaxed(desc_c + grp, kDescIncl | (pcv + gc));
                 st_relaxed(desc_b + grp, kDescIncl | (pb + go));
@@ -824,6 +863,9 @@ k_fused(DevModel m, BatchArgs a, StreamCfg cfg) {
             for (int i = tid; i < kFSlotAlloc / 4; i += kFSubThreads) reinterpret_cast<uint4*>(s_raw_alloc)[i] = make_uint4(0, 0, 0, 0);
             if (kOverflow)
                 for (int i = tid; i < kFSlotAlloc / 4; i += kFSubThreads) reinterpret_cast<uint4*>(s_acc - kFPadFront)[i] = make_uint4(0, 0, 0, 0);
+            // (the finishing pass of the overflow variant trusts the per-slot "valid boundary" flags: none may be stale)
+            if (kOverflow)
+                for (int i = tid; i < kFSlotAlloc; i += kFSubThreads) (s_meta - kFPadFront)[i] = MetaT(0);
             fsub_sync(sub);
             if (rspan) {
                 mbar_wait(s_bar, phase);
