@@ -23,6 +23,8 @@
 // Each function cites the reference file:line it follows
 // (paths relative to /root/reference/vaporetto/src).
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cstdint>
 #include <cstring>
 #include <map>
@@ -34,6 +36,11 @@
 #include <unordered_map>
 #include <utility>
 #include <vector>
+
+#if defined(__linux__)
+#include <pthread.h>
+#include <sched.h>
+#endif
 
 namespace ora {
 
@@ -539,6 +546,12 @@ struct PW {
     }
 };
 
+// Test switch (ora_set_states_only): build a tag predictor whose patterns, pattern ids and boundary weights are the
+// reference's, but skip copying the tag weights along the suffix chains (the literal restatement of the build-time
+// merge takes minutes on 20 000 tag models).  Scores, boundaries and pattern-id states are unaffected; predict_tags of
+// such a predictor is meaningless.
+static bool g_states_only = false;
+
 struct PWTag {
     std::optional<PW> weight;
     std::map<std::pair<size_t, uint8_t>, vector<int32_t>> tag_info;
@@ -549,6 +562,7 @@ struct PWTag {
         } else {
             weight = o.weight;
         }
+        if (g_states_only) return;
         for (auto& kv : o.tag_info) {
             auto it = tag_info.find(kv.first);
             if (it == tag_info.end()) {
@@ -1402,6 +1416,116 @@ int ora_predict_batch(const void* p, const char* utf8, const uint64_t* byte_offs
     }
     for (auto& t : th) t.join();
     return 0;
+    ORA_CATCH(idret)
+}
+
+void ora_set_states_only(int on) { g_states_only = on != 0; }
+
+// Pattern-id states of a whole batch (tag predictors): char_states / type_states are indexed by char_offsets[i] + k.
+int ora_predict_batch_states(const void* p, const char* utf8, const uint64_t* byte_offsets, size_t n_sent,
+                             const uint64_t* char_offsets, uint32_t* char_states, uint32_t* type_states, int nthreads) {
+    ORA_TRY
+    auto* pr = static_cast<const Predictor*>(p);
+    if (nthreads < 1) nthreads = 1;
+    std::atomic<size_t> next{0};
+    auto work = [&]() {
+        Sentence s;
+        for (;;) {
+            const size_t lo = next.fetch_add(256, std::memory_order_relaxed);
+            if (lo >= n_sent) break;
+            for (size_t i = lo; i < std::min(n_sent, lo + 256); ++i) {
+                try {
+                    s.parse_raw(utf8 + byte_offsets[i], size_t(byte_offsets[i + 1] - byte_offsets[i]));
+                    pr->predict(s);
+                    const size_t o = size_t(char_offsets[i]);
+                    for (size_t k = 0; k < s.len(); ++k) {
+                        if (char_states) char_states[o + k] = k < s.char_pma_states.size() ? s.char_pma_states[k] : 0xFFFFFFFFu;
+                        if (type_states) type_states[o + k] = k < s.type_pma_states.size() ? s.type_pma_states[k] : 0xFFFFFFFFu;
+                    }
+                } catch (const Error&) {
+                }
+            }
+        }
+    };
+    vector<std::thread> th;
+    for (int t = 1; t < nthreads; ++t) th.emplace_back(work);
+    work();
+    for (auto& t : th) t.join();
+    return 0;
+    ORA_CATCH(idret)
+}
+
+// CPU-baseline timing loop (bench.py `cpu_baseline` / `--impl reference`): the same per-sentence work as
+// ora_predict_batch (parse_raw + predict, the loop of predict/src/main.rs:152-181 minus I/O), run `reps` times by a
+// pool of `nthreads` threads that is created ONCE for the call: each thread is pinned to one CPU, the repetitions are
+// separated by barriers, and sentences are handed out dynamically in blocks (no static shards: one slow core does
+// not stall the step).  seconds[r] = wall time of repetition r between the barriers.  Returns 0 or an error code.
+int ora_bench_batch(const void* p, const char* utf8, const uint64_t* byte_offsets, size_t n_sent, int nthreads, int reps,
+                    double* seconds) {
+    ORA_TRY
+    auto* pr = static_cast<const Predictor*>(p);
+    if (nthreads < 1) nthreads = 1;
+    if (reps < 1) reps = 1;
+    const size_t kBlock = 256;
+    std::atomic<size_t> next{0};
+    std::atomic<int> arrived{0};
+    std::atomic<int> phase{0};
+    std::atomic<uint64_t> sink{0};
+    auto barrier = [&](int& local_phase) {  // sense-reversing spin barrier (threads are pinned, steps are milliseconds+)
+        const int ph = local_phase;
+        if (arrived.fetch_add(1, std::memory_order_acq_rel) + 1 == nthreads) {
+            arrived.store(0, std::memory_order_relaxed);
+            phase.store(ph + 1, std::memory_order_release);
+        } else {
+            while (phase.load(std::memory_order_acquire) == ph) {
+#if defined(__x86_64__)
+                __builtin_ia32_pause();
+#endif
+            }
+        }
+        local_phase = ph + 1;
+    };
+    const int ncpu = int(std::max(1u, std::thread::hardware_concurrency()));
+    auto worker = [&](int t) {
+#if defined(__linux__)
+        cpu_set_t set;
+        CPU_ZERO(&set);
+        CPU_SET(t % ncpu, &set);
+        pthread_setaffinity_np(pthread_self(), sizeof set, &set);
+#endif
+        Sentence s;
+        int local_phase = 0;
+        uint64_t acc = 0;
+        std::chrono::steady_clock::time_point t0;
+        for (int r = 0; r < reps; ++r) {
+            barrier(local_phase);
+            if (t == 0) t0 = std::chrono::steady_clock::now();
+            for (;;) {
+                const size_t lo = next.fetch_add(kBlock, std::memory_order_relaxed);
+                if (lo >= n_sent) break;
+                const size_t hi = std::min(n_sent, lo + kBlock);
+                for (size_t i = lo; i < hi; ++i) {
+                    try {
+                        s.parse_raw(utf8 + byte_offsets[i], size_t(byte_offsets[i + 1] - byte_offsets[i]));
+                        pr->predict(s);
+                        for (uint8_t b : s.boundaries) acc += b;
+                    } catch (const Error&) {
+                    }
+                }
+            }
+            barrier(local_phase);
+            if (t == 0) {
+                seconds[r] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+                next.store(0, std::memory_order_relaxed);
+            }
+        }
+        sink.fetch_add(acc, std::memory_order_relaxed);
+    };
+    vector<std::thread> th;
+    for (int t = 1; t < nthreads; ++t) th.emplace_back(worker, t);
+    worker(0);
+    for (auto& t : th) t.join();
+    return sink.load() == ~0ull ? 1 : 0;
     ORA_CATCH(idret)
 }
 

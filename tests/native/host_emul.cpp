@@ -28,7 +28,8 @@ struct Tab {
         slot = table_slot(geom(), seeds(), key);
         r = rec(slot);
         uint64_t k = (uint64_t(r[1]) << 32) | r[0];
-        return (k & ~(deep ? (kExtFlag | kOvfFlag) : kExtFlag)) == key;
+        const uint64_t flags = deep ? (kExtFlag | kOvfFlag) : ((key >> 42) ? kExtFlag : (kExtFlag | kChildMaskField));
+        return (k & ~flags) == key;
     }
 };
 

@@ -77,8 +77,11 @@ def _err(code):
 class OraclePredictor:
     """Model::read + Predictor::new + predict, on the CPU oracle."""
 
-    def __init__(self, model_bytes: bytes, predict_tags: bool = False):
+    def __init__(self, model_bytes: bytes, predict_tags: bool = False, states_only: bool = False):
+        """states_only: tag predictor without the build-time merge of the tag weights (pattern ids, scores and
+        boundaries are the reference's; predict_tags is not usable) -- for full-size tag models."""
         L = lib()
+        L.ora_set_states_only(1 if states_only else 0)
         m = C.c_void_p()
         consumed = C.c_size_t()
         rc = L.ora_model_read(model_bytes, len(model_bytes), C.byref(m), C.byref(consumed))
@@ -87,6 +90,7 @@ class OraclePredictor:
         self.consumed = consumed.value
         p = C.c_void_p()
         rc = L.ora_predictor_new(m, int(predict_tags), C.byref(p))
+        L.ora_set_states_only(0)
         L.ora_model_free(m)
         if rc:
             raise _err(rc)
@@ -190,6 +194,26 @@ class OraclePredictor:
             raise _err(rc)
         return scores, bounds, boff, status
 
+    def predict_batch_states(self, text: np.ndarray, offsets: np.ndarray, nthreads: int = 1):
+        """Pattern-id states of every character of the batch: (char_states, type_states, char_offsets)."""
+        L = lib()
+        n = len(offsets) - 1
+        text = np.ascontiguousarray(text, np.uint8)
+        offsets = np.ascontiguousarray(offsets, np.uint64)
+        nchars = np.zeros(n, np.uint64)
+        L.ora_count_chars(text.ctypes.data, offsets.ctypes.data, n, nchars.ctypes.data)
+        coff = np.zeros(n + 1, np.uint64)
+        np.cumsum(nchars, out=coff[1:])
+        cs = np.full(int(coff[-1]), 0xFFFFFFFF, np.uint32)
+        ts = np.full(int(coff[-1]), 0xFFFFFFFF, np.uint32)
+        L.ora_predict_batch_states.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                                               C.c_void_p, C.c_int]
+        rc = L.ora_predict_batch_states(self._p, text.ctypes.data, offsets.ctypes.data, n, coff.ctypes.data,
+                                        cs.ctypes.data, ts.ctypes.data, nthreads)
+        if rc:
+            raise _err(rc)
+        return cs, ts, coff
+
     def time_batch(self, text: np.ndarray, offsets: np.ndarray, nthreads: int = 1):
         """Run predict over the batch discarding outputs placement cost (still computed); returns seconds."""
         import time
@@ -203,6 +227,22 @@ class OraclePredictor:
         if rc:
             raise _err(rc)
         return t1 - t0
+
+
+def _bench_batch(self, text: np.ndarray, offsets: np.ndarray, nthreads: int = 1, reps: int = 3):
+    """Timing loop of the CPU baseline (ora_bench_batch): one pinned thread pool for all `reps` repetitions, dynamic
+    sentence blocks; returns the list of per-repetition seconds."""
+    L = lib()
+    n = len(offsets) - 1
+    secs = (C.c_double * reps)()
+    L.ora_bench_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p]
+    rc = L.ora_bench_batch(self._p, text.ctypes.data, offsets.ctypes.data, n, nthreads, reps, secs)
+    if rc:
+        raise _err(rc)
+    return list(secs)
+
+
+OraclePredictor.bench_batch = _bench_batch
 
 
 def char_types(text: str) -> np.ndarray:

@@ -491,10 +491,14 @@ NodeTable build_node_table(const PatternSet& ps, bool force_general, uint32_t bu
         }
         if (t.pool.empty()) t.pool.push_back(0);
     }
+    // child masks of the 2-symbol nodes (keys.hpp: kChildMaskField)
+    std::vector<uint32_t> child_mask(nodes.size(), 0);
+    for (size_t i = 1; i < nodes.size(); ++i)
+        if (nodes[i].depth == 3) child_mask[nodes[i].parent] |= 1u << child_bit(nodes[i].c1);
     for (size_t i = 1; i < nodes.size(); ++i) {
         const TrieNode& nd = nodes[i];
         const uint32_t slot = slot_of_key[i - 1];
-        const uint64_t key = keys[i - 1] | (nd.has_ext ? kExtFlag : 0);
+        const uint64_t key = keys[i - 1] | (nd.has_ext ? kExtFlag : 0) | (nd.depth == 2 ? uint64_t(child_mask[i]) << 42 : 0);
         t.slot_node[slot] = uint32_t(i);
         t.slot_pid[slot] = nd.best;
         uint8_t* dst = t.records.data() + size_t(slot) * 32;

@@ -412,7 +412,8 @@ __device__ __forceinline__ uint32_t slot_of_t(const DevTable& t, const uint8_t* 
 
 __device__ __forceinline__ bool rec_matches(const Rec32& rec, uint64_t key) {
     const uint64_t k = (uint64_t(rec.v[1]) << 32) | rec.v[0];
-    return (k & ~kExtFlag) == key;
+    // (records of 2-symbol nodes hold a child mask in the unused c1 field: not part of the key)
+    return (k & ~((key >> 42) ? kExtFlag : (kExtFlag | kChildMaskField))) == key;
 }
 
 // Continues a depth-3 hit backwards through the text for patterns longer than three characters (rare).

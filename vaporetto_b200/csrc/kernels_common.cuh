@@ -47,7 +47,9 @@ __device__ __forceinline__ bool probe(const DevTable& t, uint64_t key, Rec32& re
     slot = slot_of(t, key);
     rec = load_record(t.records, slot);
     const uint64_t k = (uint64_t(rec.v[1]) << 32) | rec.v[0];
-    return (k & ~(deep ? (kExtFlag | kOvfFlag) : kExtFlag)) == key;
+    // (records of 2-symbol nodes hold a child mask in the unused c1 field: not part of the key)
+    const uint64_t flags = deep ? (kExtFlag | kOvfFlag) : ((key >> 42) ? kExtFlag : (kExtFlag | kChildMaskField));
+    return (k & ~flags) == key;
 }
 
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {

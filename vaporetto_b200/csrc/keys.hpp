@@ -41,6 +41,12 @@ constexpr uint64_t kExtFlag = 1ull << 63;
 constexpr uint64_t kOvfFlag = 1ull << 61;
 constexpr uint64_t kDeepMarker = 0x110000ull;  // first invalid code point: marks (parent node, symbol) keys
 
+// Records of 2-symbol nodes (c1 field of the key unused) carry in that field a 19-bit mask of their 3-symbol
+// extensions: bit child_bit(c1) is set for every c1 such that (c1, c2, c3) is a node.  A clear bit proves that the
+// 3-symbol node does not exist, so the probe for it is skipped (bits 61 / 62 of the key stay clear).
+constexpr int kChildMaskBits = 19;
+constexpr uint64_t kChildMaskField = ((1ull << kChildMaskBits) - 1) << 42;
+
 // key of a node at depth <= 3: c3 is the last symbol of the suffix, c1 the first (0 if absent).
 VPT_HD uint64_t shallow_key(uint32_t c1, uint32_t c2, uint32_t c3) {
     return (uint64_t(c1) << 42) | (uint64_t(c2) << 21) | uint64_t(c3);
@@ -76,6 +82,7 @@ VPT_HD void key_hashes(uint64_t key, const HashK& k, uint32_t& ha, uint32_t& hb)
     hb = c3 * k.b[0] + c2 * k.b[1] + c1 * k.b[2];
 }
 VPT_HD uint32_t mulhi32(uint32_t a, uint32_t b) { return uint32_t((uint64_t(a) * b) >> 32); }
+VPT_HD uint32_t child_bit(uint32_t c1) { return mulhi32(c1 * 0x9E3779B1u, uint32_t(kChildMaskBits)); }
 VPT_HD uint32_t bucket_of(uint32_t ha, uint32_t nbuckets) { return mulhi32(ha, nbuckets); }
 VPT_HD uint32_t slot_with_seed(uint32_t ha, uint32_t hb, uint32_t seed, uint32_t nslots) {
     const uint32_t v = (hb + seed * (ha | 1u)) * 0x85EBCA6Bu;
