@@ -16,7 +16,7 @@ __all__ = ["Model", "Predictor", "Sentence", "VaporettoError", "CharacterBoundar
            "BatchResult", "build_blob", "shard_by_bytes"]
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_PKG, "libvaporetto_b200.so")
+_SO = os.environ.get("VPT_B200_LIBRARY") or os.path.join(_PKG, "libvaporetto_b200.so")  # (override: A/B builds)
 
 
 def build(force: bool = False) -> str:

@@ -221,7 +221,8 @@ struct WorkspaceLayout {
 };
 WorkspaceLayout workspace_layout(size_t n) {
     WorkspaceLayout l;
-    const size_t ng = (n + kGroup - 1) / kGroup;
+    // (the look-back descriptors of k_fused live in group_bound / group_char: its tiles hold at least 32 sentences)
+    const size_t ng = (n + 31) / 32;
     size_t o = 0;
     l.n_chars = o; o = align_up(o + 4 * n, 256);
     l.local_bound = o; o = align_up(o + 4 * n, 256);

@@ -36,10 +36,11 @@ namespace vpt {
 
 namespace {
 
+constexpr int kFGroup = fused_detail::kGroupSentences;  // sentences per tile
 constexpr int kFSubThreads = 256;
 constexpr int kFWarps = kFSubThreads / 32;
-constexpr int kFTextCap = 10240;   // bytes of text staged per tile (multiple of 32)
-constexpr int kFSlotCap = 3072;    // character slots (characters + separators) per tile
+constexpr int kFTextCap = 8192;   // bytes of text staged per tile (multiple of 32)
+constexpr int kFSlotCap = 2816;    // character slots (characters + separators) per tile
 constexpr int kFPadFront = 8;      // zero slots in front of slot 0 (halo of the first warp range)
 constexpr int kFPadBack = 64;      // zero slots behind the last slot (lagging outputs of the last range)
 constexpr int kFSlotAlloc = kFPadFront + kFSlotCap + kFPadBack;
@@ -51,11 +52,11 @@ constexpr int kFHalo = 8;          // slots a warp range re-reads in front of it
 constexpr uint64_t kDescAgg = 1ull << 62, kDescIncl = 2ull << 62, kDescVal = (1ull << 62) - 1;
 
 struct FTab {
-    uint64_t off[kGroup + 1];
-    uint32_t first[kGroup + 1];  // group-local index of a sentence's first character; [ns] = characters of the group
-    uint32_t lb[kGroup + 1];     // group-local index of a sentence's first boundary; [ns] = boundaries of the group
-    uint8_t st[kGroup];          // slow path: status per sentence
-    uint8_t trim[kGroup];
+    uint64_t off[kFGroup + 1];
+    uint32_t first[kFGroup + 1];  // group-local index of a sentence's first character; [ns] = characters of the group
+    uint32_t lb[kFGroup + 1];     // group-local index of a sentence's first boundary; [ns] = boundaries of the group
+    uint8_t st[kFGroup];         // slow path: status per sentence
+    uint8_t trim[kFGroup];
     uint32_t wsum[kFWarps];
     uint64_t obase, cbase;       // output index of the group's first boundary / character (without bound_base)
     uint32_t ticket;
@@ -465,7 +466,7 @@ __device__ __forceinline__ void stream_stage(const DevModel& m, const BatchArgs&
     step(0, No{}, No{}, Yes{});
     if (nchunk >= 2) {
         step(1, No{}, Yes{}, Yes{});
-#pragma unroll 2
+#pragma unroll 1
         for (int it = 2; it < nchunk; ++it) step(it, Yes{}, Yes{}, Yes{});
         step(nchunk, Yes{}, Yes{}, No{});
         step(nchunk + 1, Yes{}, No{}, No{});
@@ -545,7 +546,7 @@ k_fused(DevModel m, BatchArgs a, StreamCfg cfg) {
     if (tid == 0) mbar_init(s_bar, 1);
     __syncthreads();
 
-    const uint64_t ngroups = (a.n_sent + kGroup - 1) / kGroup;
+    const uint64_t ngroups = (a.n_sent + kFGroup - 1) / kFGroup;
     const int gap = cfg.gap;
     uint32_t phase = 0;
 
@@ -560,8 +561,8 @@ k_fused(DevModel m, BatchArgs a, StreamCfg cfg) {
         fsub_sync(sub);
         const uint64_t grp = T.ticket;
         if (grp >= ngroups) break;
-        const uint64_t s0 = grp * kGroup;
-        const int ns = int(min(uint64_t(kGroup), a.n_sent - s0));
+        const uint64_t s0 = grp * kFGroup;
+        const int ns = int(min(uint64_t(kFGroup), a.n_sent - s0));
         if (tid <= ns) T.off[tid] = a.offsets[s0 + tid];
         if (tid < ns) T.trim[tid] = a.trims ? a.trims[s0 + tid] : uint8_t(0);
         fsub_sync(sub);
@@ -945,7 +946,7 @@ cudaError_t launch_fused_t(const DevModel& m, const BatchArgs& a, const StreamCf
         if (e != cudaSuccess) return e;
         attr_set[dev] = true;
     }
-    const uint64_t ngroups = (a.n_sent + kGroup - 1) / kGroup;
+    const uint64_t ngroups = (a.n_sent + kFGroup - 1) / kFGroup;
     const unsigned grid = unsigned(std::min<uint64_t>(uint64_t(n_sm), (ngroups + Lay::kSubBlocks - 1) / Lay::kSubBlocks));
     k_fused<kSeeds, kCommon, kDeep, kStates><<<grid, Lay::kThreads, Lay::kSmem, stream>>>(m, a, cfg);
     return cudaGetLastError();

@@ -17,6 +17,10 @@ struct StreamCfg {
 namespace fused_detail {
 
 constexpr int kSeedCap = 37632;   // seed bytes the kernel keeps in shared memory
+#ifndef VPT_FUSED_GROUP
+#define VPT_FUSED_GROUP 64
+#endif
+constexpr int kGroupSentences = VPT_FUSED_GROUP;   // sentences per tile of k_fused (>= 32: vpt_workspace_size)
 constexpr int kMaxDevices = 64;
 
 template <bool kSeeds, bool kCommon>
