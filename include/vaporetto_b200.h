@@ -157,6 +157,10 @@ int vpt_predict_batch(const vpt_predictor* predictor, const uint8_t* utf8, const
  * total boundary count (an upper bound is total_bytes - 1); d_bound_offsets [n_sent+1];
  * d_status [n_sent]; d_char_states / d_type_states / d_char_offsets nullable. */
 uint64_t vpt_workspace_size(size_t n_sent);
+
+/* PCI bus id ("0000:1b:00.0") of CUDA device `device` as this process sees it (CUDA_VISIBLE_DEVICES applied): what a
+ * launcher needs to bind a rank to the GPU's NUMA node (/sys/bus/pci/devices/<id>/numa_node).  buf: >= 16 bytes. */
+int vpt_device_pci_bus_id(int device, char* buf, size_t capacity);
 int vpt_predict_batch_dev(const vpt_predictor* predictor, const uint8_t* d_utf8, const uint64_t* d_byte_offsets,
                           size_t n_sent, void* d_workspace, uint64_t workspace_bytes, int32_t* d_scores,
                           uint8_t* d_boundaries, uint64_t* d_bound_offsets, int32_t* d_status,
@@ -179,6 +183,31 @@ int vpt_predict_batch_dev_profiled(const vpt_predictor* predictor, const uint8_t
 int vpt_predict(const vpt_predictor* predictor, const uint8_t* utf8, size_t n_bytes, int32_t* scores_out,
                 uint8_t* boundaries_out, size_t out_capacity, uint32_t* char_states_out, uint32_t* type_states_out,
                 size_t states_capacity, uint64_t* n_chars_out);
+
+/* ---- tags on the device (`Predictor::predict_tags`, predictor.rs:546-637, for a whole batch) ------------------------
+ * After vpt_predict_batch_dev with state outputs: for every character position i (indexed like the states, by
+ * d_char_offsets) that ends a token known to the tag model, d_tag_token[i] = token id (else -1) and
+ * d_tag_cand[i * n_tags + k] = index of the chosen candidate of tag slot k (else -1): the arrays vpt_fill_tags writes for
+ * one sentence.  Token lookup (exact, by bytes), the weight vectors keyed by (pattern id, token, rel position) with the
+ * reference's suffix merge (PositionalWeightWithTag +=, predictor.rs:242-262) and the per-slot arg-max (first strict
+ * maximum, predictor.rs:286-304) run in one kernel, k_tags.  *d_unserved (nullable, zero it first) counts tokens whose
+ * tag model exceeds the limits of the device tables (more than 64 scores or 8 tag slots; none of the reference's
+ * models): their entries are -1 and vpt_fill_tags serves them.  Returns VPT_UNSUPPORTED when the whole model is beyond
+ * the limits, VPT_INVALID_ARGUMENT for a predictor created with predict_tags = false (the reference panics). */
+int vpt_predict_tags_batch_dev(const vpt_predictor* predictor, const uint8_t* d_utf8, const uint64_t* d_byte_offsets,
+                               size_t n_sent, const int32_t* d_status, const uint8_t* d_boundaries,
+                               const uint64_t* d_bound_offsets, const uint64_t* d_char_offsets,
+                               const uint32_t* d_char_states, const uint32_t* d_type_states, int32_t* d_tag_token,
+                               int32_t* d_tag_cand, uint32_t* d_unserved, void* cuda_stream);
+
+/* Host-buffer form: predict + predict_tags for a batch; the pattern-id states never leave the device.  Outputs as
+ * vpt_predict_batch (scores_out nullable) plus tag_token_out [chars], tag_cand_out [chars * n_tags] and
+ * char_offsets_out [n_sent + 1]; chars_capacity in characters. */
+int vpt_predict_batch_tags(const vpt_predictor* predictor, const uint8_t* utf8, const uint64_t* byte_offsets, size_t n_sent,
+                           int32_t* scores_out, uint8_t* boundaries_out, size_t out_capacity, uint64_t* bound_offsets_out,
+                           int32_t* status_out, int32_t* tag_token_out, int32_t* tag_cand_out, size_t chars_capacity,
+                           uint64_t* char_offsets_out, uint64_t* n_boundaries_out, uint64_t* n_chars_out,
+                           uint64_t* n_unserved_out);
 
 /* ---- tags (host side; `Sentence::fill_tags` -> `Predictor::predict_tags`, predictor.rs:546-637) ------ */
 

@@ -90,3 +90,23 @@ def test_fill_tags_synthetic_tag_model():
         assert got == want, (i, raw)
         n_tagged += got.count("/")
     assert n_tagged > 100  # the synthetic tag models do fire
+
+
+def test_config3_full_size_device_tags():
+    """configs[2] with tag prediction on the device (k_tags): 20 000 tag models, the whole 120 000-sentence batch in one
+    call; tag_token / tag_cand compared with the host restatement (vpt_fill_tags, itself pinned to the oracle and the
+    reference's known answers at sizes the oracle can build) on a sample of sentences."""
+    mb = synth.gen_model_bccwj_shaped(n_patterns=300_000, sample_sentences=200_000, tag_models=20_000)
+    p = vb.Predictor(vb.Model.read(mb), predict_tags=True)
+    text, offs, _ = _text(6)
+    res, tok, cand, unserved = p.predict_batch_tags(text, offs)
+    assert unserved == 0 and int(np.count_nonzero(res.status)) == 0
+    assert int((tok >= 0).sum()) > 100_000      # the synthetic tokens are frequent strings: most tokens are known
+    for i in range(0, N_SENT, N_SENT // 300):
+        raw = bytes(text[int(offs[i]):int(offs[i + 1])]).decode()
+        hs = vb.Sentence.from_raw(raw)
+        p.predict(hs)
+        hs.fill_tags()
+        c0, c1 = int(res.char_offsets[i]), int(res.char_offsets[i + 1])
+        assert tok[c0:c1].tolist() == hs._tag_token.tolist(), i
+        assert cand[c0:c1].reshape(-1).tolist() == hs._tag_cand.reshape(-1).tolist(), i

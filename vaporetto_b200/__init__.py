@@ -98,6 +98,10 @@ ABI = [
     ("vpt_tokenize_lines", C.c_int, [_P, _P, C.c_size_t, C.c_int, C.c_uint32, _P, C.c_size_t, C.POINTER(C.c_uint64),
                                      C.POINTER(C.c_uint64)]),
     ("vpt_kytea_fullwidth", C.c_uint32, [C.c_uint32]),
+    ("vpt_device_pci_bus_id", C.c_int, [C.c_int, C.c_char_p, C.c_size_t]),
+    ("vpt_predict_tags_batch_dev", C.c_int, [_P, _P, _P, C.c_size_t, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    ("vpt_predict_batch_tags", C.c_int, [_P, _P, _P, C.c_size_t, _P, _P, C.c_size_t, _P, _P, _P, _P, C.c_size_t, _P,
+                                         C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
 ]
 
 _lib = None
@@ -353,6 +357,29 @@ class Predictor:
         res.n_boundaries = nb.value
         res.n_chars = nc.value
         return res
+
+    def predict_batch_tags(self, text, offsets, want_scores: bool = True):
+        """predict + predict_tags for a batch with tag prediction on the device (vpt_predict_batch_tags).  Returns
+        (BatchResult, tag_token [chars] int32, tag_cand [chars, n_tags] int32, n_unserved): the arrays `fill_tags`
+        computes per sentence, indexed by BatchResult.char_offsets."""
+        t = np.frombuffer(text, np.uint8) if isinstance(text, (bytes, bytearray)) else np.ascontiguousarray(text, np.uint8)
+        off = np.ascontiguousarray(offsets, np.uint64)
+        n = off.size - 1
+        cap = max(int(off[-1] - off[0]) if n > 0 else 0, 1)
+        nt = max(self.n_tags, 1)
+        scores = np.empty(cap, np.int32) if want_scores else None
+        bounds = np.empty(cap, np.uint8)
+        boff = np.empty(n + 1, np.uint64)
+        coff = np.empty(n + 1, np.uint64)
+        status = np.empty(max(n, 1), np.int32)
+        tok = np.empty(cap, np.int32)
+        cand = np.empty(cap * nt, np.int32)
+        nb, nc, nu = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        _check(lib().vpt_predict_batch_tags(self._h, t.ctypes.data, off.ctypes.data, n, _ptr(scores), bounds.ctypes.data, cap,
+                                            boff.ctypes.data, status.ctypes.data, tok.ctypes.data, cand.ctypes.data, cap,
+                                            coff.ctypes.data, C.byref(nb), C.byref(nc), C.byref(nu)))
+        res = BatchResult(None if scores is None else scores[: nb.value], bounds[: nb.value], boff, status[:n], None, None, coff)
+        return res, tok[: nc.value], cand[: nc.value * nt].reshape(-1, nt), int(nu.value)
 
     def tokenize_lines(self, data, out: Optional[np.ndarray] = None, no_norm: bool = False, wsconst: str = ""):
         """The reference CLI's `predict` loop (predict/src/main.rs:126-181) over a whole buffer of raw bytes

@@ -20,6 +20,7 @@
 #include "device_model.hpp"
 #include "model.hpp"
 #include "predictor_build.hpp"
+#include "tags.hpp"
 #include "textnorm.hpp"
 
 using namespace vpt;
@@ -57,10 +58,12 @@ struct Scratch {
     void* d_blkbase = nullptr; size_t blkbase_cap = 0;
     void* d_tokg = nullptr; size_t tokg_cap = 0;
     void* d_out = nullptr; size_t out_cap = 0;
+    void* d_tok = nullptr; size_t tok_cap = 0;     // tag prediction outputs (vpt_predict_batch_tags)
+    void* d_cand = nullptr; size_t cand_cap = 0;
     uint64_t* h_totals = nullptr;  // pinned, 4 x u64: boundaries, chars, lines, output bytes
     ~Scratch() {
         for (void* p : {d_text, d_off, d_ws, d_status, d_boff, d_coff, d_scores, d_bounds, d_cst, d_tst, d_trims, d_blk,
-                        d_blkbase, d_tokg, d_out})
+                        d_blkbase, d_tokg, d_out, d_tok, d_cand})
             if (p) cudaFree(p);
         if (h_totals) cudaFreeHost(h_totals);
         if (ev_kernels) cudaEventDestroy(ev_kernels);
@@ -86,6 +89,9 @@ struct vpt_predictor : HostPredictor {
     bool from_blob = false;
     void* d_blob = nullptr;
     DevModel dm;
+    // device-side tag prediction (tags.hpp): one allocation holding all tables; dt.tok_tab == nullptr when unavailable
+    void* d_tags = nullptr;
+    DevTags dt;
     // scratch pool
     mutable std::mutex mu;
     mutable std::vector<std::unique_ptr<Scratch>> pool;
@@ -95,6 +101,7 @@ struct vpt_predictor : HostPredictor {
             cudaSetDevice(device);
             pool.clear();
             cudaFree(d_blob);
+            if (d_tags) cudaFree(d_tags);
         }
     }
 };
@@ -185,6 +192,56 @@ void upload(vpt_predictor& p) {
     p.dm.char_window = h.char_window;
     p.dm.type_window = h.type_window;
     p.dm.emit_states = h.emit_states;
+}
+
+// Tag tables of a tag predictor: built on the host (tags_build.cpp), one device allocation.
+void upload_tags(vpt_predictor& p) {
+    if (p.device == -1 || !p.predict_tags || p.n_tags == 0) return;
+    const TagTablesHost t = build_tag_tables(p);
+    if (!t.usable) return;
+    struct Part { const void* src; size_t bytes; size_t off; };
+    std::vector<Part> parts;
+    size_t total = 0;
+    auto add = [&](const void* src, size_t bytes) {
+        parts.push_back({src, bytes, total});
+        total = align_up(total + bytes, 256);
+        return parts.size() - 1;
+    };
+    const size_t i_tok = add(t.tok_tab.data(), t.tok_tab.size() * sizeof(TagTokenEntry));
+    const size_t i_bytes = add(t.tok_bytes.data(), t.tok_bytes.size());
+    const size_t i_info = add(t.tok_info.data(), t.tok_info.size() * sizeof(TagTokenInfo));
+    const size_t i_pool = add(t.pool.data(), t.pool.size() * 4);
+    const size_t i_cw = add(t.cw_tab.data(), t.cw_tab.size() * sizeof(TagWeightSlot));
+    const size_t i_tw = add(t.tw_tab.data(), t.tw_tab.size() * sizeof(TagWeightSlot));
+    const size_t i_cl = add(t.c_link.data(), t.c_link.size() * 4);
+    const size_t i_tl = add(t.t_link.data(), t.t_link.size() * 4);
+    const size_t i_ca = add(t.c_any.data(), t.c_any.size());
+    const size_t i_ta = add(t.t_any.data(), t.t_any.size());
+    cuda_check(cudaSetDevice(p.device), "cudaSetDevice");
+    cuda_check(cudaMalloc(&p.d_tags, total + 256), "cudaMalloc(tag tables)");
+    uint8_t* base = static_cast<uint8_t*>(p.d_tags);
+    for (const Part& q : parts)
+        if (q.bytes) cuda_check(cudaMemcpy(base + q.off, q.src, q.bytes, cudaMemcpyHostToDevice), "cudaMemcpy(tag tables)");
+    DevTags& d = p.dt;
+    d.tok_tab = reinterpret_cast<const TagTokenEntry*>(base + parts[i_tok].off);
+    d.tok_bytes = base + parts[i_bytes].off;
+    d.tok_info = reinterpret_cast<const TagTokenInfo*>(base + parts[i_info].off);
+    d.pool = reinterpret_cast<const int32_t*>(base + parts[i_pool].off);
+    d.cw_tab = reinterpret_cast<const TagWeightSlot*>(base + parts[i_cw].off);
+    d.tw_tab = reinterpret_cast<const TagWeightSlot*>(base + parts[i_tw].off);
+    d.c_link = reinterpret_cast<const uint32_t*>(base + parts[i_cl].off);
+    d.t_link = reinterpret_cast<const uint32_t*>(base + parts[i_tl].off);
+    d.c_any = base + parts[i_ca].off;
+    d.t_any = base + parts[i_ta].off;
+    d.tok_mask = t.tok_mask;
+    d.cw_mask = t.cw_mask;
+    d.tw_mask = t.tw_mask;
+    d.n_tags = t.n_tags;
+    d.char_rels = p.char_tags ? t.char_rels : 0;
+    d.type_rels = p.type_tags ? t.type_rels : 0;
+    d.max_token_bytes = t.max_token_bytes;
+    d.n_char_patterns = uint32_t(p.char_suffix_link.size());
+    d.n_type_patterns = uint32_t(p.type_suffix_link.size());
 }
 
 struct ScratchLease {
@@ -414,6 +471,7 @@ int vpt_predictor_new(vpt_model* model, int predict_tags, int device, vpt_predic
     static_cast<HostPredictor&>(*p) = build_host_predictor(owned->m, predict_tags != 0);
     p->device = device;
     upload(*p);
+    upload_tags(*p);
     *out = p.release();
     return kOk;
     VPT_API_END
@@ -495,6 +553,14 @@ int vpt_predictor_from_blob(const void* blob, uint64_t len, int device, vpt_pred
 }
 
 uint64_t vpt_workspace_size(size_t n_sent) { return workspace_layout(n_sent).total; }
+
+int vpt_device_pci_bus_id(int device, char* buf, size_t capacity) {
+    VPT_API_BEGIN
+    if (!buf || capacity < 16) throw Error(kInvalidArgument, "InvalidArgumentError: buf: needs at least 16 bytes");
+    cuda_check(cudaDeviceGetPCIBusId(buf, int(capacity), device), "cudaDeviceGetPCIBusId");
+    return kOk;
+    VPT_API_END
+}
 
 static void require_device(const vpt_predictor* p) {
     if (!p) throw Error(kInvalidArgument, "InvalidArgumentError: predictor: must not be NULL");
@@ -1054,6 +1120,138 @@ uint32_t vpt_tag_n_candidates(const vpt_predictor* p, uint32_t token_id, uint32_
 uint32_t vpt_tag_score_len(const vpt_predictor* p, uint32_t token_id) {
     if (!p || token_id >= p->tag_preds.size()) return 0;
     return uint32_t(p->tag_preds[token_id].bias.size());
+}
+
+int vpt_predict_tags_batch_dev(const vpt_predictor* p, const uint8_t* d_utf8, const uint64_t* d_byte_offsets, size_t n_sent,
+                               const int32_t* d_status, const uint8_t* d_boundaries, const uint64_t* d_bound_offsets,
+                               const uint64_t* d_char_offsets, const uint32_t* d_char_states, const uint32_t* d_type_states,
+                               int32_t* d_tag_token, int32_t* d_tag_cand, uint32_t* d_unserved, void* cuda_stream) {
+    VPT_API_BEGIN
+    require_device(p);
+    if (!p->predict_tags || p->from_blob)
+        throw Error(kInvalidArgument, "InvalidArgumentError: this predictor is created with predict_tags = false");
+    if (n_sent == 0) return kOk;
+    if (!p->dt.tok_tab)
+        throw Error(kUnsupported, "this tag model exceeds the limits of the device path (tags.hpp); use vpt_fill_tags");
+    if (!d_utf8 || !d_byte_offsets || !d_status || !d_boundaries || !d_bound_offsets || !d_char_offsets || !d_tag_token || !d_tag_cand)
+        throw Error(kInvalidArgument, "InvalidArgumentError: device buffers: must not be NULL");
+    if ((p->dt.char_rels && !d_char_states) || (p->dt.type_rels && !d_type_states))
+        throw Error(kInvalidArgument, "InvalidArgumentError: states: required for tag prediction");
+    TagArgs t;
+    t.text = d_utf8;
+    t.offsets = d_byte_offsets;
+    t.n_sent = n_sent;
+    t.status = d_status;
+    t.boundaries = d_boundaries;
+    t.bound_offsets = d_bound_offsets;
+    t.char_offsets = d_char_offsets;
+    t.char_states = p->dt.char_rels ? d_char_states : nullptr;
+    t.type_states = p->dt.type_rels ? d_type_states : nullptr;
+    t.tag_token = d_tag_token;
+    t.tag_cand = d_tag_cand;
+    t.n_unserved = d_unserved;
+    cuda_check(launch_tags(p->dt, t, static_cast<cudaStream_t>(cuda_stream)), "launch(tags)");
+    return kOk;
+    VPT_API_END
+}
+
+int vpt_predict_batch_tags(const vpt_predictor* p, const uint8_t* utf8, const uint64_t* byte_offsets, size_t n_sent,
+                           int32_t* scores_out, uint8_t* boundaries_out, size_t out_capacity, uint64_t* bound_offsets_out,
+                           int32_t* status_out, int32_t* tag_token_out, int32_t* tag_cand_out, size_t chars_capacity,
+                           uint64_t* char_offsets_out, uint64_t* n_boundaries_out, uint64_t* n_chars_out,
+                           uint64_t* n_unserved_out) {
+    VPT_API_BEGIN
+    require_device(p);
+    if (n_boundaries_out) *n_boundaries_out = 0;
+    if (n_chars_out) *n_chars_out = 0;
+    if (n_unserved_out) *n_unserved_out = 0;
+    if (!p->predict_tags || p->from_blob)
+        throw Error(kInvalidArgument, "InvalidArgumentError: this predictor is created with predict_tags = false");
+    if (!p->dt.tok_tab)
+        throw Error(kUnsupported, "this tag model exceeds the limits of the device path (tags.hpp); use vpt_fill_tags");
+    if (!byte_offsets || !bound_offsets_out || !char_offsets_out || !tag_token_out || !tag_cand_out || !boundaries_out)
+        throw Error(kInvalidArgument, "InvalidArgumentError: output buffers: must not be NULL");
+    if (n_sent == 0) { bound_offsets_out[0] = 0; char_offsets_out[0] = 0; return kOk; }
+    if (byte_offsets[n_sent] < byte_offsets[0])
+        throw Error(kInvalidArgument, "InvalidArgumentError: byte_offsets: must be non-decreasing");
+    cuda_check(cudaSetDevice(p->device), "cudaSetDevice");
+    // one chunk: text in, scoring with the pattern-id states kept on the device, tag prediction, results out
+    ScratchLease lease(*p);
+    Scratch& s = *lease.s;
+    cudaStream_t st = s.stream;
+    const uint64_t byte_lo = byte_offsets[0], nbytes = byte_offsets[n_sent] - byte_lo;
+    const size_t shift = size_t(byte_lo & 15);
+    const WorkspaceLayout wl = workspace_layout(n_sent);
+    const size_t nt = p->n_tags;
+    Scratch::ensure(s.d_text, s.text_cap, shift + nbytes + 64);
+    Scratch::ensure(s.d_off, s.off_cap, 8 * (n_sent + 1));
+    Scratch::ensure(s.d_ws, s.ws_cap, wl.total);
+    Scratch::ensure(s.d_status, s.status_cap, 4 * n_sent);
+    Scratch::ensure(s.d_boff, s.boff_cap, 8 * (n_sent + 1));
+    Scratch::ensure(s.d_coff, s.coff_cap, 8 * (n_sent + 1));
+    Scratch::ensure(s.d_scores, s.scores_cap, 4 * nbytes + 16);      // a character has at least one byte
+    Scratch::ensure(s.d_bounds, s.bounds_cap, nbytes + 16);
+    Scratch::ensure(s.d_cst, s.cst_cap, 4 * nbytes + 16);
+    Scratch::ensure(s.d_tst, s.tst_cap, 4 * nbytes + 16);
+    Scratch::ensure(s.d_tok, s.tok_cap, 4 * nbytes + 16);
+    Scratch::ensure(s.d_cand, s.cand_cap, 4 * nbytes * nt + 16);
+    if (nbytes)
+        cuda_check(cudaMemcpyAsync(static_cast<uint8_t*>(s.d_text) + shift, utf8 + byte_lo, nbytes, cudaMemcpyHostToDevice, st), "H2D(text)");
+    cuda_check(cudaMemcpyAsync(s.d_off, byte_offsets, 8 * (n_sent + 1), cudaMemcpyHostToDevice, st), "H2D(offsets)");
+    BatchArgs a;
+    a.text = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(s.d_text) + shift - uintptr_t(byte_lo));
+    a.offsets = static_cast<const uint64_t*>(s.d_off);
+    a.n_sent = n_sent;
+    bind_workspace(a, s.d_ws, n_sent);
+    a.status = static_cast<int32_t*>(s.d_status);
+    a.bound_offsets = static_cast<uint64_t*>(s.d_boff);
+    a.char_offsets = static_cast<uint64_t*>(s.d_coff);
+    a.scores = static_cast<int32_t*>(s.d_scores);
+    a.boundaries = static_cast<uint8_t*>(s.d_bounds);
+    a.char_states = static_cast<uint32_t*>(s.d_cst);
+    a.type_states = static_cast<uint32_t*>(s.d_tst);
+    a.totals_host = &s.h_totals[0];
+    s.h_totals[2] = 0;
+    cuda_check(launch_batch(p->dm, a, st), "launch(batch)");
+    uint32_t* d_unserved = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(s.d_ws) + wl.ticket + 128);
+    cuda_check(cudaMemsetAsync(d_unserved, 0, 4, st), "memset");
+    TagArgs t;
+    t.text = a.text;
+    t.offsets = a.offsets;
+    t.n_sent = n_sent;
+    t.status = a.status;
+    t.boundaries = a.boundaries;
+    t.bound_offsets = a.bound_offsets;
+    t.char_offsets = a.char_offsets;
+    t.char_states = p->dt.char_rels ? a.char_states : nullptr;
+    t.type_states = p->dt.type_rels ? a.type_states : nullptr;
+    t.tag_token = static_cast<int32_t*>(s.d_tok);
+    t.tag_cand = static_cast<int32_t*>(s.d_cand);
+    t.n_unserved = d_unserved;
+    cuda_check(launch_tags(p->dt, t, st), "launch(tags)");
+    cuda_check(cudaStreamSynchronize(st), "sync(tags)");  // the totals are in pinned host memory now
+    const uint64_t nb = s.h_totals[0], nc = s.h_totals[1];
+    if (n_boundaries_out) *n_boundaries_out = nb;
+    if (n_chars_out) *n_chars_out = nc;
+    if (nb > out_capacity || nc > chars_capacity)
+        throw Error(kInvalidArgument, "InvalidArgumentError: out_capacity/chars_capacity: too small for the batch");
+    uint32_t unserved = 0;
+    cuda_check(cudaMemcpyAsync(&unserved, d_unserved, 4, cudaMemcpyDeviceToHost, st), "D2H");
+    if (nb) {
+        if (scores_out) cuda_check(cudaMemcpyAsync(scores_out, s.d_scores, 4 * nb, cudaMemcpyDeviceToHost, st), "D2H(scores)");
+        cuda_check(cudaMemcpyAsync(boundaries_out, s.d_bounds, nb, cudaMemcpyDeviceToHost, st), "D2H(boundaries)");
+    }
+    cuda_check(cudaMemcpyAsync(bound_offsets_out, s.d_boff, 8 * (n_sent + 1), cudaMemcpyDeviceToHost, st), "D2H(offsets)");
+    cuda_check(cudaMemcpyAsync(char_offsets_out, s.d_coff, 8 * (n_sent + 1), cudaMemcpyDeviceToHost, st), "D2H(offsets)");
+    if (status_out) cuda_check(cudaMemcpyAsync(status_out, s.d_status, 4 * n_sent, cudaMemcpyDeviceToHost, st), "D2H(status)");
+    if (nc) {
+        cuda_check(cudaMemcpyAsync(tag_token_out, s.d_tok, 4 * nc, cudaMemcpyDeviceToHost, st), "D2H(tags)");
+        cuda_check(cudaMemcpyAsync(tag_cand_out, s.d_cand, 4 * nc * nt, cudaMemcpyDeviceToHost, st), "D2H(tags)");
+    }
+    cuda_check(cudaStreamSynchronize(st), "sync(copy-out)");
+    if (n_unserved_out) *n_unserved_out = unserved;
+    return kOk;
+    VPT_API_END
 }
 
 int vpt_fill_tags(const vpt_predictor* p, const uint8_t* utf8, size_t n_bytes, const uint8_t* boundaries,

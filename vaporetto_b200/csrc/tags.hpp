@@ -1,0 +1,130 @@
+// Device-side tag prediction (reference Predictor::predict_tags, predictor.rs:546-637; add_tag_scores,
+// char_scorer/boundary_tag_scorer.rs:154-174 and type_scorer/boundary_tag_scorer.rs:123-143; TagPredictor::predict,
+// predictor.rs:286-304): flat tables built on the host from the predictor's tag models, and the launch interface.
+//
+// Tables (one device allocation per predictor, built by build_tag_tables):
+//   * token table   open addressing over a 64-bit hash of the token's bytes; an entry holds the hash, the token id and
+//                   where the token's bytes live (compared byte by byte: the lookup is exact)
+//   * token info    per token id: bias vector (i32 pool), number of tag slots, candidates per slot
+//   * weight tables (char scorer, type scorer) open addressing over (pattern id, token id, rel position) -> the
+//                   pattern's OWN weight vector in the i32 pool.  The reference merges the vectors of a pattern's suffix
+//                   patterns into it at build time (PositionalWeightWithTag +=, predictor.rs:242-262, along
+//                   char_scorer.rs:50-78); here the kernel walks `suffix_link` and adds the chain with the same
+//                   truncation rule (element k of a shorter suffix's vector counts only while every longer pattern on
+//                   the chain has an own vector longer than k) -- identical sums, no 300-second materialisation.
+//   * chain flags   per pattern id: 1 if the pattern or one of its suffix patterns has any tag weight at all
+#pragma once
+#include <cstdint>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "predictor_build.hpp"
+
+namespace vpt {
+
+constexpr int kTagMaxScores = 64;  // score entries a token's tag model may have on the device path
+constexpr int kTagMaxSlots = 8;    // tag slots (n_tags) on the device path
+
+struct TagTokenEntry {   // 24 bytes
+    uint64_t hash;       // 0 = empty
+    uint32_t tid;
+    uint32_t str_off;
+    uint32_t len;
+    uint32_t pad;
+};
+struct TagTokenInfo {    // per token id
+    uint32_t bias_off;   // into the i32 pool
+    uint16_t bias_len;
+    uint8_t n_slots;     // tags.size() (slots beyond n_tags never exist)
+    uint8_t usable;      // 0: the token's model exceeds the device limits (never happens for the reference's models)
+    uint8_t cand[kTagMaxSlots];  // candidates per slot (255 = too many)
+};
+struct TagWeightSlot {  // 16 bytes
+    uint64_t key;        // (pid << 32 | tid << 8 | rel) + 1; 0 = empty
+    uint32_t off;        // into the i32 pool
+    uint32_t len;
+};
+
+struct TagTablesHost {
+    bool usable = false;           // false: some limit is exceeded -> only the host path (vpt_fill_tags) serves the model
+    uint32_t n_tags = 0, n_tokens = 0;
+    uint32_t tok_mask = 0;         // token table capacity - 1 (power of two)
+    uint32_t cw_mask = 0, tw_mask = 0;
+    uint32_t char_rels = 0, type_rels = 0;   // rel positions 0 .. rels-1 carry weights (window + 1)
+    uint32_t max_token_bytes = 0;
+    std::vector<TagTokenEntry> tok_tab;
+    std::vector<uint8_t> tok_bytes;
+    std::vector<TagTokenInfo> tok_info;
+    std::vector<int32_t> pool;
+    std::vector<TagWeightSlot> cw_tab, tw_tab;
+    std::vector<uint32_t> c_link, t_link;      // suffix links by pattern id
+    std::vector<uint8_t> c_any, t_any;         // chain flags
+};
+
+TagTablesHost build_tag_tables(const HostPredictor& hp);
+
+struct DevTags {
+    const TagTokenEntry* tok_tab = nullptr;
+    const uint8_t* tok_bytes = nullptr;
+    const TagTokenInfo* tok_info = nullptr;
+    const int32_t* pool = nullptr;
+    const TagWeightSlot* cw_tab = nullptr;
+    const TagWeightSlot* tw_tab = nullptr;
+    const uint32_t* c_link = nullptr;
+    const uint32_t* t_link = nullptr;
+    const uint8_t* c_any = nullptr;
+    const uint8_t* t_any = nullptr;
+    uint32_t tok_mask = 0, cw_mask = 0, tw_mask = 0;
+    uint32_t n_tags = 0, char_rels = 0, type_rels = 0, max_token_bytes = 0;
+    uint32_t n_char_patterns = 0, n_type_patterns = 0;
+};
+
+struct TagArgs {
+    const uint8_t* text = nullptr;
+    const uint64_t* offsets = nullptr;      // [n_sent + 1] byte offsets
+    const uint8_t* trims = nullptr;         // nullable
+    uint64_t n_sent = 0;
+    const int32_t* status = nullptr;        // from the scoring pass
+    const uint8_t* boundaries = nullptr;    // final boundaries (0 / 1)
+    const uint64_t* bound_offsets = nullptr;  // [n_sent + 1] (values include bound_base)
+    const uint64_t* char_offsets = nullptr;   // [n_sent + 1] (values include char_base)
+    uint64_t bound_base = 0, char_base = 0;
+    const uint32_t* char_states = nullptr;  // nullable when the char scorer has no tag weights
+    const uint32_t* type_states = nullptr;
+    int32_t* tag_token = nullptr;           // [n_chars] out: token id of the token ending at the character, or -1
+    int32_t* tag_cand = nullptr;            // [n_chars * n_tags] out: chosen candidate per slot, or -1
+    uint32_t* n_unserved = nullptr;         // nullable device counter: tokens whose model exceeds the device limits
+};
+
+// 64-bit hash of a token's bytes (host builder and kernel)
+#if defined(__CUDACC__)
+#define VPT_TAG_HD __host__ __device__ __forceinline__
+#else
+#define VPT_TAG_HD inline
+#endif
+VPT_TAG_HD uint64_t tag_hash_step(uint64_t h, uint32_t byte) {
+    h ^= byte;
+    h *= 0x100000001B3ull;  // FNV-1a
+    return h;
+}
+VPT_TAG_HD uint64_t tag_hash_finish(uint64_t h) {
+    h ^= h >> 32;
+    h *= 0x9E3779B97F4A7C15ull;
+    h ^= h >> 29;
+    return h | 1ull;  // never 0 (0 marks an empty entry)
+}
+constexpr uint64_t kTagHashInit = 0xCBF29CE484222325ull;
+
+VPT_TAG_HD uint64_t tag_weight_key(uint32_t pid, uint32_t tid, uint32_t rel) {
+    return ((uint64_t(pid) << 32) | (uint64_t(tid) << 8) | uint64_t(rel)) + 1ull;
+}
+VPT_TAG_HD uint32_t tag_weight_slot(uint64_t key, uint32_t mask) {
+    uint64_t h = key * 0x9E3779B97F4A7C15ull;
+    h ^= h >> 31;
+    return uint32_t(h) & mask;
+}
+
+cudaError_t launch_tags(const DevTags& t, const TagArgs& a, cudaStream_t stream);
+
+}  // namespace vpt
