@@ -523,6 +523,49 @@ def main():
         dist.all_reduce(tl, op=dist.ReduceOp.MAX)
     e2e_lines_value = total_bytes * args.e2e_steps / float(tl.item()) / 1e6
     lines_d2h = int(tok_len.value)
+    # the literal drop-in call: Predictor::predict for ONE sentence (vpt_predict: one pinned round trip, one launch)
+    one = bytes(text[int(offs[0]):int(offs[1])])
+    one_sc = np.empty(len(one), np.int32)
+    one_bd = np.empty(len(one), np.uint8)
+    one_n = C.c_uint64()
+
+    def step_single():
+        rc = L.vpt_predict(pred._h, one, len(one), one_sc.ctypes.data, one_bd.ctypes.data, len(one), None, None, 0, C.byref(one_n))
+        if rc:
+            raise RuntimeError(L.vpt_last_error().decode())
+
+    for _ in range(200):
+        step_single()
+    t0 = time.perf_counter()
+    n_single = 3000
+    for _ in range(n_single):
+        step_single()
+    single_us = (time.perf_counter() - t0) / n_single * 1e6
+    assert one_sc[: one_n.value - 1].tolist() == d_scores[: one_n.value - 1].cpu().numpy().tolist()
+    # config 3: predict + predict_tags with the tag prediction on the device (the states never cross PCIe)
+    e2e_tags_value = None
+    if want_states:
+        h_tok = torch.empty(n_chars_total, dtype=torch.int32).pin_memory()
+        h_cand = torch.empty(n_chars_total * max(pred.n_tags, 1), dtype=torch.int32).pin_memory()
+        nu_out = C.c_uint64()
+
+        def step_tags():
+            rc = L.vpt_predict_batch_tags(pred._h, h_text.data_ptr(), h_off.data_ptr(), n, h_scores.data_ptr(), h_bounds.data_ptr(),
+                                          n_bound, h_boff.data_ptr(), h_status.data_ptr(), h_tok.data_ptr(), h_cand.data_ptr(),
+                                          n_chars_total, h_coff.data_ptr(), C.byref(nb_out), C.byref(nc_out), C.byref(nu_out))
+            if rc:
+                raise RuntimeError(L.vpt_last_error().decode())
+
+        step_tags()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            step_tags()
+        torch.cuda.synchronize()
+        tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_tags_value = total_bytes * args.e2e_steps / float(tt.item()) / 1e6
     h2d = nbytes + 8 * (n + 1)
     d2h = 4 * n_bound + n_bound + 8 * (n + 1) + 4 * n + 16 + (8 * n_chars_total + 8 * (n + 1) if want_states else 0)
 
@@ -592,6 +635,9 @@ def main():
             "e2e": {"value": round(e2e_value, 1), "unit": "MB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": args.e2e_steps, "api": "vpt_predict_batch (pinned host buffers; scores+boundaries returned)",
                     "boundaries_only_value": round(e2e_nb_value, 1),
+                    "single_call_us": round(single_us, 1),
+                    "single_call": "vpt_predict on one 40-character sentence (host buffers, one launch, one pinned round trip)",
+                    "predict_tags_on_device_value": None if e2e_tags_value is None else round(e2e_tags_value, 1),
                     "tokenize_lines": {"value": round(e2e_lines_value, 1), "unit": "MB/s",
                                        "api": "vpt_tokenize_lines, no_norm = 1 (raw lines in, tokenised text out; split + "
                                               "materialisation on the device)",

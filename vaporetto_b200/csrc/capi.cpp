@@ -61,11 +61,15 @@ struct Scratch {
     void* d_tok = nullptr; size_t tok_cap = 0;     // tag prediction outputs (vpt_predict_batch_tags)
     void* d_cand = nullptr; size_t cand_cap = 0;
     uint64_t* h_totals = nullptr;  // pinned, 4 x u64: boundaries, chars, lines, output bytes
+    uint8_t* h_io = nullptr;       // pinned staging of the single-sentence call (vpt_predict), kSingleIoBytes
+    void* d_io = nullptr;          // its device twin
     ~Scratch() {
         for (void* p : {d_text, d_off, d_ws, d_status, d_boff, d_coff, d_scores, d_bounds, d_cst, d_tst, d_trims, d_blk,
                         d_blkbase, d_tokg, d_out, d_tok, d_cand})
             if (p) cudaFree(p);
         if (h_totals) cudaFreeHost(h_totals);
+        if (h_io) cudaFreeHost(h_io);
+        if (d_io) cudaFree(d_io);
         if (ev_kernels) cudaEventDestroy(ev_kernels);
         if (ev_out) cudaEventDestroy(ev_out);
         if (stream_out) cudaStreamDestroy(stream_out);
@@ -1070,6 +1074,90 @@ int vpt_tokenize_lines(const vpt_predictor* p, const uint8_t* utf8, size_t n_byt
     VPT_API_END
 }
 
+namespace {
+
+constexpr size_t kSingleMaxBytes = 2048;   // sentences up to this size take the one-round-trip path of vpt_predict
+constexpr size_t kSingleIoBytes = 65536;
+
+// Predictor::predict for ONE sentence (reference predictor.rs:518-543) as one pinned round trip: the text, the offsets and
+// the zeroed look-back words go down in one copy, k_fused runs as a single group, the packed results come back in one
+// copy.  (The batch pipeline costs several copies, a memset node and three synchronisations per call.)
+bool predict_single_fast(const vpt_predictor* p, const uint8_t* utf8, size_t n_bytes, int32_t* scores_out, uint8_t* boundaries_out,
+                         size_t out_capacity, uint32_t* char_states_out, uint32_t* type_states_out, size_t states_capacity,
+                         uint64_t* n_chars_out) {
+    if (n_bytes == 0 || n_bytes > kSingleMaxBytes || !fused_ok(p->dm) || (p->dm.ct.present && p->dm.ct.has_overflow)) return false;
+    cuda_check(cudaSetDevice(p->device), "cudaSetDevice");
+    ScratchLease lease(*p);
+    Scratch& s = *lease.s;
+    if (!s.h_io) {
+        cuda_check(cudaMallocHost(reinterpret_cast<void**>(&s.h_io), kSingleIoBytes), "cudaMallocHost");
+        cuda_check(cudaMalloc(&s.d_io, kSingleIoBytes), "cudaMalloc(single)");
+    }
+    // layout (offsets into both buffers): input part first, then the outputs
+    const size_t o_text = 0;                                   // text, then 64 readable bytes
+    const size_t o_off = align_up(n_bytes + 64, 16);           // u64 offsets[2]
+    const size_t o_desc = o_off + 16;                          // group_bound[2], group_char[2], ticket (zero)
+    const size_t in_bytes = o_desc + 64;
+    const size_t o_boff = align_up(in_bytes, 16);              // u64 bound_offsets[2]
+    const size_t o_coff = o_boff + 16;                         // u64 char_offsets[2]
+    const size_t o_stat = o_coff + 16;                         // i32 status, u32 n_chars
+    const size_t o_bnd = o_stat + 16;                          // u8 boundaries
+    const size_t o_sc = align_up(o_bnd + n_bytes, 16);         // i32 scores
+    const size_t o_cst = o_sc + 4 * n_bytes;                   // u32 states
+    const size_t o_tst = o_cst + 4 * n_bytes;
+    const size_t end = o_tst + 4 * n_bytes;
+    if (end > kSingleIoBytes) return false;
+    memcpy(s.h_io + o_text, utf8, n_bytes);
+    memset(s.h_io + o_text + n_bytes, 0, o_off - n_bytes);
+    uint64_t offs[2] = {0, n_bytes};
+    memcpy(s.h_io + o_off, offs, 16);
+    memset(s.h_io + o_desc, 0, 64);
+    cudaStream_t st = s.stream;
+    uint8_t* d = static_cast<uint8_t*>(s.d_io);
+    cuda_check(cudaMemcpyAsync(d, s.h_io, in_bytes, cudaMemcpyHostToDevice, st), "H2D(single)");
+    BatchArgs a;
+    a.text = d + o_text;
+    a.offsets = reinterpret_cast<const uint64_t*>(d + o_off);
+    a.n_sent = 1;
+    a.group_bound = reinterpret_cast<uint64_t*>(d + o_desc);
+    a.group_char = reinterpret_cast<uint64_t*>(d + o_desc + 16);
+    a.ticket = reinterpret_cast<uint32_t*>(d + o_desc + 32);
+    a.prezeroed = true;
+    a.n_chars = reinterpret_cast<uint32_t*>(d + o_stat + 4);
+    a.status = reinterpret_cast<int32_t*>(d + o_stat);
+    a.bound_offsets = reinterpret_cast<uint64_t*>(d + o_boff);
+    a.char_offsets = reinterpret_cast<uint64_t*>(d + o_coff);
+    a.boundaries = d + o_bnd;
+    a.scores = scores_out ? reinterpret_cast<int32_t*>(d + o_sc) : nullptr;
+    const bool want_states = char_states_out || type_states_out;
+    if (want_states) {
+        a.char_states = reinterpret_cast<uint32_t*>(d + o_cst);
+        a.type_states = reinterpret_cast<uint32_t*>(d + o_tst);
+    }
+    cuda_check(launch_fused(p->dm, a, st), "launch(single)");
+    const size_t out_end = want_states ? end : (scores_out ? o_cst : o_sc);
+    cuda_check(cudaMemcpyAsync(s.h_io + o_boff, d + o_boff, out_end - o_boff, cudaMemcpyDeviceToHost, st), "D2H(single)");
+    cuda_check(cudaStreamSynchronize(st), "sync(single)");
+    int32_t status;
+    uint32_t n;
+    memcpy(&status, s.h_io + o_stat, 4);
+    memcpy(&n, s.h_io + o_stat + 4, 4);
+    if (n_chars_out) *n_chars_out = n;
+    if (status != 0) throw Error(kInternal, "internal error: device validation disagrees with host validation");
+    const size_t nb = n > 0 ? n - 1 : 0;
+    if (nb > out_capacity || (nb && !boundaries_out) || (want_states && n > states_capacity))
+        throw Error(kInvalidArgument, "InvalidArgumentError: out_capacity/states_capacity: too small for the batch");
+    if (nb) {
+        memcpy(boundaries_out, s.h_io + o_bnd, nb);
+        if (scores_out) memcpy(scores_out, s.h_io + o_sc, 4 * nb);
+    }
+    if (char_states_out) memcpy(char_states_out, s.h_io + o_cst, 4 * size_t(n));
+    if (type_states_out) memcpy(type_states_out, s.h_io + o_tst, 4 * size_t(n));
+    return true;
+}
+
+}  // namespace
+
 int vpt_predict(const vpt_predictor* p, const uint8_t* utf8, size_t n_bytes, int32_t* scores_out, uint8_t* boundaries_out,
                 size_t out_capacity, uint32_t* char_states_out, uint32_t* type_states_out, size_t states_capacity,
                 uint64_t* n_chars_out) {
@@ -1077,6 +1165,10 @@ int vpt_predict(const vpt_predictor* p, const uint8_t* utf8, size_t n_bytes, int
     if (!p) throw Error(kInvalidArgument, "InvalidArgumentError: predictor: must not be NULL");
     if (n_bytes && !utf8) throw Error(kInvalidArgument, "InvalidArgumentError: utf8: must not be NULL");
     check_raw_text(utf8, n_bytes);
+    require_device(p);
+    if (predict_single_fast(p, utf8, n_bytes, scores_out, boundaries_out, out_capacity, char_states_out, type_states_out,
+                            states_capacity, n_chars_out))
+        return kOk;
     const uint64_t offs[2] = {0, n_bytes};
     uint64_t boff[2], nb = 0, nc = 0;
     int32_t status = 0;

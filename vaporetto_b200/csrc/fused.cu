@@ -47,8 +47,10 @@ cudaError_t launch_fused(const DevModel& m, const BatchArgs& a, cudaStream_t str
     }
     // group_bound, group_char and the ticket are one contiguous, 256-byte aligned region of the workspace
     const size_t clear_bytes = size_t(reinterpret_cast<const uint8_t*>(a.ticket) - reinterpret_cast<const uint8_t*>(a.group_bound)) + 256;
-    e = cudaMemsetAsync(a.group_bound, 0, clear_bytes, stream);
-    if (e != cudaSuccess) return e;
+    if (!a.prezeroed) {
+        e = cudaMemsetAsync(a.group_bound, 0, clear_bytes, stream);
+        if (e != cudaSuccess) return e;
+    }
     StreamCfg cfg;
     cfg.lag = fused_lag(m);
     cfg.r0 = m.ct.present ? m.ct.r0 : 0;
