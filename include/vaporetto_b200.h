@@ -62,6 +62,12 @@ const char* vpt_last_error(void);
  * `data` is the raw (already un-zstd'd) model image; `*consumed` (nullable) receives the bytes used. */
 int vpt_model_read(const uint8_t* data, size_t len, vpt_model** out, size_t* consumed);
 
+/* The model loading of the reference's `predict` command (predict/src/main.rs:110-111:
+ * `Model::read(&mut zstd::Decoder::new(File::open(path)?)?)`): `data` is the content of a *.model.zst file.  The zstd
+ * frames are decoded inside the library (libzstd.so.1, opened at run time; IOError when it is absent); an image that
+ * does not start with a zstd magic number is read as a raw model, as `vpt_model_read` does. */
+int vpt_model_read_zstd(const uint8_t* data, size_t len, vpt_model** out);
+
 /* `KyteaModel::read` + `Model::try_from(KyteaModel)` (kytea_model.rs:423-450, :453-550; the reference's
  * `convert_kytea_model` tool): a KyTea binary model becomes a vaporetto model — the word-segmentation linear model's
  * character / type n-gram weights (i16 -> i32, truncated to the window), bias, and the dictionary words with their
@@ -233,6 +239,13 @@ uint32_t vpt_tag_n_tokens(const vpt_predictor* predictor);
  * Returns the reference's InvalidArgument errors for empty text / NUL.  *n_chars_out receives n. */
 int vpt_char_types(const uint8_t* utf8, size_t n_bytes, uint8_t* types_out, size_t capacity, uint64_t* n_chars_out);
 
+/* `ConcatGraphemeClustersFilter::filter(&mut Sentence)` (vaporetto_rules/src/sentence_filters/
+ * concat_grapheme_clusters.rs:10-35) on the host, for the Sentence API: `boundaries` (n_chars - 1 values, 0 / 1, as
+ * vpt_predict returns them) loses every boundary inside an extended grapheme cluster of the text (UAX #29 as in
+ * unicode-segmentation 1.12 `graphemes(true)`; the rule engine vpt_tokenize_lines runs on the device for
+ * VPT_WSCONST_GRAPHEME). */
+int vpt_concat_grapheme_clusters(const uint8_t* utf8, size_t n_bytes, uint8_t* boundaries, size_t n_boundaries);
+
 /* `Sentence::write_tokenized_text` (sentence.rs:850-886): tokens joined by ' ', with '/tag' suffixes when
  * tag_token/tag_cand are given (NULL otherwise), escaping ' ', '\\', '/'.  Tokens adjacent to an Unknown
  * boundary are skipped.  Returns the byte length needed in *len_out; writes at most `capacity` bytes. */
@@ -254,11 +267,13 @@ int vpt_write_tokenized_text(const vpt_predictor* predictor, const uint8_t* utf8
  * (' ' between tokens; '\\' before ' ', '\\', '/': sentence.rs:850-886) is materialised on the device: the only
  * transfers are the input bytes in and the output bytes out.  Lines that update_raw rejects (empty, or
  * containing U+0000) produce an empty line as in the CLI; so do lines that are not valid UTF-8 (the CLI stops
- * with an I/O error on those).  Tags, `--wsconst G` (grapheme clusters) and score printing are not part of this path.
+ * with an I/O error on those).  Tags and score printing are not part of this path.
  * `no_norm`: the CLI flag of the same name (0 = apply KyteaFullwidthFilter, the CLI default).
  * `wsconst_types`: the CLI's `--wsconst D/R/H/T/K/O` options as a bit set, bit t for CharacterType t (VPT_WSCONST_*):
  * `KyteaWsConstFilter` (vaporetto_rules/src/sentence_filters/kytea_wsconst.rs:27-44) clears the boundary between two
- * characters of such a type after prediction (types of the filtered text when no_norm == 0, main.rs:157).
+ * characters of such a type after prediction (types of the filtered text when no_norm == 0, main.rs:157);
+ * VPT_WSCONST_GRAPHEME is `--wsconst G`: `ConcatGraphemeClustersFilter` (sentence_filters/concat_grapheme_clusters.rs:
+ * 10-35) clears the boundaries inside every extended grapheme cluster (UAX #29 as in unicode-segmentation 1.12).
  * `out` receives the output lines, each terminated by '\n' (at most 3 * n_bytes + n_lines bytes); *out_len
  * the number of bytes produced (also when `out_capacity` was too small, which returns InvalidArgument);
  * *n_lines the number of input lines.  Chunk size of the internal pipeline: env VPT_CHUNK_BYTES (16 MiB, with
@@ -269,6 +284,7 @@ int vpt_write_tokenized_text(const vpt_predictor* predictor, const uint8_t* utf8
 #define VPT_WSCONST_KATAKANA (1u << 4) /* --wsconst T */
 #define VPT_WSCONST_KANJI (1u << 5)    /* --wsconst K */
 #define VPT_WSCONST_OTHER (1u << 6)    /* --wsconst O */
+#define VPT_WSCONST_GRAPHEME (1u << 7) /* --wsconst G: ConcatGraphemeClustersFilter */
 int vpt_tokenize_lines(const vpt_predictor* predictor, const uint8_t* utf8, size_t n_bytes, int no_norm,
                        uint32_t wsconst_types, uint8_t* out, size_t out_capacity, uint64_t* out_len, uint64_t* n_lines);
 

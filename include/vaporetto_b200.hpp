@@ -56,6 +56,12 @@ public:
     /// `Model::read(R: Read)`: the whole buffer is the model.
     static Model read(const std::vector<uint8_t>& bytes) { return read_slice(bytes.data(), bytes.size()).first; }
 
+    /// `Model::read(&mut zstd::Decoder::new(file)?)` (predict/src/main.rs:110-111): a *.model.zst image (or a raw one).
+    static Model read_zstd(const std::vector<uint8_t>& bytes) {
+        vpt_model* h = nullptr;
+        detail::check(vpt_model_read_zstd(bytes.data(), bytes.size(), &h));
+        return Model(h);
+    }
     /// `KyteaModel::read` + `Model::try_from(KyteaModel)` (kytea_model.rs:423-550): converts a KyTea binary model.
     static Model read_kytea(const std::vector<uint8_t>& bytes) {
         vpt_model* h = nullptr;

@@ -37,6 +37,8 @@
 #include <utility>
 #include <vector>
 
+#include "grapheme_tables.hpp"
+
 #if defined(__linux__)
 #include <pthread.h>
 #include <sched.h>
@@ -1295,7 +1297,83 @@ static void wsconst_filter(Sentence& s, uint8_t char_type) {
         if (s.char_types[i] == char_type && s.char_types[i + 1] == char_type) s.boundaries[i] = 0;
 }
 
-// `wsconst_types`: bit t set = a `--wsconst` option for CharacterType t (post_filters, main.rs:100-106; applied to
+// ConcatGraphemeClustersFilter::filter (vaporetto_rules/src/sentence_filters/concat_grapheme_clusters.rs:10-35): every
+// boundary inside an extended grapheme cluster becomes NotWordBoundary.  The clusters are those of
+// unicode-segmentation 1.12 `graphemes(true)` (a Cargo dependency that is not vendored under /root/reference: UAX #29
+// rules GB3-GB13, GB999, restated here rule by rule with look-back loops; property data grapheme_tables.hpp, pinned in
+// tests/test_oracle_lines.py against the `regex` module's \X and the reference's own test vectors).
+static uint32_t grapheme_class_of(uint32_t c) {
+    int lo = 0, hi = ora_tables::kGraphemeRanges - 1;
+    while (lo <= hi) {
+        const int mid = (lo + hi) / 2;
+        const auto& r = ora_tables::kGraphemeTable[mid];
+        if (c < r.lo) hi = mid - 1;
+        else if (c > r.hi) lo = mid + 1;
+        else return r.cls;
+    }
+    return 0;
+}
+// true when there is NO cluster boundary between characters i-1 and i of `cw` (class words)
+static bool grapheme_joined(const vector<uint32_t>& cw, size_t i) {
+    enum { Other, CR, LF, Control, Extend, ZWJ, RI, Prepend, SpacingMark, L, V, T, LV, LVT };
+    const uint32_t p = cw[i - 1] & 15u, c = cw[i] & 15u;
+    if (p == CR && c == LF) return true;                                            // GB3
+    if (p == Control || p == CR || p == LF) return false;                           // GB4
+    if (c == Control || c == CR || c == LF) return false;                           // GB5
+    if (p == L && (c == L || c == V || c == LV || c == LVT)) return true;           // GB6
+    if ((p == LV || p == V) && (c == V || c == T)) return true;                     // GB7
+    if ((p == LVT || p == T) && c == T) return true;                                // GB8
+    if (c == Extend || c == ZWJ) return true;                                       // GB9
+    if (c == SpacingMark) return true;                                              // GB9a
+    if (p == Prepend) return true;                                                  // GB9b
+    if (((cw[i] >> 5) & 3u) == 1u) {                                                // GB9c: Consonant [Extend Linker]* Linker [Extend Linker]* x Consonant
+        bool linker = false;
+        size_t j = i;
+        while (j > 0) {
+            const uint32_t b = (cw[j - 1] >> 5) & 3u;
+            if (b == 3u) linker = true;
+            else if (b != 2u) break;
+            --j;
+        }
+        if (linker && j > 0 && ((cw[j - 1] >> 5) & 3u) == 1u) return true;
+    }
+    if ((cw[i] & 0x10u) && p == ZWJ) {                                              // GB11: ExtPict Extend* ZWJ x ExtPict
+        size_t j = i - 1;
+        while (j > 0 && (cw[j - 1] & 15u) == Extend) --j;
+        if (j > 0 && (cw[j - 1] & 0x10u)) return true;
+    }
+    if (p == RI && c == RI) {                                                       // GB12, GB13: pairs of RI
+        size_t n = 0;
+        for (size_t j = i; j > 0 && (cw[j - 1] & 15u) == RI; --j) ++n;
+        if (n % 2 == 1) return true;
+    }
+    return false;                                                                   // GB999
+}
+static void grapheme_filter(Sentence& s) {
+    vector<uint32_t> cw(s.chars.size());
+    for (size_t i = 0; i < cw.size(); ++i) cw[i] = grapheme_class_of(s.chars[i]);
+    for (size_t i = 1; i < cw.size(); ++i)
+        if (grapheme_joined(cw, i)) s.boundaries[i - 1] = 0;
+}
+// grapheme cluster lengths (in characters) of a string: test hook for the pin against regex \X
+long ora_grapheme_lengths(const char* utf8, size_t nbytes, uint32_t* lens, size_t cap) {
+    auto neg = [](int c) { return -long(c); };
+    ORA_TRY
+    Sentence s;
+    s.parse_raw(utf8, nbytes);
+    s.boundaries.assign(s.chars.size() ? s.chars.size() - 1 : 0, 1);
+    grapheme_filter(s);
+    size_t n = 0, run = 1;
+    for (size_t i = 0; i < s.chars.size(); ++i) {
+        const bool last = i + 1 == s.chars.size();
+        if (last || s.boundaries[i]) { if (n < cap) lens[n] = uint32_t(run); ++n; run = 1; }
+        else ++run;
+    }
+    return long(n);
+    ORA_CATCH(neg)
+}
+
+// `wsconst_types`: bit t set = a `--wsconst` option for CharacterType t, bit 7 = `--wsconst G` (post_filters, main.rs:100-106; applied to
 // the sentence that was predicted, main.rs:138,157).
 long ora_tokenize_lines(const void* p, const char* utf8, size_t nbytes, int no_norm, uint32_t wsconst_types, char* buf,
                         size_t cap, uint64_t* n_lines) {
@@ -1318,12 +1396,14 @@ long ora_tokenize_lines(const void* p, const char* utf8, size_t nbytes, int no_n
             if (no_norm) {
                 pr->predict(s_orig);
                 for (uint8_t t = 1; t <= 6; ++t) if (wsconst_types & (1u << t)) wsconst_filter(s_orig, t);
+                if (wsconst_types & 0x80u) grapheme_filter(s_orig);
             } else {
                 string pre;
                 for (uint32_t c : s_orig.chars) append_utf8(pre, kytea_fullwidth_cp(c));
                 s.parse_raw(pre.data(), pre.size());
                 pr->predict(s);
                 for (uint8_t t = 1; t <= 6; ++t) if (wsconst_types & (1u << t)) wsconst_filter(s, t);
+                if (wsconst_types & 0x80u) grapheme_filter(s);
                 s_orig.boundaries = s.boundaries;
             }
             out += write_tokenized(*pr, s_orig, nullptr, nullptr);

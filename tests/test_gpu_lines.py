@@ -15,7 +15,7 @@ from test_gpu_parity import _random_model, make, read
 pytestmark = pytest.mark.gpu
 
 
-def check(p, o, data: bytes, wsconsts=("", "D", "HK", "DRHTKO")):
+def check(p, o, data: bytes, wsconsts=("", "D", "HK", "DRHTKO", "G", "GD")):
     for no_norm in (True, False):
         for ws in wsconsts:
             got, nl = p.tokenize_lines(data, no_norm=no_norm, wsconst=ws)
@@ -70,7 +70,37 @@ def test_wsconst_reference_vectors():
     got, _ = p.tokenize_lines("5\n5000\n2021年8月24日\n".encode(), no_norm=True, wsconst="D")
     assert got.tobytes().decode() == "5\n5000\n2021 年 8 月 24 日\n"
     with pytest.raises(vb.VaporettoError):
-        p.tokenize_lines(b"a\n", wsconst="G")
+        p.tokenize_lines(b"a\n", wsconst="X")
+
+
+def test_grapheme_filter_on_device():
+    """--wsconst G (ConcatGraphemeClustersFilter, concat_grapheme_clusters.rs:10-35): the reference's unit-test vectors and
+    random lines over marks, emoji sequences, flags, jamo, conjuncts and controls, device vs oracle, byte-exact."""
+    import random
+    from test_oracle_lines import GRAPHEME_POOL
+    mb = encode_model(dict(char_ngrams=[], type_ngrams=[], dict=[], bias=1, char_window=1, type_window=1, tag_models=[]))
+    p, o = make(mb), OraclePredictor(mb)
+    got, _ = p.tokenize_lines("\u200d\n\U0001f468\u200d\U0001f469\u200d\U0001f466\n\U0001f44f\U0001f3fd\nこれは手\U0001f44f\U0001f3fdです\n".encode(),
+                              no_norm=True, wsconst="G")
+    assert got.tobytes().decode() == ("\u200d\n\U0001f468\u200d\U0001f469\u200d\U0001f466\n\U0001f44f\U0001f3fd\n"
+                                      "こ れ は 手 \U0001f44f\U0001f3fd で す\n")
+    rng = random.Random(5)
+    pool = GRAPHEME_POOL.replace("\n", "").replace("\r", "")
+    lines = []
+    for _ in range(20000):
+        n = rng.choice((1, 2, 3, 5, 8, 13, 31, 32, 33, 40, 64, 65, 130, 300))
+        if rng.random() < 0.5:   # mostly plain text with a few special characters (the windows' fast path and its edges)
+            line = "".join(rng.choice(pool) if rng.random() < 0.05 else rng.choice("あいう漢字カナab1 ") for _ in range(n))
+        else:
+            line = "".join(rng.choice(pool) for _ in range(n))
+        lines.append(line)
+    data = ("\n".join(lines) + "\n").encode()
+    for no_norm in (True, False):
+        for ws in ("G", "GHK"):
+            got, nl = p.tokenize_lines(data, no_norm=no_norm, wsconst=ws)
+            want, wl = o.tokenize_lines(data, no_norm=no_norm, wsconst=ws)
+            assert nl == wl == len(lines)
+            assert got.tobytes() == want, (no_norm, ws)
 
 
 def test_tantivy_pipeline_vectors():

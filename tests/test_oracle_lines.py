@@ -7,7 +7,8 @@ import os
 import vaporetto_b200 as vb
 from vpt_testlib.oracle import OraclePredictor, lib as oracle_lib
 
-GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLDEN = os.path.join(HERE, "golden")
 
 
 def rust_lines(data: bytes):
@@ -154,3 +155,85 @@ def test_tokenized_escape_vector():
     s = vb.Sentence.from_raw(case["text"])
     s.boundaries_mut()[:] = case["boundaries"]
     assert s.write_tokenized_text() == case["tokenized"]
+
+
+# ---- --wsconst G: ConcatGraphemeClustersFilter (concat_grapheme_clusters.rs:10-35) ---------------------------------------
+
+GRAPHEME_POOL = (
+    "aZ 0。あア漢ｶﾞ" "\r\n\t‍‌゙゚̀́️︎⃣"
+    "\U0001f468\U0001f469\U0001f466\U0001f44f\U0001f3fd\U0001f3fb❤©™\U0001f1ef\U0001f1f5\U0001f1fa\U0001f1f8\U0001f1e9"
+    "각가각ힰퟋ؀؅ःाक्ष্ી്കำຳ"
+    "ཀཱါ᭄ꢴ\U000110bd\U00011000\U0001d165\U000e0020\U000e007f\U000e0001 ­"
+)
+
+
+def _regex_cluster_lengths(text):
+    import regex
+    return [len(m) for m in regex.findall(r"\X", text)]
+
+
+def test_grapheme_rules_against_regex():
+    """The oracle's rule engine (UAX #29 extended grapheme clusters, what unicode-segmentation's graphemes(true) yields)
+    against the `regex` module's \\X on 30000 random strings over marks, emoji sequences, flags, Hangul jamo, Indic
+    conjuncts, prepended marks and controls."""
+    import random
+    from vpt_testlib.oracle import grapheme_lengths
+    rng = random.Random(29)
+    for it in range(30000):
+        n = rng.randint(1, 14)
+        text = "".join(rng.choice(GRAPHEME_POOL) for _ in range(n))
+        assert grapheme_lengths(text) == _regex_cluster_lengths(text), [hex(ord(c)) for c in text]
+    # every code point that starts a range of a non-default class, next to a few neighbours
+    import re
+    src = open(os.path.join(HERE, "..", "oracle", "grapheme_tables.hpp")).read()
+    firsts = [int(m.group(1), 16) for m in re.finditer(r"\{0x([0-9A-F]+), 0x", src)]
+    for c in firsts:
+        if 0xD800 <= c <= 0xDFFF or c == 0:
+            continue
+        for text in ("あ" + chr(c) + "あ", chr(c) + chr(c), "क" + chr(c) + "क",
+                     "\U0001f468" + chr(c) + "\U0001f469"):
+            assert grapheme_lengths(text) == _regex_cluster_lengths(text), [hex(ord(x)) for x in text]
+
+
+def test_grapheme_filter_reference_vectors():
+    """concat_grapheme_clusters.rs:36-83 (the filter's unit tests): clusters written as one token each."""
+    from vpt_testlib.bincode_model import encode_model
+    from golden import reference_kat as kat
+    # a model that splits everywhere (positive bias, no patterns): the filter alone decides
+    m = {**kat.TOKENIZED_ESCAPE["model"], "char_ngrams": [], "type_ngrams": [], "dict": [], "bias": 1, "tag_models": []}
+    o = OraclePredictor(encode_model(m))
+    for text, want in (
+        ("‍", "‍"),
+        ("\U0001f468‍\U0001f469‍\U0001f466", "\U0001f468‍\U0001f469‍\U0001f466"),
+        ("\U0001f44f\U0001f3fd", "\U0001f44f\U0001f3fd"),
+        ("これは手\U0001f44f\U0001f3fdです", "こ れ は 手 \U0001f44f\U0001f3fd で す"),
+    ):
+        got, _ = o.tokenize_lines((text + "\n").encode(), no_norm=True, wsconst="G")
+        assert got.decode() == want + "\n", text
+        assert o.tokenize_lines((text + "\n").encode(), no_norm=True)[0].decode() == " ".join(text) + "\n"
+
+
+def test_host_grapheme_filter_matches_oracle():
+    """vpt_concat_grapheme_clusters (the rule engine the device kernel runs, as a per-character state machine) against
+    the oracle's look-back restatement on random strings, and the reference's vectors through the Sentence mirror."""
+    import random
+    from vpt_testlib.oracle import grapheme_lengths
+    rng = random.Random(31)
+    for it in range(20000):
+        text = "".join(rng.choice(GRAPHEME_POOL.replace("\0", "")) for _ in range(rng.randint(1, 40)))
+        s = vb.Sentence.from_raw(text)
+        s.boundaries_mut()[:] = 1
+        s.concat_grapheme_clusters()
+        lens, run = [], 1
+        for b in s.boundaries().tolist():
+            if b:
+                lens.append(run)
+                run = 1
+            else:
+                run += 1
+        lens.append(run)
+        assert lens == grapheme_lengths(text), [hex(ord(c)) for c in text]
+    s = vb.Sentence.from_raw("これは手\U0001f44f\U0001f3fdです")
+    s.boundaries_mut()[:] = 1
+    s.concat_grapheme_clusters()
+    assert s.write_tokenized_text() == "こ れ は 手 \U0001f44f\U0001f3fd で す"

@@ -51,6 +51,8 @@ def lib():
         L.ora_tokenize_lines.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_int, C.c_uint32, C.c_char_p,
                                          C.c_size_t, C.POINTER(C.c_uint64)]
         L.ora_tokenize_lines.restype = C.c_long
+        L.ora_grapheme_lengths.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t]
+        L.ora_grapheme_lengths.restype = C.c_long
         L.ora_kytea_fullwidth.argtypes = [C.c_uint32]
         L.ora_kytea_fullwidth.restype = C.c_uint32
         L.ora_predict_tags.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_void_p, C.c_void_p]
@@ -132,7 +134,7 @@ class OraclePredictor:
         cap = 3 * len(data) + data.count(b"\n") + 16
         buf = C.create_string_buffer(cap)
         nl = C.c_uint64(0)
-        mask = sum(1 << ("DRHTKO".index(ch) + 1) for ch in set(wsconst))
+        mask = sum(1 << ("DRHTKOG".index(ch) + 1) for ch in set(wsconst))
         n = lib().ora_tokenize_lines(self._p, data, len(data), int(no_norm), mask, buf, cap, C.byref(nl))
         if n < 0:
             raise _err(-n)
@@ -271,3 +273,13 @@ def kytea_to_model_bytes(data: bytes) -> bytes:
             cap = -n
     finally:
         L.ora_model_free(m)
+
+
+def grapheme_lengths(text: str):
+    """Lengths (in characters) of the extended grapheme clusters of `text`, by the oracle's rule engine."""
+    b = text.encode("utf-8")
+    lens = np.zeros(max(len(b), 1), np.uint32)
+    n = lib().ora_grapheme_lengths(b, len(b), lens.ctypes.data, len(lens))
+    if n < 0:
+        raise _err(-n)
+    return lens[:n].tolist()

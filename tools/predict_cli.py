@@ -5,7 +5,7 @@ output text) on the GPU.
 
     python tools/predict_cli.py --model model.bin[.zst] [--no-norm] [--wsconst D] [--wsconst R] ... < in.txt > out.txt
 
-Options not on the device path (--predict-tags, --scores, --tag-scores, --wsconst G) are rejected; use the Sentence API
+Options not on the device path (--predict-tags, --scores, --tag-scores) are rejected; use the Sentence API
 (vaporetto_b200.Sentence / include/vaporetto_b200.hpp) for tags."""
 import argparse
 import os
@@ -15,33 +15,24 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-ZSTD_MAGIC = b"\x28\xb5\x2f\xfd"
-
-
 def read_model(path: str) -> bytes:
-    """The CLI reads a zstd-compressed model (main.rs:110-111); raw model files are accepted as well."""
+    """The CLI reads a zstd-compressed model (main.rs:110-111); the library decodes it (vpt_model_read_zstd)."""
     with open(path, "rb") as f:
-        head = f.read(4)
-    if head != ZSTD_MAGIC:
-        with open(path, "rb") as f:
-            return f.read()
-    import pyarrow as pa  # the only zstd decoder in this image
-    with pa.input_stream(path, compression="zstd") as s:
-        return s.read()
+        return f.read()
 
 
 def main(argv=None) -> int:
     ap = argparse.ArgumentParser(description="A program to perform word segmentation (vaporetto_b200).")
     ap.add_argument("--model", required=True, help="The model file to use when analyzing text")
-    ap.add_argument("--wsconst", action="append", default=[], choices=list("DRHTKO"),
-                    help="Do not segment some character types: D Digit, R Roman, H Hiragana, T Katakana, K Kanji, O Other")
+    ap.add_argument("--wsconst", action="append", default=[], choices=list("DRHTKOG"),
+                    help="Do not segment some character types: D Digit, R Roman, H Hiragana, T Katakana, K Kanji, O Other, G Grapheme cluster")
     ap.add_argument("--no-norm", action="store_true", help="Do not normalize input strings before prediction")
     ap.add_argument("--device", type=int, default=0, help="CUDA device ordinal")
     args = ap.parse_args(argv)
 
     import vaporetto_b200 as vb
     print("Loading model file...", file=sys.stderr)
-    predictor = vb.Predictor(vb.Model.read(read_model(args.model)), predict_tags=False, device=args.device)
+    predictor = vb.Predictor(vb.Model.read_zstd(read_model(args.model)), predict_tags=False, device=args.device)
     print("Start tokenization", file=sys.stderr)
     data = sys.stdin.buffer.read()
     t0 = time.perf_counter()

@@ -67,6 +67,8 @@ ABI = [
     ("vpt_model_read", C.c_int, [C.c_char_p, C.c_size_t, C.POINTER(_P), C.POINTER(C.c_size_t)]),
     ("vpt_model_free", None, [_P]),
     ("vpt_model_read_kytea", C.c_int, [C.c_char_p, C.c_size_t, C.POINTER(_P)]),
+    ("vpt_concat_grapheme_clusters", C.c_int, [C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t]),
+    ("vpt_model_read_zstd", C.c_int, [C.c_char_p, C.c_size_t, C.POINTER(_P)]),
     ("vpt_model_to_vec", C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_uint64)]),
     ("vpt_model_dictionary_len", C.c_uint64, [_P]),
     ("vpt_model_dictionary_get", C.c_int, [_P, C.c_uint64, C.POINTER(C.c_char_p), C.POINTER(_P), C.POINTER(C.c_uint64),
@@ -152,6 +154,16 @@ class Model:
         used = C.c_size_t()
         _check(lib().vpt_model_read(data, len(data), C.byref(h), C.byref(used)))
         return cls(h, used.value), data[used.value:]
+
+    @classmethod
+    def read_zstd(cls, src) -> "Model":
+        """`Model::read(&mut zstd::Decoder::new(file)?)` (predict/src/main.rs:110-111): a *.model.zst image, decoded by
+        the library (libzstd.so.1); a raw model image is accepted as well."""
+        data = src if isinstance(src, (bytes, bytearray, memoryview)) else src.read()
+        data = bytes(data)
+        h = _P()
+        _check(lib().vpt_model_read_zstd(data, len(data), C.byref(h)))
+        return cls(h, len(data))
 
     @classmethod
     def read_kytea(cls, src) -> "Model":
@@ -384,13 +396,13 @@ class Predictor:
     def tokenize_lines(self, data, out: Optional[np.ndarray] = None, no_norm: bool = False, wsconst: str = ""):
         """The reference CLI's `predict` loop (predict/src/main.rs:126-181) over a whole buffer of raw bytes
         (vpt_tokenize_lines): lines are split, scored (on KyteaFullwidthFilter(line) unless no_norm) and written
-        out as space-separated tokens on the device; `wsconst`: letters of the CLI's --wsconst options ("D", "DR", ...;
-        KyteaWsConstFilter).  Returns (uint8 view of the output lines, number of lines)."""
+        out as space-separated tokens on the device; `wsconst`: letters of the CLI's --wsconst options ("D", "DR", ...:
+        KyteaWsConstFilter; "G": ConcatGraphemeClustersFilter).  Returns (uint8 view of the output lines, number of lines)."""
         mask = 0
         for ch in wsconst:
-            if ch not in "DRHTKO":
-                raise VaporettoError(2, "InvalidArgumentError: wsconst: one of D, R, H, T, K, O")
-            mask |= 1 << ("DRHTKO".index(ch) + 1)
+            if ch not in "DRHTKOG":
+                raise VaporettoError(2, "InvalidArgumentError: wsconst: one of D, R, H, T, K, O, G")
+            mask |= 1 << ("DRHTKOG".index(ch) + 1)
         t = np.frombuffer(data, np.uint8) if isinstance(data, (bytes, bytearray)) else np.ascontiguousarray(data, np.uint8)
         if out is None:
             out = np.empty(3 * t.size + int(np.count_nonzero(t == 10)) + 16, np.uint8)
@@ -471,6 +483,13 @@ class Sentence:
 
     def boundaries_mut(self) -> np.ndarray:
         return self._boundaries
+
+    def concat_grapheme_clusters(self) -> None:
+        """`ConcatGraphemeClustersFilter::filter(&mut sentence)` (vaporetto_rules, concat_grapheme_clusters.rs:10-35)."""
+        b = self.as_raw_text().encode("utf-8")
+        bd = np.ascontiguousarray(self._boundaries, np.uint8)
+        _check(lib().vpt_concat_grapheme_clusters(b, len(b), bd.ctypes.data, bd.size))
+        self._boundaries[:] = bd
 
     def boundary_scores(self) -> np.ndarray:
         """`Sentence::boundary_scores` (sentence.rs:1040-1046)."""

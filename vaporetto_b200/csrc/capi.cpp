@@ -20,7 +20,9 @@
 #include "device_model.hpp"
 #include "model.hpp"
 #include "predictor_build.hpp"
+#include "grapheme.hpp"
 #include "tags.hpp"
+#include "zstd_loader.hpp"
 #include "textnorm.hpp"
 
 using namespace vpt;
@@ -60,12 +62,16 @@ struct Scratch {
     void* d_out = nullptr; size_t out_cap = 0;
     void* d_tok = nullptr; size_t tok_cap = 0;     // tag prediction outputs (vpt_predict_batch_tags)
     void* d_cand = nullptr; size_t cand_cap = 0;
-    uint64_t* h_totals = nullptr;  // pinned, 4 x u64: boundaries, chars, lines, output bytes
+    void* d_bits = nullptr; size_t bits_cap = 0;   // compact outputs (vpt_predict_batch_compact)
+    void* d_st8 = nullptr; size_t st8_cap = 0;
+    void* d_ntok = nullptr; size_t ntok_cap = 0;
+    void* d_tokbase = nullptr; size_t tokbase_cap = 0;
+    uint64_t* h_totals = nullptr;  // pinned, 8 x u64: boundaries, chars, lines, output bytes, tokens, first bit word
     uint8_t* h_io = nullptr;       // pinned staging of the single-sentence call (vpt_predict), kSingleIoBytes
     void* d_io = nullptr;          // its device twin
     ~Scratch() {
         for (void* p : {d_text, d_off, d_ws, d_status, d_boff, d_coff, d_scores, d_bounds, d_cst, d_tst, d_trims, d_blk,
-                        d_blkbase, d_tokg, d_out, d_tok, d_cand})
+                        d_blkbase, d_tokg, d_out, d_tok, d_cand, d_bits, d_st8, d_ntok, d_tokbase})
             if (p) cudaFree(p);
         if (h_totals) cudaFreeHost(h_totals);
         if (h_io) cudaFreeHost(h_io);
@@ -262,7 +268,7 @@ struct ScratchLease {
             cuda_check(cudaStreamCreateWithFlags(&s->stream_out, cudaStreamNonBlocking), "cudaStreamCreate");
             cuda_check(cudaEventCreateWithFlags(&s->ev_kernels, cudaEventDisableTiming), "cudaEventCreate");
             cuda_check(cudaEventCreateWithFlags(&s->ev_out, cudaEventDisableTiming), "cudaEventCreate");
-            cuda_check(cudaMallocHost(reinterpret_cast<void**>(&s->h_totals), 32), "cudaMallocHost");
+            cuda_check(cudaMallocHost(reinterpret_cast<void**>(&s->h_totals), 64), "cudaMallocHost");
         }
     }
     ~ScratchLease() {
@@ -392,6 +398,23 @@ int vpt_model_read(const uint8_t* data, size_t len, vpt_model** out, size_t* con
     *out = nullptr;
     std::unique_ptr<vpt_model> m(new vpt_model());
     m->m = Model::read(data, len, consumed);
+    *out = m.release();
+    return kOk;
+    VPT_API_END
+}
+
+int vpt_model_read_zstd(const uint8_t* data, size_t len, vpt_model** out) {
+    VPT_API_BEGIN
+    if (!out) throw Error(kInvalidArgument, "InvalidArgumentError: out: must not be NULL");
+    *out = nullptr;
+    if (len && !data) throw Error(kInvalidArgument, "InvalidArgumentError: data: must not be NULL");
+    std::unique_ptr<vpt_model> m(new vpt_model());
+    if (is_zstd_frame(data, len)) {
+        const std::vector<uint8_t> raw = zstd_decode_all(data, len);
+        m->m = Model::read(raw.data(), raw.size(), nullptr);
+    } else {
+        m->m = Model::read(data, len, nullptr);
+    }
     *out = m.release();
     return kOk;
     VPT_API_END
@@ -970,6 +993,7 @@ void lines_stage1(const vpt_predictor& p, Scratch& s, LineChunk& ch, bool normal
     t.total_host = &s.h_totals[3];
     t.out = static_cast<uint8_t*>(s.d_out);
     cuda_check(launch_wsconst(t, a.boundaries, wsconst, normalize, st), "launch(wsconst)");
+    if (wsconst & 0x80u) cuda_check(launch_grapheme(t, a.boundaries, normalize, st), "launch(grapheme)");
     cuda_check(launch_tokenize(t, st), "launch(tok)");
     if (pipeline_trace()) ch.tr.mark(2, st);
     cuda_check(cudaEventRecord(ch.done, st), "cudaEventRecord");
@@ -985,8 +1009,8 @@ int vpt_tokenize_lines(const vpt_predictor* p, const uint8_t* utf8, size_t n_byt
     require_device(p);
     if (out_len) *out_len = 0;
     if (n_lines_out) *n_lines_out = 0;
-    if (wsconst_types & ~0x7Eu)
-        throw Error(kInvalidArgument, "InvalidArgumentError: wsconst_types: bits 1..6 (Digit .. Other) only");
+    if (wsconst_types & ~0xFEu)
+        throw Error(kInvalidArgument, "InvalidArgumentError: wsconst_types: bits 1..6 (Digit .. Other) and 7 (grapheme clusters) only");
     if (n_bytes && !utf8) throw Error(kInvalidArgument, "InvalidArgumentError: utf8: must not be NULL");
     if (n_bytes == 0) return kOk;
     cuda_check(cudaSetDevice(p->device), "cudaSetDevice");
@@ -1194,6 +1218,22 @@ int vpt_char_types(const uint8_t* utf8, size_t n_bytes, uint8_t* types_out, size
     VPT_API_END
 }
 
+int vpt_concat_grapheme_clusters(const uint8_t* utf8, size_t n_bytes, uint8_t* boundaries, size_t n_boundaries) {
+    VPT_API_BEGIN
+    if (n_bytes && !utf8) throw Error(kInvalidArgument, "InvalidArgumentError: utf8: must not be NULL");
+    check_raw_text(utf8, n_bytes);
+    const std::vector<uint32_t> cps = utf8_to_codepoints(std::string(reinterpret_cast<const char*>(utf8), n_bytes));
+    if (cps.size() != n_boundaries + 1 || (n_boundaries && !boundaries))
+        throw Error(kInvalidArgument, "InvalidArgumentError: boundaries: one per pair of adjacent characters");
+    GraphemeState st;
+    for (size_t i = 0; i < cps.size(); ++i) {
+        const bool brk = grapheme_step(st, grapheme_class(kGraphemeTable, cps[i]));
+        if (!brk && i > 0) boundaries[i - 1] = 0;
+    }
+    return kOk;
+    VPT_API_END
+}
+
 uint32_t vpt_tag_n_tokens(const vpt_predictor* p) { return p ? uint32_t(p->tag_preds.size()) : 0; }
 
 const char* vpt_tag_string(const vpt_predictor* p, uint32_t token_id, uint32_t slot, uint32_t cand) {
@@ -1342,6 +1382,225 @@ int vpt_predict_batch_tags(const vpt_predictor* p, const uint8_t* utf8, const ui
     }
     cuda_check(cudaStreamSynchronize(st), "sync(copy-out)");
     if (n_unserved_out) *n_unserved_out = unserved;
+    return kOk;
+    VPT_API_END
+}
+
+int vpt_predict_batch_compact(const vpt_predictor* p, const uint8_t* utf8, const uint64_t* byte_offsets, size_t n_sent,
+                              uint32_t* boundary_bits_out, size_t bits_capacity_words, uint32_t* n_chars_out,
+                              uint8_t* status_out, uint32_t* n_tokens_out, int32_t* token_ids_out, uint8_t* token_cands_out,
+                              size_t token_capacity, uint64_t* n_boundaries_out, uint64_t* n_tokens_total_out,
+                              uint64_t* n_unserved_out) {
+    VPT_API_BEGIN
+    require_device(p);
+    if (n_boundaries_out) *n_boundaries_out = 0;
+    if (n_tokens_total_out) *n_tokens_total_out = 0;
+    if (n_unserved_out) *n_unserved_out = 0;
+    const bool want_tags = token_ids_out != nullptr || token_cands_out != nullptr;
+    const bool want_tokens = want_tags || n_tokens_out != nullptr;
+    if (want_tags) {
+        if (!p->predict_tags || p->from_blob)
+            throw Error(kInvalidArgument, "InvalidArgumentError: this predictor is created with predict_tags = false");
+        if (!p->dt.tok_tab)
+            throw Error(kUnsupported, "this tag model exceeds the limits of the device path (tags.hpp); use vpt_fill_tags");
+        if (!token_ids_out || (p->n_tags && !token_cands_out) || !n_tokens_out)
+            throw Error(kInvalidArgument, "InvalidArgumentError: token_ids_out/token_cands_out/n_tokens_out: must not be NULL");
+    }
+    if (!byte_offsets || !n_chars_out || !status_out)
+        throw Error(kInvalidArgument, "InvalidArgumentError: byte_offsets/n_chars_out/status_out: must not be NULL");
+    if (n_sent == 0) return kOk;
+    if (byte_offsets[n_sent] < byte_offsets[0])
+        throw Error(kInvalidArgument, "InvalidArgumentError: byte_offsets: must be non-decreasing");
+    if (byte_offsets[n_sent] > byte_offsets[0] && !utf8)
+        throw Error(kInvalidArgument, "InvalidArgumentError: utf8: must not be NULL");
+    cuda_check(cudaSetDevice(p->device), "cudaSetDevice");
+
+    // Chunks flow through three host-side stages, each one chunk behind the previous one, so that the device always has
+    // the next chunk's kernels queued while the host waits for a chunk's totals:
+    //   A  copy-in + count pass                         -> boundaries / characters of the chunk (pinned host words)
+    //   B  scoring (+ tag prediction) + compaction      -> the chunk's first boundary bit is known from A's totals
+    //   C  copy-out (bit words, per-sentence words, token records at the running token total)
+    const size_t kChunkSentences = chunk_sentences();
+    const std::vector<size_t> sizes = ramp_schedule(n_sent, kChunkSentences, kChunkSentences / 8, kChunkSentences / 4);
+    const size_t nchunks = sizes.size();
+    constexpr int kDepth = 4;
+    std::unique_ptr<ScratchLease> lease[kDepth];
+    for (int i = 0; i < kDepth && size_t(i) < nchunks; ++i) lease[i].reset(new ScratchLease(*p));
+    struct CChunk {
+        ChunkState cs;
+        uint64_t nb = 0, nc = 0, nb_base = 0;
+        cudaEvent_t kernels = nullptr;
+        bool issued = false;
+    };
+    std::vector<CChunk> chunks(nchunks);
+    struct EventGuard {
+        std::vector<CChunk>& c;
+        ~EventGuard() { for (auto& x : c) { if (x.cs.counted) cudaEventDestroy(x.cs.counted); if (x.kernels) cudaEventDestroy(x.kernels); x.cs.tr.destroy(); } }
+    } guard{chunks};
+    for (size_t c = 0, lo = 0; c < nchunks; lo += sizes[c], ++c) {
+        ChunkState& ch = chunks[c].cs;
+        ch.s_lo = lo;
+        ch.n = sizes[c];
+        ch.byte_lo = byte_offsets[ch.s_lo];
+        if (byte_offsets[ch.s_lo + ch.n] < ch.byte_lo)
+            throw Error(kInvalidArgument, "InvalidArgumentError: byte_offsets: must be non-decreasing");
+        ch.nbytes = byte_offsets[ch.s_lo + ch.n] - ch.byte_lo;
+    }
+    const size_t nt = want_tags ? p->n_tags : 0;
+    uint64_t nb_total = 0, tok_total = 0, unserved_total = 0;
+    bool overflow = false;
+    std::vector<std::pair<uint64_t, const uint64_t*>> side_words;  // (word index, pinned word) of every chunk's first bit word
+    std::vector<uint32_t> h_unserved(nchunks, 0);
+
+    auto stage_b = [&](size_t c) {
+        CChunk& cc = chunks[c];
+        ChunkState& ch = cc.cs;
+        Scratch& s = *lease[c % kDepth]->s;
+        cudaStream_t st = s.stream;
+        cuda_check(cudaEventSynchronize(ch.counted), "sync(count)");
+        cc.nb = s.h_totals[0];
+        cc.nc = s.h_totals[1];
+        cc.nb_base = nb_total;
+        nb_total += cc.nb;
+        if (!cc.kernels) cuda_check(cudaEventCreateWithFlags(&cc.kernels, cudaEventDisableTiming), "cudaEventCreate");
+        if ((nb_total + 31) / 32 > bits_capacity_words || (nb_total && !boundary_bits_out)) { overflow = true; return; }
+        BatchArgs& a = ch.a;
+        Scratch::ensure(s.d_bounds, s.bounds_cap, cc.nb + 4);
+        a.scores = nullptr;
+        if (!scores_optional(p->dm)) {
+            Scratch::ensure(s.d_scores, s.scores_cap, 4 * cc.nb + 4);
+            a.scores = static_cast<int32_t*>(s.d_scores);
+        }
+        a.boundaries = static_cast<uint8_t*>(s.d_bounds);
+        if (want_tags) {
+            Scratch::ensure(s.d_cst, s.cst_cap, 4 * cc.nc + 4);
+            Scratch::ensure(s.d_tst, s.tst_cap, 4 * cc.nc + 4);
+            a.char_states = static_cast<uint32_t*>(s.d_cst);
+            a.type_states = static_cast<uint32_t*>(s.d_tst);
+        }
+        // (chunk-local offsets: bound_base / char_base stay 0)
+        if (pipeline_trace()) ch.tr.mark(1, st);
+        cuda_check(launch_score(p->dm, a, st), "launch(score)");
+        CompactArgs k;
+        k.n_sent = ch.n;
+        k.status = a.status;
+        k.n_chars = a.n_chars;
+        k.boundaries = a.boundaries;
+        k.bound_offsets = a.bound_offsets;
+        k.n_bound = cc.nb;
+        k.bit_base = uint32_t(cc.nb_base & 31);
+        const size_t nwords = size_t((k.bit_base + cc.nb + 31) / 32);
+        Scratch::ensure(s.d_bits, s.bits_cap, 4 * nwords + 16);
+        Scratch::ensure(s.d_st8, s.st8_cap, ch.n + 16);
+        k.bits = static_cast<uint32_t*>(s.d_bits);
+        k.status8 = static_cast<uint8_t*>(s.d_st8);
+        if (want_tokens) {
+            Scratch::ensure(s.d_ntok, s.ntok_cap, 4 * ch.n + 16);
+            Scratch::ensure(s.d_tokbase, s.tokbase_cap, 8 * (ch.n + 1) + 16);
+            k.n_tokens = static_cast<uint32_t*>(s.d_ntok);
+            k.tok_base = static_cast<uint64_t*>(s.d_tokbase);
+            k.tok_total_host = &s.h_totals[4];
+        }
+        s.h_totals[4] = 0;
+        cuda_check(launch_compact(k, st), "launch(compact)");
+        if (want_tags) {
+            // a token has at least one character
+            Scratch::ensure(s.d_tok, s.tok_cap, 4 * cc.nc + 16);
+            Scratch::ensure(s.d_cand, s.cand_cap, cc.nc * std::max<size_t>(nt, 1) + 16);
+            uint32_t* d_unserved = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(s.d_ws) + workspace_layout(ch.n).ticket + 128);
+            cuda_check(cudaMemsetAsync(d_unserved, 0, 4, st), "memset");
+            TagArgs t;
+            t.text = a.text;
+            t.offsets = a.offsets;
+            t.n_sent = ch.n;
+            t.status = a.status;
+            t.boundaries = a.boundaries;
+            t.bound_offsets = a.bound_offsets;
+            t.char_offsets = a.char_offsets;
+            t.char_states = p->dt.char_rels ? a.char_states : nullptr;
+            t.type_states = p->dt.type_rels ? a.type_states : nullptr;
+            t.n_unserved = d_unserved;
+            t.tok_base = k.tok_base;
+            t.tok_ids = static_cast<int32_t*>(s.d_tok);
+            t.tok_cands = static_cast<uint8_t*>(s.d_cand);
+            cuda_check(launch_tags(p->dt, t, st), "launch(tags)");
+            cuda_check(cudaMemcpyAsync(&h_unserved[c], d_unserved, 4, cudaMemcpyDeviceToHost, st), "D2H(unserved)");
+        }
+        if (pipeline_trace()) ch.tr.mark(2, st);
+        cuda_check(cudaEventRecord(cc.kernels, st), "cudaEventRecord");
+        cc.issued = true;
+    };
+    auto stage_c = [&](size_t c) {
+        CChunk& cc = chunks[c];
+        ChunkState& ch = cc.cs;
+        Scratch& s = *lease[c % kDepth]->s;
+        if (!cc.issued) return;
+        cuda_check(cudaEventSynchronize(cc.kernels), "sync(kernels)");
+        const uint64_t ntok = want_tokens ? s.h_totals[4] : 0;
+        if (want_tags && tok_total + ntok > token_capacity) { overflow = true; cc.issued = false; }
+        cudaStream_t so = s.stream_out;
+        cuda_check(cudaStreamWaitEvent(so, cc.kernels, 0), "cudaStreamWaitEvent");
+        if (!overflow) {
+            const uint32_t bit_base = uint32_t(cc.nb_base & 31);
+            const size_t nwords = size_t((bit_base + cc.nb + 31) / 32);
+            const uint64_t w0 = cc.nb_base >> 5;
+            if (nwords) {
+                // the chunk's first word may share its low bits with the previous chunk: it comes back through a pinned
+                // word and is merged on the host at the end; the other words go straight to their place
+                if (bit_base == 0) boundary_bits_out[w0] = 0;
+                cuda_check(cudaMemcpyAsync(&s.h_totals[5], s.d_bits, 4, cudaMemcpyDeviceToHost, so), "D2H(bits)");
+                if (nwords > 1)
+                    cuda_check(cudaMemcpyAsync(boundary_bits_out + w0 + 1, static_cast<uint32_t*>(s.d_bits) + 1, 4 * (nwords - 1),
+                                               cudaMemcpyDeviceToHost, so), "D2H(bits)");
+            }
+            cuda_check(cudaMemcpyAsync(n_chars_out + ch.s_lo, ch.a.n_chars, 4 * ch.n, cudaMemcpyDeviceToHost, so), "D2H(n_chars)");
+            cuda_check(cudaMemcpyAsync(status_out + ch.s_lo, s.d_st8, ch.n, cudaMemcpyDeviceToHost, so), "D2H(status)");
+            if (n_tokens_out) cuda_check(cudaMemcpyAsync(n_tokens_out + ch.s_lo, s.d_ntok, 4 * ch.n, cudaMemcpyDeviceToHost, so), "D2H(n_tokens)");
+            if (want_tags && ntok) {
+                cuda_check(cudaMemcpyAsync(token_ids_out + tok_total, s.d_tok, 4 * ntok, cudaMemcpyDeviceToHost, so), "D2H(tokens)");
+                if (nt) cuda_check(cudaMemcpyAsync(token_cands_out + tok_total * nt, s.d_cand, ntok * nt, cudaMemcpyDeviceToHost, so), "D2H(tokens)");
+            }
+        }
+        cuda_check(cudaEventRecord(s.ev_out, so), "cudaEventRecord");
+        if (pipeline_trace()) ch.tr.mark(3, so);
+        if (!overflow && cc.nb) {
+            // the pinned word is reused by the chunk that takes this scratch next: read it once the copy has landed
+            cuda_check(cudaEventSynchronize(s.ev_out), "sync(copy-out)");
+            boundary_bits_out[cc.nb_base >> 5] |= uint32_t(s.h_totals[5]);
+        }
+        tok_total += ntok;
+    };
+    // A runs kDepth - 2 chunks ahead of B, B one chunk ahead of C (a scratch is free again when its chunk's C is done)
+    constexpr size_t kAheadA = kDepth - 2;
+    for (size_t c = 0; c < std::min<size_t>(kAheadA, nchunks); ++c) chunk_count(*lease[c % kDepth]->s, chunks[c].cs, utf8, byte_offsets);
+    for (size_t step = 0; step < nchunks + 1; ++step) {
+        if (step + kAheadA < nchunks) chunk_count(*lease[(step + kAheadA) % kDepth]->s, chunks[step + kAheadA].cs, utf8, byte_offsets);
+        if (step < nchunks) stage_b(step);
+        if (step >= 1) stage_c(step - 1);
+    }
+    for (int i = 0; i < kDepth; ++i)
+        if (lease[i]) {
+            cuda_check(cudaStreamSynchronize(lease[i]->s->stream), "sync(score)");
+            cuda_check(cudaStreamSynchronize(lease[i]->s->stream_out), "sync(copy-out)");
+        }
+    for (uint32_t u : h_unserved) unserved_total += u;
+    if (pipeline_trace())
+        for (size_t c = 0; c < nchunks; ++c) chunks[c].cs.tr.print("compact", c, chunks[c].cs.n, chunks[0].cs.tr);
+    if (n_boundaries_out) *n_boundaries_out = nb_total;
+    if (n_tokens_total_out) *n_tokens_total_out = tok_total;
+    if (n_unserved_out) *n_unserved_out = unserved_total;
+    if (overflow) throw Error(kInvalidArgument, "InvalidArgumentError: bits_capacity_words/token_capacity: too small for the batch");
+    return kOk;
+    VPT_API_END
+}
+
+int vpt_unpack_boundaries(const uint32_t* boundary_bits, uint64_t first_bit, uint64_t n, uint8_t* boundaries_out) {
+    VPT_API_BEGIN
+    if (n && (!boundary_bits || !boundaries_out)) throw Error(kInvalidArgument, "InvalidArgumentError: buffers: must not be NULL");
+    for (uint64_t i = 0; i < n; ++i) {
+        const uint64_t b = first_bit + i;
+        boundaries_out[i] = uint8_t((boundary_bits[b >> 5] >> (b & 31)) & 1u);
+    }
     return kOk;
     VPT_API_END
 }

@@ -127,5 +127,6 @@ cudaError_t launch_tokenize(const TokArgs& t, cudaStream_t stream);
 // KyteaWsConstFilter for the character types in `mask` (bit t = CharacterType t): clears boundaries between two
 // characters of such a type; uses text / offsets / trims / status / n_chars / bound_offsets of `t`
 cudaError_t launch_wsconst(const TokArgs& t, uint8_t* boundaries, uint32_t mask, bool norm, cudaStream_t stream);
+cudaError_t launch_grapheme(const TokArgs& t, uint8_t* boundaries, bool norm, cudaStream_t stream);
 
 }  // namespace vpt

@@ -12,8 +12,11 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <mutex>
+#include <vector>
 
 #include "device_model.hpp"
+#include "grapheme.hpp"
 #include "textnorm.hpp"
 
 namespace vpt {
@@ -21,6 +24,7 @@ namespace vpt {
 namespace {
 
 constexpr unsigned kFull = 0xFFFFFFFFu;
+constexpr int kGraphemeSubPages = 160;  // 256-entry sub-tables of the grapheme class table (145 in Unicode 16)
 
 __device__ __forceinline__ uint32_t warp_incl_scan_u32(uint32_t v, int lane) {
 #pragma unroll
@@ -444,7 +448,122 @@ __global__ void __launch_bounds__(kTokThreads) k_wsconst(TokArgs t, uint8_t* __r
     }
 }
 
+// ConcatGraphemeClustersFilter (vaporetto_rules/src/sentence_filters/concat_grapheme_clusters.rs:10-35) — the CLI's
+// `--wsconst G`: every boundary inside an extended grapheme cluster (UAX #29, grapheme.hpp) becomes NotWordBoundary.
+// One warp per sentence, 128 bytes per step: the lanes decode their characters and look their classes up in a two-level
+// table; a window whose characters all have the default class (Japanese text: almost every window) has a cluster
+// boundary before each of its characters and leaves the rule state clean, so only windows with marks, emoji, Hangul
+// jamo, regional indicators ... run the rule engine, all lanes in step over the window's class words in shared memory.
+__device__ uint16_t g_gr_page[0x1100];              // page c >> 8: 0x8000 | class for a uniform page, else sub-table index
+__device__ uint8_t g_gr_cls[kGraphemeSubPages * 256];
+
+__device__ __forceinline__ uint32_t grapheme_class_dev(uint32_t c) {
+    const uint32_t pg = g_gr_page[c >> 8];
+    return (pg & 0x8000u) ? (pg & 0x7Fu) : uint32_t(g_gr_cls[(pg << 8) + (c & 255u)]);
+}
+
+__global__ void __launch_bounds__(kTokThreads) k_grapheme(TokArgs t, uint8_t* __restrict__ boundaries, int norm) {
+    __shared__ uint8_t s_cw[kTokThreads / 32][128];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t gbase = uint64_t(blockIdx.x) * kGroup;
+    const int ns = int(min(uint64_t(kGroup), t.n_sent - gbase));
+    for (int i = warp; i < ns; i += kTokThreads / 32) {
+        const uint64_t s = gbase + i;
+        if (t.status[s] != 0 || t.n_chars[s] < 2) continue;
+        const uint64_t o0 = t.offsets[s];
+        const uint64_t a0 = o0 & ~3ull;
+        const uint32_t b0 = uint32_t(o0 - a0), b1 = uint32_t(t.offsets[s + 1] - a0) - (t.trims ? t.trims[s] : 0);
+        const uint8_t* __restrict__ base = t.text + a0;
+        uint8_t* __restrict__ bnd = boundaries + t.bound_offsets[s];
+        uint32_t chars = 0;  // characters before this window
+        GraphemeState st;    // (the same in every lane)
+        for (uint32_t w0 = 0; w0 < b1; w0 += 128) {
+            const uint32_t addr = w0 + 4u * uint32_t(lane);
+            uint32_t lo = 0, hi = 0, in80 = 0;
+            if (addr < b1) {
+                lo = __ldg(reinterpret_cast<const uint32_t*>(base + addr));
+                if (addr + 4 < b1) hi = __ldg(reinterpret_cast<const uint32_t*>(base + addr + 4));
+                in80 = inside80(addr, b0, b1);
+            }
+            const uint32_t st80 = ~(lo & ~(lo << 1)) & in80;  // character starts (not 10xxxxxx)
+            const uint32_t nst = __popc(st80);
+            const uint32_t st_incl = warp_incl_scan_u32(nst, lane);
+            const uint32_t nwin = __shfl_sync(kFull, st_incl, 31);
+            uint32_t k = st_incl - nst, any = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (st80 & (0x80u << (8 * j))) {
+                    uint32_t c = decode_cp(__funnelshift_r(lo, hi, 8 * j));
+                    if (norm) c = kytea_fullwidth(c);
+                    const uint32_t cw = grapheme_class_dev(c);
+                    s_cw[warp][k++] = uint8_t(cw);
+                    any |= cw;
+                }
+            }
+            // (a default-class character still joins a Prepend character in front of it: GB9b)
+            if (__any_sync(kFull, any != 0) || (st.started && (st.prev & 15u) == kGcbPrepend)) {
+                __syncwarp();
+                for (uint32_t q = 0; q < nwin; ++q) {
+                    const bool brk = grapheme_step(st, s_cw[warp][q]);
+                    if (!brk && chars + q > 0 && lane == 0) bnd[chars + q - 1] = 0;
+                }
+                __syncwarp();
+            } else if (nwin) {
+                st = GraphemeState();
+                st.started = 1;
+            }
+            chars += nwin;
+        }
+    }
+}
+
 }  // namespace
+
+namespace {
+// two-level class table from the sorted ranges of grapheme_tables.hpp (built once, uploaded once per device)
+struct GraphemeHostTable {
+    std::vector<uint16_t> page;
+    std::vector<uint8_t> cls;
+    GraphemeHostTable() : page(0x1100, uint16_t(0x8000)) {
+        std::vector<uint8_t> flat(0x110000, 0);
+        for (int r = 0; r < kGraphemeRanges; ++r)
+            for (uint32_t c = kGraphemeTable[r].lo; c <= kGraphemeTable[r].hi; ++c) flat[c] = uint8_t(kGraphemeTable[r].cls);
+        for (uint32_t p = 0; p < 0x1100; ++p) {
+            bool uniform = true;
+            for (uint32_t c = 1; c < 256 && uniform; ++c) uniform = flat[(p << 8) + c] == flat[p << 8];
+            if (uniform) { page[p] = uint16_t(0x8000u | flat[p << 8]); continue; }
+            page[p] = uint16_t(cls.size() >> 8);
+            cls.insert(cls.end(), flat.begin() + (p << 8), flat.begin() + (p << 8) + 256);
+        }
+    }
+};
+}  // namespace
+
+cudaError_t launch_grapheme(const TokArgs& t, uint8_t* boundaries, bool norm, cudaStream_t stream) {
+    if (t.n_sent == 0) return cudaSuccess;
+    static std::mutex mu;
+    static bool uploaded[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+        if (!uploaded[dev]) {
+            static const GraphemeHostTable tab;
+            if (tab.cls.size() > size_t(kGraphemeSubPages) * 256) return cudaErrorInvalidValue;
+            // (synchronous copies: the table is in place before any kernel of any stream reads it)
+            e = cudaMemcpyToSymbol(g_gr_page, tab.page.data(), tab.page.size() * 2);
+            if (e != cudaSuccess) return e;
+            e = cudaMemcpyToSymbol(g_gr_cls, tab.cls.data(), tab.cls.size());
+            if (e != cudaSuccess) return e;
+            uploaded[dev] = true;
+        }
+    }
+    const uint64_t ngroups = (t.n_sent + kGroup - 1) / kGroup;
+    k_grapheme<<<unsigned(ngroups), kTokThreads, 0, stream>>>(t, boundaries, norm ? 1 : 0);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_wsconst(const TokArgs& t, uint8_t* boundaries, uint32_t mask, bool norm, cudaStream_t stream) {
     if (t.n_sent == 0 || (mask & 0x7Eu) == 0) return cudaSuccess;

@@ -69,6 +69,7 @@ __global__ void __launch_bounds__(kTagWarps * 32) k_tags(DevTags t, TagArgs a) {
     const uint64_t bo = a.bound_offsets[s] - a.bound_base;
     const uint32_t nt = t.n_tags;
     if (a.status[s] != 0) {
+        if (a.tok_base) return;  // a rejected sentence has no tokens
         for (uint32_t i = lane; i < n; i += 32) {
             a.tag_token[cb + i] = -1;
             for (uint32_t k = 0; k < nt; ++k) a.tag_cand[(cb + i) * nt + k] = -1;
@@ -77,6 +78,7 @@ __global__ void __launch_bounds__(kTagWarps * 32) k_tags(DevTags t, TagArgs a) {
     }
     uint64_t wpos = b0 & ~3ull;
     uint32_t nd = 0;
+    uint32_t tok_rank = 0;  // tokens that end before this chunk of characters
     for (uint32_t c0 = 0; c0 < n; c0 += 32) {
         // byte positions of the characters up to c0 + 32 (one more: the end of the chunk's last character)
         const uint32_t need = min(n, c0 + 33u);
@@ -86,12 +88,12 @@ __global__ void __launch_bounds__(kTagWarps * 32) k_tags(DevTags t, TagArgs a) {
         }
         __syncwarp();
         const uint32_t i = c0 + lane;
-        if (i < n) {
-            int32_t tok = -1;
-            int32_t cand[kTagMaxSlots];
+        int32_t tok = -1;
+        int32_t cand[kTagMaxSlots];
 #pragma unroll
-            for (int k = 0; k < kTagMaxSlots; ++k) cand[k] = -1;
-            const bool ends = i + 1 == n || a.boundaries[bo + i] == 1;
+        for (int k = 0; k < kTagMaxSlots; ++k) cand[k] = -1;
+        const bool ends = i < n && (i + 1 == n || a.boundaries[bo + i] == 1);
+        if (i < n) {
             if (ends) {
                 uint32_t start = i;
                 while (start > 0 && a.boundaries[bo + start - 1] == 0) --start;
@@ -143,6 +145,18 @@ __global__ void __launch_bounds__(kTagWarps * 32) k_tags(DevTags t, TagArgs a) {
                     atomicAdd(a.n_unserved, 1u);  // a token longer than the ring: left to the host path
                 }
             }
+        }
+        __syncwarp();
+        if (a.tok_base) {
+            // per-token records: the token's rank is the number of boundaries before its last character
+            const unsigned endm = __ballot_sync(kFull, ends);
+            if (ends) {
+                const uint64_t rec = a.tok_base[s] + tok_rank + __popc(endm & ((1u << lane) - 1u));
+                a.tok_ids[rec] = tok;
+                for (uint32_t k = 0; k < nt; ++k) a.tok_cands[rec * nt + k] = (tok >= 0 && cand[k] >= 0) ? uint8_t(cand[k]) : uint8_t(255);
+            }
+            tok_rank += __popc(endm);
+        } else if (i < n) {
             a.tag_token[cb + i] = tok;
             for (uint32_t k = 0; k < nt; ++k) a.tag_cand[(cb + i) * nt + k] = tok >= 0 ? cand[k] : -1;
         }
@@ -150,7 +164,86 @@ __global__ void __launch_bounds__(kTagWarps * 32) k_tags(DevTags t, TagArgs a) {
     }
 }
 
+// ---- compact outputs -----------------------------------------------------------------------------------------------------
+
+constexpr int kPackThreads = 256;
+
+// boundaries (one byte each) -> one bit each; thread per output word
+__global__ void __launch_bounds__(kPackThreads) k_pack_bits(CompactArgs c) {
+    const uint64_t w = uint64_t(blockIdx.x) * kPackThreads + threadIdx.x;
+    const uint64_t nwords = (uint64_t(c.bit_base) + c.n_bound + 31) / 32;
+    if (w >= nwords) return;
+    // word w holds the boundaries [32 w - bit_base, 32 w - bit_base + 32)
+    const int64_t first = int64_t(32 * w) - int64_t(c.bit_base);
+    uint32_t v = 0;
+    if (first >= 0 && uint64_t(first) + 32 <= c.n_bound && ((reinterpret_cast<uintptr_t>(c.boundaries) + first) & 3) == 0) {
+        const uint32_t* q = reinterpret_cast<const uint32_t*>(c.boundaries + first);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t x = __ldg(q + j) & 0x01010101u;  // bytes are 0 / 1
+            v |= (((x * 0x01020408u) >> 24) & 15u) << (4 * j);
+        }
+    } else {
+        for (int j = 0; j < 32; ++j) {
+            const int64_t i = first + j;
+            if (i >= 0 && uint64_t(i) < c.n_bound && c.boundaries[i]) v |= 1u << j;
+        }
+    }
+    c.bits[w] = v;
+}
+
+// status as one byte, tokens per sentence (boundaries set + 1 for a scored sentence)
+__global__ void __launch_bounds__(kPackThreads) k_sentence_info(CompactArgs c) {
+    const uint64_t s = uint64_t(blockIdx.x) * kPackThreads + threadIdx.x;
+    if (s >= c.n_sent) return;
+    const int32_t st = c.status[s];
+    c.status8[s] = uint8_t(st);
+    if (!c.n_tokens) return;
+    uint32_t ntok = 0;
+    const uint32_t n = c.n_chars[s];
+    if (st == 0 && n > 0) {
+        const uint8_t* b = c.boundaries + (c.bound_offsets[s] - c.bound_base);
+        ntok = 1;
+        for (uint32_t i = 0; i + 1 < n; ++i) ntok += b[i];
+    }
+    c.n_tokens[s] = ntok;
+}
+
+// exclusive prefix of n_tokens (one block; a chunk has at most a few hundred thousand sentences)
+__global__ void __launch_bounds__(1024) k_token_scan(CompactArgs c) {
+    __shared__ uint64_t s_part[1024];
+    const uint64_t per = (c.n_sent + 1023) / 1024;
+    const uint64_t lo = min(c.n_sent, per * threadIdx.x), hi = min(c.n_sent, lo + per);
+    uint64_t sum = 0;
+    for (uint64_t i = lo; i < hi; ++i) sum += c.n_tokens[i];
+    s_part[threadIdx.x] = sum;
+    __syncthreads();
+    // Hillis-Steele over the 1024 partial sums
+    for (int d = 1; d < 1024; d <<= 1) {
+        const uint64_t v = threadIdx.x >= unsigned(d) ? s_part[threadIdx.x - d] : 0;
+        __syncthreads();
+        s_part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    uint64_t run = s_part[threadIdx.x] - sum;
+    for (uint64_t i = lo; i < hi; ++i) { c.tok_base[i] = run; run += c.n_tokens[i]; }
+    if (threadIdx.x == 1023) {
+        c.tok_base[c.n_sent] = s_part[1023];
+        if (c.tok_total_host) *c.tok_total_host = s_part[1023];
+    }
+}
+
 }  // namespace
+
+cudaError_t launch_compact(const CompactArgs& c, cudaStream_t stream) {
+    const uint64_t nwords = (uint64_t(c.bit_base) + c.n_bound + 31) / 32;
+    if (nwords) k_pack_bits<<<unsigned((nwords + kPackThreads - 1) / kPackThreads), kPackThreads, 0, stream>>>(c);
+    if (c.n_sent) {
+        k_sentence_info<<<unsigned((c.n_sent + kPackThreads - 1) / kPackThreads), kPackThreads, 0, stream>>>(c);
+        if (c.n_tokens) k_token_scan<<<1, 1024, 0, stream>>>(c);
+    }
+    return cudaGetLastError();
+}
 
 cudaError_t launch_tags(const DevTags& t, const TagArgs& a, cudaStream_t stream) {
     if (a.n_sent == 0) return cudaSuccess;

@@ -95,7 +95,30 @@ struct TagArgs {
     int32_t* tag_token = nullptr;           // [n_chars] out: token id of the token ending at the character, or -1
     int32_t* tag_cand = nullptr;            // [n_chars * n_tags] out: chosen candidate per slot, or -1
     uint32_t* n_unserved = nullptr;         // nullable device counter: tokens whose model exceeds the device limits
+    // per-TOKEN output (vpt_predict_batch_compact) instead of the per-character arrays above: token r of sentence s
+    // (in text order) is record tok_base[s] + r
+    const uint64_t* tok_base = nullptr;     // [n_sent + 1] exclusive prefix of the tokens per sentence; selects this mode
+    int32_t* tok_ids = nullptr;             // [n_tokens] token id or -1
+    uint8_t* tok_cands = nullptr;           // [n_tokens * n_tags] chosen candidate per slot, 255 = none
 };
+
+// Compact outputs (vpt_predict_batch_compact): boundaries as one bit each, tokens per sentence and their prefix.
+struct CompactArgs {
+    uint64_t n_sent = 0;
+    const int32_t* status = nullptr;          // [n_sent] from the scoring pass
+    const uint32_t* n_chars = nullptr;        // [n_sent]
+    const uint8_t* boundaries = nullptr;      // [n_bound] 0 / 1
+    const uint64_t* bound_offsets = nullptr;  // [n_sent + 1], values include bound_base
+    uint64_t bound_base = 0;
+    uint64_t n_bound = 0;
+    uint32_t bit_base = 0;                    // the chunk's first boundary is bit `bit_base` (0..31) of bits[0]
+    uint32_t* bits = nullptr;                 // [(bit_base + n_bound + 31) / 32]
+    uint8_t* status8 = nullptr;               // [n_sent]
+    uint32_t* n_tokens = nullptr;             // [n_sent] tokens per sentence (0 for a rejected sentence); nullable
+    uint64_t* tok_base = nullptr;             // [n_sent + 1]; nullable with n_tokens
+    uint64_t* tok_total_host = nullptr;       // nullable: pinned host word that receives the number of tokens
+};
+cudaError_t launch_compact(const CompactArgs& c, cudaStream_t stream);
 
 // 64-bit hash of a token's bytes (host builder and kernel)
 #if defined(__CUDACC__)
