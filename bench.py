@@ -425,6 +425,28 @@ def main():
         stage_acc += np.array(list(stage))
     stage_ms = stage_acc / reps
     clocks = sampler.stop() if rank == 0 else None
+    # config 3: the tag prediction kernel alone, on the device-resident states / boundaries of the step above
+    k_tags_ms = None
+    if want_states and pred.info.get("predict_tags"):
+        d_tagtok = torch.empty(n_bound + n, dtype=torch.int32, device=dev)
+        d_tagcand = torch.empty((n_bound + n) * max(int(pred.n_tags), 1), dtype=torch.int32, device=dev)
+        d_uns = torch.zeros(1, dtype=torch.int32, device=dev)
+
+        def step_ktags():
+            rc = L.vpt_predict_tags_batch_dev(pred._h, d_text.data_ptr(), d_off.data_ptr(), n, d_status.data_ptr(),
+                                              d_bounds.data_ptr(), d_boff.data_ptr(), p_coff, p_cst, p_tst,
+                                              d_tagtok.data_ptr(), d_tagcand.data_ptr(), d_uns.data_ptr(), sp)
+            if rc:
+                raise RuntimeError(L.vpt_last_error().decode())
+
+        step_ktags()
+        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0e.record(stream)
+        for _ in range(5):
+            step_ktags()
+        t1e.record(stream)
+        torch.cuda.synchronize()
+        k_tags_ms = t0e.elapsed_time(t1e) / 5
 
     tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
     tot = torch.tensor([float(nbytes)], dtype=torch.float64, device=dev)
@@ -488,6 +510,43 @@ def main():
     if world > 1:
         dist.all_reduce(tnb, op=dist.ReduceOp.MAX)
     e2e_nb_value = total_bytes * args.e2e_steps / float(tnb.item()) / 1e6
+    # compact results (vpt_predict_batch_compact): one bit per boundary, n_chars / status per sentence -- and, for a
+    # predictor with tags, one record per token (token id + one byte per tag slot) with the tag prediction on the device
+    h_bits = torch.zeros((n_bound + 31) // 32 + 1, dtype=torch.int32).pin_memory()
+    h_nch = torch.empty(n, dtype=torch.int32).pin_memory()
+    h_st8 = torch.empty(n, dtype=torch.uint8).pin_memory()
+    h_ntok = torch.empty(n, dtype=torch.int32).pin_memory()
+    n_tags = int(pred.n_tags) if want_states else 0
+    h_tokid = torch.empty(n_chars_total, dtype=torch.int32).pin_memory() if want_states else None
+    h_tokcand = torch.empty(n_chars_total * max(n_tags, 1), dtype=torch.uint8).pin_memory() if want_states else None
+    ntok_out, nuns_out = C.c_uint64(), C.c_uint64()
+
+    def step_compact():
+        rc = L.vpt_predict_batch_compact(pred._h, h_text.data_ptr(), h_off.data_ptr(), n, h_bits.data_ptr(), h_bits.numel(),
+                                         h_nch.data_ptr(), h_st8.data_ptr(), h_ntok.data_ptr(),
+                                         h_tokid.data_ptr() if want_states else None,
+                                         h_tokcand.data_ptr() if want_states else None,
+                                         n_chars_total if want_states else 0, C.byref(nb_out), C.byref(ntok_out), C.byref(nuns_out))
+        if rc:
+            raise RuntimeError(L.vpt_last_error().decode())
+
+    step_compact()
+    step_compact()
+    assert nb_out.value == n_bound
+    bits_np = np.unpackbits(h_bits.numpy().view(np.uint8), bitorder="little")[:n_bound]
+    assert np.array_equal(bits_np, h_bounds.numpy()), "compact boundary bits"
+    assert int(h_ntok.numpy().sum()) == int(np.count_nonzero(h_bounds.numpy() == 1)) + n
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        step_compact()
+    torch.cuda.synchronize()
+    tcp = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tcp, op=dist.ReduceOp.MAX)
+    e2e_compact_value = total_bytes * args.e2e_steps / float(tcp.item()) / 1e6
+    compact_d2h = 4 * ((n_bound + 31) // 32) + 4 * n + n + 4 * n + (int(ntok_out.value) * (4 + n_tags) if want_states else 0)
+    compact_known = int(np.count_nonzero(h_tokid.numpy()[: ntok_out.value] >= 0)) if want_states else None
     # the reference CLI loop on the device (vpt_tokenize_lines): raw lines in, space-separated tokens out; line
     # splitting and output materialisation run on the GPU, so no offsets / scores cross PCIe
     starts = offs[:-1].astype(np.int64) + np.arange(n, dtype=np.int64)
@@ -638,6 +697,13 @@ def main():
                     "single_call_us": round(single_us, 1),
                     "single_call": "vpt_predict on one 40-character sentence (host buffers, one launch, one pinned round trip)",
                     "predict_tags_on_device_value": None if e2e_tags_value is None else round(e2e_tags_value, 1),
+                    "k_tags_ms": None if k_tags_ms is None else round(k_tags_ms, 4),
+                    "compact": {"value": round(e2e_compact_value, 1), "unit": "MB/s",
+                                "api": "vpt_predict_batch_compact (1 bit per boundary, n_chars/status/n_tokens per sentence"
+                                       + (", token id + %d candidate bytes per token: tag prediction on the device)" % n_tags
+                                          if want_states else "; no scores, no tags)"),
+                                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": compact_d2h,
+                                "tokens": int(ntok_out.value), "tokens_with_tag_model": compact_known},
                     "tokenize_lines": {"value": round(e2e_lines_value, 1), "unit": "MB/s",
                                        "api": "vpt_tokenize_lines, no_norm = 1 (raw lines in, tokenised text out; split + "
                                               "materialisation on the device)",

@@ -233,11 +233,41 @@ uint32_t vpt_tag_n_candidates(const vpt_predictor* predictor, uint32_t token_id,
 uint32_t vpt_tag_score_len(const vpt_predictor* predictor, uint32_t token_id);
 uint32_t vpt_tag_n_tokens(const vpt_predictor* predictor);
 
+/* predict (+ fill_tags) of a batch with COMPACT results, for callers that want the segmentation and the tags rather
+ * than the score strip: what crosses PCIe is one bit per boundary and one small record per token.
+ *   boundary_bits_out  the boundaries of all sentences as one bit stream (bit k of the stream = bit k % 32 of word
+ *                      k / 32; 1 = WordBoundary): sentence s owns the bits [B_s, B_s + max(n_chars_out[s], 1) - 1)
+ *                      with B_s = the sum over the earlier sentences (CharacterBoundary values of
+ *                      `Sentence::boundaries()`, sentence.rs:1016-1046; vpt_unpack_boundaries gives the byte form);
+ *   n_chars_out[s]     characters of the sentence (a rejected sentence, status_out[s] >= 2, keeps its count and owns
+ *                      zero bits; an empty one has 0); status_out[s] as in vpt_predict_batch;
+ *   n_tokens_out[s]    (nullable unless tags are requested) tokens of the sentence = boundaries set + 1;
+ *   token_ids_out / token_cands_out (both NULL: no tag prediction; needs predict_tags = true otherwise): token r of
+ *                      sentence s in text order is record T_s + r (T_s = the sum of n_tokens_out over the earlier
+ *                      sentences): the token id for vpt_tag_string (-1: the token has no tag model) and, per tag slot,
+ *                      the chosen candidate as one byte (255: none) -- `Predictor::predict_tags`, predictor.rs:546-637,
+ *                      the same choice vpt_predict_batch_tags reports per character.
+ * The totals come back in *n_boundaries_out / *n_tokens_total_out; *n_unserved_out counts tokens whose tag model
+ * exceeds the device limits (0 for the reference's models; vpt_fill_tags serves those).  Too small capacities return
+ * InvalidArgument with the totals set. */
+int vpt_predict_batch_compact(const vpt_predictor* predictor, const uint8_t* utf8, const uint64_t* byte_offsets,
+                              size_t n_sent, uint32_t* boundary_bits_out, size_t bits_capacity_words,
+                              uint32_t* n_chars_out, uint8_t* status_out, uint32_t* n_tokens_out, int32_t* token_ids_out,
+                              uint8_t* token_cands_out, size_t token_capacity, uint64_t* n_boundaries_out,
+                              uint64_t* n_tokens_total_out, uint64_t* n_unserved_out);
+/* bits [first_bit, first_bit + n) of a boundary bit stream as bytes (0 / 1) */
+int vpt_unpack_boundaries(const uint32_t* boundary_bits, uint64_t first_bit, uint64_t n, uint8_t* boundaries_out);
+
 /* ---- Sentence helpers (host side) ----------------------------------------------------------------- */
 
 /* `CharacterType::get_type` per character (sentence.rs:50-67) / `Sentence::char_types()` (sentence.rs:993).
  * Returns the reference's InvalidArgument errors for empty text / NUL.  *n_chars_out receives n. */
 int vpt_char_types(const uint8_t* utf8, size_t n_bytes, uint8_t* types_out, size_t capacity, uint64_t* n_chars_out);
+
+/* `SplitLinebreaksFilter::filter(&mut Sentence)` (vaporetto_rules/src/sentence_filters/split_linebreaks.rs:9-37) on the
+ * host, for the Sentence API: the boundary on either side of every '\r' / '\n' becomes WordBoundary (1).  (The lines
+ * path never sees these characters inside a sentence: it splits at them.) */
+int vpt_split_linebreaks(const uint8_t* utf8, size_t n_bytes, uint8_t* boundaries, size_t n_boundaries);
 
 /* `ConcatGraphemeClustersFilter::filter(&mut Sentence)` (vaporetto_rules/src/sentence_filters/
  * concat_grapheme_clusters.rs:10-35) on the host, for the Sentence API: `boundaries` (n_chars - 1 values, 0 / 1, as
@@ -267,7 +297,7 @@ int vpt_write_tokenized_text(const vpt_predictor* predictor, const uint8_t* utf8
  * (' ' between tokens; '\\' before ' ', '\\', '/': sentence.rs:850-886) is materialised on the device: the only
  * transfers are the input bytes in and the output bytes out.  Lines that update_raw rejects (empty, or
  * containing U+0000) produce an empty line as in the CLI; so do lines that are not valid UTF-8 (the CLI stops
- * with an I/O error on those).  Tags and score printing are not part of this path.
+ * with an I/O error on those).  Score printing (--scores, --tag-scores) is not part of this path; tags: below.
  * `no_norm`: the CLI flag of the same name (0 = apply KyteaFullwidthFilter, the CLI default).
  * `wsconst_types`: the CLI's `--wsconst D/R/H/T/K/O` options as a bit set, bit t for CharacterType t (VPT_WSCONST_*):
  * `KyteaWsConstFilter` (vaporetto_rules/src/sentence_filters/kytea_wsconst.rs:27-44) clears the boundary between two
@@ -287,6 +317,15 @@ int vpt_write_tokenized_text(const vpt_predictor* predictor, const uint8_t* utf8
 #define VPT_WSCONST_GRAPHEME (1u << 7) /* --wsconst G: ConcatGraphemeClustersFilter */
 int vpt_tokenize_lines(const vpt_predictor* predictor, const uint8_t* utf8, size_t n_bytes, int no_norm,
                        uint32_t wsconst_types, uint8_t* out, size_t out_capacity, uint64_t* out_len, uint64_t* n_lines);
+
+/* The same loop with the CLI's `--predict-tags` (predict/src/main.rs:130-136,159-166): `fill_tags` on the sentence that
+ * was predicted (after the post-filters), tags copied to the original line, `write_tokenized_text` with tags
+ * (sentence.rs:850-886: every token is followed by '/' + tag for its tag slots up to the last one that has a tag, the
+ * tag strings escaped like the surface).  Tag prediction (token lookup by the bytes of the pre-filtered token, tag
+ * weights, arg-max) and the output with its tag strings run on the device; the predictor must have been created with
+ * predict_tags = 1.  `out` needs room for the tags: at most 3 * n_bytes + n_lines + n_bytes * (longest tag suffix). */
+int vpt_tokenize_lines_tags(const vpt_predictor* predictor, const uint8_t* utf8, size_t n_bytes, int no_norm,
+                            uint32_t wsconst_types, uint8_t* out, size_t out_capacity, uint64_t* out_len, uint64_t* n_lines);
 
 /* `KyteaFullwidthFilter` for one character (vaporetto_rules/src/string_filters/kytea_fullwidth.rs:13-118): the
  * same function the kernels apply (csrc/textnorm.hpp). */

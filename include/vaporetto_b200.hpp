@@ -166,6 +166,18 @@ public:
     size_t n_tags() const { return tags_filled_ ? n_tags_ : 0; }
     const std::vector<std::optional<std::string>>& tags() const { return tags_; }
 
+    /// `vaporetto_rules::sentence_filters::SplitLinebreaksFilter::filter(&mut sentence)` (split_linebreaks.rs:9-37).
+    void split_linebreaks() {
+        detail::check(vpt_split_linebreaks(reinterpret_cast<const uint8_t*>(text_.data()), text_.size(), boundaries_.data(),
+                                           boundaries_.size()));
+    }
+    /// `vaporetto_rules::sentence_filters::ConcatGraphemeClustersFilter::filter(&mut sentence)`
+    /// (concat_grapheme_clusters.rs:10-35).
+    void concat_grapheme_clusters() {
+        detail::check(vpt_concat_grapheme_clusters(reinterpret_cast<const uint8_t*>(text_.data()), text_.size(),
+                                                   boundaries_.data(), boundaries_.size()));
+    }
+
     /// `Sentence::fill_tags(&mut self)` (sentence.rs:1144) -> `Predictor::predict_tags` (predictor.rs:546-637).
     void fill_tags() {
         if (!predictor_) return;

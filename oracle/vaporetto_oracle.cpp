@@ -1375,8 +1375,10 @@ long ora_grapheme_lengths(const char* utf8, size_t nbytes, uint32_t* lens, size_
 
 // `wsconst_types`: bit t set = a `--wsconst` option for CharacterType t, bit 7 = `--wsconst G` (post_filters, main.rs:100-106; applied to
 // the sentence that was predicted, main.rs:138,157).
-long ora_tokenize_lines(const void* p, const char* utf8, size_t nbytes, int no_norm, uint32_t wsconst_types, char* buf,
-                        size_t cap, uint64_t* n_lines) {
+// `predict_tags` != 0: the CLI's --predict-tags (main.rs:130-136,159-166: fill_tags on the sentence that was predicted,
+// tags copied to the original line's sentence before write_tokenized_text).
+static long tokenize_lines_impl(const void* p, const char* utf8, size_t nbytes, int no_norm, uint32_t wsconst_types,
+                                int predict_tags, char* buf, size_t cap, uint64_t* n_lines) {
     auto neg = [](int c) { return -long(c); };
     ORA_TRY
     auto* pr = static_cast<const Predictor*>(p);
@@ -1384,6 +1386,7 @@ long ora_tokenize_lines(const void* p, const char* utf8, size_t nbytes, int no_n
     uint64_t nl = 0;
     size_t lo = 0;
     Sentence s, s_orig;
+    vector<int32_t> tt, ti;
     while (lo < nbytes) {
         const void* q = memchr(utf8 + lo, '\n', nbytes - lo);
         size_t end = q ? size_t(static_cast<const char*>(q) - utf8) : nbytes;
@@ -1397,6 +1400,7 @@ long ora_tokenize_lines(const void* p, const char* utf8, size_t nbytes, int no_n
                 pr->predict(s_orig);
                 for (uint8_t t = 1; t <= 6; ++t) if (wsconst_types & (1u << t)) wsconst_filter(s_orig, t);
                 if (wsconst_types & 0x80u) grapheme_filter(s_orig);
+                if (predict_tags) pr->fill_tags(s_orig, tt, ti, nullptr);
             } else {
                 string pre;
                 for (uint32_t c : s_orig.chars) append_utf8(pre, kytea_fullwidth_cp(c));
@@ -1404,9 +1408,10 @@ long ora_tokenize_lines(const void* p, const char* utf8, size_t nbytes, int no_n
                 pr->predict(s);
                 for (uint8_t t = 1; t <= 6; ++t) if (wsconst_types & (1u << t)) wsconst_filter(s, t);
                 if (wsconst_types & 0x80u) grapheme_filter(s);
+                if (predict_tags) pr->fill_tags(s, tt, ti, nullptr);
                 s_orig.boundaries = s.boundaries;
             }
-            out += write_tokenized(*pr, s_orig, nullptr, nullptr);
+            out += write_tokenized(*pr, s_orig, predict_tags ? &tt : nullptr, predict_tags ? &ti : nullptr);
         }
         out.push_back('\n');
         lo = next;
@@ -1416,6 +1421,15 @@ long ora_tokenize_lines(const void* p, const char* utf8, size_t nbytes, int no_n
     memcpy(buf, out.data(), out.size());
     return long(out.size());
     ORA_CATCH(neg)
+}
+
+long ora_tokenize_lines(const void* p, const char* utf8, size_t nbytes, int no_norm, uint32_t wsconst_types, char* buf,
+                        size_t cap, uint64_t* n_lines) {
+    return tokenize_lines_impl(p, utf8, nbytes, no_norm, wsconst_types, 0, buf, cap, n_lines);
+}
+long ora_tokenize_lines_tags(const void* p, const char* utf8, size_t nbytes, int no_norm, uint32_t wsconst_types, char* buf,
+                             size_t cap, uint64_t* n_lines) {
+    return tokenize_lines_impl(p, utf8, nbytes, no_norm, wsconst_types, 1, buf, cap, n_lines);
 }
 
 // predict + fill_tags: tag_token[n_chars], tag_idx[n_chars*n_tags]. Returns n_chars.

@@ -186,3 +186,43 @@ def test_lines_full_size():
     # restores the input
     assert b"/" not in data and b"\\" not in data
     assert g.replace(b"\\ ", b"\x00").replace(b" ", b"").replace(b"\x00", b" ") == data
+
+
+def test_lines_with_tags_reference_model():
+    """--predict-tags through vpt_tokenize_lines_tags: the bundled model's documented output (README / predictor.rs doctest:
+    "まぁ/名詞/マー 社長/名詞/シャチョー ...") and mixed lines, with and without the full-width pre-filter and post-filters,
+    byte-exact against the oracle's CLI loop (fill_tags on the predicted sentence, main.rs:157-166)."""
+    mb = read("model.bin")
+    p, o = vb.Predictor(vb.Model.read(mb), predict_tags=True), OraclePredictor(mb, predict_tags=True)
+    data = ("まぁ社長は火星猫だ\r\n\nまぁ良いだろう\nVaporetto 1.5/2 a\\b\n社長は社長だ火星猫\n" + "火星猫は社長だ" * 40 + "\n" + "猫\n").encode()
+    got, nl = p.tokenize_lines(data, no_norm=True, predict_tags=True)
+    assert got.tobytes().decode().split("\n")[0] == "まぁ/名詞/マー 社長/名詞/シャチョー は/助詞/ワ 火星/名詞/カセー 猫/名詞/ネコ だ/助動詞/ダ"
+    for no_norm in (True, False):
+        for ws in ("", "K", "GD"):
+            got, nl = p.tokenize_lines(data, no_norm=no_norm, wsconst=ws, predict_tags=True)
+            want, wl = o.tokenize_lines(data, no_norm=no_norm, wsconst=ws, predict_tags=True)
+            assert nl == wl and got.tobytes() == want, (no_norm, ws)
+    p0 = make(mb)
+    with pytest.raises(vb.VaporettoError):
+        p0.tokenize_lines(data, predict_tags=True)
+
+
+def test_lines_with_tags_synthetic(monkeypatch):
+    """1 500 tag models (tokens of ASCII and Japanese characters, tag strings with characters that need escapes) on a
+    30 000-pattern model, 20 000 lines, default normalisation (tokens are looked up by their full-width image)."""
+    from vpt_testlib import synth
+    mb = synth.gen_model_bccwj_shaped(n_patterns=30_000, sample_sentences=50_000, tag_models=1_500)
+    p, o = vb.Predictor(vb.Model.read(mb), predict_tags=True), OraclePredictor(mb, predict_tags=True)
+    text, offs, _ = synth.gen_text(20_000, 40, seed=synth.TEXT_SEED + 21)
+    lines = [text[int(offs[i]):int(offs[i + 1])].tobytes() for i in range(len(offs) - 1)]
+    lines[3] = b""
+    lines[17] = b"a\x00b"
+    lines[18] = b"\xff\xfe"
+    data = b"\n".join(lines) + b"\n"
+    monkeypatch.setenv("VPT_CHUNK_BYTES", "300000")
+    for no_norm in (False, True):
+        got, nl = p.tokenize_lines(data, no_norm=no_norm, predict_tags=True)
+        want, wl = o.tokenize_lines(data, no_norm=no_norm, predict_tags=True)
+        assert nl == wl == len(lines)
+        assert got.tobytes() == want, no_norm
+    assert got.tobytes().count(b"/") > 1000

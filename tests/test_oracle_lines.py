@@ -237,3 +237,16 @@ def test_host_grapheme_filter_matches_oracle():
     s.boundaries_mut()[:] = 1
     s.concat_grapheme_clusters()
     assert s.write_tokenized_text() == "こ れ は 手 \U0001f44f\U0001f3fd で す"
+
+
+def test_split_linebreaks_reference_vectors():
+    """split_linebreaks.rs:45-76 (the filter's unit tests) through the Sentence mirror (vpt_split_linebreaks)."""
+    for text, want in (("前の行\n次の行", "前の行 \n 次の行"), ("前の行\r次の行", "前の行 \r 次の行"),
+                       ("前の行\r\n次の行", "前の行 \r \n 次の行")):
+        s = vb.Sentence.from_raw(text)
+        s.boundaries_mut()[:] = 0       # Sentence::from_tokenized of an unsegmented string: no boundary anywhere
+        s.split_linebreaks()
+        assert s.write_tokenized_text() == want
+    s = vb.Sentence.from_raw("\n")
+    s.split_linebreaks()
+    assert s.boundaries().size == 0

@@ -51,6 +51,8 @@ def lib():
         L.ora_tokenize_lines.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_int, C.c_uint32, C.c_char_p,
                                          C.c_size_t, C.POINTER(C.c_uint64)]
         L.ora_tokenize_lines.restype = C.c_long
+        L.ora_tokenize_lines_tags.argtypes = L.ora_tokenize_lines.argtypes
+        L.ora_tokenize_lines_tags.restype = C.c_long
         L.ora_grapheme_lengths.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t]
         L.ora_grapheme_lengths.restype = C.c_long
         L.ora_kytea_fullwidth.argtypes = [C.c_uint32]
@@ -129,13 +131,14 @@ class OraclePredictor:
             raise _err(-n)
         return buf.raw[:n].decode("utf-8")
 
-    def tokenize_lines(self, data: bytes, no_norm: bool = False, wsconst: str = ""):
+    def tokenize_lines(self, data: bytes, no_norm: bool = False, wsconst: str = "", predict_tags: bool = False):
         """The reference CLI's loop over a buffer of raw bytes -> (output bytes, n_lines)."""
-        cap = 3 * len(data) + data.count(b"\n") + 16
+        cap = (3 + (64 if predict_tags else 0)) * len(data) + data.count(b"\n") + 16
         buf = C.create_string_buffer(cap)
         nl = C.c_uint64(0)
         mask = sum(1 << ("DRHTKOG".index(ch) + 1) for ch in set(wsconst))
-        n = lib().ora_tokenize_lines(self._p, data, len(data), int(no_norm), mask, buf, cap, C.byref(nl))
+        fn = lib().ora_tokenize_lines_tags if predict_tags else lib().ora_tokenize_lines
+        n = fn(self._p, data, len(data), int(no_norm), mask, buf, cap, C.byref(nl))
         if n < 0:
             raise _err(-n)
         return buf.raw[:n], int(nl.value)

@@ -5,7 +5,7 @@ output text) on the GPU.
 
     python tools/predict_cli.py --model model.bin[.zst] [--no-norm] [--wsconst D] [--wsconst R] ... < in.txt > out.txt
 
-Options not on the device path (--predict-tags, --scores, --tag-scores) are rejected; use the Sentence API
+Options not on the device path (--scores, --tag-scores) are rejected; use the Sentence API
 (vaporetto_b200.Sentence / include/vaporetto_b200.hpp) for tags."""
 import argparse
 import os
@@ -26,17 +26,18 @@ def main(argv=None) -> int:
     ap.add_argument("--model", required=True, help="The model file to use when analyzing text")
     ap.add_argument("--wsconst", action="append", default=[], choices=list("DRHTKOG"),
                     help="Do not segment some character types: D Digit, R Roman, H Hiragana, T Katakana, K Kanji, O Other, G Grapheme cluster")
+    ap.add_argument("--predict-tags", action="store_true", help="Predicts POS tags")
     ap.add_argument("--no-norm", action="store_true", help="Do not normalize input strings before prediction")
     ap.add_argument("--device", type=int, default=0, help="CUDA device ordinal")
     args = ap.parse_args(argv)
 
     import vaporetto_b200 as vb
     print("Loading model file...", file=sys.stderr)
-    predictor = vb.Predictor(vb.Model.read_zstd(read_model(args.model)), predict_tags=False, device=args.device)
+    predictor = vb.Predictor(vb.Model.read_zstd(read_model(args.model)), predict_tags=args.predict_tags, device=args.device)
     print("Start tokenization", file=sys.stderr)
     data = sys.stdin.buffer.read()
     t0 = time.perf_counter()
-    out, _ = predictor.tokenize_lines(data, no_norm=args.no_norm, wsconst="".join(args.wsconst))
+    out, _ = predictor.tokenize_lines(data, no_norm=args.no_norm, wsconst="".join(args.wsconst), predict_tags=args.predict_tags)
     dt = time.perf_counter() - t0
     sys.stdout.buffer.write(out.tobytes())
     print(f"Elapsed: {dt} [sec]", file=sys.stderr)

@@ -68,6 +68,7 @@ ABI = [
     ("vpt_model_free", None, [_P]),
     ("vpt_model_read_kytea", C.c_int, [C.c_char_p, C.c_size_t, C.POINTER(_P)]),
     ("vpt_concat_grapheme_clusters", C.c_int, [C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t]),
+    ("vpt_split_linebreaks", C.c_int, [C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t]),
     ("vpt_model_read_zstd", C.c_int, [C.c_char_p, C.c_size_t, C.POINTER(_P)]),
     ("vpt_model_to_vec", C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_uint64)]),
     ("vpt_model_dictionary_len", C.c_uint64, [_P]),
@@ -104,6 +105,11 @@ ABI = [
     ("vpt_predict_tags_batch_dev", C.c_int, [_P, _P, _P, C.c_size_t, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     ("vpt_predict_batch_tags", C.c_int, [_P, _P, _P, C.c_size_t, _P, _P, C.c_size_t, _P, _P, _P, _P, C.c_size_t, _P,
                                          C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    ("vpt_predict_batch_compact", C.c_int, [_P, _P, _P, C.c_size_t, _P, C.c_size_t, _P, _P, _P, _P, _P, C.c_size_t,
+                                            C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    ("vpt_unpack_boundaries", C.c_int, [_P, C.c_uint64, C.c_uint64, _P]),
+    ("vpt_tokenize_lines_tags", C.c_int, [_P, _P, C.c_size_t, C.c_int, C.c_uint32, _P, C.c_size_t,
+                                          C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
 ]
 
 _lib = None
@@ -393,11 +399,40 @@ class Predictor:
         res = BatchResult(None if scores is None else scores[: nb.value], bounds[: nb.value], boff, status[:n], None, None, coff)
         return res, tok[: nc.value], cand[: nc.value * nt].reshape(-1, nt), int(nu.value)
 
-    def tokenize_lines(self, data, out: Optional[np.ndarray] = None, no_norm: bool = False, wsconst: str = ""):
+    def tag_string(self, token_id: int, slot: int, cand: int) -> Optional[str]:
+        """Tag string of (token id, tag slot, candidate) as the token records of predict_batch_compact name it."""
+        v = lib().vpt_tag_string(self._h, int(token_id), int(slot), int(cand))
+        return None if v is None else v.decode("utf-8")
+
+    def predict_batch_compact(self, text, offsets, tags: bool = False) -> "CompactResult":
+        """predict (+ predict_tags) for a batch with compact results (vpt_predict_batch_compact): one bit per boundary, one
+        record per token; see CompactResult."""
+        t = np.frombuffer(text, np.uint8) if isinstance(text, (bytes, bytearray)) else np.ascontiguousarray(text, np.uint8)
+        off = np.ascontiguousarray(offsets, np.uint64)
+        n = off.size - 1
+        cap = max(int(off[-1] - off[0]) if n > 0 else 0, 1)
+        nt = self.n_tags if tags else 0
+        bits = np.zeros((cap + 31) // 32 + 1, np.uint32)
+        n_chars = np.zeros(max(n, 1), np.uint32)
+        status = np.zeros(max(n, 1), np.uint8)
+        n_tokens = np.zeros(max(n, 1), np.uint32)
+        tok = np.empty(cap, np.int32) if tags else None
+        cand = np.empty(cap * max(nt, 1), np.uint8) if tags else None
+        nb, ntok, nu = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        _check(lib().vpt_predict_batch_compact(self._h, t.ctypes.data, off.ctypes.data, n, bits.ctypes.data, bits.size,
+                                               n_chars.ctypes.data, status.ctypes.data, n_tokens.ctypes.data, _ptr(tok), _ptr(cand),
+                                               cap if tags else 0, C.byref(nb), C.byref(ntok), C.byref(nu)))
+        return CompactResult(bits[: (nb.value + 31) // 32], int(nb.value), n_chars[:n], status[:n], n_tokens[:n],
+                             None if tok is None else tok[: ntok.value],
+                             None if cand is None else cand[: ntok.value * max(nt, 1)].reshape(-1, max(nt, 1)), int(nu.value))
+
+    def tokenize_lines(self, data, out: Optional[np.ndarray] = None, no_norm: bool = False, wsconst: str = "",
+                       predict_tags: bool = False):
         """The reference CLI's `predict` loop (predict/src/main.rs:126-181) over a whole buffer of raw bytes
         (vpt_tokenize_lines): lines are split, scored (on KyteaFullwidthFilter(line) unless no_norm) and written
         out as space-separated tokens on the device; `wsconst`: letters of the CLI's --wsconst options ("D", "DR", ...:
-        KyteaWsConstFilter; "G": ConcatGraphemeClustersFilter).  Returns (uint8 view of the output lines, number of lines)."""
+        KyteaWsConstFilter; "G": ConcatGraphemeClustersFilter); `predict_tags`: the CLI's --predict-tags
+        (vpt_tokenize_lines_tags).  Returns (uint8 view of the output lines, number of lines)."""
         mask = 0
         for ch in wsconst:
             if ch not in "DRHTKOG":
@@ -405,12 +440,40 @@ class Predictor:
             mask |= 1 << ("DRHTKOG".index(ch) + 1)
         t = np.frombuffer(data, np.uint8) if isinstance(data, (bytes, bytearray)) else np.ascontiguousarray(data, np.uint8)
         if out is None:
-            out = np.empty(3 * t.size + int(np.count_nonzero(t == 10)) + 16, np.uint8)
+            out = np.empty((3 + (16 if predict_tags else 0)) * t.size + int(np.count_nonzero(t == 10)) + 16, np.uint8)
         n = C.c_uint64()
         nl = C.c_uint64()
-        _check(lib().vpt_tokenize_lines(self._h, t.ctypes.data, t.size, int(no_norm), mask, out.ctypes.data, out.size,
-                                        C.byref(n), C.byref(nl)))
+        fn = lib().vpt_tokenize_lines_tags if predict_tags else lib().vpt_tokenize_lines
+        for _ in range(2):
+            rc = fn(self._h, t.ctypes.data, t.size, int(no_norm), mask, out.ctypes.data, out.size, C.byref(n), C.byref(nl))
+            if rc == 2 and predict_tags and n.value > out.size:
+                out = np.empty(n.value + 16, np.uint8)   # long tag strings: the call reported the size it needs
+                continue
+            break
+        _check(rc)
         return out[: n.value], int(nl.value)
+
+
+class CompactResult:
+    """Result of Predictor.predict_batch_compact: `boundary_bits` (uint32 words of the batch's boundary bit stream),
+    `n_chars` / `status` / `n_tokens` per sentence, `token_ids` [tokens] and `token_cands` [tokens, n_tags] (uint8, 255 =
+    none) when tags were requested.  Sentence s owns the bits [bit_offsets[s], bit_offsets[s + 1]) and the token records
+    [token_offsets[s], token_offsets[s + 1])."""
+
+    def __init__(self, bits, n_boundaries, n_chars, status, n_tokens, token_ids, token_cands, n_unserved):
+        self.boundary_bits, self.n_boundaries = bits, n_boundaries
+        self.n_chars, self.status, self.n_tokens = n_chars, status, n_tokens
+        self.token_ids, self.token_cands, self.n_unserved = token_ids, token_cands, n_unserved
+        nb = np.where(n_chars > 0, n_chars.astype(np.int64) - 1, 0)
+        self.bit_offsets = np.concatenate(([0], np.cumsum(nb))).astype(np.uint64)
+        self.token_offsets = np.concatenate(([0], np.cumsum(n_tokens.astype(np.int64)))).astype(np.uint64)
+
+    def boundaries(self, s: Optional[int] = None) -> np.ndarray:
+        """Boundaries as bytes (0 / 1): of sentence `s`, or of the whole batch (vpt_unpack_boundaries)."""
+        lo, hi = (0, self.n_boundaries) if s is None else (int(self.bit_offsets[s]), int(self.bit_offsets[s + 1]))
+        out = np.empty(hi - lo, np.uint8)
+        _check(lib().vpt_unpack_boundaries(self.boundary_bits.ctypes.data, lo, hi - lo, out.ctypes.data))
+        return out
 
 
 class Token:
@@ -483,6 +546,13 @@ class Sentence:
 
     def boundaries_mut(self) -> np.ndarray:
         return self._boundaries
+
+    def split_linebreaks(self) -> None:
+        """`SplitLinebreaksFilter::filter(&mut sentence)` (vaporetto_rules, split_linebreaks.rs:9-37)."""
+        b = self.as_raw_text().encode("utf-8")
+        bd = np.ascontiguousarray(self._boundaries, np.uint8)
+        _check(lib().vpt_split_linebreaks(b, len(b), bd.ctypes.data, bd.size))
+        self._boundaries[:] = bd
 
     def concat_grapheme_clusters(self) -> None:
         """`ConcatGraphemeClustersFilter::filter(&mut sentence)` (vaporetto_rules, concat_grapheme_clusters.rs:10-35)."""

@@ -66,15 +66,20 @@ struct Scratch {
     void* d_st8 = nullptr; size_t st8_cap = 0;
     void* d_ntok = nullptr; size_t ntok_cap = 0;
     void* d_tokbase = nullptr; size_t tokbase_cap = 0;
+    void* d_tokdesc = nullptr; size_t tokdesc_cap = 0;
+    void* d_toklocal = nullptr; size_t toklocal_cap = 0;
+    void* d_tokblk = nullptr; size_t tokblk_cap = 0;
     uint64_t* h_totals = nullptr;  // pinned, 8 x u64: boundaries, chars, lines, output bytes, tokens, first bit word
+    uint32_t* h_side = nullptr; size_t side_cap = 0;  // pinned: first bit word of every chunk (vpt_predict_batch_compact)
     uint8_t* h_io = nullptr;       // pinned staging of the single-sentence call (vpt_predict), kSingleIoBytes
     void* d_io = nullptr;          // its device twin
     ~Scratch() {
         for (void* p : {d_text, d_off, d_ws, d_status, d_boff, d_coff, d_scores, d_bounds, d_cst, d_tst, d_trims, d_blk,
-                        d_blkbase, d_tokg, d_out, d_tok, d_cand, d_bits, d_st8, d_ntok, d_tokbase})
+                        d_blkbase, d_tokg, d_out, d_tok, d_cand, d_bits, d_st8, d_ntok, d_tokbase, d_tokdesc, d_toklocal, d_tokblk})
             if (p) cudaFree(p);
         if (h_totals) cudaFreeHost(h_totals);
         if (h_io) cudaFreeHost(h_io);
+        if (h_side) cudaFreeHost(h_side);
         if (d_io) cudaFree(d_io);
         if (ev_kernels) cudaEventDestroy(ev_kernels);
         if (ev_out) cudaEventDestroy(ev_out);
@@ -221,12 +226,15 @@ void upload_tags(vpt_predictor& p) {
     const size_t i_bytes = add(t.tok_bytes.data(), t.tok_bytes.size());
     const size_t i_info = add(t.tok_info.data(), t.tok_info.size() * sizeof(TagTokenInfo));
     const size_t i_pool = add(t.pool.data(), t.pool.size() * 4);
-    const size_t i_cw = add(t.cw_tab.data(), t.cw_tab.size() * sizeof(TagWeightSlot));
-    const size_t i_tw = add(t.tw_tab.data(), t.tw_tab.size() * sizeof(TagWeightSlot));
+    const size_t i_keys = add(t.keys.data(), t.keys.size() * sizeof(TagKey));
+    const size_t i_tss = add(t.ts_slot.data(), t.ts_slot.size() * 4);
+    const size_t i_tsc = add(t.ts_cand.data(), t.ts_cand.size() * 4);
+    const size_t i_tsr = add(t.ts_ref.data(), t.ts_ref.size() * 4);
+    const size_t i_tsb = add(t.ts_bytes.data(), t.ts_bytes.size());
+    const size_t i_cc = add(t.c_chain.data(), t.c_chain.size() * sizeof(TagChain));
+    const size_t i_tc = add(t.t_chain.data(), t.t_chain.size() * sizeof(TagChain));
     const size_t i_cl = add(t.c_link.data(), t.c_link.size() * 4);
     const size_t i_tl = add(t.t_link.data(), t.t_link.size() * 4);
-    const size_t i_ca = add(t.c_any.data(), t.c_any.size());
-    const size_t i_ta = add(t.t_any.data(), t.t_any.size());
     cuda_check(cudaSetDevice(p.device), "cudaSetDevice");
     cuda_check(cudaMalloc(&p.d_tags, total + 256), "cudaMalloc(tag tables)");
     uint8_t* base = static_cast<uint8_t*>(p.d_tags);
@@ -237,15 +245,17 @@ void upload_tags(vpt_predictor& p) {
     d.tok_bytes = base + parts[i_bytes].off;
     d.tok_info = reinterpret_cast<const TagTokenInfo*>(base + parts[i_info].off);
     d.pool = reinterpret_cast<const int32_t*>(base + parts[i_pool].off);
-    d.cw_tab = reinterpret_cast<const TagWeightSlot*>(base + parts[i_cw].off);
-    d.tw_tab = reinterpret_cast<const TagWeightSlot*>(base + parts[i_tw].off);
+    d.keys = reinterpret_cast<const TagKey*>(base + parts[i_keys].off);
+    d.ts_slot = reinterpret_cast<const uint32_t*>(base + parts[i_tss].off);
+    d.ts_cand = reinterpret_cast<const uint32_t*>(base + parts[i_tsc].off);
+    d.ts_ref = reinterpret_cast<const uint2*>(base + parts[i_tsr].off);
+    d.ts_bytes = base + parts[i_tsb].off;
+    d.max_suffix = t.max_suffix;
+    d.c_chain = reinterpret_cast<const TagChain*>(base + parts[i_cc].off);
+    d.t_chain = reinterpret_cast<const TagChain*>(base + parts[i_tc].off);
     d.c_link = reinterpret_cast<const uint32_t*>(base + parts[i_cl].off);
     d.t_link = reinterpret_cast<const uint32_t*>(base + parts[i_tl].off);
-    d.c_any = base + parts[i_ca].off;
-    d.t_any = base + parts[i_ta].off;
     d.tok_mask = t.tok_mask;
-    d.cw_mask = t.cw_mask;
-    d.tw_mask = t.tw_mask;
     d.n_tags = t.n_tags;
     d.char_rels = p.char_tags ? t.char_rels : 0;
     d.type_rels = p.type_tags ? t.type_rels : 0;
@@ -930,7 +940,7 @@ void lines_stage0(Scratch& s, LineChunk& ch, const uint8_t* utf8) {
 }
 
 // stage 1: line offsets, count + score, tokenised bytes; the output size to pinned host memory
-void lines_stage1(const vpt_predictor& p, Scratch& s, LineChunk& ch, bool normalize, uint32_t wsconst) {
+void lines_stage1(const vpt_predictor& p, Scratch& s, LineChunk& ch, bool normalize, uint32_t wsconst, bool tags) {
     cudaStream_t st = s.stream;
     cuda_check(cudaEventSynchronize(ch.split), "sync(split)");
     const size_t n = size_t(s.h_totals[2]);
@@ -948,7 +958,8 @@ void lines_stage1(const vpt_predictor& p, Scratch& s, LineChunk& ch, bool normal
     Scratch::ensure(s.d_bounds, s.bounds_cap, ch.nbytes + 4);
     Scratch::ensure(s.d_tokg, s.tokg_cap, 8 * (ng + 2));
     // surface bytes + at most one '\\' per byte + at most one ' ' per character + one '\n' per line
-    Scratch::ensure(s.d_out, s.out_cap, 3 * ch.nbytes + n + 4);
+    // (with tags: every token -- at most one per byte -- may get the longest "/tag/.." suffix of the model)
+    Scratch::ensure(s.d_out, s.out_cap, 3 * ch.nbytes + n + 4 + (tags ? size_t(ch.nbytes) * p.dt.max_suffix : 0));
     ch.sp.offsets = static_cast<uint64_t*>(s.d_off);
     ch.sp.trims = static_cast<uint8_t*>(s.d_trims);
     // the kernels overwrite d_out, which the previous chunk of this scratch may still be copying out
@@ -973,6 +984,15 @@ void lines_stage1(const vpt_predictor& p, Scratch& s, LineChunk& ch, bool normal
         a.scores = static_cast<int32_t*>(s.d_scores);
     }
     a.boundaries = static_cast<uint8_t*>(s.d_bounds);
+    if (tags) {
+        // tag prediction needs the pattern-id states and the character offsets of the sentences
+        Scratch::ensure(s.d_cst, s.cst_cap, 4 * ch.nbytes + 16);
+        Scratch::ensure(s.d_tst, s.tst_cap, 4 * ch.nbytes + 16);
+        Scratch::ensure(s.d_coff, s.coff_cap, 8 * (n + 1));
+        a.char_states = static_cast<uint32_t*>(s.d_cst);
+        a.type_states = static_cast<uint32_t*>(s.d_tst);
+        a.char_offsets = static_cast<uint64_t*>(s.d_coff);
+    }
     if (pipeline_trace()) ch.tr.mark_sub(0, st);  // after the line offsets
     if (!fused_ok(dm)) cuda_check(launch_count(a, st), "launch(count)");
     if (pipeline_trace()) ch.tr.mark_sub(1, st);  // after count + scan (none when the scoring launch is fused)
@@ -994,6 +1014,57 @@ void lines_stage1(const vpt_predictor& p, Scratch& s, LineChunk& ch, bool normal
     t.out = static_cast<uint8_t*>(s.d_out);
     cuda_check(launch_wsconst(t, a.boundaries, wsconst, normalize, st), "launch(wsconst)");
     if (wsconst & 0x80u) cuda_check(launch_grapheme(t, a.boundaries, normalize, st), "launch(grapheme)");
+    if (tags) {
+        // tokens per sentence and their prefix, then the tag prediction into per-token records (the post-filters ran:
+        // fill_tags sees the final boundaries, predict/src/main.rs:157-160)
+        CompactArgs k;
+        k.n_sent = n;
+        k.status = a.status;
+        k.n_chars = a.n_chars;
+        k.boundaries = a.boundaries;
+        k.bound_offsets = a.bound_offsets;
+        k.n_bound = 0;  // no bit stream on this path
+        Scratch::ensure(s.d_st8, s.st8_cap, n + 16);
+        Scratch::ensure(s.d_ntok, s.ntok_cap, 4 * n + 16);
+        Scratch::ensure(s.d_tokbase, s.tokbase_cap, 8 * (n + 1) + 16);
+        Scratch::ensure(s.d_toklocal, s.toklocal_cap, 4 * n + 16);
+        Scratch::ensure(s.d_tokblk, s.tokblk_cap, 8 * (n / 256 + 4));
+        k.status8 = static_cast<uint8_t*>(s.d_st8);
+        k.n_tokens = static_cast<uint32_t*>(s.d_ntok);
+        k.tok_base = static_cast<uint64_t*>(s.d_tokbase);
+        k.tok_local = static_cast<uint32_t*>(s.d_toklocal);
+        k.tok_blk = static_cast<uint64_t*>(s.d_tokblk);
+        cuda_check(launch_compact(k, st), "launch(compact)");
+        Scratch::ensure(s.d_tok, s.tok_cap, 4 * ch.nbytes + 16);
+        Scratch::ensure(s.d_cand, s.cand_cap, ch.nbytes * std::max<size_t>(p.n_tags, 1) + 16);
+        Scratch::ensure(s.d_tokdesc, s.tokdesc_cap, 16 * ch.nbytes + 16);
+        TagArgs g;
+        g.text = a.text;
+        g.offsets = a.offsets;
+        g.trims = a.trims;
+        g.n_sent = n;
+        g.status = a.status;
+        g.boundaries = a.boundaries;
+        g.bound_offsets = a.bound_offsets;
+        g.char_offsets = a.char_offsets;
+        g.char_states = p.dt.char_rels ? a.char_states : nullptr;
+        g.type_states = p.dt.type_rels ? a.type_states : nullptr;
+        g.tok_base = k.tok_base;
+        g.tok_ids = static_cast<int32_t*>(s.d_tok);
+        g.tok_cands = static_cast<uint8_t*>(s.d_cand);
+        g.tok_desc = static_cast<uint4*>(s.d_tokdesc);
+        g.max_tokens = ch.nbytes;
+        g.norm = normalize ? 1 : 0;
+        cuda_check(launch_tags(p.dt, g, st), "launch(tags)");
+        t.tok_base = k.tok_base;
+        t.tok_ids = g.tok_ids;
+        t.tok_cands = g.tok_cands;
+        t.n_tags = uint32_t(p.n_tags);
+        t.ts_slot = p.dt.ts_slot;
+        t.ts_cand = p.dt.ts_cand;
+        t.ts_ref = p.dt.ts_ref;
+        t.ts_bytes = p.dt.ts_bytes;
+    }
     cuda_check(launch_tokenize(t, st), "launch(tok)");
     if (pipeline_trace()) ch.tr.mark(2, st);
     cuda_check(cudaEventRecord(ch.done, st), "cudaEventRecord");
@@ -1003,10 +1074,18 @@ void lines_stage1(const vpt_predictor& p, Scratch& s, LineChunk& ch, bool normal
 
 uint32_t vpt_kytea_fullwidth(uint32_t code_point) { return kytea_fullwidth(code_point); }
 
-int vpt_tokenize_lines(const vpt_predictor* p, const uint8_t* utf8, size_t n_bytes, int no_norm, uint32_t wsconst_types,
-                       uint8_t* out, size_t out_capacity, uint64_t* out_len, uint64_t* n_lines_out) {
+namespace {
+int tokenize_lines_impl(const vpt_predictor* p, const uint8_t* utf8, size_t n_bytes, int no_norm, uint32_t wsconst_types, bool tags,
+                        uint8_t* out, size_t out_capacity, uint64_t* out_len, uint64_t* n_lines_out) {
     VPT_API_BEGIN
     require_device(p);
+    if (tags) {
+        if (!p->predict_tags || p->from_blob)
+            throw Error(kInvalidArgument, "InvalidArgumentError: this predictor is created with predict_tags = false");
+        if (p->n_tags && !p->dt.tok_tab)
+            throw Error(kUnsupported, "this tag model exceeds the limits of the device path (tags.hpp); use vpt_fill_tags");
+        if (p->n_tags == 0) tags = false;  // predictor.rs:553-555: nothing to predict
+    }
     if (out_len) *out_len = 0;
     if (n_lines_out) *n_lines_out = 0;
     if (wsconst_types & ~0xFEu)
@@ -1062,12 +1141,12 @@ int vpt_tokenize_lines(const vpt_predictor* p, const uint8_t* utf8, size_t n_byt
     const auto host_t0 = std::chrono::steady_clock::now();
     auto host_ms = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count(); };
     for (size_t c = 0; c < std::min<size_t>(3, nchunks); ++c) lines_stage0(*lease[c % kDepth]->s, chunks[c], utf8);
-    lines_stage1(*p, *lease[0]->s, chunks[0], no_norm == 0, wsconst_types);
+    lines_stage1(*p, *lease[0]->s, chunks[0], no_norm == 0, wsconst_types, tags);
     for (size_t c = 0; c < nchunks; ++c) {
         const double h0 = host_ms();
         if (c + 3 < nchunks) lines_stage0(*lease[(c + 3) % kDepth]->s, chunks[c + 3], utf8);
         const double h1 = host_ms();
-        if (c + 1 < nchunks) lines_stage1(*p, *lease[(c + 1) % kDepth]->s, chunks[c + 1], no_norm == 0, wsconst_types);
+        if (c + 1 < nchunks) lines_stage1(*p, *lease[(c + 1) % kDepth]->s, chunks[c + 1], no_norm == 0, wsconst_types, tags);
         const double h2 = host_ms();
         Scratch& s = *lease[c % kDepth]->s;
         cuda_check(cudaEventSynchronize(chunks[c].done), "sync(tokenize)");
@@ -1096,6 +1175,17 @@ int vpt_tokenize_lines(const vpt_predictor* p, const uint8_t* utf8, size_t n_byt
     if (overflow) throw Error(kInvalidArgument, "InvalidArgumentError: out_capacity: too small for the tokenized text");
     return kOk;
     VPT_API_END
+}
+}  // namespace
+
+int vpt_tokenize_lines(const vpt_predictor* p, const uint8_t* utf8, size_t n_bytes, int no_norm, uint32_t wsconst_types,
+                       uint8_t* out, size_t out_capacity, uint64_t* out_len, uint64_t* n_lines_out) {
+    return tokenize_lines_impl(p, utf8, n_bytes, no_norm, wsconst_types, false, out, out_capacity, out_len, n_lines_out);
+}
+
+int vpt_tokenize_lines_tags(const vpt_predictor* p, const uint8_t* utf8, size_t n_bytes, int no_norm, uint32_t wsconst_types,
+                            uint8_t* out, size_t out_capacity, uint64_t* out_len, uint64_t* n_lines_out) {
+    return tokenize_lines_impl(p, utf8, n_bytes, no_norm, wsconst_types, true, out, out_capacity, out_len, n_lines_out);
 }
 
 namespace {
@@ -1214,6 +1304,20 @@ int vpt_char_types(const uint8_t* utf8, size_t n_bytes, uint8_t* types_out, size
     if (n_chars_out) *n_chars_out = cps.size();
     if (cps.size() > capacity) throw Error(kInvalidArgument, "InvalidArgumentError: capacity: too small");
     for (size_t i = 0; i < cps.size(); ++i) types_out[i] = host_char_type(cps[i]);
+    return kOk;
+    VPT_API_END
+}
+
+int vpt_split_linebreaks(const uint8_t* utf8, size_t n_bytes, uint8_t* boundaries, size_t n_boundaries) {
+    VPT_API_BEGIN
+    if (n_bytes && !utf8) throw Error(kInvalidArgument, "InvalidArgumentError: utf8: must not be NULL");
+    check_raw_text(utf8, n_bytes);
+    const std::vector<uint32_t> cps = utf8_to_codepoints(std::string(reinterpret_cast<const char*>(utf8), n_bytes));
+    if (cps.size() != n_boundaries + 1 || (n_boundaries && !boundaries))
+        throw Error(kInvalidArgument, "InvalidArgumentError: boundaries: one per pair of adjacent characters");
+    auto lb = [](uint32_t c) { return c == 0x0D || c == 0x0A; };
+    for (size_t i = 0; i + 1 < cps.size(); ++i)
+        if (lb(cps[i]) || lb(cps[i + 1])) boundaries[i] = 1;
     return kOk;
     VPT_API_END
 }
@@ -1430,7 +1534,7 @@ int vpt_predict_batch_compact(const vpt_predictor* p, const uint8_t* utf8, const
         ChunkState cs;
         uint64_t nb = 0, nc = 0, nb_base = 0;
         cudaEvent_t kernels = nullptr;
-        bool issued = false;
+        bool issued = false, copied = false;
     };
     std::vector<CChunk> chunks(nchunks);
     struct EventGuard {
@@ -1449,7 +1553,15 @@ int vpt_predict_batch_compact(const vpt_predictor* p, const uint8_t* utf8, const
     const size_t nt = want_tags ? p->n_tags : 0;
     uint64_t nb_total = 0, tok_total = 0, unserved_total = 0;
     bool overflow = false;
-    std::vector<std::pair<uint64_t, const uint64_t*>> side_words;  // (word index, pinned word) of every chunk's first bit word
+    // pinned words that receive every chunk's first bit word (merged into the output at the end)
+    Scratch& s0 = *lease[0]->s;
+    if (s0.side_cap < nchunks) {
+        if (s0.h_side) { cudaFreeHost(s0.h_side); s0.h_side = nullptr; s0.side_cap = 0; }
+        const size_t want = std::max<size_t>(256, 2 * nchunks);
+        cuda_check(cudaMallocHost(reinterpret_cast<void**>(&s0.h_side), 4 * want), "cudaMallocHost");
+        s0.side_cap = want;
+    }
+    uint32_t* const h_side = s0.h_side;
     std::vector<uint32_t> h_unserved(nchunks, 0);
 
     auto stage_b = [&](size_t c) {
@@ -1499,6 +1611,10 @@ int vpt_predict_batch_compact(const vpt_predictor* p, const uint8_t* utf8, const
             Scratch::ensure(s.d_tokbase, s.tokbase_cap, 8 * (ch.n + 1) + 16);
             k.n_tokens = static_cast<uint32_t*>(s.d_ntok);
             k.tok_base = static_cast<uint64_t*>(s.d_tokbase);
+            Scratch::ensure(s.d_toklocal, s.toklocal_cap, 4 * ch.n + 16);
+            Scratch::ensure(s.d_tokblk, s.tokblk_cap, 8 * (ch.n / 256 + 4));
+            k.tok_local = static_cast<uint32_t*>(s.d_toklocal);
+            k.tok_blk = static_cast<uint64_t*>(s.d_tokblk);
             k.tok_total_host = &s.h_totals[4];
         }
         s.h_totals[4] = 0;
@@ -1523,6 +1639,10 @@ int vpt_predict_batch_compact(const vpt_predictor* p, const uint8_t* utf8, const
             t.tok_base = k.tok_base;
             t.tok_ids = static_cast<int32_t*>(s.d_tok);
             t.tok_cands = static_cast<uint8_t*>(s.d_cand);
+            Scratch::ensure(s.d_tokdesc, s.tokdesc_cap, 16 * cc.nc + 16);
+            t.tok_desc = static_cast<uint4*>(s.d_tokdesc);
+            t.max_tokens = cc.nc;
+            t.text_base = 0;
             cuda_check(launch_tags(p->dt, t, st), "launch(tags)");
             cuda_check(cudaMemcpyAsync(&h_unserved[c], d_unserved, 4, cudaMemcpyDeviceToHost, st), "D2H(unserved)");
         }
@@ -1548,7 +1668,7 @@ int vpt_predict_batch_compact(const vpt_predictor* p, const uint8_t* utf8, const
                 // the chunk's first word may share its low bits with the previous chunk: it comes back through a pinned
                 // word and is merged on the host at the end; the other words go straight to their place
                 if (bit_base == 0) boundary_bits_out[w0] = 0;
-                cuda_check(cudaMemcpyAsync(&s.h_totals[5], s.d_bits, 4, cudaMemcpyDeviceToHost, so), "D2H(bits)");
+                cuda_check(cudaMemcpyAsync(&h_side[c], s.d_bits, 4, cudaMemcpyDeviceToHost, so), "D2H(bits)");
                 if (nwords > 1)
                     cuda_check(cudaMemcpyAsync(boundary_bits_out + w0 + 1, static_cast<uint32_t*>(s.d_bits) + 1, 4 * (nwords - 1),
                                                cudaMemcpyDeviceToHost, so), "D2H(bits)");
@@ -1563,11 +1683,7 @@ int vpt_predict_batch_compact(const vpt_predictor* p, const uint8_t* utf8, const
         }
         cuda_check(cudaEventRecord(s.ev_out, so), "cudaEventRecord");
         if (pipeline_trace()) ch.tr.mark(3, so);
-        if (!overflow && cc.nb) {
-            // the pinned word is reused by the chunk that takes this scratch next: read it once the copy has landed
-            cuda_check(cudaEventSynchronize(s.ev_out), "sync(copy-out)");
-            boundary_bits_out[cc.nb_base >> 5] |= uint32_t(s.h_totals[5]);
-        }
+        cc.copied = !overflow && cc.nb != 0;
         tok_total += ntok;
     };
     // A runs kDepth - 2 chunks ahead of B, B one chunk ahead of C (a scratch is free again when its chunk's C is done)
@@ -1584,6 +1700,8 @@ int vpt_predict_batch_compact(const vpt_predictor* p, const uint8_t* utf8, const
             cuda_check(cudaStreamSynchronize(lease[i]->s->stream_out), "sync(copy-out)");
         }
     for (uint32_t u : h_unserved) unserved_total += u;
+    for (size_t c = 0; c < nchunks; ++c)
+        if (chunks[c].copied) boundary_bits_out[chunks[c].nb_base >> 5] |= h_side[c];
     if (pipeline_trace())
         for (size_t c = 0; c < nchunks; ++c) chunks[c].cs.tr.print("compact", c, chunks[c].cs.n, chunks[0].cs.tr);
     if (n_boundaries_out) *n_boundaries_out = nb_total;

@@ -121,6 +121,16 @@ struct TokArgs {
     uint64_t* total = nullptr;              // device scalar out: total output bytes
     uint64_t* total_host = nullptr;         // nullable: pinned host memory, receives the same number
     uint8_t* out = nullptr;                 // tokenised lines, each terminated by '\n'
+    // tags (vpt_tokenize_lines_tags): the per-token records of the tag prediction and the model's tag strings; a token's
+    // "/tag" suffixes are written behind its surface (Sentence::write_tokenized_text, sentence.rs:850-886)
+    const uint64_t* tok_base = nullptr;     // [n_sent + 1] index of a sentence's first token record; nullptr = no tags
+    const int32_t* tok_ids = nullptr;       // [n_tokens] token id or -1
+    const uint8_t* tok_cands = nullptr;     // [n_tokens * n_tags] chosen candidate per slot, 255 = none
+    uint32_t n_tags = 0;
+    const uint32_t* ts_slot = nullptr;      // [n_token_ids] first slot entry of a token id
+    const uint32_t* ts_cand = nullptr;      // [sum of slots] first string reference of a slot
+    const uint2* ts_ref = nullptr;          // [sum of candidates] (offset, length) of the escaped tag string
+    const uint8_t* ts_bytes = nullptr;
 };
 // zeroes tok_state[0 .. n_groups] (ticket included), then one pass: lengths, offsets (look-back), output bytes
 cudaError_t launch_tokenize(const TokArgs& t, cudaStream_t stream);

@@ -376,6 +376,199 @@ __global__ void __launch_bounds__(kTokThreads) k_tok_write(TokArgs t, uint64_t n
     }
 }
 
+// ---- tokenised output with tags (the CLI's --predict-tags: main.rs:130-136,159-166 + sentence.rs:850-886) ------------------
+// Same three steps as k_tok_write; every token's surface is followed by '/' + tag for its tag slots up to the last one
+// that has a tag (an empty string for a slot without one), the strings escaped like the surface.  The suffix of the
+// token that ends in front of a character travels with that character's ' ' (it is written right before it); the last
+// token's suffix goes in front of the '\n'.  A token's record is tok_base[sentence] + (word boundaries before it).
+__device__ __forceinline__ uint32_t tag_suffix_len(const TokArgs& t, uint64_t rec) {
+    const int32_t tid = t.tok_ids[rec];
+    if (tid < 0) return 0;
+    const uint32_t sb = __ldg(t.ts_slot + tid);
+    uint32_t len = 0, run = 0;
+    for (uint32_t k = 0; k < t.n_tags; ++k) {
+        const uint32_t c = t.tok_cands[rec * t.n_tags + k];
+        ++run;  // the '/'
+        if (c != 255u) {
+            run += __ldg(t.ts_ref + __ldg(t.ts_cand + sb + k) + c).y;
+            len += run;  // slots up to this one count
+            run = 0;
+        }
+    }
+    return len;
+}
+__device__ __forceinline__ void tag_suffix_write(const TokArgs& t, uint64_t rec, uint8_t* __restrict__ out) {
+    const int32_t tid = t.tok_ids[rec];
+    if (tid < 0) return;
+    const uint32_t sb = __ldg(t.ts_slot + tid);
+    int last = -1;
+    for (uint32_t k = 0; k < t.n_tags; ++k) if (t.tok_cands[rec * t.n_tags + k] != 255u) last = int(k);
+    uint32_t at = 0;
+    for (int k = 0; k <= last; ++k) {
+        out[at++] = 0x2F;
+        const uint32_t c = t.tok_cands[rec * t.n_tags + k];
+        if (c == 255u) continue;
+        const uint2 ref = __ldg(t.ts_ref + __ldg(t.ts_cand + sb + k) + c);
+        for (uint32_t j = 0; j < ref.y; ++j) out[at++] = __ldg(t.ts_bytes + ref.x + j);
+    }
+}
+
+// One sentence by one warp: returns the output length without the '\n'; writes the bytes when kWrite.
+template <bool kWrite>
+__device__ __forceinline__ uint32_t tagged_sentence(const TokArgs& t, uint64_t s, uint64_t o0, uint64_t o1, uint32_t trim, uint32_t nch,
+                                                    uint8_t* __restrict__ out, int lane) {
+    const uint64_t a0 = o0 & ~3ull;
+    const uint32_t b0 = uint32_t(o0 - a0), b1 = uint32_t(o1 - a0) - trim;
+    const uint8_t* __restrict__ base = t.text + a0;
+    const uint8_t* __restrict__ bnd = t.boundaries + t.bound_offsets[s];
+    const uint64_t rec0 = t.tok_base[s];
+    uint32_t chars = 0, extra = 0, toks = 0;  // characters / inserted bytes / tokens that ended before this window
+    for (uint32_t w0 = 0; w0 < b1; w0 += 128) {
+        const uint32_t addr = w0 + 4u * uint32_t(lane);
+        uint32_t lo = 0, in80 = 0;
+        if (addr < b1) {
+            lo = __ldg(reinterpret_cast<const uint32_t*>(base + addr));
+            in80 = inside80(addr, b0, b1);
+        }
+        const uint32_t st80 = ~(lo & ~(lo << 1)) & in80;
+        const uint32_t nst = __popc(st80);
+        const uint32_t st_incl = warp_incl_scan_u32(nst, lane);
+        // a ' ' (and the suffix of the token that just ended) goes before character k >= 1 when boundary k-1 is set
+        uint32_t sp80 = 0;
+        {
+            uint32_t k = chars + st_incl - nst;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (st80 & (0x80u << (8 * j))) {
+                    if (k >= 1 && bnd[k - 1] == 1) sp80 |= 0x80u << (8 * j);
+                    ++k;
+                }
+            }
+        }
+        const uint32_t nsp = __popc(sp80);
+        const uint32_t sp_incl = warp_incl_scan_u32(nsp, lane);
+        uint32_t sl[4] = {0, 0, 0, 0}, sl_sum = 0;
+        {
+            uint64_t rec = rec0 + toks + sp_incl - nsp;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (sp80 & (0x80u << (8 * j))) {
+                    sl[j] = tag_suffix_len(t, rec);
+                    sl_sum += sl[j];
+                    ++rec;
+                }
+            }
+        }
+        const uint32_t esc80 = (eq_bytes(lo, 0x20u) | eq_bytes(lo, 0x2Fu) | eq_bytes(lo, 0x5Cu)) & in80;
+        const uint32_t nex = nsp + __popc(esc80) + sl_sum;
+        const uint32_t ex_incl = warp_incl_scan_u32(nex, lane);
+        if (kWrite) {
+            uint32_t at = (addr - b0) + extra + ex_incl - nex;  // output index of byte 0 of this word (if inside)
+            uint64_t rec = rec0 + toks + sp_incl - nsp;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t bit = 0x80u << (8 * j);
+                if (in80 & bit) {
+                    if (sp80 & bit) {
+                        tag_suffix_write(t, rec, out + at);
+                        at += sl[j];
+                        ++rec;
+                        out[at++] = 0x20;
+                    }
+                    if (esc80 & bit) out[at++] = 0x5C;
+                    out[at] = uint8_t(lo >> (8 * j));
+                }
+                ++at;
+            }
+        }
+        extra += __shfl_sync(kFull, ex_incl, 31);
+        chars += __shfl_sync(kFull, st_incl, 31);
+        toks += __shfl_sync(kFull, sp_incl, 31);
+    }
+    uint32_t len = (b1 - b0) + extra;
+    if (nch > 0) {
+        const uint32_t last = tag_suffix_len(t, rec0 + toks);
+        if (kWrite && lane == 0) tag_suffix_write(t, rec0 + toks, out + len);
+        len += last;
+    }
+    return len;
+}
+
+__global__ void __launch_bounds__(kTokThreads) k_tok_write_tags(TokArgs t, uint64_t ngroups) {
+    __shared__ uint64_t s_off[kGroup + 1];
+    __shared__ uint32_t s_nch[kGroup], s_len[kGroup], s_excl[kGroup];
+    __shared__ uint8_t s_trim[kGroup], s_bad[kGroup];
+    __shared__ uint64_t s_base;
+    __shared__ uint32_t s_grp;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_grp = atomicAdd(t.ticket, 1u);
+    __syncthreads();
+    const uint64_t grp = s_grp;
+    const uint64_t gbase = grp * kGroup;
+    const int ns = int(min(uint64_t(kGroup), t.n_sent - gbase));
+    if (threadIdx.x <= ns) s_off[threadIdx.x] = t.offsets[gbase + threadIdx.x];
+    if (threadIdx.x < kGroup) s_len[threadIdx.x] = 0;
+    if (threadIdx.x < ns) {
+        const uint64_t s = gbase + threadIdx.x;
+        s_nch[threadIdx.x] = t.n_chars[s];
+        s_trim[threadIdx.x] = t.trims ? t.trims[s] : uint8_t(0);
+        s_bad[threadIdx.x] = t.status[s] != 0;
+    }
+    __syncthreads();
+    // 1. output bytes per sentence
+    for (int i = warp; i < ns; i += kTokThreads / 32) {
+        uint32_t len = 1;  // the '\n'
+        if (!s_bad[i]) len += tagged_sentence<false>(t, gbase + i, s_off[i], s_off[i + 1], s_trim[i], s_nch[i], nullptr, lane);
+        if (lane == 0) s_len[i] = len;
+    }
+    __syncthreads();
+    // 2. offsets: scan inside the group, look-back across groups (as k_tok_write)
+    if (warp == 0) {
+        const uint32_t v0 = s_len[2 * lane], v1 = s_len[2 * lane + 1];
+        const uint32_t iv = warp_incl_scan_u32(v0 + v1, lane);
+        s_excl[2 * lane] = iv - v0 - v1;
+        s_excl[2 * lane + 1] = iv - v1;
+        const uint64_t total = __shfl_sync(kFull, iv, 31);
+        volatile uint64_t* state = t.tok_state;
+        if (lane == 0) state[grp] = (grp == 0 ? kStIncl : kStAgg) | total;
+        uint64_t prefix = 0;
+        if (grp > 0) {
+            int64_t idx = int64_t(grp) - 1;
+            for (;;) {
+                const int64_t j = idx - lane;
+                uint64_t v = kStIncl;
+                if (j >= 0) {
+                    do { v = state[j]; } while ((v >> 62) == 0);
+                }
+                const unsigned incl = __ballot_sync(kFull, (v >> 62) == 2);
+                const int stop = incl ? __ffs(incl) - 1 : 32;
+                uint64_t add = lane <= stop ? (v & kStMask) : 0;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) add += __shfl_xor_sync(kFull, add, d);
+                prefix += add;
+                if (incl) break;
+                idx -= 32;
+            }
+            if (lane == 0) state[grp] = kStIncl | (prefix + total);
+        }
+        if (lane == 0) {
+            s_base = prefix;
+            if (grp + 1 == ngroups) {
+                *t.total = prefix + total;
+                if (t.total_host) *t.total_host = prefix + total;
+            }
+        }
+    }
+    __syncthreads();
+    // 3. write
+    const uint64_t gout = s_base;
+    for (int i = warp; i < ns; i += kTokThreads / 32) {
+        uint8_t* __restrict__ out = t.out + gout + s_excl[i];
+        if (lane == 0) out[s_len[i] - 1] = 0x0A;
+        if (!s_bad[i]) tagged_sentence<true>(t, gbase + i, s_off[i], s_off[i + 1], s_trim[i], s_nch[i], out, lane);
+    }
+}
+
 // KyteaWsConstFilter (vaporetto_rules/src/sentence_filters/kytea_wsconst.rs:27-44) for a set of character types —
 // the CLI's --wsconst D/R/H/T/K/O options, applied after prediction (predict/src/main.rs:100-106,157): boundary i
 // becomes NotWordBoundary when characters i and i+1 have the same type and that type is in `mask` (bit t = type t).
@@ -592,7 +785,8 @@ cudaError_t launch_tokenize(const TokArgs& t, cudaStream_t stream) {
     // look-back state words + the ticket that follows them
     cudaError_t e = cudaMemsetAsync(t.tok_state, 0, 8 * (ngroups + 1), stream);
     if (e != cudaSuccess) return e;
-    k_tok_write<<<unsigned(ngroups), kTokThreads, 0, stream>>>(t, ngroups);
+    if (t.tok_base) k_tok_write_tags<<<unsigned(ngroups), kTokThreads, 0, stream>>>(t, ngroups);
+    else k_tok_write<<<unsigned(ngroups), kTokThreads, 0, stream>>>(t, ngroups);
     return cudaGetLastError();
 }
 

@@ -5,14 +5,20 @@
 // Tables (one device allocation per predictor, built by build_tag_tables):
 //   * token table   open addressing over a 64-bit hash of the token's bytes; an entry holds the hash, the token id and
 //                   where the token's bytes live (compared byte by byte: the lookup is exact)
-//   * token info    per token id: bias vector (i32 pool), number of tag slots, candidates per slot
-//   * weight tables (char scorer, type scorer) open addressing over (pattern id, token id, rel position) -> the
-//                   pattern's OWN weight vector in the i32 pool.  The reference merges the vectors of a pattern's suffix
-//                   patterns into it at build time (PositionalWeightWithTag +=, predictor.rs:242-262, along
-//                   char_scorer.rs:50-78); here the kernel walks `suffix_link` and adds the chain with the same
-//                   truncation rule (element k of a shorter suffix's vector counts only while every longer pattern on
-//                   the chain has an own vector longer than k) -- identical sums, no 300-second materialisation.
-//   * chain flags   per pattern id: 1 if the pattern or one of its suffix patterns has any tag weight at all
+//   * token info    per token id: bias vector (i32 pool), number of tag slots, candidates per slot, and where the
+//                   token's KEY LIST lives
+//   * key lists     per token, contiguous: one 16-byte entry per (pattern id, rel position) that carries an OWN weight
+//                   vector for this token -- the char scorer's entries first, then the type scorer's; each part sorted by
+//                   rel position and, within one rel position, by pattern length (suffix-chain depth), longest first.
+//                   The reference merges the vectors of a pattern's suffix patterns into it at build time
+//                   (PositionalWeightWithTag +=, predictor.rs:242-262, along char_scorer.rs:50-78); here the kernel
+//                   adds, for the pattern found at a position, the own vectors of the patterns on its suffix chain with
+//                   the same truncation rule (element k of a shorter suffix's vector counts only while every longer
+//                   pattern on the chain has an own vector longer than k) -- identical sums, no 300-second
+//                   materialisation.  Scanning the token's short list in this order visits the chain members longest
+//                   first, which is the order the rule needs.
+//   * chain tables  per pattern id: the next four patterns on its suffix chain (16 bytes, one load); longer chains
+//                   (dictionary words) continue through `link`
 #pragma once
 #include <cstdint>
 #include <vector>
@@ -33,33 +39,48 @@ struct TagTokenEntry {   // 24 bytes
     uint32_t len;
     uint32_t pad;
 };
-struct TagTokenInfo {    // per token id
+struct alignas(16) TagTokenInfo {    // per token id, 32 bytes
     uint32_t bias_off;   // into the i32 pool
     uint16_t bias_len;
     uint8_t n_slots;     // tags.size() (slots beyond n_tags never exist)
     uint8_t usable;      // 0: the token's model exceeds the device limits (never happens for the reference's models)
     uint8_t cand[kTagMaxSlots];  // candidates per slot (255 = too many)
+    uint32_t key_off;    // first entry of the token's key list
+    uint8_t ckeys[4];    // char scorer entries with rel position 0 .. 3, then
+    uint8_t tkeys[4];    // type scorer entries with rel position 0 .. 3 (after all char entries)
+    uint16_t c_rest;     // char scorer entries with rel position >= 4 (windows wider than 3), after ckeys
+    uint16_t t_rest;     // type scorer entries with rel position >= 4
 };
-struct TagWeightSlot {  // 16 bytes
-    uint64_t key;        // (pid << 32 | tid << 8 | rel) + 1; 0 = empty
-    uint32_t off;        // into the i32 pool
+static_assert(sizeof(TagTokenInfo) == 32, "TagTokenInfo layout");
+struct TagKey {          // 16 bytes
+    uint32_t pid;        // pattern id
+    uint32_t off;        // the own weight vector, into the i32 pool
     uint32_t len;
+    uint32_t rel;        // rel position
+};
+struct TagChain {        // 16 bytes: patterns 1..4 steps down the suffix chain of a pattern (kNoPattern = end)
+    uint32_t next[4];
 };
 
 struct TagTablesHost {
     bool usable = false;           // false: some limit is exceeded -> only the host path (vpt_fill_tags) serves the model
     uint32_t n_tags = 0, n_tokens = 0;
     uint32_t tok_mask = 0;         // token table capacity - 1 (power of two)
-    uint32_t cw_mask = 0, tw_mask = 0;
     uint32_t char_rels = 0, type_rels = 0;   // rel positions 0 .. rels-1 carry weights (window + 1)
     uint32_t max_token_bytes = 0;
     std::vector<TagTokenEntry> tok_tab;
     std::vector<uint8_t> tok_bytes;
     std::vector<TagTokenInfo> tok_info;
     std::vector<int32_t> pool;
-    std::vector<TagWeightSlot> cw_tab, tw_tab;
+    // tag strings, escaped as write_tokenized_text writes them (' ', '\\', '/' behind a '\\'): ts_slot[tid] -> first slot
+    // entry, ts_cand[slot entry] -> first string reference, ts_ref = (offset, length) into ts_bytes
+    std::vector<uint32_t> ts_slot, ts_cand;
+    std::vector<uint32_t> ts_ref;              // pairs
+    std::vector<uint8_t> ts_bytes;
+    uint32_t max_suffix = 0;                   // longest "/tag/tag..." suffix a token can get
+    std::vector<TagKey> keys;
+    std::vector<TagChain> c_chain, t_chain;
     std::vector<uint32_t> c_link, t_link;      // suffix links by pattern id
-    std::vector<uint8_t> c_any, t_any;         // chain flags
 };
 
 TagTablesHost build_tag_tables(const HostPredictor& hp);
@@ -69,13 +90,17 @@ struct DevTags {
     const uint8_t* tok_bytes = nullptr;
     const TagTokenInfo* tok_info = nullptr;
     const int32_t* pool = nullptr;
-    const TagWeightSlot* cw_tab = nullptr;
-    const TagWeightSlot* tw_tab = nullptr;
+    const uint32_t* ts_slot = nullptr;
+    const uint32_t* ts_cand = nullptr;
+    const uint2* ts_ref = nullptr;
+    const uint8_t* ts_bytes = nullptr;
+    uint32_t max_suffix = 0;
+    const TagKey* keys = nullptr;
+    const TagChain* c_chain = nullptr;
+    const TagChain* t_chain = nullptr;
     const uint32_t* c_link = nullptr;
     const uint32_t* t_link = nullptr;
-    const uint8_t* c_any = nullptr;
-    const uint8_t* t_any = nullptr;
-    uint32_t tok_mask = 0, cw_mask = 0, tw_mask = 0;
+    uint32_t tok_mask = 0;
     uint32_t n_tags = 0, char_rels = 0, type_rels = 0, max_token_bytes = 0;
     uint32_t n_char_patterns = 0, n_type_patterns = 0;
 };
@@ -100,6 +125,14 @@ struct TagArgs {
     const uint64_t* tok_base = nullptr;     // [n_sent + 1] exclusive prefix of the tokens per sentence; selects this mode
     int32_t* tok_ids = nullptr;             // [n_tokens] token id or -1
     uint8_t* tok_cands = nullptr;           // [n_tokens * n_tags] chosen candidate per slot, 255 = none
+    // with tok_desc the sentence-warp kernel only LOCATES the tokens (16 bytes each: byte offset from text + text_base,
+    // index of the last character, byte length | characters left in the sentence << 16) and a second kernel, one thread per
+    // token, predicts the tags: full lanes and short dependent-load chains instead of one sentence per warp
+    uint4* tok_desc = nullptr;              // [max_tokens] scratch; nullable (then k_tags does everything itself)
+    uint64_t max_tokens = 0;                // bound on the number of tokens (e.g. the number of characters)
+    uint64_t text_base = 0;                 // byte offset the descriptors are relative to (keeps them below 2^64 safely)
+    int norm = 0;                           // tokens are looked up by their KyteaFullwidthFilter image (the CLI default:
+                                            // fill_tags runs on the pre-filtered sentence, predict/src/main.rs:153-166)
 };
 
 // Compact outputs (vpt_predict_batch_compact): boundaries as one bit each, tokens per sentence and their prefix.
@@ -116,6 +149,8 @@ struct CompactArgs {
     uint8_t* status8 = nullptr;               // [n_sent]
     uint32_t* n_tokens = nullptr;             // [n_sent] tokens per sentence (0 for a rejected sentence); nullable
     uint64_t* tok_base = nullptr;             // [n_sent + 1]; nullable with n_tokens
+    uint32_t* tok_local = nullptr;            // [n_sent] scratch: prefix inside a block of 256 sentences
+    uint64_t* tok_blk = nullptr;              // [n_sent / 256 + 2] scratch: block totals, then their prefix
     uint64_t* tok_total_host = nullptr;       // nullable: pinned host word that receives the number of tokens
 };
 cudaError_t launch_compact(const CompactArgs& c, cudaStream_t stream);
@@ -138,15 +173,6 @@ VPT_TAG_HD uint64_t tag_hash_finish(uint64_t h) {
     return h | 1ull;  // never 0 (0 marks an empty entry)
 }
 constexpr uint64_t kTagHashInit = 0xCBF29CE484222325ull;
-
-VPT_TAG_HD uint64_t tag_weight_key(uint32_t pid, uint32_t tid, uint32_t rel) {
-    return ((uint64_t(pid) << 32) | (uint64_t(tid) << 8) | uint64_t(rel)) + 1ull;
-}
-VPT_TAG_HD uint32_t tag_weight_slot(uint64_t key, uint32_t mask) {
-    uint64_t h = key * 0x9E3779B97F4A7C15ull;
-    h ^= h >> 31;
-    return uint32_t(h) & mask;
-}
 
 cudaError_t launch_tags(const DevTags& t, const TagArgs& a, cudaStream_t stream);
 

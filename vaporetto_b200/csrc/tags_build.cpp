@@ -16,54 +16,55 @@ uint32_t pow2_at_least(size_t n) {
     return c;
 }
 
-void fill_weight_table(const TagWeightMap& tw, std::vector<TagWeightSlot>& tab, uint32_t& mask, std::vector<int32_t>& pool,
-                       uint32_t& rels) {
-    size_t n = 0;
-    rels = 0;
-    for (const auto& per_rel : tw) {
-        rels = std::max<uint32_t>(rels, uint32_t(per_rel.size()));
-        for (const auto& m : per_rel) n += m.size();
-    }
-    const uint32_t cap = pow2_at_least(2 * n + 16);
-    mask = cap - 1;
-    tab.assign(cap, TagWeightSlot{0, 0, 0});
-    for (size_t tid = 0; tid < tw.size(); ++tid)
-        for (size_t rel = 0; rel < tw[tid].size(); ++rel)
-            for (const auto& kv : tw[tid][rel]) {
-                const uint64_t key = tag_weight_key(kv.first, uint32_t(tid), uint32_t(rel));
-                uint32_t s = tag_weight_slot(key, mask);
-                while (tab[s].key != 0) s = (s + 1) & mask;
-                tab[s].key = key;
-                tab[s].off = uint32_t(pool.size());
-                tab[s].len = uint32_t(kv.second.size());
-                pool.insert(pool.end(), kv.second.begin(), kv.second.end());
-            }
-}
-
-// 1 for every pattern that has an own tag weight or whose suffix chain reaches one
-std::vector<uint8_t> chain_flags(const TagWeightMap& tw, const std::vector<uint32_t>& link) {
-    std::vector<uint8_t> own(link.size(), 0), any(link.size(), 2);  // 2 = unknown
-    for (const auto& per_rel : tw)
-        for (const auto& m : per_rel)
-            for (const auto& kv : m)
-                if (kv.first < own.size()) own[kv.first] = 1;
+// suffix-chain depth of every pattern (1 = no suffix pattern): along a chain the depth falls by one per link
+std::vector<uint32_t> chain_depths(const std::vector<uint32_t>& link) {
+    std::vector<uint32_t> depth(link.size(), 0);
     std::vector<uint32_t> path;
     for (uint32_t p = 0; p < link.size(); ++p) {
-        if (any[p] != 2) continue;
+        if (depth[p]) continue;
         path.clear();
         uint32_t q = p;
-        uint8_t v = 0;
-        while (true) {
-            if (any[q] != 2) { v = any[q]; break; }
-            path.push_back(q);
-            if (own[q]) { v = 1; break; }
-            if (link[q] == kNoPattern) { v = 0; break; }
-            q = link[q];
-        }
-        for (uint32_t x : path) any[x] = v;
-        // (nodes after an own entry on the path keep "unknown" and are resolved by their own iteration)
+        while (q != kNoPattern && q < link.size() && depth[q] == 0 && path.size() <= link.size()) { path.push_back(q); q = link[q]; }
+        uint32_t d = (q != kNoPattern && q < link.size()) ? depth[q] : 0;
+        for (size_t i = path.size(); i-- > 0;) depth[path[i]] = ++d;
     }
-    return any;
+    return depth;
+}
+
+std::vector<TagChain> chain_table(const std::vector<uint32_t>& link) {
+    std::vector<TagChain> t(link.size());
+    for (uint32_t p = 0; p < link.size(); ++p) {
+        uint32_t q = p;
+        for (int k = 0; k < 4; ++k) {
+            q = (q != kNoPattern && q < link.size()) ? link[q] : kNoPattern;
+            t[p].next[k] = q;
+        }
+    }
+    return t;
+}
+
+// the entries of token `tid` of one scorer, sorted by (rel, chain depth descending)
+void append_keys(const TagWeightMap& tw, size_t tid, const std::vector<uint32_t>& depth, std::vector<TagKey>& keys,
+                 std::vector<int32_t>& pool, uint32_t& rels) {
+    if (tid >= tw.size()) return;
+    const size_t first = keys.size();
+    rels = std::max<uint32_t>(rels, uint32_t(tw[tid].size()));
+    for (size_t rel = 0; rel < tw[tid].size(); ++rel)
+        for (const auto& kv : tw[tid][rel]) {
+            TagKey k;
+            k.pid = kv.first;
+            k.off = uint32_t(pool.size());
+            k.len = uint32_t(kv.second.size());
+            k.rel = uint32_t(rel);
+            pool.insert(pool.end(), kv.second.begin(), kv.second.end());
+            keys.push_back(k);
+        }
+    std::sort(keys.begin() + first, keys.end(), [&](const TagKey& a, const TagKey& b) {
+        if (a.rel != b.rel) return a.rel < b.rel;
+        const uint32_t da = a.pid < depth.size() ? depth[a.pid] : 0, db = b.pid < depth.size() ? depth[b.pid] : 0;
+        if (da != db) return da > db;
+        return a.pid < b.pid;
+    });
 }
 
 }  // namespace
@@ -91,6 +92,33 @@ TagTablesHost build_tag_tables(const HostPredictor& hp) {
         }
         t.pool.insert(t.pool.end(), tp.bias.begin(), tp.bias.end());
     }
+    // tag strings, escaped
+    for (size_t i = 0; i < hp.tag_preds.size(); ++i) {
+        const TagPredictorHost& tp = hp.tag_preds[i];
+        t.ts_slot.push_back(uint32_t(t.ts_cand.size()));
+        uint32_t suffix = 0;
+        for (size_t k = 0; k < tp.tags.size(); ++k) {
+            t.ts_cand.push_back(uint32_t(t.ts_ref.size() / 2));
+            uint32_t longest = 0;
+            for (const std::string& tag : tp.tags[k]) {
+                const uint32_t off = uint32_t(t.ts_bytes.size());
+                for (unsigned char c : tag) {
+                    if (c == ' ' || c == '\\' || c == '/') t.ts_bytes.push_back('\\');
+                    t.ts_bytes.push_back(c);
+                }
+                const uint32_t len = uint32_t(t.ts_bytes.size()) - off;
+                t.ts_ref.push_back(off);
+                t.ts_ref.push_back(len);
+                longest = std::max(longest, len);
+            }
+            suffix += 1 + longest;
+        }
+        t.max_suffix = std::max(t.max_suffix, suffix);
+    }
+    t.ts_slot.push_back(uint32_t(t.ts_cand.size()));
+    t.ts_cand.push_back(uint32_t(t.ts_ref.size() / 2));
+    t.ts_ref.push_back(0); t.ts_ref.push_back(0);
+    t.ts_bytes.resize(t.ts_bytes.size() + 16, 0);
     // token table (the map already holds "last insert wins" for duplicate tokens)
     const uint32_t cap = pow2_at_least(2 * hp.token_ids.size() + 16);
     t.tok_mask = cap - 1;
@@ -109,19 +137,38 @@ TagTablesHost build_tag_tables(const HostPredictor& hp) {
         t.max_token_bytes = std::max<uint32_t>(t.max_token_bytes, uint32_t(kv.first.size()));
     }
     t.tok_bytes.resize(t.tok_bytes.size() + 16, 0);
-    if (hp.char_tags) fill_weight_table(hp.char_tag_weight, t.cw_tab, t.cw_mask, t.pool, t.char_rels);
-    if (hp.type_tags) fill_weight_table(hp.type_tag_weight, t.tw_tab, t.tw_mask, t.pool, t.type_rels);
-    if (t.cw_tab.empty()) { t.cw_tab.assign(16, TagWeightSlot{0, 0, 0}); t.cw_mask = 15; }
-    if (t.tw_tab.empty()) { t.tw_tab.assign(16, TagWeightSlot{0, 0, 0}); t.tw_mask = 15; }
     t.c_link = hp.char_suffix_link;
     t.t_link = hp.type_suffix_link;
-    if (hp.char_tags) t.c_any = chain_flags(hp.char_tag_weight, t.c_link);
-    if (hp.type_tags) t.t_any = chain_flags(hp.type_tag_weight, t.t_link);
-    if (t.c_link.empty()) t.c_link.push_back(kNoPattern);
-    if (t.t_link.empty()) t.t_link.push_back(kNoPattern);
-    if (t.c_any.empty()) t.c_any.assign(t.c_link.size(), 0);
-    if (t.t_any.empty()) t.t_any.assign(t.t_link.size(), 0);
-    t.usable = true;
+    // key lists: per token, the char scorer's own (pattern, rel) vectors, then the type scorer's
+    const std::vector<uint32_t> c_depth = chain_depths(t.c_link), t_depth = chain_depths(t.t_link);
+    for (size_t i = 0; i < hp.tag_preds.size(); ++i) {
+        TagTokenInfo& ti = t.tok_info[i];
+        ti.key_off = uint32_t(t.keys.size());
+        size_t before = t.keys.size();
+        if (hp.char_tags) append_keys(hp.char_tag_weight, i, c_depth, t.keys, t.pool, t.char_rels);
+        const size_t nc = t.keys.size() - before;
+        before = t.keys.size();
+        if (hp.type_tags) append_keys(hp.type_tag_weight, i, t_depth, t.keys, t.pool, t.type_rels);
+        const size_t ntk = t.keys.size() - before;
+        // per-rel counts (the lists are sorted by rel): rel 0 .. 3 in bytes, the rest (wider windows) as one count
+        size_t ccnt[5] = {0, 0, 0, 0, 0}, tcnt[5] = {0, 0, 0, 0, 0};
+        for (size_t j = 0; j < nc; ++j) ++ccnt[std::min<uint32_t>(t.keys[ti.key_off + j].rel, 4)];
+        for (size_t j = 0; j < ntk; ++j) ++tcnt[std::min<uint32_t>(t.keys[ti.key_off + nc + j].rel, 4)];
+        for (int r = 0; r < 4; ++r) {
+            if (ccnt[r] > 255 || tcnt[r] > 255) ti.usable = 0;
+            ti.ckeys[r] = uint8_t(std::min<size_t>(ccnt[r], 255));
+            ti.tkeys[r] = uint8_t(std::min<size_t>(tcnt[r], 255));
+        }
+        if (ccnt[4] > 65535 || tcnt[4] > 65535) ti.usable = 0;
+        ti.c_rest = uint16_t(std::min<size_t>(ccnt[4], 65535));
+        ti.t_rest = uint16_t(std::min<size_t>(tcnt[4], 65535));
+    }
+    if (t.keys.empty()) t.keys.push_back(TagKey{kNoPattern, 0, 0, 0});
+    t.c_chain = chain_table(t.c_link);
+    t.t_chain = chain_table(t.t_link);
+    if (t.c_link.empty()) { t.c_link.push_back(kNoPattern); t.c_chain.push_back(TagChain{{kNoPattern, kNoPattern, kNoPattern, kNoPattern}}); }
+    if (t.t_link.empty()) { t.t_link.push_back(kNoPattern); t.t_chain.push_back(TagChain{{kNoPattern, kNoPattern, kNoPattern, kNoPattern}}); }
+    t.usable = t.keys.size() < (1ull << 32) && t.pool.size() < (1ull << 32);
     return t;
 }
 
