@@ -582,6 +582,32 @@ def main():
         dist.all_reduce(tl, op=dist.ReduceOp.MAX)
     e2e_lines_value = total_bytes * args.e2e_steps / float(tl.item()) / 1e6
     lines_d2h = int(tok_len.value)
+    # the same with the CLI's --predict-tags (config 3): tagged output text materialised on the device
+    e2e_lines_tags = None
+    if want_states and pred.info.get("predict_tags"):
+        h_tok2 = torch.empty(8 * (nbytes + n), dtype=torch.uint8).pin_memory()
+        tl_len, tl_lines = C.c_uint64(), C.c_uint64()
+
+        def step_lines_tags():
+            rc = L.vpt_tokenize_lines_tags(pred._h, h_lines.data_ptr(), nbytes + n, 1, 0, h_tok2.data_ptr(), h_tok2.numel(),
+                                           C.byref(tl_len), C.byref(tl_lines))
+            if rc:
+                raise RuntimeError(L.vpt_last_error().decode())
+
+        step_lines_tags()
+        step_lines_tags()
+        assert tl_lines.value == n
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            step_lines_tags()
+        torch.cuda.synchronize()
+        tlt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tlt, op=dist.ReduceOp.MAX)
+        e2e_lines_tags = {"value": round(total_bytes * args.e2e_steps / float(tlt.item()) / 1e6, 1), "unit": "MB/s",
+                          "api": "vpt_tokenize_lines_tags, no_norm = 1 (raw lines in, tokens with /tag suffixes out)",
+                          "h2d_bytes_per_step": nbytes + n, "d2h_bytes_per_step": int(tl_len.value)}
     # the literal drop-in call: Predictor::predict for ONE sentence (vpt_predict: one pinned round trip, one launch)
     one = bytes(text[int(offs[0]):int(offs[1])])
     one_sc = np.empty(len(one), np.int32)
@@ -704,6 +730,7 @@ def main():
                                           if want_states else "; no scores, no tags)"),
                                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": compact_d2h,
                                 "tokens": int(ntok_out.value), "tokens_with_tag_model": compact_known},
+                    "tokenize_lines_tags": e2e_lines_tags,
                     "tokenize_lines": {"value": round(e2e_lines_value, 1), "unit": "MB/s",
                                        "api": "vpt_tokenize_lines, no_norm = 1 (raw lines in, tokenised text out; split + "
                                               "materialisation on the device)",

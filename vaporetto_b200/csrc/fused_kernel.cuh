@@ -626,7 +626,7 @@ k_fused(DevModel m, BatchArgs a, StreamCfg cfg) {
             uint32_t u_starts[2] = {0, 0}, u_sbits[2] = {0, 0}, u_excl[2] = {0, 0};
             uint32_t carry = 0;  // packed totals of the earlier pass: chars | sentence starts << 14 | non-empty starts << 22
 #pragma unroll
-            for (int pass = 0; pass < 1; ++pass) {
+            for (int pass = 0; pass < 2; ++pass) {
                 const int u = pass * kFSubThreads + tid;
                 uint32_t packed = 0;
                 if (pass == 0 || nunits > kFSubThreads) {
@@ -692,35 +692,33 @@ k_fused(DevModel m, BatchArgs a, StreamCfg cfg) {
                 }
                 // the separator slots behind the last sentence and the padding the lagging outputs read
                 if (tid < gap + kFPadBack) s_raw[S - gap + tid] = 0;
-                // Warp w owns the 32 units (1 KiB of text) its lanes counted.  It walks them 128 bytes at a time with one
-                // 4-byte word per lane, so that all lanes step through at most four characters together (a thread
-                // walking its own 32-byte unit would leave half the warp idle): the unit's masks and exclusive counts
-                // come from the lane that counted it, the position inside the unit from a population count.
-                static_assert(kFTextCap / 32 <= kFSubThreads, "one count pass covers the tile buffer");
-                {
-                    const uint32_t* s_words = reinterpret_cast<const uint32_t*>(s_text);
-                    const uint32_t shift = 4u * (uint32_t(lane) & 7u), below = (1u << shift) - 1u;
-#pragma unroll 1
-                    for (int q = 0; q < 8; ++q) {
-                        const int owner = 4 * q + (lane >> 3);
-                        const uint32_t st = __shfl_sync(kFull, u_starts[0], owner);
-                        const uint32_t sb = __shfl_sync(kFull, u_sbits[0], owner);
-                        const uint32_t ex = __shfl_sync(kFull, u_excl[0], owner);
-                        const uint32_t st_nib = (st >> shift) & 15u, sb_nib = (sb >> shift) & 15u;
-                        uint32_t mset = st_nib | sb_nib;
-                        if (!__any_sync(kFull, mset != 0)) continue;
-                        uint32_t G = (ex & 0x3FFFu) + __popc(st & below), K = ((ex >> 14) & 0xFFu) + __popc(sb & below);
-                        uint32_t NE = (ex >> 22) + __popc(sb & st & below);
-                        uint32_t slot = G + uint32_t(gap) * K;  // slot of the next character
-                        uint32_t ol = G - NE + 1;               // its boundary index (valid once its sentence has started)
-                        const uint32_t widx = (uint32_t(warp) << 8) + (uint32_t(q) << 5) + uint32_t(lane);
-                        const uint32_t w0 = s_words[widx], w1 = s_words[widx + 1];
-                        while (mset) {
-                            const int jj = __ffs(mset) - 1;
-                            mset &= mset - 1;
-                            const uint32_t bit = 1u << jj;
-                            const bool is_start = (st_nib & bit) != 0;
-                            if (sb_nib & bit) {
+#pragma unroll
+                for (int pass = 0; pass < 2; ++pass) {
+                    const uint32_t mset = u_starts[pass] | u_sbits[pass];
+                    if (mset == 0) continue;
+                    const uint32_t ub = uint32_t(pass * kFSubThreads + tid) << 5;
+                    uint32_t G = u_excl[pass] & 0x3FFFu, K = (u_excl[pass] >> 14) & 0xFFu, NE = u_excl[pass] >> 22;
+                    uint32_t slot = G + uint32_t(gap) * K;  // slot of the next character
+                    uint32_t ol = G - NE + 1;               // its boundary index (valid once its sentence has started)
+                    // the unit's bytes travel in registers: a character's four-byte window is a funnel shift of two of
+                    // them (per-character loads from the text buffer would hit four banks: the lanes are 32 bytes apart)
+                    uint32_t w[9];
+                    {
+                        const uint4 q0 = *reinterpret_cast<const uint4*>(s_text + ub);
+                        const uint4 q1 = *reinterpret_cast<const uint4*>(s_text + ub + 16);
+                        w[0] = q0.x; w[1] = q0.y; w[2] = q0.z; w[3] = q0.w;
+                        w[4] = q1.x; w[5] = q1.y; w[6] = q1.z; w[7] = q1.w;
+                        w[8] = *reinterpret_cast<const uint32_t*>(s_text + ub + 32);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        uint32_t nib = (mset >> (4 * k)) & 15u;
+                        while (nib) {
+                            const int jj = __ffs(nib) - 1;
+                            nib &= nib - 1;
+                            const uint32_t bit = 1u << (4 * k + jj);
+                            const bool is_start = (u_starts[pass] & bit) != 0;
+                            if (u_sbits[pass] & bit) {
                                 // a sentence starts here: `gap` more separator slots; a non-empty one loses one boundary index
                                 T.first[K] = G;
                                 T.lb[K] = G - NE;
@@ -730,7 +728,7 @@ k_fused(DevModel m, BatchArgs a, StreamCfg cfg) {
                                 if (is_start) { ++NE; --ol; }
                             }
                             if (is_start) {
-                                s_raw[slot] = __funnelshift_r(w0, w1, 8 * jj);
+                                s_raw[slot] = __funnelshift_r(w[k], w[k + 1], 8 * jj);
                                 s_meta[slot] = kStates ? MetaT(ol | (G << 12)) : MetaT(ol);
                                 ++G; ++slot; ++ol;
                             }
