@@ -410,8 +410,9 @@ __device__ __forceinline__ void stream_stage(const DevModel& m, const BatchArgs&
                 if (ok) { atomicAdd(s_acc + b, v); s_meta[b] = MetaT(s_meta[b] | kValid); }
             } else if (ok) {
                 const uint32_t ol = uint32_t(s_meta[b]) & 0xFFFu;
-                if (scores) scores[ol] = v;
-                bounds[ol] = v > 0 ? 1 : 0;
+                // (streaming stores: the outputs are not read again by this kernel)
+                if (scores) __stcs(scores + ol, v);
+                __stcs(bounds + ol, uint8_t(v > 0 ? 1 : 0));
             }
         }
         // ================= stage 2: chunk it-1 — first probe result, second probe =====================================

@@ -24,10 +24,13 @@ struct Rec32 {
     uint32_t v[8];
 };
 
+// One 32-byte node record.  The records of a batch are spread over the whole table (perfect-hash slots) and are not
+// re-used while they could still sit in L1 (hit rate 5 %): the load does not allocate there (A/B on one box: 0.759 ->
+// 0.718 ms per step of config 2, profiles/r02_ab_loads.txt).
 __device__ __forceinline__ Rec32 load_record(const void* base, uint32_t slot) {
     Rec32 r;
     const char* p = static_cast<const char*>(base) + (size_t(slot) << 5);
-    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]),
                    "=r"(r.v[7])
                  : "l"(p));
