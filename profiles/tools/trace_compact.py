@@ -4,7 +4,7 @@ usage (GPU box): python profiles/tools/trace_compact.py [n_sentences] [tags] 2> 
 import os
 import sys
 
-os.environ["VPT_TRACE"] = "1"
+os.environ.setdefault("VPT_TRACE", "1")
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))

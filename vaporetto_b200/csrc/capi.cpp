@@ -1193,9 +1193,12 @@ namespace {
 constexpr size_t kSingleMaxBytes = 2048;   // sentences up to this size take the one-round-trip path of vpt_predict
 constexpr size_t kSingleIoBytes = 65536;
 
-// Predictor::predict for ONE sentence (reference predictor.rs:518-543) as one pinned round trip: the text, the offsets and
-// the zeroed look-back words go down in one copy, k_fused runs as a single group, the packed results come back in one
-// copy.  (The batch pipeline costs several copies, a memset node and three synchronisations per call.)
+// Predictor::predict for ONE sentence (reference predictor.rs:518-543) with one launch and no copy calls: the text and the
+// offsets are written into pinned host memory the kernel reads directly (zero-copy over PCIe; the tile loader's bulk copy
+// takes a host address like any other), the results are stored straight into the same pinned block, and the look-back
+// words + ticket live in a small device block that the kernel itself leaves zeroed (BatchArgs::self_clean).  The call is
+// a memcpy into the pinned block, one kernel launch, one stream synchronisation.  (The batch pipeline costs several copies,
+// a memset node and three synchronisations per call.)
 bool predict_single_fast(const vpt_predictor* p, const uint8_t* utf8, size_t n_bytes, int32_t* scores_out, uint8_t* boundaries_out,
                          size_t out_capacity, uint32_t* char_states_out, uint32_t* type_states_out, size_t states_capacity,
                          uint64_t* n_chars_out) {
@@ -1204,14 +1207,14 @@ bool predict_single_fast(const vpt_predictor* p, const uint8_t* utf8, size_t n_b
     ScratchLease lease(*p);
     Scratch& s = *lease.s;
     if (!s.h_io) {
-        cuda_check(cudaMallocHost(reinterpret_cast<void**>(&s.h_io), kSingleIoBytes), "cudaMallocHost");
-        cuda_check(cudaMalloc(&s.d_io, kSingleIoBytes), "cudaMalloc(single)");
+        cuda_check(cudaHostAlloc(reinterpret_cast<void**>(&s.h_io), kSingleIoBytes, cudaHostAllocMapped), "cudaHostAlloc");
+        cuda_check(cudaMalloc(&s.d_io, 256), "cudaMalloc(single)");
+        cuda_check(cudaMemset(s.d_io, 0, 256), "cudaMemset(single)");
     }
-    // layout (offsets into both buffers): input part first, then the outputs
+    // layout of the pinned block: input part first, then the outputs
     const size_t o_text = 0;                                   // text, then 64 readable bytes
     const size_t o_off = align_up(n_bytes + 64, 16);           // u64 offsets[2]
-    const size_t o_desc = o_off + 16;                          // group_bound[2], group_char[2], ticket (zero)
-    const size_t in_bytes = o_desc + 64;
+    const size_t in_bytes = o_off + 16;
     const size_t o_boff = align_up(in_bytes, 16);              // u64 bound_offsets[2]
     const size_t o_coff = o_boff + 16;                         // u64 char_offsets[2]
     const size_t o_stat = o_coff + 16;                         // i32 status, u32 n_chars
@@ -1225,32 +1228,31 @@ bool predict_single_fast(const vpt_predictor* p, const uint8_t* utf8, size_t n_b
     memset(s.h_io + o_text + n_bytes, 0, o_off - n_bytes);
     uint64_t offs[2] = {0, n_bytes};
     memcpy(s.h_io + o_off, offs, 16);
-    memset(s.h_io + o_desc, 0, 64);
     cudaStream_t st = s.stream;
+    uint8_t* hd = nullptr;  // the device's address of the pinned block (the same value under unified addressing)
+    cuda_check(cudaHostGetDevicePointer(reinterpret_cast<void**>(&hd), s.h_io, 0), "cudaHostGetDevicePointer");
     uint8_t* d = static_cast<uint8_t*>(s.d_io);
-    cuda_check(cudaMemcpyAsync(d, s.h_io, in_bytes, cudaMemcpyHostToDevice, st), "H2D(single)");
     BatchArgs a;
-    a.text = d + o_text;
-    a.offsets = reinterpret_cast<const uint64_t*>(d + o_off);
+    a.text = hd + o_text;
+    a.offsets = reinterpret_cast<const uint64_t*>(hd + o_off);
     a.n_sent = 1;
-    a.group_bound = reinterpret_cast<uint64_t*>(d + o_desc);
-    a.group_char = reinterpret_cast<uint64_t*>(d + o_desc + 16);
-    a.ticket = reinterpret_cast<uint32_t*>(d + o_desc + 32);
+    a.group_bound = reinterpret_cast<uint64_t*>(d);
+    a.group_char = reinterpret_cast<uint64_t*>(d + 64);
+    a.ticket = reinterpret_cast<uint32_t*>(d + 128);
     a.prezeroed = true;
-    a.n_chars = reinterpret_cast<uint32_t*>(d + o_stat + 4);
-    a.status = reinterpret_cast<int32_t*>(d + o_stat);
-    a.bound_offsets = reinterpret_cast<uint64_t*>(d + o_boff);
-    a.char_offsets = reinterpret_cast<uint64_t*>(d + o_coff);
-    a.boundaries = d + o_bnd;
-    a.scores = scores_out ? reinterpret_cast<int32_t*>(d + o_sc) : nullptr;
+    a.self_clean = true;
+    a.n_chars = reinterpret_cast<uint32_t*>(hd + o_stat + 4);
+    a.status = reinterpret_cast<int32_t*>(hd + o_stat);
+    a.bound_offsets = reinterpret_cast<uint64_t*>(hd + o_boff);
+    a.char_offsets = reinterpret_cast<uint64_t*>(hd + o_coff);
+    a.boundaries = hd + o_bnd;
+    a.scores = scores_out ? reinterpret_cast<int32_t*>(hd + o_sc) : nullptr;
     const bool want_states = char_states_out || type_states_out;
     if (want_states) {
-        a.char_states = reinterpret_cast<uint32_t*>(d + o_cst);
-        a.type_states = reinterpret_cast<uint32_t*>(d + o_tst);
+        a.char_states = reinterpret_cast<uint32_t*>(hd + o_cst);
+        a.type_states = reinterpret_cast<uint32_t*>(hd + o_tst);
     }
     cuda_check(launch_fused(p->dm, a, st), "launch(single)");
-    const size_t out_end = want_states ? end : (scores_out ? o_cst : o_sc);
-    cuda_check(cudaMemcpyAsync(s.h_io + o_boff, d + o_boff, out_end - o_boff, cudaMemcpyDeviceToHost, st), "D2H(single)");
     cuda_check(cudaStreamSynchronize(st), "sync(single)");
     int32_t status;
     uint32_t n;

@@ -59,6 +59,7 @@ struct BatchArgs {
     uint64_t* group_char = nullptr;       // [n_groups + 1]
     uint32_t* ticket = nullptr;           // work counter of the persistent tile kernel (zeroed by the scan)
     bool prezeroed = false;               // k_fused: group_bound / group_char / ticket are already zero (no memset node)
+    bool self_clean = false;              // k_fused, single-CTA launches only: zero them again before the kernel ends
     uint64_t* totals_host = nullptr;      // nullable: pinned host memory [2]; the scan also stores the batch's boundary
                                           // and character totals there (no D2H copy queued behind bulk copies)
     // outputs

@@ -39,11 +39,20 @@ namespace {
 constexpr int kFGroup = fused_detail::kGroupSentences;  // sentences per tile
 constexpr int kFSubThreads = 256;
 constexpr int kFWarps = kFSubThreads / 32;
-constexpr int kFTextCap = 8192;   // bytes of text staged per tile (multiple of 32)
-constexpr int kFSlotCap = 2816;    // character slots (characters + separators) per tile
+// Tile buffers: bytes of text staged per tile (multiple of 32) and character slots (characters + separators) per tile.
+// 64 sentences of 40 characters need 7.4 KB and 2 760 slots; the buffers are sized so that 64 sentences of ragged
+// natural-length text (log-normal, mean 41 characters: 7.6 +- 0.6 KB, 2 840 +- 220 slots) still fit -- a group that does
+// not fit takes the slow path, and every later group waits in its look-back for the slow group's totals (measured on
+// ragged text: 1.41 ms per step with 8 192 B / 2 816 slots, 0.76 ms with 10 240 B / 3 840 slots; the fixed-length batch
+// pays 1 %: profiles/r02_ab_ragged.txt).  The variants with 4-byte slot words (pattern-id states) get the largest buffers
+// that keep four sub-blocks per SM.
+template <bool kStates, bool kOverflow>
+struct FCaps {
+    static constexpr int kText = kStates ? 9216 : 10240;
+    static constexpr int kSlots = kStates ? (kOverflow ? 3264 : 3328) : 3840;
+};
 constexpr int kFPadFront = 8;      // zero slots in front of slot 0 (halo of the first warp range)
 constexpr int kFPadBack = 64;      // zero slots behind the last slot (lagging outputs of the last range)
-constexpr int kFSlotAlloc = kFPadFront + kFSlotCap + kFPadBack;
 constexpr int kFSeedCap = fused_detail::kSeedCap;   // seed bytes kept in shared memory
 constexpr int kFTypeSub = 4096;    // entries of each split type table
 constexpr int kFHalo = 8;          // slots a warp range re-reads in front of its first output
@@ -70,6 +79,10 @@ template <bool kSeedsSmem, bool kCommon, int kDeep, bool kStates>
 struct FLayout {
     static constexpr bool kOverflow = kDeep == 2;
     using MetaT = typename std::conditional<kStates, uint32_t, uint16_t>::type;
+    static constexpr int kFTextCap = FCaps<kStates, kDeep == 2>::kText;
+    static constexpr int kFSlotCap = FCaps<kStates, kDeep == 2>::kSlots;
+    static constexpr int kFSlotAlloc = kFPadFront + kFSlotCap + kFPadBack;
+    static_assert(kFSlotCap < 4096, "output indices inside a tile are 12-bit");
     // CTA-shared part
     static constexpr int kOffSeeds = 0;
     static constexpr int kOffTypeA = kOffSeeds + (kSeedsSmem ? kFSeedCap : 0);
@@ -90,7 +103,7 @@ struct FLayout {
     static constexpr int kSubBlocks = kMaxSub >= 4 ? 4 : kMaxSub;
     static constexpr int kThreads = kSubBlocks * kFSubThreads;
     static constexpr int kSmem = kOffSub + kSubBlocks * kSubBytes;
-    static_assert(kSubBlocks >= 2, "shared memory budget");
+    static_assert(kSubBlocks >= (kOverflow ? 3 : 4), "shared memory budget: four sub-blocks per SM (three with the overflow sums)");
     static_assert(int(sizeof(Rings)) <= 4 * kFSlotAlloc, "fallback ring aliases the slot array");
 };
 
@@ -240,6 +253,23 @@ __device__ __forceinline__ void slow_validate(const uint8_t* __restrict__ text, 
     if (conts != expect) flags |= 2;
     nch = starts;
     status = (flags & 2) ? 3 : (flags & 1) ? 2 : (starts == 0 ? 1 : 0);
+}
+
+// Characters (bytes that are not continuation bytes) of the sentence [b0, b1): one 4-byte word per lane and 128-byte step.
+// The text buffer is readable up to a multiple of 16 bytes (include/vaporetto_b200.h), and an address has the alignment of
+// its offset (the batch's text pointer is biased that way).
+__device__ __forceinline__ uint32_t slow_count(const uint8_t* __restrict__ text, uint64_t b0, uint64_t b1, int lane) {
+    uint32_t cnt = 0;
+    for (uint64_t addr = (b0 & ~3ull) + 4u * uint64_t(lane); addr < b1; addr += 128) {
+        const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(text + addr));
+        uint32_t in80 = 0x80808080u;  // bit 7 of the bytes of this word that lie inside [b0, b1)
+        if (addr < b0) in80 &= 0xFFFFFFFFu << (8u * uint32_t(b0 - addr));
+        if (addr + 4 > b1) in80 &= 0xFFFFFFFFu >> (8u * uint32_t(addr + 4 - b1));
+        cnt += __popc(~(w & ~(w << 1)) & in80);  // not 10xxxxxx
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(kFull, cnt, d);
+    return cnt;
 }
 
 // Zero outputs of a rejected sentence (the reference never scores it: Sentence::from_raw fails).
@@ -500,6 +530,7 @@ k_fused(DevModel m, BatchArgs a, StreamCfg cfg) {
     using Lay = FLayout<kSeedsSmem, kCommon, kDeep, kStates>;
     using MetaT = typename Lay::MetaT;
     constexpr bool kOverflow = kDeep == 2;
+    constexpr int kFTextCap = Lay::kFTextCap, kFSlotCap = Lay::kFSlotCap, kFSlotAlloc = Lay::kFSlotAlloc;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* s_seeds = smem + Lay::kOffSeeds;
     int32_t* s_ta = reinterpret_cast<int32_t*>(smem + Lay::kOffTypeA);
@@ -787,14 +818,14 @@ k_fused(DevModel m, BatchArgs a, StreamCfg cfg) {
         }
 
         // ================= slow path: exact per-sentence count, then the stream stage a sentence range at a time ========
+        // The character counts come first, from word loads (one round trip per 128 bytes of a sentence): every group
+        // behind this one waits in its look-back for this group's totals, the byte-exact validation can follow them.
         for (int k = warp; k < ns; k += kFWarps) {
             uint64_t b0 = T.off[k], b1 = T.off[k + 1];
             const uint32_t tr = T.trim[k];
             b1 = (b1 >= b0 && b1 - b0 >= tr) ? b1 - tr : b0;  // offsets out of order: an empty sentence
-            uint32_t nch;
-            int st;
-            slow_validate(text, b0, b1, lane, nch, st);
-            if (lane == 0) { T.first[k] = nch; T.st[k] = uint8_t(st); }
+            const uint32_t nch = slow_count(text, b0, b1, lane);
+            if (lane == 0) T.first[k] = nch;
         }
         fsub_sync(sub);
         if (warp == 0) {
@@ -819,6 +850,15 @@ k_fused(DevModel m, BatchArgs a, StreamCfg cfg) {
                 T.obase = pb;
                 T.cbase = pcv;
             }
+        }
+        for (int k = warp; k < ns; k += kFWarps) {
+            uint64_t b0 = T.off[k], b1 = T.off[k + 1];
+            const uint32_t tr = T.trim[k];
+            b1 = (b1 >= b0 && b1 - b0 >= tr) ? b1 - tr : b0;
+            uint32_t nch;
+            int st;
+            slow_validate(text, b0, b1, lane, nch, st);  // (nch: the count the totals were built from)
+            if (lane == 0) T.st[k] = uint8_t(st);
         }
         fsub_sync(sub);
         if (tid < ns) {
@@ -928,6 +968,15 @@ k_fused(DevModel m, BatchArgs a, StreamCfg cfg) {
             fsub_sync(sub);
             if (kOverflow) { finish_overflow<MetaT>(a, s_meta, s_acc, T.obase + T.lb[k0], Sr, tid); fsub_sync(sub); }
             k0 = k1;
+        }
+    }
+    if (a.self_clean) {
+        // single-CTA launch of the one-sentence call: the descriptors and the ticket are left zeroed for the next call
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint64_t ng = (a.n_sent + kFGroup - 1) / kFGroup;
+            for (uint64_t g = 0; g < ng; ++g) { st_relaxed(desc_b + g, 0); st_relaxed(desc_c + g, 0); }
+            *a.ticket = 0;
         }
     }
 }
