@@ -121,15 +121,65 @@ public:
     /// The loop of the reference's `predict` CLI over a buffer of raw lines (predict/src/main.rs:126-181;
     /// `vpt_tokenize_lines`): line splitting, the KyteaFullwidthFilter pre-filter (unless `no_norm`), prediction and
     /// `write_tokenized_text` + '\n' all run on the device.  Returns the output text.
-    std::string tokenize_lines(const std::string& text, bool no_norm = false, uint32_t wsconst_types = 0) const {
+    /// `predict_tags`: the CLI's --predict-tags (`vpt_tokenize_lines_tags`: fill_tags + tags in the output text).
+    std::string tokenize_lines(const std::string& text, bool no_norm = false, uint32_t wsconst_types = 0,
+                               bool predict_tags = false) const {
         size_t n_lines = 0;
         for (char c : text) n_lines += c == '\n';
-        std::string out(3 * text.size() + n_lines + 1, '\0');
+        std::string out((predict_tags ? 19 : 3) * text.size() + n_lines + 1, '\0');
         uint64_t n_out = 0, nl = 0;
-        detail::check(vpt_tokenize_lines(h_, reinterpret_cast<const uint8_t*>(text.data()), text.size(), no_norm ? 1 : 0,
-                                         wsconst_types, reinterpret_cast<uint8_t*>(&out[0]), out.size(), &n_out, &nl));
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            const int rc = predict_tags
+                ? vpt_tokenize_lines_tags(h_, reinterpret_cast<const uint8_t*>(text.data()), text.size(), no_norm ? 1 : 0,
+                                          wsconst_types, reinterpret_cast<uint8_t*>(&out[0]), out.size(), &n_out, &nl)
+                : vpt_tokenize_lines(h_, reinterpret_cast<const uint8_t*>(text.data()), text.size(), no_norm ? 1 : 0,
+                                     wsconst_types, reinterpret_cast<uint8_t*>(&out[0]), out.size(), &n_out, &nl);
+            if (rc != 0 && attempt == 0 && n_out > out.size()) { out.assign(size_t(n_out) + 1, '\0'); continue; }  // long tag strings
+            detail::check(rc);
+            break;
+        }
         out.resize(size_t(n_out));
         return out;
+    }
+
+    /// Result of `predict_batch_compact`: see `vpt_predict_batch_compact` (include/vaporetto_b200.h).
+    struct CompactResult {
+        std::vector<uint32_t> boundary_bits;   // the batch's boundaries, one bit each
+        std::vector<uint32_t> n_chars;         // per sentence
+        std::vector<uint8_t> status;           // per sentence
+        std::vector<uint32_t> n_tokens;        // per sentence
+        std::vector<int32_t> token_ids;        // per token (tags requested)
+        std::vector<uint8_t> token_cands;      // per token x n_tags, 255 = none
+        uint64_t n_boundaries = 0, n_unserved = 0;
+        /// boundaries [first_bit, first_bit + n) as bytes (0 / 1)
+        std::vector<uint8_t> boundaries(uint64_t first_bit, uint64_t n) const {
+            std::vector<uint8_t> out(n);
+            detail::check(vpt_unpack_boundaries(boundary_bits.data(), first_bit, n, out.data()));
+            return out;
+        }
+    };
+    /// predict (+ predict_tags when `tags`) for a batch of sentences given as concatenated UTF-8 + byte offsets, with
+    /// compact results: one bit per boundary, one record per token.
+    CompactResult predict_batch_compact(const std::string& text, const std::vector<uint64_t>& byte_offsets, bool tags = false) const {
+        CompactResult r;
+        const size_t n = byte_offsets.empty() ? 0 : byte_offsets.size() - 1;
+        const size_t cap = text.size() + 1;
+        r.boundary_bits.assign(cap / 32 + 2, 0);
+        r.n_chars.assign(n, 0);
+        r.status.assign(n, 0);
+        r.n_tokens.assign(n, 0);
+        const size_t nt = tags ? size_t(info_.n_tags) : 0;
+        if (tags) { r.token_ids.assign(cap, -1); r.token_cands.assign(cap * (nt ? nt : 1), 255); }
+        uint64_t ntok = 0;
+        if (n)
+            detail::check(vpt_predict_batch_compact(h_, reinterpret_cast<const uint8_t*>(text.data()), byte_offsets.data(), n,
+                                                    r.boundary_bits.data(), r.boundary_bits.size(), r.n_chars.data(), r.status.data(),
+                                                    r.n_tokens.data(), tags ? r.token_ids.data() : nullptr,
+                                                    tags ? r.token_cands.data() : nullptr, tags ? cap : 0, &r.n_boundaries, &ntok,
+                                                    &r.n_unserved));
+        r.boundary_bits.resize(size_t((r.n_boundaries + 31) / 32));
+        if (tags) { r.token_ids.resize(size_t(ntok)); r.token_cands.resize(size_t(ntok) * (nt ? nt : 1)); }
+        return r;
     }
 
     const vpt_predictor_info& info() const { return info_; }

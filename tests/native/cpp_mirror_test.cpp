@@ -79,6 +79,39 @@ int main(int argc, char** argv) {
     // the CLI loop (predict/src/main.rs:126-181): CRLF, an empty line, an unterminated last line
     CHECK(plain.tokenize_lines("まぁ社長は火星猫だ\r\n\nまぁ良いだろう") == "まぁ 社長 は 火星 猫 だ\n\nまぁ 良い だろう\n");
     CHECK(plain.tokenize_lines("") == "");
+    // --predict-tags and --wsconst G through the same call (main.rs:100-107,130-136,159-166)
+    CHECK(predictor.tokenize_lines("まぁ社長は火星猫だ\nまぁ良いだろう\n", true, 0, true) ==
+          "まぁ/名詞/マー 社長/名詞/シャチョー は/助詞/ワ 火星/名詞/カセー 猫/名詞/ネコ だ/助動詞/ダ\nまぁ/副詞/マー 良い/形容詞/ヨイ だろう/助動詞/ダロー\n");
+    CHECK(plain.tokenize_lines("まぁ社長は火星猫だ\n", true, VPT_WSCONST_GRAPHEME) == "まぁ 社長 は 火星 猫 だ\n");
+    // compact results: bits and per-token records against the Sentence API
+    {
+        const std::string a = "まぁ社長は火星猫だ", b = "まぁ良いだろう";
+        const std::vector<uint64_t> offs = {0, a.size(), a.size() + b.size()};
+        const Predictor::CompactResult r = predictor.predict_batch_compact(a + b, offs, true);
+        CHECK(r.n_chars.size() == 2 && r.n_chars[0] == 9 && r.n_chars[1] == 7 && r.n_boundaries == 14);
+        CHECK(r.n_tokens[0] == 6 && r.n_tokens[1] == 3 && r.token_ids.size() == 9 && r.n_unserved == 0);
+        Sentence w = Sentence::from_raw(a);
+        predictor.predict(w);
+        CHECK(r.boundaries(0, 8) == w.boundaries());
+        w.fill_tags();
+        const auto wt = w.iter_tokens();
+        for (size_t k = 0; k < wt.size(); ++k) {
+            const auto tags = wt[k].tags();
+            for (size_t sl = 0; sl < 2; ++sl) {
+                const uint8_t c = r.token_cands[k * 2 + sl];
+                const char* name = c == 255 ? nullptr : vpt_tag_string(predictor.handle(), uint32_t(r.token_ids[k]), uint32_t(sl), c);
+                CHECK((name == nullptr) == !tags[sl].has_value());
+                if (name) CHECK(*tags[sl] == name);
+            }
+        }
+        // filters of vaporetto_rules on a Sentence
+        Sentence f = Sentence::from_raw("前の行\r\n次の行");
+        for (auto& x : f.boundaries_mut()) x = 0;
+        f.split_linebreaks();
+        std::string fb;
+        f.write_tokenized_text(fb);
+        CHECK(fb == "前の行 \r \n 次の行");
+    }
     std::printf("cpp mirror (gpu) ok\n");
     return 0;
 }

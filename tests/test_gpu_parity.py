@@ -299,6 +299,37 @@ def test_synthetic_config2_shape(synth_model):
     check_batch(p, o, text, offs)
 
 
+def test_groups_that_do_not_fit_a_tile(synth_model):
+    """64-sentence groups of long sentences (a group's text and slots exceed the tile buffers: slow path, totals published
+    after the word-wise count) between groups of short ones (fast path), and mixed inside a group: offsets, scores and
+    boundaries of every group depend on the totals of all groups before it."""
+    p, o = make(synth_model), OraclePredictor(synth_model)
+    short_t, short_o, _ = synth.gen_text(64 * 40, 40, seed=synth.TEXT_SEED + 31)
+    long_t, long_o, _ = synth.gen_text(64 * 16, 170, seed=synth.TEXT_SEED + 32)
+    mid_t, mid_o, _ = synth.gen_text(64 * 12, 61, seed=synth.TEXT_SEED + 33)   # 64 x 61 characters: just over the buffers
+    sents = []
+    for t, of in ((short_t, short_o), (long_t, long_o), (mid_t, mid_o)):
+        sents.append([bytes(t[int(of[i]):int(of[i + 1])]) for i in range(len(of) - 1)])
+    short_s, long_s, mid_s = sents
+    order = []
+    si = li = mi = 0
+    for blk in range(52):
+        kind = blk % 5
+        if kind in (0, 2):
+            order += short_s[si:si + 64]; si += 64
+        elif kind == 1:
+            order += long_s[li:li + 64]; li += 64
+        elif kind == 3:
+            order += mid_s[mi:mi + 64]; mi += 64
+        else:   # mixed group
+            order += short_s[si:si + 40] + long_s[li:li + 24]; si += 40; li += 24
+    order = [x for x in order if x]
+    enc = b"".join(order)
+    offs = np.zeros(len(order) + 1, np.uint64)
+    np.cumsum([len(x) for x in order], out=offs[1:])
+    check_batch(p, o, np.frombuffer(enc, np.uint8), offs)
+
+
 @pytest.mark.parametrize("budget", ["3", "300"])
 def test_table_layout_variants_gpu(budget, monkeypatch):
     """dense 16-bit-seed tables (large dictionaries) and fat buckets, forced on a small model"""
