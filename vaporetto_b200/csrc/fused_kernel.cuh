@@ -46,10 +46,14 @@ constexpr int kFWarps = kFSubThreads / 32;
 // ragged text: 1.41 ms per step with 8 192 B / 2 816 slots, 0.76 ms with 10 240 B / 3 840 slots; the fixed-length batch
 // pays 1 %: profiles/r02_ab_ragged.txt).  The variants with 4-byte slot words (pattern-id states) get the largest buffers
 // that keep four sub-blocks per SM.
-template <bool kStates, bool kOverflow>
+// (With the overflow sums -- 4 more bytes per slot -- the buffers are what keeps four sub-blocks per SM when the seeds
+// live in global memory, the large-dictionary case, and three when they take 37 KB of shared memory.)
+template <bool kSeedsSmem, bool kStates, bool kOverflow>
 struct FCaps {
-    static constexpr int kText = kStates ? 9216 : 10240;
-    static constexpr int kSlots = kStates ? (kOverflow ? 3264 : 3328) : 3840;
+    static constexpr int kText = (kStates || (kOverflow && !kSeedsSmem)) ? 9216 : 10240;
+    static constexpr int kSlots = !kOverflow ? (kStates ? 3328 : 3840)
+                                  : kSeedsSmem ? (kStates ? 3264 : 3840)
+                                               : (kStates ? 2944 : 3584);
 };
 constexpr int kFPadFront = 8;      // zero slots in front of slot 0 (halo of the first warp range)
 constexpr int kFPadBack = 64;      // zero slots behind the last slot (lagging outputs of the last range)
@@ -79,8 +83,8 @@ template <bool kSeedsSmem, bool kCommon, int kDeep, bool kStates>
 struct FLayout {
     static constexpr bool kOverflow = kDeep == 2;
     using MetaT = typename std::conditional<kStates, uint32_t, uint16_t>::type;
-    static constexpr int kFTextCap = FCaps<kStates, kDeep == 2>::kText;
-    static constexpr int kFSlotCap = FCaps<kStates, kDeep == 2>::kSlots;
+    static constexpr int kFTextCap = FCaps<kSeedsSmem, kStates, kDeep == 2>::kText;
+    static constexpr int kFSlotCap = FCaps<kSeedsSmem, kStates, kDeep == 2>::kSlots;
     static constexpr int kFSlotAlloc = kFPadFront + kFSlotCap + kFPadBack;
     static_assert(kFSlotCap < 4096, "output indices inside a tile are 12-bit");
     // CTA-shared part
@@ -103,7 +107,8 @@ struct FLayout {
     static constexpr int kSubBlocks = kMaxSub >= 4 ? 4 : kMaxSub;
     static constexpr int kThreads = kSubBlocks * kFSubThreads;
     static constexpr int kSmem = kOffSub + kSubBlocks * kSubBytes;
-    static_assert(kSubBlocks >= (kOverflow ? 3 : 4), "shared memory budget: four sub-blocks per SM (three with the overflow sums)");
+    static_assert(kSubBlocks >= ((kOverflow && kSeedsSmem) ? 3 : 4),
+                  "shared memory budget: four sub-blocks per SM (three with the overflow sums next to the seed table)");
     static_assert(int(sizeof(Rings)) <= 4 * kFSlotAlloc, "fallback ring aliases the slot array");
 };
 
