@@ -26,6 +26,23 @@ for kw, tags in ((dict(), False), (dict(dict_words=2000), False), (dict(tag_mode
             got, nl = p.tokenize_lines(data, no_norm=no_norm)
             want, wl = o.tokenize_lines(data, no_norm=no_norm)
             assert nl == wl and got.tobytes() == want, (kw, chunk, no_norm)
+    os.environ["VPT_CHUNK_BYTES"] = "4096"
+    got, nl = p.tokenize_lines(data, wsconst="GD")          # k_grapheme + k_wsconst
+    want, wl = o.tokenize_lines(data, wsconst="GD")
+    assert nl == wl and got.tobytes() == want, kw
+    cr = p.predict_batch_compact(text, offs)                # k_pack_bits, k_sentence_info, k_token_scan, k_token_base
+    assert np.array_equal(cr.boundaries(), r.boundaries), kw
+    if tags:
+        res, tok, cand, uns = p.predict_batch_tags(text, offs)      # k_tags (single kernel)
+        ct = p.predict_batch_compact(text, offs, tags=True)         # k_tags<locate> + k_tok_tag
+        assert np.array_equal(ct.boundaries(), res.boundaries) and ct.token_ids.size == int(ct.n_tokens.sum())
+        assert int((ct.token_ids >= 0).sum()) == int((tok >= 0).sum())
+        for no_norm in (True, False):                               # k_tok_write_tags
+            got, nl = p.tokenize_lines(data, no_norm=no_norm, predict_tags=True)
+            want, wl = o.tokenize_lines(data, no_norm=no_norm, predict_tags=True)
+            assert nl == wl and got.tobytes() == want, (kw, no_norm)
+    one = vb.Sentence.from_raw("まぁ社長は火星猫だ")                 # vpt_predict: zero-copy single-sentence path
+    p.predict(one)
 print("sanitizer workload ok")
 PY
 for tool in memcheck racecheck; do

@@ -101,13 +101,44 @@ def main():
             data = data[:-1]
         os.environ["VPT_CHUNK_BYTES"] = str(int(rng.choice([64, 777, 1 << 14, 16 << 20])))
         for no_norm in (True, False):
-            ws = "".join(rng.choice(list("DRHTKO"), size=rng.integers(0, 3)))  # --wsconst options
-            got, nl = p.tokenize_lines(data, no_norm=no_norm, wsconst=ws)
-            want, wl = o.tokenize_lines(data, no_norm=no_norm, wsconst=ws)
+            ws = "".join(rng.choice(list("DRHTKOG"), size=rng.integers(0, 3)))  # --wsconst options
+            with_tags = tags and rng.random() < 0.7                              # --predict-tags
+            try:
+                got, nl = p.tokenize_lines(data, no_norm=no_norm, wsconst=ws, predict_tags=with_tags)
+            except vb.VaporettoError as e:
+                if with_tags and e.code == 17:   # tag model beyond the device limits: the host path serves it
+                    continue
+                raise
+            want, wl = o.tokenize_lines(data, no_norm=no_norm, wsconst=ws, predict_tags=with_tags)
             if nl != wl or got.tobytes() != want:
                 np.save("/tmp/fuzz_fail_model.npy", np.frombuffer(mb, np.uint8))
                 open("/tmp/fuzz_fail_lines.bin", "wb").write(data)
-                raise SystemExit(f"iteration {it}: tokenize_lines MISMATCH (no_norm={no_norm}), path {key}")
+                raise SystemExit(f"iteration {it}: tokenize_lines MISMATCH (no_norm={no_norm}, wsconst={ws!r}, tags={with_tags}), path {key}")
+        # compact results: the bit stream against the byte boundaries; the token records against the oracle's tags
+        try:
+            cr = p.predict_batch_compact(text, offs, tags=tags)
+        except vb.VaporettoError as e:
+            if not (tags and e.code == 17):
+                raise
+            cr = p.predict_batch_compact(text, offs, tags=False)
+        if not (np.array_equal(cr.boundaries(), bd) and np.array_equal(cr.status.astype(np.int32) == 0, st == 0)):
+            raise SystemExit(f"iteration {it}: compact boundaries MISMATCH, path {key}")
+        if tags and cr.token_ids is not None and cr.n_unserved == 0:
+            for i in rng.integers(0, len(sents), size=3):
+                if st[i] != 0:
+                    continue
+                try:
+                    ott, oti = o.predict_tags(sents[i])
+                except Exception:
+                    continue   # a tag model the reference rejects at prediction time
+                lo, hi = int(cr.token_offsets[i]), int(cr.token_offsets[i + 1])
+                ends = np.nonzero(np.concatenate([cr.boundaries(int(i)) == 1, [True]]))[0]
+                if hi - lo != len(ends):
+                    raise SystemExit(f"iteration {it}: token count mismatch, path {key}")
+                got_known = cr.token_ids[lo:hi] >= 0
+                got_c = np.where(cr.token_cands[lo:hi] == 255, -1, cr.token_cands[lo:hi].astype(np.int64))
+                if not (np.array_equal(got_known, ott[ends] >= 0) and np.array_equal(got_c[got_known], oti[ends][got_known])):
+                    raise SystemExit(f"iteration {it}: token records MISMATCH (sentence {i}), path {key}")
         if tags:
             for i in rng.integers(0, len(sents), size=3):
                 _, _, ocs, ots = o.predict(sents[i], states=True)
