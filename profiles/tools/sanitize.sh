@@ -46,6 +46,6 @@ for kw, tags in ((dict(), False), (dict(dict_words=2000), False), (dict(tag_mode
 print("sanitizer workload ok")
 PY
 for tool in memcheck racecheck; do
-  timeout 900 compute-sanitizer --tool $tool --print-limit 20 python /tmp/san_small.py > gpurun_out/sanitize_$tool.log 2>&1
+  timeout 900 compute-sanitizer --tool $tool --print-limit 60 python /tmp/san_small.py > gpurun_out/sanitize_$tool.log 2>&1
   echo "== $tool: exit $?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|sanitizer workload ok|Error|hazard" gpurun_out/sanitize_$tool.log | head -12
 done

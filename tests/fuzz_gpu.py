@@ -17,6 +17,9 @@ import vaporetto_b200 as vb  # noqa: E402
 from vpt_testlib.bincode_model import encode_model  # noqa: E402
 from vpt_testlib.oracle import OraclePredictor  # noqa: E402
 
+os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+FAIL_MODEL = os.path.join(ROOT, "gpurun_out", "fuzz_fail_model.npy")   # (gpurun_out/ travels back from the GPU box)
+FAIL_LINES = os.path.join(ROOT, "gpurun_out", "fuzz_fail_lines.bin")
 ALPHA = list("あいうえおかきアイウエ人火星地球猫社長漢字aBc1 9。、🤌𠀋é")
 LINE_EXTRA = list("/\\.-ａ１。－―｢")  # escapes and sources / targets of the full-width filter
 
@@ -81,8 +84,13 @@ def main():
         r = p.predict_batch(text, offs, want_states=tags)
         sc, bd, boff, st = o.predict_batch(text, offs, nthreads=4)
         if not (np.array_equal(r.scores, sc) and np.array_equal(r.boundaries, bd) and np.array_equal(r.bound_offsets, boff)):
-            np.save("/tmp/fuzz_fail_model.npy", np.frombuffer(mb, np.uint8))
-            raise SystemExit(f"iteration {it}: MISMATCH (model saved to /tmp/fuzz_fail_model.npy), path {key}")
+            np.save(FAIL_MODEL, np.frombuffer(mb, np.uint8))
+            np.save(os.path.join(ROOT, "gpurun_out", "fuzz_fail_text.npy"), text)
+            np.save(os.path.join(ROOT, "gpurun_out", "fuzz_fail_offs.npy"), offs)
+            r_again = p.predict_batch(text, offs, want_states=tags)
+            print("second run of the same batch equal to the first:", np.array_equal(r_again.scores, r.scores),
+                  "equal to the oracle:", np.array_equal(r_again.scores, sc), file=sys.stderr)
+            raise SystemExit(f"iteration {it}: MISMATCH (model saved to gpurun_out/fuzz_fail_model.npy), path {key}")
         # the CLI loop on the device (untagged output): the same sentences as lines
         parts = []
         for sline in sents[: 120]:
@@ -111,8 +119,8 @@ def main():
                 raise
             want, wl = o.tokenize_lines(data, no_norm=no_norm, wsconst=ws, predict_tags=with_tags)
             if nl != wl or got.tobytes() != want:
-                np.save("/tmp/fuzz_fail_model.npy", np.frombuffer(mb, np.uint8))
-                open("/tmp/fuzz_fail_lines.bin", "wb").write(data)
+                np.save(FAIL_MODEL, np.frombuffer(mb, np.uint8))
+                open(FAIL_LINES, "wb").write(data)
                 raise SystemExit(f"iteration {it}: tokenize_lines MISMATCH (no_norm={no_norm}, wsconst={ws!r}, tags={with_tags}), path {key}")
         # compact results: the bit stream against the byte boundaries; the token records against the oracle's tags
         try:

@@ -299,6 +299,15 @@ def test_synthetic_config2_shape(synth_model):
     check_batch(p, o, text, offs)
 
 
+def test_fuzz_case_deep_key_vs_bigram():
+    """A case the fuzzer found (tests/fuzz_gpu.py, seed 12345, model 1266): a (parent node, symbol) record whose parent id
+    equals a code point has the low 42 key bits of a 2-character key; the first probe of that absent bigram landed on it."""
+    d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fuzz_cases")
+    mb = np.load(os.path.join(d, "case1266_model.npy")).tobytes()
+    text, offs = np.load(os.path.join(d, "case1266_text.npy")), np.load(os.path.join(d, "case1266_offs.npy"))
+    check_batch(make(mb), OraclePredictor(mb), text, offs)
+
+
 def test_groups_that_do_not_fit_a_tile(synth_model):
     """64-sentence groups of long sentences (a group's text and slots exceed the tile buffers: slow path, totals published
     after the word-wise count) between groups of short ones (fast path), and mixed inside a group: offsets, scores and

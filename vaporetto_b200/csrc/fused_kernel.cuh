@@ -455,7 +455,11 @@ __device__ __forceinline__ void stream_stage(const DevModel& m, const BatchArgs&
             const uint32_t klo = cA | (c2A << 21), khi = c2A >> 11;
             const bool act = cA != 0 && have_ct;
             // (bits 10..28 of the second key word of a 2-character record: the mask of its 3-character extensions)
-            const bool f1 = act && rA.v[0] == klo && (rA.v[1] & 0x3FFu) == khi;
+            // bits 29 / 30 of the word (61 / 62 of the key) are clear in a 2-symbol record and the deep-key marker sets
+            // bit 30: a (parent node, symbol) record whose parent id equals c2 as a number has the same low 42 bits and
+            // must not pass for the 2-character node when that node does not exist (found by the fuzzer: 1 case in 1 300
+            // random models; tests/golden/fuzz_cases/)
+            const bool f1 = act && rA.v[0] == klo && (rA.v[1] & 0x600003FFu) == khi;
             // the 3-character node if the 2-character node may have this extension, the 1-character node if the
             // 2-character node does not exist
             const bool w3 = f1 && c1A != 0 && ((rA.v[1] >> (10u + child_bit(c1A))) & 1u) != 0, w1 = act && !f1 && c2A != 0;
@@ -588,16 +592,18 @@ k_fused(DevModel m, BatchArgs a, StreamCfg cfg) {
     uint32_t phase = 0;
 
     for (;;) {
+        if (tid == 0) T.ticket = atomicAdd(a.ticket, 1u);
+        fsub_sync(sub);
+        const uint64_t grp = T.ticket;
+        if (grp >= ngroups) break;
+        // (the per-group flags are cleared behind the barrier: the other threads read them after the last barrier of
+        //  the previous group, bytes_have / bad_chars below; their first use in this group is two barriers away)
         if (tid == 0) {
-            T.ticket = atomicAdd(a.ticket, 1u);
             T.anomaly = 0;
             T.bad_chars = 0;
             T.bytes_want = 0;  // (first: the sum of the excluded bytes)
             T.bytes_have = 0;
         }
-        fsub_sync(sub);
-        const uint64_t grp = T.ticket;
-        if (grp >= ngroups) break;
         const uint64_t s0 = grp * kFGroup;
         const int ns = int(min(uint64_t(kFGroup), a.n_sent - s0));
         if (tid <= ns) T.off[tid] = a.offsets[s0 + tid];
