@@ -221,9 +221,9 @@ class Model:
         return h
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().vpt_model_free(self._h)
-            self._h = None
+        h, self._h = getattr(self, "_h", None), None
+        if h and _lib is not None:  # (module globals are already gone when the interpreter shuts down)
+            _lib.vpt_model_free(h)
 
 
 def build_blob(model: Model, predict_tags: bool = False) -> np.ndarray:
@@ -321,9 +321,9 @@ class Predictor:
         return out
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().vpt_predictor_free(self._h)
-            self._h = None
+        h, self._h = getattr(self, "_h", None), None
+        if h and _lib is not None:  # (module globals are already gone when the interpreter shuts down)
+            _lib.vpt_predictor_free(h)
 
     # -- predict ------------------------------------------------------------------------------------
     def predict(self, sentence: "Sentence") -> None:

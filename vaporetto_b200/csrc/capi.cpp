@@ -67,6 +67,7 @@ struct Scratch {
     void* d_ntok = nullptr; size_t ntok_cap = 0;
     void* d_tokbase = nullptr; size_t tokbase_cap = 0;
     void* d_tokdesc = nullptr; size_t tokdesc_cap = 0;
+    void* d_tokwork = nullptr; size_t tokwork_cap = 0;  // work list of the per-token tag kernels (TagArgs::tok_work)
     void* d_toklocal = nullptr; size_t toklocal_cap = 0;
     void* d_tokblk = nullptr; size_t tokblk_cap = 0;
     uint64_t* h_totals = nullptr;  // pinned, 8 x u64: boundaries, chars, lines, output bytes, tokens, first bit word
@@ -75,7 +76,7 @@ struct Scratch {
     void* d_io = nullptr;          // its device twin
     ~Scratch() {
         for (void* p : {d_text, d_off, d_ws, d_status, d_boff, d_coff, d_scores, d_bounds, d_cst, d_tst, d_trims, d_blk,
-                        d_blkbase, d_tokg, d_out, d_tok, d_cand, d_bits, d_st8, d_ntok, d_tokbase, d_tokdesc, d_toklocal, d_tokblk})
+                        d_blkbase, d_tokg, d_out, d_tok, d_cand, d_bits, d_st8, d_ntok, d_tokbase, d_tokdesc, d_tokwork, d_toklocal, d_tokblk})
             if (p) cudaFree(p);
         if (h_totals) cudaFreeHost(h_totals);
         if (h_io) cudaFreeHost(h_io);
@@ -1054,6 +1055,8 @@ void lines_stage1(const vpt_predictor& p, Scratch& s, LineChunk& ch, bool normal
         g.tok_cands = static_cast<uint8_t*>(s.d_cand);
         g.tok_desc = static_cast<uint4*>(s.d_tokdesc);
         g.max_tokens = ch.nbytes;
+        Scratch::ensure(s.d_tokwork, s.tokwork_cap, 4 * ch.nbytes + 32);
+        g.tok_work = static_cast<uint32_t*>(s.d_tokwork);
         g.norm = normalize ? 1 : 0;
         cuda_check(launch_tags(p.dt, g, st), "launch(tags)");
         t.tok_base = k.tok_base;
@@ -1644,6 +1647,8 @@ int vpt_predict_batch_compact(const vpt_predictor* p, const uint8_t* utf8, const
             Scratch::ensure(s.d_tokdesc, s.tokdesc_cap, 16 * cc.nc + 16);
             t.tok_desc = static_cast<uint4*>(s.d_tokdesc);
             t.max_tokens = cc.nc;
+            Scratch::ensure(s.d_tokwork, s.tokwork_cap, 4 * cc.nc + 32);
+            t.tok_work = static_cast<uint32_t*>(s.d_tokwork);
             t.text_base = 0;
             cuda_check(launch_tags(p->dt, t, st), "launch(tags)");
             cuda_check(cudaMemcpyAsync(&h_unserved[c], d_unserved, 4, cudaMemcpyDeviceToHost, st), "D2H(unserved)");

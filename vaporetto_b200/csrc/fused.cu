@@ -1,6 +1,7 @@
 // vaporetto_b200 — host side of k_fused (fused_kernel.cuh): model-shape checks and the dispatch to the kernel variants,
 // which are instantiated in fused_ss.cu / fused_sg.cu / fused_gs.cu / fused_gg.cu (one translation unit per
 // (seeds in shared memory, common shape) pair, so that they compile in parallel).
+#include <atomic>
 #include <algorithm>
 
 #include "device_model.hpp"
@@ -34,7 +35,7 @@ bool fused_ok(const DevModel& m) {
 // One launch for the whole batch (plus the memset node that clears the look-back descriptors and the ticket).
 cudaError_t launch_fused(const DevModel& m, const BatchArgs& a, cudaStream_t stream) {
     if (a.n_sent == 0) return cudaSuccess;
-    static int sm_count[fused_detail::kMaxDevices] = {};
+    static std::atomic<int> sm_count[fused_detail::kMaxDevices] = {};  // (idempotent cache: every writer stores the same value)
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
@@ -59,7 +60,8 @@ cudaError_t launch_fused(const DevModel& m, const BatchArgs& a, cudaStream_t str
     cfg.norm = m.kytea_norm != 0;
     const bool seeds_smem = m.ct.present && !m.ct.seed16 && m.ct.nbuckets <= uint32_t(fused_detail::kSeedCap);
     // the usual shape: char window 3 (inline window starts at -3) + type window 3 with split tables
-    const bool common = m.type_a != nullptr && m.type_cache_window == 3 && m.ct.present && m.ct.r0 == -3;
+    const bool common = m.type_a != nullptr && m.type_cache_window == 3 && m.ct.present && m.ct.r0 == -3 &&
+                        cfg.gap == fused_detail::kCommonGap;
     const int n_sm = sm_count[dev];
     if (seeds_smem) return common ? fused_detail::launch_fused_group<true, true>(m, a, cfg, stream, dev, n_sm) : fused_detail::launch_fused_group<true, false>(m, a, cfg, stream, dev, n_sm);
     return common ? fused_detail::launch_fused_group<false, true>(m, a, cfg, stream, dev, n_sm) : fused_detail::launch_fused_group<false, false>(m, a, cfg, stream, dev, n_sm);

@@ -22,6 +22,7 @@ constexpr int kSeedCap = 37632;   // seed bytes the kernel keeps in shared memor
 #endif
 constexpr int kGroupSentences = VPT_FUSED_GROUP;   // sentences per tile of k_fused (>= 32: vpt_workspace_size)
 constexpr int kMaxDevices = 64;
+constexpr int kCommonGap = 2;     // separator slots between sentences for the common shape (char window 3, type window 3)
 
 template <bool kSeeds, bool kCommon>
 cudaError_t launch_fused_group(const DevModel& m, const BatchArgs& a, const StreamCfg& cfg, cudaStream_t stream, int dev, int n_sm);

@@ -20,6 +20,7 @@
 //   k_score_general  same skeleton for models whose rows do not fit the inline window, for the type
 //                  automaton variant and for tag-state output: rows scatter with global atomics.
 // No tensor cores: integer indexing + scatter/gather add.
+#include <atomic>
 #include <algorithm>
 #include <cstdint>
 
@@ -918,7 +919,7 @@ constexpr int kMaxDevices = 64;
 
 template <bool kSeeds, int kR0, bool kGeneral, bool kSplit3, bool kOverflow>
 static cudaError_t launch_tile_t(const DevModel& m, const BatchArgs& a, cudaStream_t stream, int dev, int n_sm) {
-    static bool attr_set[kMaxDevices] = {};  // the opt-in shared memory size is a per-device function attribute
+    static std::atomic<bool> attr_set[kMaxDevices] = {};  // the opt-in shared memory size is a per-device function attribute
     if (!attr_set[dev]) {
         cudaError_t e = cudaFuncSetAttribute(k_tile_fast<kSeeds, kR0, kGeneral, kSplit3, kOverflow>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem);
         if (e != cudaSuccess) return e;
@@ -949,7 +950,7 @@ cudaError_t launch_batch(const DevModel& m, const BatchArgs& a, cudaStream_t str
 cudaError_t launch_score(const DevModel& m, const BatchArgs& a, cudaStream_t stream) {
     if (a.n_sent == 0) return cudaSuccess;
     if (fused_ok(m)) return launch_fused(m, a, stream);  // self-contained: does not need the count pass
-    static int sm_count[kMaxDevices] = {};
+    static std::atomic<int> sm_count[kMaxDevices] = {};  // (idempotent cache: every writer stores the same value)
     int dev = 0;
     cudaError_t e0 = cudaGetDevice(&dev);
     if (e0 != cudaSuccess) return e0;

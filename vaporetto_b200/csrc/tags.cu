@@ -7,6 +7,9 @@
 // by (pattern id at characters last .. last + rel, token, rel) of both scorers -- the pattern's own vector plus those of
 // its suffix patterns with the reference's truncation (tags.hpp) -- and takes the first strict maximum of every tag slot
 // with at least two candidates (predictor.rs:286-304).  Integer adds wrap as in the reference's release build.
+#include <algorithm>
+#include <atomic>
+
 #include "kernels_common.cuh"
 #include "tags.hpp"
 
@@ -129,11 +132,10 @@ __device__ __forceinline__ void add_scorer(const TagKey* __restrict__ keys, cons
 // sentence's `n` characters whose pattern-id states start at cst / tst): token lookup, bias + tag weights of both scorers,
 // first strict maximum per tag slot (TagPredictor::predict, predictor.rs:286-304).  Returns the token id or -1 and the
 // chosen candidates in cand[].
-__device__ __forceinline__ int32_t tag_token_at(const DevTags& t, const uint8_t* __restrict__ bytes, uint32_t len,
-                                                const uint32_t* __restrict__ cst, const uint32_t* __restrict__ tst, uint32_t i,
-                                                uint32_t n, int32_t* cand, uint32_t* n_unserved, int norm) {
-    uint32_t tid = 0;
-    if (!token_lookup(t, bytes, len, norm, tid)) return -1;
+// (the part behind the token lookup: `tid` is a token of the table)
+__device__ __forceinline__ int32_t tag_score_token(const DevTags& t, uint32_t tid, const uint32_t* __restrict__ cst,
+                                                   const uint32_t* __restrict__ tst, uint32_t i, uint32_t n, int32_t* cand,
+                                                   uint32_t* n_unserved) {
     TagTokenInfo ti;
     {
         const uint4* q = reinterpret_cast<const uint4*>(t.tok_info + tid);
@@ -177,11 +179,21 @@ __device__ __forceinline__ int32_t tag_token_at(const DevTags& t, const uint8_t*
     return int32_t(tid);
 }
 
+__device__ __forceinline__ int32_t tag_token_at(const DevTags& t, const uint8_t* __restrict__ bytes, uint32_t len,
+                                                const uint32_t* __restrict__ cst, const uint32_t* __restrict__ tst, uint32_t i,
+                                                uint32_t n, int32_t* cand, uint32_t* n_unserved, int norm) {
+    uint32_t tid = 0;
+    if (!token_lookup(t, bytes, len, norm, tid)) return -1;
+    return tag_score_token(t, tid, cst, tst, i, n, cand, n_unserved);
+}
+
 // kLocateOnly: phase 1 of the per-token path (descriptors for k_tok_tag); otherwise the kernel predicts the tags itself.
 template <bool kLocateOnly>
 __global__ void __launch_bounds__(kTagWarps * 32, kLocateOnly ? 8 : 1) k_tags(DevTags t, TagArgs a) {
     __shared__ Rings s_rings[kTagWarps];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // (the work list of the per-token kernels starts empty: they run behind this kernel on the stream)
+    if (kLocateOnly && a.tok_work && blockIdx.x == 0 && threadIdx.x == 0) a.tok_work[0] = 0;
     const uint64_t s = uint64_t(blockIdx.x) * kTagWarps + warp;
     if (s >= a.n_sent) return;
     Rings& r = s_rings[warp];
@@ -264,27 +276,67 @@ __global__ void __launch_bounds__(kTagWarps * 32, kLocateOnly ? 8 : 1) k_tags(De
     }
 }
 
-// Phase 2 of the per-token path: one thread per token record (descriptor written by k_tags): every lane has a token,
-// consecutive lanes read consecutive text, the records are written coalesced.
+// Phase 2 of the per-token path, one thread per token record (descriptor written by k_tags): consecutive lanes read
+// consecutive text.  Two kernels, because only some tokens have a tag model (41 % on the config-3 workload) and the work
+// behind the lookup is 5-10 x the lookup: with both in one kernel a warp runs the long path at the lane density of the
+// tokens that have a model.
+//   k_tok_lookup  every token: hash + table lookup; the token id (or -1) is final here; tokens with a model are appended
+//                 to a work list (one atomic per warp)
+//   k_tok_score   the listed tokens, dense lanes: bias + tag weights + arg-max
+// Both are grid-stride loops over a resident grid (the token count is known on the device only).
 constexpr int kTokTagThreads = 128;
-__global__ void __launch_bounds__(kTokTagThreads) k_tok_tag(DevTags t, TagArgs a) {
-    const uint64_t rec = uint64_t(blockIdx.x) * kTokTagThreads + threadIdx.x;
-    if (rec >= a.tok_base[a.n_sent]) return;
-    const uint4 d = a.tok_desc[rec];
-    const uint32_t len = d.w & 0xFFFFu, n_after = d.w >> 16;
-    int32_t cand[kTagMaxSlots];
-#pragma unroll
-    for (int k = 0; k < kTagMaxSlots; ++k) cand[k] = -1;
-    int32_t tok = -1;
-    if (len) {
-        const uint64_t off = (uint64_t(d.y) << 32) | d.x;
-        // (characters [d.z, d.z + n_after) are the token's last character and what follows it in its sentence)
-        tok = tag_token_at(t, a.text + a.text_base + off, len, a.char_states ? a.char_states + d.z : nullptr,
-                           a.type_states ? a.type_states + d.z : nullptr, 0, n_after, cand, a.n_unserved, a.norm);
-    }
-    a.tok_ids[rec] = tok;
+constexpr int kTokWorkHead = 4;  // words in front of the work list: [0] = entries
+__global__ void __launch_bounds__(kTokTagThreads) k_tok_lookup(DevTags t, TagArgs a) {
+    const uint64_t ntok = a.tok_base[a.n_sent];
     const uint32_t nt = t.n_tags;
-    for (uint32_t k = 0; k < nt; ++k) a.tok_cands[rec * nt + k] = (tok >= 0 && cand[k] >= 0) ? uint8_t(cand[k]) : uint8_t(255);
+    const int lane = threadIdx.x & 31;
+    const uint64_t stride = uint64_t(gridDim.x) * kTokTagThreads;
+    // (warp-uniform trip count: the list append is a warp operation)
+    for (uint64_t rec0 = uint64_t(blockIdx.x) * kTokTagThreads + (threadIdx.x & ~31u); rec0 < ntok; rec0 += stride) {
+        const uint64_t rec = rec0 + uint32_t(lane);
+        bool listed = false;
+        if (rec < ntok) {
+            const uint4 d = a.tok_desc[rec];
+            const uint32_t len = d.w & 0xFFFFu;
+            int32_t tok = -1;
+            uint32_t tid = 0;
+            if (len && token_lookup(t, a.text + a.text_base + ((uint64_t(d.y) << 32) | d.x), len, a.norm, tid)) {
+                if (__ldg(&t.tok_info[tid].usable)) {
+                    tok = int32_t(tid);
+                    listed = true;
+                } else if (a.n_unserved) {
+                    atomicAdd(a.n_unserved, 1u);
+                }
+            }
+            a.tok_ids[rec] = tok;
+            if (!listed)
+                for (uint32_t k = 0; k < nt; ++k) a.tok_cands[rec * nt + k] = uint8_t(255);
+        }
+        const unsigned m = __ballot_sync(kFull, listed);
+        if (m) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(a.tok_work, uint32_t(__popc(m)));
+            base = __shfl_sync(kFull, base, 0);
+            if (listed) a.tok_work[kTokWorkHead + base + __popc(m & ((1u << lane) - 1u))] = uint32_t(rec);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kTokTagThreads) k_tok_score(DevTags t, TagArgs a) {
+    const uint32_t nw = a.tok_work[0];
+    const uint32_t nt = t.n_tags;
+    for (uint32_t w = blockIdx.x * kTokTagThreads + threadIdx.x; w < nw; w += gridDim.x * kTokTagThreads) {
+        const uint32_t rec = a.tok_work[kTokWorkHead + w];
+        const uint4 d = a.tok_desc[rec];
+        int32_t cand[kTagMaxSlots];
+#pragma unroll
+        for (int k = 0; k < kTagMaxSlots; ++k) cand[k] = -1;
+        // (characters [d.z, d.z + n_after) are the token's last character and what follows it in its sentence)
+        const int32_t tok = tag_score_token(t, uint32_t(a.tok_ids[rec]), a.char_states ? a.char_states + d.z : nullptr,
+                                            a.type_states ? a.type_states + d.z : nullptr, 0, d.w >> 16, cand, a.n_unserved);
+        if (tok < 0) a.tok_ids[rec] = -1;
+        for (uint32_t k = 0; k < nt; ++k) a.tok_cands[uint64_t(rec) * nt + k] = (tok >= 0 && cand[k] >= 0) ? uint8_t(cand[k]) : uint8_t(255);
+    }
 }
 
 // ---- compact outputs -----------------------------------------------------------------------------------------------------
@@ -408,9 +460,23 @@ cudaError_t launch_tags(const DevTags& t, const TagArgs& a, cudaStream_t stream)
     if (a.tok_desc && a.tok_base) k_tags<true><<<unsigned(nblocks), kTagWarps * 32, 0, stream>>>(t, a);
     else k_tags<false><<<unsigned(nblocks), kTagWarps * 32, 0, stream>>>(t, a);
     if (a.tok_desc && a.tok_base && a.max_tokens) {
-        // (the number of tokens is known on the device only: the grid covers the bound, the surplus threads leave at once)
-        const uint64_t nb2 = (a.max_tokens + kTokTagThreads - 1) / kTokTagThreads;
-        k_tok_tag<<<unsigned(nb2), kTokTagThreads, 0, stream>>>(t, a);
+        // (the number of tokens is known on the device only: resident grids, grid-stride loops)
+        if (!a.tok_work || a.max_tokens > 0xFFFFFFFFull) return cudaErrorInvalidValue;
+        static std::atomic<int> sm_count[64] = {};  // (written with the same value by whoever comes first)
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+        if (sm_count[dev] == 0) {
+            int v = 0;
+            e = cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+            if (e != cudaSuccess) return e;
+            sm_count[dev] = v;
+        }
+        const uint64_t want = (a.max_tokens + kTokTagThreads - 1) / kTokTagThreads;
+        // (resident blocks per SM: 16 x 128 threads at 32 registers, 8 x 128 at 56)
+        k_tok_lookup<<<unsigned(std::min<uint64_t>(want, uint64_t(sm_count[dev]) * 16)), kTokTagThreads, 0, stream>>>(t, a);
+        k_tok_score<<<unsigned(std::min<uint64_t>(want, uint64_t(sm_count[dev]) * 8)), kTokTagThreads, 0, stream>>>(t, a);
     }
     return cudaGetLastError();
 }

@@ -126,10 +126,13 @@ struct TagArgs {
     int32_t* tok_ids = nullptr;             // [n_tokens] token id or -1
     uint8_t* tok_cands = nullptr;           // [n_tokens * n_tags] chosen candidate per slot, 255 = none
     // with tok_desc the sentence-warp kernel only LOCATES the tokens (16 bytes each: byte offset from text + text_base,
-    // index of the last character, byte length | characters left in the sentence << 16) and a second kernel, one thread per
-    // token, predicts the tags: full lanes and short dependent-load chains instead of one sentence per warp
+    // index of the last character, byte length | characters left in the sentence << 16) and two more kernels, one thread per
+    // token, look the tokens up and predict the tags of those that have a model: full lanes and short dependent-load
+    // chains instead of one sentence per warp
     uint4* tok_desc = nullptr;              // [max_tokens] scratch; nullable (then k_tags does everything itself)
     uint64_t max_tokens = 0;                // bound on the number of tokens (e.g. the number of characters)
+    uint32_t* tok_work = nullptr;           // [4 + max_tokens] scratch, needed with tok_desc: [0] counts the tokens that have a
+                                            // tag model, their record indices follow from [4] on (k_tok_lookup -> k_tok_score)
     uint64_t text_base = 0;                 // byte offset the descriptors are relative to (keeps them below 2^64 safely)
     int norm = 0;                           // tokens are looked up by their KyteaFullwidthFilter image (the CLI default:
                                             // fill_tags runs on the pre-filtered sentence, predict/src/main.rs:153-166)
