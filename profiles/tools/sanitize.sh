@@ -34,7 +34,7 @@ for kw, tags in ((dict(), False), (dict(dict_words=2000), False), (dict(tag_mode
     assert np.array_equal(cr.boundaries(), r.boundaries), kw
     if tags:
         res, tok, cand, uns = p.predict_batch_tags(text, offs)      # k_tags (single kernel)
-        ct = p.predict_batch_compact(text, offs, tags=True)         # k_tags<locate> + k_tok_tag
+        ct = p.predict_batch_compact(text, offs, tags=True)         # k_tags<locate> + k_tok_lookup + k_tok_score
         assert np.array_equal(ct.boundaries(), res.boundaries) and ct.token_ids.size == int(ct.n_tokens.sum())
         assert int((ct.token_ids >= 0).sum()) == int((tok >= 0).sum())
         for no_norm in (True, False):                               # k_tok_write_tags

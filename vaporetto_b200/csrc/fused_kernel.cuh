@@ -33,14 +33,6 @@
 #include "fused_launch.hpp"
 #include "kernels_common.cuh"
 
-// A/B switches of the round's last two changes (profiles/r02_ab_micro.txt)
-#ifndef VPT_OPT_ADDR
-#define VPT_OPT_ADDR 1
-#endif
-#ifndef VPT_OPT_COMMON
-#define VPT_OPT_COMMON 1
-#endif
-
 namespace vpt {
 
 namespace {
@@ -358,16 +350,12 @@ template <bool kSeedsSmem>
 __device__ __forceinline__ Rec32 probe_load(const DevTable& ct, const uint8_t* s_seeds, uint32_t h, uint32_t g, uint32_t& slot) {
     const uint32_t seed = seed_of<kSeedsSmem>(ct, s_seeds, mulhi32(h, ct.nbuckets));
     // (as PTX: the compiler otherwise folds "high word of the product, times 32" into a 64-bit shift/mask sequence of six
-    //  ALU-pipe instructions; this is IMAD.HI + IMAD.WIDE on the FMA pipe -- the kernel's ALU pipe is its busiest unit)
-#if VPT_OPT_ADDR
+    //  ALU-pipe instructions; this is IMAD.HI + IMAD.WIDE on the FMA pipe -- the kernel's ALU pipe is its busiest unit:
+    //  0.728 -> 0.713 ms per step of config 2, profiles/r02_ab_micro.txt)
     uint64_t addr;
     asm("mul.hi.u32 %0, %1, %2;" : "=r"(slot) : "r"((g + seed * (h | 1u)) * 0x85EBCA6Bu), "r"(ct.nslots));
     asm("mad.wide.u32 %0, %1, 32, %2;" : "=l"(addr) : "r"(slot), "l"(ct.records));
     return load_record(reinterpret_cast<const void*>(addr), 0);
-#else
-    slot = mulhi32((g + seed * (h | 1u)) * 0x85EBCA6Bu, ct.nslots);
-    return load_record(ct.records, slot);
-#endif
 }
 
 // ---- the stream stage: slots [0, S) of the tile's flat slot stream -> scores / boundaries / states ----------------
@@ -390,7 +378,7 @@ __device__ __forceinline__ void stream_stage(const DevModel& m, const BatchArgs&
     const int p0 = ra - kFHalo;
     const int nchunk = (rb + L - p0 + 31) >> 5;
     const DevTable& ct = m.ct;
-    const bool have_ct = (VPT_OPT_COMMON && kCommon) || ct.present != 0;  // (the common shape has a char scorer: fused.cu)
+    const bool have_ct = kCommon || ct.present != 0;  // (the common shape has a char scorer: fused.cu)
     const uint32_t ka0 = ct.hk.a[0], ka1 = ct.hk.a[1], ka2 = ct.hk.a[2], kb0 = ct.hk.b[0], kb1 = ct.hk.b[1], kb2 = ct.hk.b[2];
     int32_t* const scores = a.scores ? a.scores + obase : nullptr;
     uint8_t* const bounds = a.boundaries + obase;
@@ -607,8 +595,9 @@ k_fused(DevModel m, BatchArgs a, StreamCfg cfg) {
 
     const uint64_t ngroups = (a.n_sent + kFGroup - 1) / kFGroup;
     // (the common shape separates sentences by two slots -- fused.cu checks it --: the separator loop of the scatter step,
-    //  which a whole warp walks for the one lane that sees a sentence start, unrolls to two stores)
-    const int gap = (VPT_OPT_COMMON && kCommon) ? fused_detail::kCommonGap : cfg.gap;
+    //  which a whole warp walks for the one lane that sees a sentence start, unrolls to two stores: with the constant
+    //  char-scorer flag of the stream stage 0.713 -> 0.687 ms per step, profiles/r02_ab_micro.txt)
+    const int gap = kCommon ? fused_detail::kCommonGap : cfg.gap;
     uint32_t phase = 0;
 
     for (;;) {

@@ -187,7 +187,7 @@ __device__ __forceinline__ int32_t tag_token_at(const DevTags& t, const uint8_t*
     return tag_score_token(t, tid, cst, tst, i, n, cand, n_unserved);
 }
 
-// kLocateOnly: phase 1 of the per-token path (descriptors for k_tok_tag); otherwise the kernel predicts the tags itself.
+// kLocateOnly: phase 1 of the per-token path (descriptors for k_tok_lookup / k_tok_score); otherwise the kernel predicts the tags itself.
 template <bool kLocateOnly>
 __global__ void __launch_bounds__(kTagWarps * 32, kLocateOnly ? 8 : 1) k_tags(DevTags t, TagArgs a) {
     __shared__ Rings s_rings[kTagWarps];
@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(kTagWarps * 32, kLocateOnly ? 8 : 1) k_tags(De
                 const uint32_t sb = near ? r.bp[start & kRingMask] : 0u;
                 const uint32_t eb = i + 1 < n ? r.bp[(i + 1) & kRingMask] : uint32_t(b1 - b0);
                 if (kLocateOnly) {
-                    // phase 1 of the per-token path: where the token is; k_tok_tag does the rest, one thread per token
+                    // phase 1 of the per-token path: where the token is; k_tok_lookup and k_tok_score do the rest, one thread per token
                     desc_x = near ? uint32_t(b0 + sb - a.text_base) : 0u;
                     desc_y = uint32_t((b0 + sb - a.text_base) >> 32);
                     desc_z = uint32_t(cb + i);
