@@ -142,10 +142,10 @@ class ClockSampler:
 
 
 CPU_NOTE = ("C++ restatement of the reference algorithm (oracle/vaporetto_oracle.cpp: parse_raw + predict per sentence, "
-            "trie+failure Aho-Corasick with a hashed goto function, merged weights, type table), text pre-loaded; one "
-            "pinned thread pool for the whole measurement, sentences handed out in blocks of 256.  The Rust reference "
-            "cannot be built here (no cargo/rustc); its daachorse double-array automaton is probably faster per "
-            "transition than this port's hashed goto, so the port under-estimates the real CPU baseline")
+            "Aho-Corasick automaton walked as a double array with a code-point mapper -- the layout of the reference's "
+            "daachorse CharwiseDoubleArrayAhoCorasick: 16-byte states, child = base XOR code --, merged weights, type "
+            "table), text pre-loaded; one pinned thread pool for the whole measurement, sentences handed out in blocks of "
+            "256.  The Rust reference cannot be built here (no cargo/rustc): a port, not the reference binary")
 
 
 def usable_cpus():

@@ -14,9 +14,10 @@
 // Third-party arithmetic restated from its published behaviour:
 //  * daachorse 1.x (vaporetto/Cargo.toml:17) `find_overlapping_no_suffix_iter`:
 //    at every text position report only the longest pattern ending there;
-//    `find_overlapping_iter`: all patterns ending there.  Implemented here as a
-//    classic goto/failure Aho-Corasick automaton (no double array: layout does
-//    not affect results).
+//    `find_overlapping_iter`: all patterns ending there.  Built here as a
+//    classic goto/failure Aho-Corasick automaton and walked as a double array
+//    with a code-point mapper (daachorse's charwise layout; the layout does not
+//    affect results, it only keeps the timed CPU arm honest: struct AC).
 //  * bincode 2.0.1 `config::standard()` (vaporetto/Cargo.toml:16): varint
 //    integers, zigzag for signed, length-prefixed Vec/String.
 //
@@ -26,6 +27,8 @@
 #include <atomic>
 #include <chrono>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -632,6 +635,17 @@ struct Merger {
 // goto function: open-addressing hash (state, symbol) -> state; classic failure links.
 // ---------------------------------------------------------------------------
 struct AC {
+    // Double-array form of the finished automaton (the layout daachorse's CharwiseDoubleArrayAhoCorasick walks:
+    // 16-byte states {base, check, fail, output}, child = base XOR code, code = the symbol's rank by frequency from a
+    // mapper table, bases unique so that `check == code` identifies the edge).  Same transitions as the hash form below
+    // -- the layout does not affect results -- but one state record per transition instead of two hash-table lines:
+    // this is what the timed CPU arm walks, so that it is not slower than the reference for a reason the reference
+    // does not have.  ORA_AC=hash in the environment keeps the hash walk (tests compare the two).
+    struct DAState { uint32_t base, check, fail; int32_t out; };
+    static constexpr uint32_t kNone = 0xFFFFFFFFu;
+    vector<DAState> da;
+    vector<uint32_t> code_of;  // symbol -> code (1-based), 0 = the symbol occurs in no pattern
+    bool use_da = false;
     vector<int32_t> fail, out, own, depth;
     vector<uint64_t> hkey;   // (state << 21 | symbol) + 1, 0 = empty
     vector<int32_t> hval;
@@ -706,6 +720,11 @@ struct AC {
                 q.push_back(e.second);
             }
         }
+        {
+            const char* e = std::getenv("ORA_AC");
+            use_da = !(e && string(e) == "hash");
+            if (use_da) build_da(kids);
+        }
         // rehash compactly (2 slots per transition) and pack key+value side by side for the walk
         size_t ncap = 16;
         while (ncap < fail.size() * 2) ncap <<= 1;
@@ -724,7 +743,110 @@ struct AC {
             hval[j] = ov[i];
         }
     }
-    inline int step(int s, uint32_t c) const {
+    // Lays the automaton out as a double array: states in breadth-first order, every state's children at base XOR code.
+    void build_da(const vector<vector<std::pair<uint32_t, int>>>& kids) {
+        // codes by symbol frequency over the edges (frequent symbols get small codes: children stay close to the base)
+        std::unordered_map<uint32_t, uint64_t> freq;
+        uint32_t max_sym = 0;
+        for (auto& ks : kids) for (auto& e : ks) { ++freq[e.first]; max_sym = std::max(max_sym, e.first); }
+        vector<std::pair<uint64_t, uint32_t>> order;
+        for (auto& kv : freq) order.emplace_back(kv.second, kv.first);
+        std::sort(order.begin(), order.end(), [](auto& a, auto& b) { return a.first != b.first ? a.first > b.first : a.second < b.second; });
+        code_of.assign(size_t(max_sym) + 1, 0);
+        for (size_t i = 0; i < order.size(); ++i) code_of[order[i].second] = uint32_t(i + 1);
+        uint32_t span = 1;  // XOR with a code changes only the bits below `span`
+        while (span <= order.size()) span <<= 1;
+        const size_t n = kids.size();
+        vector<uint32_t> pos(n, kNone);  // trie state -> double-array index
+        vector<uint8_t> occ, base_used;
+        // free slots as a doubly linked list in ascending order (index `cap` = list end); a search that does not find
+        // a base among the first kTries free slots opens a fresh block of `span` slots (keeps the build linear)
+        vector<uint32_t> nxt, prv;
+        uint32_t head = kNone, tail = kNone;
+        auto grow = [&]() {
+            const size_t old = da.size();
+            da.resize(old + span, DAState{kNone, kNone, 0, -1});
+            occ.resize(old + span, 0);
+            base_used.resize(old + span, 0);
+            nxt.resize(old + span, kNone);
+            prv.resize(old + span, kNone);
+            for (size_t i = old; i < old + span; ++i) {
+                prv[i] = tail;
+                if (tail != kNone) nxt[tail] = uint32_t(i); else head = uint32_t(i);
+                tail = uint32_t(i);
+            }
+            return uint32_t(old);
+        };
+        auto take = [&](uint32_t i) {
+            occ[i] = 1;
+            if (prv[i] != kNone) nxt[prv[i]] = nxt[i]; else head = nxt[i];
+            if (nxt[i] != kNone) prv[nxt[i]] = prv[i]; else tail = prv[i];
+        };
+        da.clear();
+        grow();
+        pos[0] = 0;
+        take(0);
+        constexpr int kTries = 16384;  // (fill 60-90 % on the bench models; the build stays at seconds)
+        uint32_t cursor = kNone;
+        vector<int> q{0};
+        vector<uint32_t> codes;
+        for (size_t h = 0; h < q.size(); ++h) {
+            const int st = q[h];
+            if (kids[st].empty()) continue;
+            codes.clear();
+            for (auto& e : kids[st]) codes.push_back(code_of[e.first]);
+            uint32_t base = kNone;
+            int tries = 0;
+            bool wrapped = false;
+            // next fit: the search resumes where the last one ended (slots in front of the cursor were rejected by recent
+            // states; single-child states still come back to them through the wrap-around at the list end)
+            // (a taken slot keeps its forward link: following the links from it reaches the next free slot behind it)
+            while (cursor != kNone && occ[cursor]) cursor = nxt[cursor];
+            if (cursor == kNone) cursor = head;
+            for (uint32_t f = cursor;; f = nxt[f]) {
+                if (f == kNone && !wrapped) { f = head; wrapped = true; }
+                if (f == kNone || ++tries > kTries) f = grow();  // (a fresh block: every slot free, no base used)
+                cursor = f;
+                const uint32_t b = f ^ codes[0];
+                if (base_used[b]) continue;
+                bool ok = true;
+                for (uint32_t c : codes)
+                    if (occ[b ^ c]) { ok = false; break; }
+                if (ok) { base = b; break; }
+            }
+            base_used[base] = 1;
+            da[pos[st]].base = base;
+            for (size_t k = 0; k < kids[st].size(); ++k) {
+                const uint32_t idx = base ^ codes[k];
+                take(idx);
+                da[idx].check = codes[k];
+                pos[kids[st][k].second] = idx;
+                q.push_back(kids[st][k].second);
+            }
+        }
+        if (std::getenv("ORA_AC_DEBUG")) fprintf(stderr, "[oracle] double array: %zu states in %zu slots\n", n, da.size());
+        for (size_t st = 0; st < n; ++st) {
+            da[pos[st]].fail = pos[fail[st]];
+            da[pos[st]].out = out[st];
+        }
+    }
+    inline int da_child(int s, uint32_t code) const {
+        const uint32_t b = da[s].base;
+        if (b == kNone) return -1;
+        const uint32_t idx = b ^ code;
+        return idx < da.size() && da[idx].check == code ? int(idx) : -1;
+    }
+    inline int step_da(int s, uint32_t c) const {
+        const uint32_t code = c < code_of.size() ? code_of[c] : 0u;
+        if (code == 0) return 0;  // a symbol outside every pattern: all the way back to the root
+        for (;;) {
+            const int nx = da_child(s, code);
+            if (nx >= 0) return nx;
+            if (s == 0) return 0;
+            s = int(da[s].fail);
+        }
+    }
+    inline int step_hash(int s, uint32_t c) const {
         for (;;) {
             const int nx = find(s, c);
             if (nx >= 0) return nx;
@@ -732,6 +854,9 @@ struct AC {
             s = fail[s];
         }
     }
+    // (state numbers are indices of whichever form is walked: callers only feed them back)
+    inline int step(int s, uint32_t c) const { return use_da ? step_da(s, c) : step_hash(s, c); }
+    inline int out_of(int s) const { return use_da ? da[s].out : out[s]; }
 };
 
 // CharacterType::get_type (sentence.rs:50-67)
@@ -823,6 +948,10 @@ struct PmaScorer {
     vector<int32_t> w_off, w_len;
     vector<uint32_t> w_begin;
     vector<int32_t> w_data;
+    // one record per pattern for the walk: short rows inline (the reference's WeightVector::Fixed([i32; 8]) lives inside
+    // its Option<PositionalWeight> the same way, predictor.rs:60-70): one cache line per match instead of four arrays
+    struct WRec { int32_t off, len; uint32_t begin; int32_t fixed[8]; uint32_t pad; };
+    vector<WRec> w_rec;
     TagTable tag_weight;
     bool tag_variant = false;
     bool is_char = true;
@@ -871,6 +1000,12 @@ struct PmaScorer {
             if (w) { w_off.push_back(w->offset); w_len.push_back(int32_t(w->weight.size())); w_data.insert(w_data.end(), w->weight.begin(), w->weight.end()); }
             else { w_off.push_back(0); w_len.push_back(-1); }
         }
+        w_rec.assign(weights.size(), WRec{});
+        for (size_t i = 0; i < weights.size(); ++i) {
+            WRec& r = w_rec[i];
+            r.off = w_off[i]; r.len = w_len[i]; r.begin = w_begin[i];
+            for (int k = 0; k < 8; ++k) r.fixed[k] = (k < w_len[i]) ? w_data[w_begin[i] + size_t(k)] : 0;
+        }
     }
 
     // add_scores: walk, longest match per end position (boundary_scorer.rs:93-113 etc.)
@@ -886,18 +1021,26 @@ struct PmaScorer {
         int32_t* ys = s.boundary_scores.data();
         for (size_t i = 0; i < n; ++i) {
             st = pma.step(st, is_char ? s.chars[i] : uint32_t(s.char_types[i]));
-            const int p = pma.out[st];
+            const int p = pma.out_of(st);
             if (p < 0) continue;
             const size_t end = i + 1;  // char index (== str_to_char_pos[m.end()] of the bytewise reference path)
-            if (w_len[p] >= 0) {
+            const WRec& wr = w_rec[size_t(p)];
+            if (wr.len >= 0) {
                 // PositionalWeight::add_score (predictor.rs:176-213), ragged add clipped at both strip ends
-                const long pos = long(end + s.score_padding) - 1 + w_off[p];
-                const int32_t* w = w_data.data() + w_begin[p];
-                for (long k = 0; k < w_len[p]; ++k) {
-                    const long q = pos + k;
-                    if (q < 0) continue;
-                    if (q >= ny) break;
-                    ys[q] = wadd(ys[q], w[k]);
+                const long pos = long(end + s.score_padding) - 1 + wr.off;
+                const int32_t* w = wr.len <= 8 ? wr.fixed : w_data.data() + wr.begin;
+                if (pos >= 0 && pos + wr.len <= ny) {
+                    // the row lies inside the strip (always, for the reference's Fixed rows over its padded strip):
+                    // straight adds, no per-element clipping
+                    int32_t* y = ys + pos;
+                    for (long k = 0; k < wr.len; ++k) y[k] = wadd(y[k], w[k]);
+                } else {
+                    for (long k = 0; k < wr.len; ++k) {
+                        const long q = pos + k;
+                        if (q < 0) continue;
+                        if (q >= ny) break;
+                        ys[q] = wadd(ys[q], w[k]);
+                    }
                 }
             }
             if (states) (*states)[end - 1] = uint32_t(p);

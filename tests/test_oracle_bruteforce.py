@@ -59,3 +59,30 @@ def test_oracle_equals_bruteforce(model, text):
     want, wb = bruteforce.predict(model, text)
     assert got.tolist() == want
     assert gb.tolist() == wb
+
+
+def test_oracle_double_array_walk_equals_hash_walk(monkeypatch):
+    """The oracle walks the automaton as a double array (the layout of the reference's daachorse matcher: what the
+    timed CPU arm runs); ORA_AC=hash keeps the hash-probed goto function it is built from.  Same transitions: scores,
+    boundaries and pattern-id states agree on a synthetic model with n-grams, dictionary words and tags."""
+    import numpy as np
+    from vpt_testlib import synth
+
+    mb = synth.gen_model_bccwj_shaped(n_patterns=20000, sample_sentences=50000, dict_words=30000)
+    text, offs, _ = synth.gen_text(3000, 40)
+    outs = []
+    for mode in ("hash", "da"):
+        monkeypatch.setenv("ORA_AC", mode)
+        o = OraclePredictor(mb)
+        sc, bd, boff, st_ = o.predict_batch(text, offs, nthreads=2)
+        outs.append((sc.copy(), bd.copy(), boff.copy(), st_.copy()))
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)
+    mt = synth.gen_model_bccwj_shaped(n_patterns=5000, sample_sentences=20000, tag_models=300)
+    souts = []
+    for mode in ("hash", "da"):
+        monkeypatch.setenv("ORA_AC", mode)
+        o = OraclePredictor(mt, predict_tags=True)
+        souts.append([np.copy(x) for x in o.predict_batch_states(text[:int(offs[500])], offs[:501], nthreads=1)])
+    for a, b in zip(*souts):
+        assert np.array_equal(a, b)
