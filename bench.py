@@ -307,7 +307,8 @@ def workload_config(args, n_sent):
                         "n-grams, %s), synthetic JP sentences%s%s" %
                         (cfg_index, args.patterns, extra, " (ragged lognormal lengths)" if args.ragged else " of 40 chars", shard),
             "sentences_per_gpu": n_sent, "parallelism": "dp%d (sentences sharded, NCCL model broadcast only)" % args.gpus,
-            "l2": "batch (115 MB in + 195 MB out per GPU) exceeds L2; no flush needed"}
+            "l2": "batch (%d MB in + %d MB out per GPU) exceeds L2; no flush needed" % (round(n_sent * 114.8e-6),
+                                                                                            round(n_sent * 195e-6))}
 
 
 def main():
