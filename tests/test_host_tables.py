@@ -23,15 +23,20 @@ CSRC = os.path.join(ROOT, "vaporetto_b200", "csrc")
 def emul():
     so = os.path.join(HERE, "native", "libhost_emul.so")
     srcs = [os.path.join(HERE, "native", "host_emul.cpp")] + [os.path.join(CSRC, f) for f in
-                                                             ("predictor_build.cpp", "builder.cpp", "model.cpp")]
-    deps = srcs + [os.path.join(CSRC, f) for f in ("builder.hpp", "keys.hpp", "predictor_build.hpp", "common.hpp")]
+                                                             ("predictor_build.cpp", "builder.cpp", "model.cpp", "tags_build.cpp")]
+    deps = srcs + [os.path.join(CSRC, f) for f in ("builder.hpp", "keys.hpp", "predictor_build.hpp", "common.hpp", "tags.hpp")]
     if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in deps):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so] + srcs)
+        # (tags.hpp declares the launch interface next to the tables: cuda_runtime.h for the types only, nothing is linked)
+        cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I" + cuda_inc, "-o", so] + srcs)
     L = C.CDLL(so)
     L.emul_predict.restype = C.c_long
     L.emul_predict.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_char_p, C.c_size_t, C.c_void_p, C.c_void_p,
                                C.c_void_p, C.c_void_p]
     L.emul_last_error.restype = C.c_char_p
+    L.emul_predict_tags.restype = C.c_long
+    L.emul_predict_tags.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p]
     return L
 
 
@@ -176,3 +181,62 @@ def test_builder_survives_mutated_models(tmp_path):
     out = subprocess.run([exe, str(tmp_path / "samples.bin"), "3000"], capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "build fuzz done" in out.stdout
+
+
+# ---- tag tables (tags_build.cpp: token table, key lists, chain tables) interpreted with the kernels' steps ---------------
+
+def run_tags(L, model_bytes, text, o):
+    """Tag prediction from the product's flat tag tables on the CPU (tests/native/host_emul.cpp: emul_predict_tags) on
+    the oracle's boundaries and the emulated pattern-id states; returns (tag_token, tag_cand[n, n_tags], unserved)."""
+    _, bd = o.predict(text)
+    _, cs, ts, _ = run(L, model_bytes, text, tags=True)
+    b = text.encode()
+    n = len(cs)
+    nt = max(o.n_tags, 1)
+    bd = np.ascontiguousarray(np.asarray(bd, np.uint8))
+    cs = np.asarray(cs, np.uint32)
+    ts = np.asarray(ts, np.uint32)
+    tok = np.zeros(n, np.int32)
+    cand = np.zeros(n * nt, np.int32)
+    uns = np.zeros(1, np.int32)
+    rc = L.emul_predict_tags(model_bytes, len(model_bytes), b, len(b), bd.ctypes.data, cs.ctypes.data, ts.ctypes.data,
+                             tok.ctypes.data, cand.ctypes.data, uns.ctypes.data)
+    assert rc == o.n_tags, L.emul_last_error()
+    return tok, cand.reshape(n, nt)[:, :o.n_tags], int(uns[0])
+
+
+def _check_tags(L, mb, texts):
+    o = OraclePredictor(mb, predict_tags=True)
+    for text in texts:
+        tok, cand, uns = run_tags(L, mb, text, o)
+        ott, oti = o.predict_tags(text)
+        assert uns == 0
+        # (token ids may be numbered differently only if tokens repeat in the model; the candidates must agree)
+        assert (tok >= 0).tolist() == (ott >= 0).tolist(), text
+        assert cand.tolist() == oti.tolist(), text
+
+
+def test_tag_tables_on_reference_vectors(emul):
+    # predictor.rs:863-903 (tags of "この人は地球人だ") and the bundled model's doctest sentences
+    _check_tags(emul, encode_model(kat.PREDICTOR_TEST_MODEL), ["この人は地球人だ", "地球人", "この人"])
+    with open(os.path.join(GOLDEN, "model.bin"), "rb") as f:
+        _check_tags(emul, f.read(), ["まぁ社長は火星猫だ", "まぁ良いだろう", "火星", "社長は社長だ" * 5])
+
+
+@pytest.mark.parametrize("cw,tw,maxdict,tags", [(3, 3, 5, 3), (1, 5, 3, 2), (2, 2, 2, 4), (3, 3, 9, 6), (5, 4, 4, 3)])
+def test_tag_tables_random_models(emul, cw, tw, maxdict, tags):
+    """Random tag models (suffix chains through n-grams and dictionary words, several rel positions, windows wider than
+    three): the key-list scan with the truncation rule gives the sums of the reference's build-time merge."""
+    from test_gpu_parity import _random_model
+    rng = np.random.default_rng(177 + 1000 * cw + 100 * tw + maxdict + tags)
+    for _ in range(4):
+        model, alpha = _random_model(rng, cw, tw, maxdict=maxdict, tags=tags)
+        texts = ["".join(rng.choice(list(alpha), size=rng.integers(1, 50))) for _ in range(60)]
+        _check_tags(emul, encode_model(model), texts)
+
+
+def test_tag_tables_synthetic_model(emul):
+    from vpt_testlib import synth
+    mb = synth.gen_model_bccwj_shaped(n_patterns=8000, sample_sentences=20000, tag_models=400)
+    text, offs, _ = synth.gen_text(40, 40, seed=synth.TEXT_SEED + 13)
+    _check_tags(emul, mb, [bytes(text[int(offs[i]):int(offs[i + 1])]).decode() for i in range(len(offs) - 1)])
