@@ -68,6 +68,50 @@ bool find_node(const Tab& t, const std::vector<uint32_t>& sym, size_t g, const u
     return found;
 }
 
+// The probe order of k_fused (fused_kernel.cuh, stages 1-3 of the stream stage), word for word: the node of the last TWO
+// symbols first (one symbol at a sentence start), compared on its 32-bit halves with the child mask and the deep-key marker
+// bits masked as the kernel masks them; then the 3-symbol node if the 2-symbol record's child mask has the bit of the
+// third symbol, or the 1-symbol node if the 2-symbol node does not exist; a 3-symbol node with extensions walks on.
+// Must select the same record as find_node (which asks for the longest node first): that is what the builder's child
+// masks promise.
+bool find_node_fused(const Tab& t, const std::vector<uint32_t>& sym, size_t g, const uint32_t*& rec, uint32_t& slot, bool& deep_hit) {
+    deep_hit = false;
+    const uint32_t c = sym[g], c2 = g >= 1 ? sym[g - 1] : 0, c1 = g >= 2 ? sym[g - 2] : 0;
+    const uint32_t slotA = table_slot(t.geom(), t.seeds(), shallow_key(0, c2, c));
+    const uint32_t* rA = t.rec(slotA);
+    const uint32_t klo = c | (c2 << 21), khi = c2 >> 11;
+    const bool f1 = rA[0] == klo && (rA[1] & 0x600003FFu) == khi;
+    const bool w3 = f1 && c1 != 0 && ((rA[1] >> (10u + child_bit(c1))) & 1u) != 0, w1 = !f1 && c2 != 0;
+    bool f2 = false;
+    uint32_t slotB = 0;
+    const uint32_t* rB = nullptr;
+    if (w3 || w1) {
+        slotB = table_slot(t.geom(), t.seeds(), w3 ? shallow_key(c1, c2, c) : shallow_key(0, 0, c));
+        rB = t.rec(slotB);
+        const uint32_t kloB = w3 ? klo : c, khiB = w3 ? (khi | (c1 << 10)) : 0u;
+        f2 = rB[0] == kloB && (rB[1] & 0x7FFFFFFFu) == khiB;
+    }
+    if (f2) {
+        rec = rB;
+        slot = slotB;
+        if (w3 && (rec[1] >> 31) && g >= 3) {
+            size_t i = g - 2;
+            uint32_t node = t.slot_node()[slot];
+            while (i > 0) {
+                --i;
+                const uint32_t* nrec; uint32_t nslot;
+                if (!t.probe(deep_key(node, sym[i]), nrec, nslot, true)) break;
+                rec = nrec; slot = nslot; deep_hit = true;
+                if (!(rec[1] >> 31)) break;
+                node = t.slot_node()[slot];
+            }
+        }
+        return true;
+    }
+    if (f1) { rec = rA; slot = slotA; return true; }
+    return false;
+}
+
 }  // namespace
 
 extern "C" {
@@ -125,7 +169,15 @@ long emul_predict(const uint8_t* model, size_t model_len, int predict_tags, cons
             const std::vector<uint32_t>& sym = which ? tys : cps;
             for (size_t g = 0; g < n; ++g) {
                 const uint32_t* rec; uint32_t slot; bool deep_hit;
-                if (!find_node(t, sym, g, rec, slot, deep_hit)) continue;
+                const bool found = find_node(t, sym, g, rec, slot, deep_hit);
+                if (which == 0 && t.bt->fast) {
+                    // (the char table in the inline format is what k_fused reads: its probe order must agree)
+                    const uint32_t* rec2 = nullptr; uint32_t slot2 = 0; bool deep2 = false;
+                    const bool found2 = find_node_fused(t, sym, g, rec2, slot2, deep2);
+                    if (found2 != found || (found && (slot2 != slot || deep2 != deep_hit)))
+                        throw Error(kInternal, "k_fused probe order selects a different node record");
+                }
+                if (!found) continue;
                 if (t.bt->fast) {
                     if (h.emit_states && which == 0 && cstates) cstates[g] = t.slot_pid()[slot];
                     for (int j = 0; j < kInlineWidth; ++j) {

@@ -240,3 +240,18 @@ def test_tag_tables_synthetic_model(emul):
     mb = synth.gen_model_bccwj_shaped(n_patterns=8000, sample_sentences=20000, tag_models=400)
     text, offs, _ = synth.gen_text(40, 40, seed=synth.TEXT_SEED + 13)
     _check_tags(emul, mb, [bytes(text[int(offs[i]):int(offs[i + 1])]).decode() for i in range(len(offs) - 1)])
+
+
+def test_fused_probe_order_on_the_fuzz_case(emul):
+    """emul_predict also walks the char table in k_fused's probe order (2-symbol node first, child mask, then the 3- or the
+    1-symbol node) and fails when it selects another record than the longest-first order.  The model the GPU fuzzer found
+    (a (parent node, symbol) record whose parent id equals a code point aliases an absent bigram unless the deep-key marker
+    bits are compared: tests/golden/fuzz_cases) passes with the kernel's compare."""
+    d = os.path.join(GOLDEN, "fuzz_cases")
+    mb = np.load(os.path.join(d, "case1266_model.npy")).tobytes()
+    text, offs = np.load(os.path.join(d, "case1266_text.npy")), np.load(os.path.join(d, "case1266_offs.npy"))
+    o = OraclePredictor(mb)
+    for i in range(len(offs) - 1):
+        s = bytes(text[int(offs[i]):int(offs[i + 1])]).decode()
+        sc, _, _, info = run(emul, mb, s)
+        assert sc == o.predict(s)[0].tolist()
