@@ -32,6 +32,7 @@
 
 #include "fused_launch.hpp"
 #include "kernels_common.cuh"
+#include "utf8_window.hpp"
 
 namespace vpt {
 
@@ -177,33 +178,13 @@ __device__ __forceinline__ int32_t up_i(int32_t cur, int32_t prev, int d, int la
     return int32_t(up_u(uint32_t(cur), uint32_t(prev), d, lane));
 }
 
-// Code point of the character whose lead byte is the low byte of x (x = the four bytes from the lead on).  `len` is
-// the length the lead byte announces (0 for an empty slot); `bad` is set when the bytes after the lead are not the
-// continuation bytes it asks for, for overlong forms, surrogates, values above U+10FFFF and the lead bytes F8..FF.
-// Together with "the lengths add up to the bytes of the tile" and "no sentence starts on a continuation byte" this
-// is str::from_utf8 (reference sentence.rs:160-196).
-__device__ __forceinline__ uint32_t decode_any(uint32_t x, bool& bad, uint32_t& len) {
-    const uint32_t b0 = x & 0xFFu;
-    const uint32_t t = ((x << 4) & 0x3F000u) | ((x >> 10) & 0xFC0u) | ((x >> 24) & 0x3Fu);  // b1<<12 | b2<<6 | b3
-    const uint32_t l = (b0 >= 0xC0u) + (b0 >= 0xE0u) + (b0 >= 0xF0u);                      // continuation bytes
-    const uint32_t tail = t >> (18u - 6u * l);
-    const uint32_t head = (b0 & (0x3Fu >> l)) << (6u * l);
-    const uint32_t c = b0 < 0x80u ? b0 : (head | tail);
-    const uint32_t minc = 1u << ((0x100B0700u >> (8u * l)) & 31u);  // 1, 0x80, 0x800, 0x10000
-    const uint32_t cm = (0xC0C0C0C0u >> (8u * (3u - l))) & 0xFFFFFF00u;  // bits 7..6 of the bytes 1 .. l
-    bad = b0 >= 0x80u && (c < minc || c - 0xD800u < 0x800u || c > 0x10FFFFu || b0 >= 0xF8u || (x & cm) != (0x80808080u & cm));
-    len = x ? l + 1u : 0u;
-    return c;
-}
-// The same for a warp: Japanese text is three-byte characters and ASCII; the general decoder runs only for a chunk
+// (decode_any / decode_ascii_or_three: utf8_window.hpp -- plain arithmetic, also compiled and tested on the host)
+// The decoder of a warp: Japanese text is three-byte characters and ASCII; the general decoder runs only for a chunk
 // that holds another lead byte.
 __device__ __forceinline__ uint32_t decode_checked(uint32_t x, bool& bad, uint32_t& len) {
     const bool ascii = (x & 0x80u) == 0, three = (x & 0xF0u) == 0xE0u;
     if (__any_sync(kFull, !(ascii || three))) return decode_any(x, bad, len);
-    const uint32_t c3 = ((x & 0x0Fu) << 12) | ((x >> 2) & 0xFC0u) | ((x >> 16) & 0x3Fu);
-    bad = three && (c3 < 0x800u || c3 - 0xD800u < 0x800u || (x & 0x00C0C000u) != 0x00808000u);
-    len = three ? 3u : (x ? 1u : 0u);
-    return ascii ? (x & 0xFFu) : c3;
+    return decode_ascii_or_three(x, ascii, three, bad, len);
 }
 
 __device__ __forceinline__ uint32_t type_of(uint32_t c, const uint8_t* s_tytab) {
