@@ -4,10 +4,12 @@
 //   decode_any:             every lead byte that is not a continuation byte x every combination of the bytes behind it
 //   decode_ascii_or_three:  every ASCII / E0..EF lead x every combination of the two bytes behind it; must also agree
 //                           with decode_any there
+//   char_type / the BMP type table of the tile kernels (textnorm.hpp): every code point against the reference's ranges
 // Prints "utf8 window ok <cases>" and exits 0, or the first mismatch and exits 1.
 #include <cstdint>
 #include <cstdio>
 
+#include "../../vaporetto_b200/csrc/textnorm.hpp"
 #include "../../vaporetto_b200/csrc/utf8_window.hpp"
 
 namespace {
@@ -39,9 +41,38 @@ bool ref_decode(const uint8_t* b, uint32_t& cp, uint32_t& len) {
     return false;
 }
 
+// CharacterType::get_type, range by range as the reference lists them (sentence.rs:50-67)
+uint32_t ref_type(uint32_t c) {
+    auto in = [c](uint32_t lo, uint32_t hi) { return c >= lo && c <= hi; };
+    if (in(0x30, 0x39) || in(0xFF10, 0xFF19)) return 1;
+    if (in(0x41, 0x5A) || in(0x61, 0x7A) || in(0xFF21, 0xFF3A) || in(0xFF41, 0xFF5A)) return 2;
+    if (in(0x3040, 0x3096)) return 3;
+    if (in(0x30A0, 0x30FA) || in(0x30FC, 0x30FF) || in(0xFF66, 0xFF9F)) return 4;
+    if (in(0x3400, 0x4DBF) || in(0x4E00, 0x9FFF) || in(0xF900, 0xFAFF) || in(0x20000, 0x2A6DF) || in(0x2A700, 0x2B73F) ||
+        in(0x2B740, 0x2B81F) || in(0x2B820, 0x2CEAF) || in(0x2F800, 0x2FA1F))
+        return 5;
+    return 6;
+}
+
+// the arithmetic char_type against the reference's ranges for every code point, and the tile kernels' BMP type table
+// (page table + sub-tables of the mixed pages) against char_type for every BMP code point
+bool check_types() {
+    for (uint32_t c = 0; c < 0x110000u; ++c)
+        if (vpt::char_type(c) != ref_type(c)) { printf("char_type mismatch at U+%04X: %u, want %u\n", c, vpt::char_type(c), ref_type(c)); return false; }
+    uint8_t tab[vpt::kTypeTableBytes];
+    for (int i = 0; i < vpt::kTypeTableBytes; ++i) tab[i] = uint8_t(vpt::type_table_entry(uint32_t(i)));
+    for (uint32_t c = 0; c < 0x10000u; ++c)
+        if (vpt::type_from_table(tab, c) != ref_type(c)) {
+            printf("type table mismatch at U+%04X: %u, want %u\n", c, vpt::type_from_table(tab, c), ref_type(c));
+            return false;
+        }
+    return true;
+}
+
 }  // namespace
 
 int main() {
+    if (!check_types()) return 1;
     uint64_t cases = 0;
     const uint8_t probes3[] = {0x00, 0x41, 0x7F, 0x80, 0xBF, 0xC0, 0xE3, 0xFF};
     for (uint32_t b0 = 0; b0 < 256; ++b0) {

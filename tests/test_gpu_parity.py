@@ -284,6 +284,36 @@ def test_random_models_vs_oracle(cw, tw, maxdict, tags):
                 assert r.type_states[c0:c0 + len(ots)].tolist() == ots.tolist()
 
 
+@pytest.mark.parametrize("cw,tw", [(3, 3), (3, 2), (4, 4), (0, 3)])
+def test_character_types_at_range_edges(cw, tw):
+    """Both sides of every edge of CharacterType::get_type's ranges (sentence.rs:50-67), mixed into kana text: the tile
+    kernels type BMP characters from a page table, and a page that holds two types needs its own sub-table -- U+4DBF | U+4DC0
+    (the end of CJK Extension A inside page 4D) was the one that had none."""
+    edges = [0x2F, 0x30, 0x39, 0x3A, 0x40, 0x41, 0x5A, 0x5B, 0x60, 0x61, 0x7A, 0x7B, 0x303F, 0x3040, 0x3096, 0x3097, 0x309F, 0x30A0,
+             0x30FA, 0x30FB, 0x30FC, 0x30FF, 0x3100, 0x33FF, 0x3400, 0x4D00, 0x4DBF, 0x4DC0, 0x4DFF, 0x4E00, 0x9FFF, 0xA000,
+             0xF8FF, 0xF900, 0xFAFF, 0xFB00, 0xFF0F, 0xFF10, 0xFF19, 0xFF1A, 0xFF20, 0xFF21, 0xFF3A, 0xFF3B, 0xFF40, 0xFF41, 0xFF5A,
+             0xFF5B, 0xFF65, 0xFF66, 0xFF9F, 0xFFA0, 0x1FFFF, 0x20000, 0x2A6DF, 0x2A6E0, 0x2A6FF, 0x2A700, 0x2B73F, 0x2B740, 0x2B81F,
+             0x2B820, 0x2CEAF, 0x2CEB0, 0x2F7FF, 0x2F800, 0x2FA1F, 0x2FA20]
+    rng = np.random.default_rng(4242 + 10 * cw + tw)
+    model, alpha = _random_model(rng, cw, tw, maxdict=3)
+    # every type n-gram up to length 3 carries a weight: a wrong type changes a score
+    tng = {}
+    for n in (1, 2, 3):
+        for k in range(6 ** n):
+            g = bytes(1 + (k // 6 ** j) % 6 for j in range(n))
+            tng[g] = rng.integers(-32767, 32768, size=max(2 * tw - n + 1, 0)).tolist()
+    model["type_ngrams"] = list(tng.items()) if tw else []
+    mb = encode_model(model)
+    p, o = make(mb), OraclePredictor(mb)
+    pool = [chr(c) for c in edges] + list(alpha)
+    sents = ["".join(rng.choice(pool, size=rng.integers(1, 70))) for _ in range(600)]
+    sents += ["".join(chr(c) for c in edges), "".join(chr(c) for c in range(0x4DB0, 0x4E10))]
+    lens = [len(x.encode()) for x in sents]
+    offs = np.zeros(len(lens) + 1, np.uint64)
+    np.cumsum(lens, out=offs[1:])
+    check_batch(p, o, np.frombuffer("".join(sents).encode(), np.uint8), offs)
+
+
 @pytest.fixture(scope="module")
 def synth_model():
     return synth.gen_model_bccwj_shaped(n_patterns=30000, sample_sentences=60000)

@@ -94,7 +94,7 @@ struct FLayout {
     static constexpr int kOffTypeA = kOffSeeds + (kSeedsSmem ? kFSeedCap : 0);
     static constexpr int kOffTypeB = kOffTypeA + (kCommon ? 4 * kFTypeSub : 0);
     static constexpr int kOffTyTab = kOffTypeB + (kCommon ? 4 * kFTypeSub : 0);
-    static constexpr int kOffSub = kOffTyTab + 1024;
+    static constexpr int kOffSub = kOffTyTab + kTypeTableBytes;
     // per sub-block
     static constexpr int kSText = 0;
     static constexpr int kSRaw = kSText + kFTextCap + 32;
@@ -189,9 +189,7 @@ __device__ __forceinline__ uint32_t decode_checked(uint32_t x, bool& bad, uint32
 
 __device__ __forceinline__ uint32_t type_of(uint32_t c, const uint8_t* s_tytab) {
     if (c >= 0x10000u) return char_type(c);
-    uint32_t ty = s_tytab[c >> 8];
-    if (ty & 0x80u) ty = s_tytab[256u + ((ty & 3u) << 8) + (c & 255u)];
-    return ty;
+    return type_from_table(s_tytab, c);
 }
 
 __device__ __forceinline__ uint32_t lds_window(const uint8_t* s_text, uint32_t pos) {
@@ -560,17 +558,8 @@ k_fused(DevModel m, BatchArgs a, StreamCfg cfg) {
             s_tb[i] = __ldg(m.type_b + i);
         }
     }
-    for (int i = threadIdx.x; i < 1024; i += Lay::kThreads) {
-        // character types by table: page table over c >> 8 (entries >= 0x80 select a 256-entry sub-table)
-        uint32_t v;
-        if (i < 256) {
-            v = i == 0x00 ? 0x80u : i == 0x30 ? 0x81u : i == 0xFF ? 0x82u : char_type(uint32_t(i) << 8);
-        } else {
-            const uint32_t page = i < 512 ? 0x00u : i < 768 ? 0x30u : 0xFFu;
-            v = char_type((page << 8) | uint32_t(i & 255));
-        }
-        s_tytab[i] = uint8_t(v);
-    }
+    // character types by table: page table over c >> 8 + the sub-tables of the mixed pages (textnorm.hpp)
+    for (int i = threadIdx.x; i < kTypeTableBytes; i += Lay::kThreads) s_tytab[i] = uint8_t(type_table_entry(uint32_t(i)));
     if (tid == 0) mbar_init(s_bar, 1);
     __syncthreads();
 

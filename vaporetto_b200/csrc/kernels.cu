@@ -388,8 +388,8 @@ constexpr int kSubBytes = (kOffBar + 16 + 15) & ~15;
 constexpr int kOffSeeds = 0;
 constexpr int kOffTypeA = kOffSeeds + kSeedCap;
 constexpr int kOffTypeB = kOffTypeA + 4 * kTypeSub;
-constexpr int kOffTyTab = kOffTypeB + 4 * kTypeSub;  // character-type page table (256 B) + 3 sub-tables (768 B)
-constexpr int kOffSub = kOffTyTab + 1024;
+constexpr int kOffTyTab = kOffTypeB + 4 * kTypeSub;  // character-type page table (256 B) + 4 sub-tables (textnorm.hpp)
+constexpr int kOffSub = kOffTyTab + kTypeTableBytes;
 constexpr int kTileSmem = kOffSub + kSubBlocks * kSubBytes;
 static_assert(4 * kSlotCap <= kTextCap, "sc aliases the text buffer");
 static_assert(2 * (kSlotCap / 32) * 8 * 4 <= 2 * kSlotCap, "spill arrays alias the position buffer");
@@ -563,18 +563,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_fast(DevModel m, Batch
     }
     // character types by table: page table over c >> 8 (entries >= 0x80 select a 256-entry sub-table)
     uint8_t* s_tytab = smem + kOffTyTab;
-    {
-        const int i = threadIdx.x;  // 1024 threads fill 1024 bytes
-        uint32_t v;
-        if (i < 256) {
-            v = i == 0x00 ? 0x80u : i == 0x30 ? 0x81u : i == 0xFF ? 0x82u : char_type(uint32_t(i) << 8);
-            // a page maps to one class only if its first and last code point agree (true for all other BMP pages)
-        } else {
-            const uint32_t page = i < 512 ? 0x00u : i < 768 ? 0x30u : 0xFFu;
-            v = char_type((page << 8) | uint32_t(i & 255));
-        }
-        s_tytab[i] = uint8_t(v);
-    }
+    for (int i = threadIdx.x; i < kTypeTableBytes; i += kTileThreads) s_tytab[i] = uint8_t(type_table_entry(uint32_t(i)));
     if (tid == 0) mbar_init(s_bar, 1);
     if (tid < 8) reinterpret_cast<uint32_t*>(sb + kOffTy)[tid] = 0;  // front guard of s_ty
     __syncthreads();
@@ -712,8 +701,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_fast(DevModel m, Batch
                     const uint32_t hi = *reinterpret_cast<const uint32_t*>(s_text + al + 4);
                     c = decode_cp(__funnelshift_r(lo, hi, 8 * (pos & 3u)));
                     if (c < 0x10000u) {
-                        ty = s_tytab[c >> 8];
-                        if (ty & 0x80u) ty = s_tytab[256u + ((ty & 3u) << 8) + (c & 255u)];
+                        ty = type_from_table(s_tytab, c);
                     } else {
                         ty = char_type(c);
                     }

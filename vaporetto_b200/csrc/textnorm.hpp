@@ -36,6 +36,26 @@ VPT_HD uint32_t char_type(uint32_t c) {
     return 6;
 }
 
+// Character types of the BMP by table, for the tile kernels' shared memory: entries [0, 256) are indexed by c >> 8 and
+// hold the type of the whole 256-code-point page, or 0x80 | k for the four pages that hold more than one type (00: ASCII,
+// 30: kana, 4D: CJK Extension A ends at U+4DBF, FF: full-width / half-width forms); entries [256 + 256 k, 256 + 256 (k + 1))
+// are sub-table k, indexed by c & 255.  (tests/native/utf8_window_test.cpp checks every BMP code point against the
+// reference's ranges: every other page is uniform.  Until the last session of round 2 page 4D was taken for uniform:
+// U+4DC0..U+4DFF, the Yijing hexagram symbols, were typed Kanji instead of Other by the tile kernels.)
+constexpr int kTypeTableBytes = 256 + 4 * 256;
+VPT_HD uint32_t type_table_entry(uint32_t i) {
+    if (i < 256u) return i == 0x00u ? 0x80u : i == 0x30u ? 0x81u : i == 0xFFu ? 0x82u : i == 0x4Du ? 0x83u : char_type(i << 8);
+    const uint32_t k = (i - 256u) >> 8;
+    const uint32_t page = k == 0u ? 0x00u : k == 1u ? 0x30u : k == 2u ? 0xFFu : 0x4Du;
+    return char_type((page << 8) | (i & 255u));
+}
+// type of c < 0x10000 from the table built of type_table_entry(0 .. kTypeTableBytes)
+VPT_HD uint32_t type_from_table(const uint8_t* tab, uint32_t c) {
+    uint32_t ty = tab[c >> 8];
+    if (ty & 0x80u) ty = tab[256u + ((ty & 3u) << 8) + (c & 255u)];
+    return ty;
+}
+
 // Decodes the code point whose lead byte is the low byte of x (valid UTF-8 assumed).
 VPT_HD uint32_t decode_cp(uint32_t x) {
     const uint32_t b0 = x & 0xFF;
