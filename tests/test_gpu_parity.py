@@ -293,7 +293,9 @@ def test_character_types_at_range_edges(cw, tw):
              0x30FA, 0x30FB, 0x30FC, 0x30FF, 0x3100, 0x33FF, 0x3400, 0x4D00, 0x4DBF, 0x4DC0, 0x4DFF, 0x4E00, 0x9FFF, 0xA000,
              0xF8FF, 0xF900, 0xFAFF, 0xFB00, 0xFF0F, 0xFF10, 0xFF19, 0xFF1A, 0xFF20, 0xFF21, 0xFF3A, 0xFF3B, 0xFF40, 0xFF41, 0xFF5A,
              0xFF5B, 0xFF65, 0xFF66, 0xFF9F, 0xFFA0, 0x1FFFF, 0x20000, 0x2A6DF, 0x2A6E0, 0x2A6FF, 0x2A700, 0x2B73F, 0x2B740, 0x2B81F,
-             0x2B820, 0x2CEAF, 0x2CEB0, 0x2F7FF, 0x2F800, 0x2FA1F, 0x2FA20]
+             0x2B820, 0x2CEAF, 0x2CEB0, 0x2F7FF, 0x2F800, 0x2FA1F, 0x2FA20,
+             # and the edges of the UTF-8 encoding lengths, the surrogate gap and the code space
+             0x01, 0x7F, 0x80, 0xE9, 0x3A9, 0x7FF, 0x800, 0xD7FF, 0xE000, 0xFFFD, 0xFFFF, 0x10000, 0x10FFFF]
     rng = np.random.default_rng(4242 + 10 * cw + tw)
     model, alpha = _random_model(rng, cw, tw, maxdict=3)
     # every type n-gram up to length 3 carries a weight: a wrong type changes a score
