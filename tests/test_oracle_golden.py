@@ -174,3 +174,27 @@ def test_batch_matches_single():
         for i, s in enumerate(sents[:-1]):
             want = p.predict(s)[0]
             assert scores[int(boff[i]):int(boff[i + 1])].tolist() == want.tolist()
+
+
+def test_char_types_every_code_point():
+    """CharacterType::get_type (sentence.rs:50-67) over the whole code space: the oracle's restatement and the library's
+    host function (vpt_char_types: the arithmetic form the kernels use) against the reference's ranges, listed as the
+    reference lists them."""
+    import numpy as np
+    import vaporetto_b200 as vb
+    ranges = [(1, [(0x30, 0x39), (0xFF10, 0xFF19)]),
+              (2, [(0x41, 0x5A), (0x61, 0x7A), (0xFF21, 0xFF3A), (0xFF41, 0xFF5A)]),
+              (3, [(0x3040, 0x3096)]),
+              (4, [(0x30A0, 0x30FA), (0x30FC, 0x30FF), (0xFF66, 0xFF9F)]),
+              (5, [(0x3400, 0x4DBF), (0x4E00, 0x9FFF), (0xF900, 0xFAFF), (0x20000, 0x2A6DF), (0x2A700, 0x2B73F),
+                   (0x2B740, 0x2B81F), (0x2B820, 0x2CEAF), (0x2F800, 0x2FA1F)])]
+    want = np.full(0x110000, 6, np.uint8)
+    for ty, rs in ranges:
+        for lo, hi in rs:
+            want[lo:hi + 1] = ty
+    cps = [c for c in range(1, 0x110000) if not 0xD800 <= c <= 0xDFFF]
+    for lo in range(0, len(cps), 65536):
+        chunk = cps[lo:lo + 65536]
+        text = "".join(map(chr, chunk))
+        assert char_types(text).tolist() == want[chunk].tolist()
+        assert vb.Sentence.from_raw(text).char_types().tolist() == want[chunk].tolist()
