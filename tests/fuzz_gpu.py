@@ -21,6 +21,10 @@ os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 FAIL_MODEL = os.path.join(ROOT, "gpurun_out", "fuzz_fail_model.npy")   # (gpurun_out/ travels back from the GPU box)
 FAIL_LINES = os.path.join(ROOT, "gpurun_out", "fuzz_fail_lines.bin")
 ALPHA = list("あいうえおかきアイウエ人火星地球猫社長漢字aBc1 9。、🤌𠀋é")
+# both sides of the edges of CharacterType::get_type's ranges that lie inside a 256-code-point page, and of the encoding
+# lengths (the tile kernels type the BMP from a page table: a page with two types needs a sub-table; U+4DBF | U+4DC0 had none)
+ALPHA += [chr(c) for c in (0x3096, 0x3097, 0x30FA, 0x30FB, 0x4DBF, 0x4DC0, 0x9FFF, 0xA000, 0xFAFF, 0xFB00, 0xFF19, 0xFF1A, 0xFF9F,
+                           0xFFA0, 0x7F, 0x80, 0x7FF, 0x800, 0xFFFF, 0x10000, 0x2A6DF, 0x2A6E0, 0x10FFFF)]
 LINE_EXTRA = list("/\\.-ａ１。－―｢")  # escapes and sources / targets of the full-width filter
 
 
