@@ -12,6 +12,7 @@
 #include "../../vaporetto_b200/csrc/predictor_build.hpp"
 #include "../../vaporetto_b200/csrc/common.hpp"
 #include "../../vaporetto_b200/csrc/tags.hpp"
+#include "../../vaporetto_b200/csrc/tags_token.hpp"
 
 using namespace vpt;
 
@@ -214,15 +215,15 @@ long emul_predict(const uint8_t* model, size_t model_len, int predict_tags, cons
     }
 }
 
-// Tag prediction from the flat tag tables (tags_build.cpp: token table, token info, key lists, chain tables), following
-// the kernels' steps (tags.cu: token_lookup, add_scorer, tag_score_token): token by hash + byte compare, bias, for every
-// rel position the own vectors of the patterns on the suffix chain of the pattern found there (longest first, element k
-// of a shorter one only while every longer one is longer than k), first strict maximum per tag slot.
-// boundaries: n_chars - 1 bytes (1 = token boundary); cstates / tstates: the pattern ids emul_predict returns.
-// tag_token: n_chars (token id at a token's last character, else -1); tag_cand: n_chars x n_tags.  Returns n_tags
-// or -(status); *unserved counts tokens whose model exceeds the device limits.
+// Tag prediction from the flat tag tables (tags_build.cpp: token table, token info, key lists, chain tables) with the
+// kernels' OWN per-token code (csrc/tags_token.hpp: token_lookup, add_scorer, tag_score_token compile for the host too):
+// token by hash + byte compare (over the bytes of its KyteaFullwidthFilter image when norm != 0), bias, for every rel
+// position the own vectors of the patterns on the suffix chain of the pattern found there, first strict maximum per slot.
+// boundaries: n_chars - 1 bytes (1 = token boundary); cstates / tstates: pattern ids per character (of the text the
+// scorer saw: the filtered text when norm != 0).  tag_token: n_chars (token id at a token's last character, else -1);
+// tag_cand: n_chars x n_tags.  Returns n_tags or -(status); *unserved counts tokens beyond the device limits.
 long emul_predict_tags(const uint8_t* model, size_t model_len, const uint8_t* utf8, size_t nbytes, const uint8_t* boundaries,
-                       const uint32_t* cstates, const uint32_t* tstates, int32_t* tag_token, int32_t* tag_cand,
+                       const uint32_t* cstates, const uint32_t* tstates, int norm, int32_t* tag_token, int32_t* tag_cand,
                        int32_t* unserved) {
     try {
         size_t consumed = 0;
@@ -230,108 +231,45 @@ long emul_predict_tags(const uint8_t* model, size_t model_len, const uint8_t* ut
         HostPredictor hp = build_host_predictor(m, true);
         const TagTablesHost t = build_tag_tables(hp);
         if (!t.usable) throw Error(kInternal, "tag tables not usable");
-        const uint32_t char_rels = hp.char_tags ? t.char_rels : 0, type_rels = hp.type_tags ? t.type_rels : 0;
-        // character start offsets
+        DevTags d;  // the same fields capi.cpp fills, pointing at the host tables
+        d.tok_tab = t.tok_tab.data();
+        d.tok_bytes = t.tok_bytes.data();
+        d.tok_info = t.tok_info.data();
+        d.pool = t.pool.data();
+        d.keys = t.keys.data();
+        d.c_chain = t.c_chain.data();
+        d.t_chain = t.t_chain.data();
+        d.c_link = t.c_link.data();
+        d.t_link = t.t_link.data();
+        d.tok_mask = t.tok_mask;
+        d.n_tags = t.n_tags;
+        d.char_rels = hp.char_tags ? t.char_rels : 0;
+        d.type_rels = hp.type_tags ? t.type_rels : 0;
+        d.max_token_bytes = t.max_token_bytes;
+        d.n_char_patterns = uint32_t(hp.char_suffix_link.size());
+        d.n_type_patterns = uint32_t(hp.type_suffix_link.size());
         std::vector<uint32_t> start;
         for (size_t i = 0; i < nbytes; ++i) if ((utf8[i] & 0xC0) != 0x80) start.push_back(uint32_t(i));
         const size_t n = start.size();
         start.push_back(uint32_t(nbytes));
         const uint32_t nt = t.n_tags;
-        for (size_t i = 0; i < n; ++i) { tag_token[i] = -1; for (uint32_t k = 0; k < nt; ++k) tag_cand[i * nt + k] = -1; }
-        if (unserved) *unserved = 0;
-        auto on_chain = [&](uint32_t want, uint32_t pid, const TagChain& ch, const std::vector<uint32_t>& link) {
-            if (want == pid) return true;
-            for (int k = 0; k < 4; ++k) if (want == ch.next[k]) return true;
-            if (ch.next[3] == kNoPattern) return false;
-            for (uint32_t q = link[ch.next[3]]; q != kNoPattern; q = link[q]) if (q == want) return true;
-            return false;
-        };
-        auto add_scorer = [&](const TagKey* keys, const uint8_t* cnt, uint32_t rest, const std::vector<TagChain>& chains,
-                              const std::vector<uint32_t>& link, const uint32_t* states, uint32_t npat, uint32_t rels, size_t i,
-                              std::vector<int32_t>& scores) {
-            const uint32_t ns = uint32_t(scores.size());
-            for (uint32_t r = 0; r < 4; ++r) {
-                const uint32_t nk = cnt[r];
-                uint32_t pid = kNoPattern;
-                if (nk != 0 && r < rels && i + r < n) pid = states[i + r];
-                if (pid >= npat) pid = kNoPattern;
-                if (pid != kNoPattern) {
-                    uint32_t limit = ns;
-                    for (uint32_t j = 0; j < nk && limit; ++j) {
-                        const TagKey& e = keys[j];
-                        if (on_chain(e.pid, pid, chains[pid], link)) {
-                            const uint32_t upto = std::min(limit, e.len);
-                            for (uint32_t k = 0; k < upto; ++k) scores[k] = wrapping_add(scores[k], t.pool[e.off + k]);
-                            limit = upto;
-                        }
-                    }
-                }
-                keys += nk;
-            }
-            uint32_t cur_rel = 0xFFFFFFFFu, limit = 0;
-            for (uint32_t j = 0; j < rest; ++j) {
-                const TagKey& e = keys[j];
-                if (e.rel != cur_rel) { cur_rel = e.rel; limit = ns; }
-                if (limit == 0 || e.rel >= rels || i + e.rel >= n) continue;
-                const uint32_t q = states[i + e.rel];
-                if (q < npat && on_chain(e.pid, q, chains[q], link)) {
-                    const uint32_t upto = std::min(limit, e.len);
-                    for (uint32_t k = 0; k < upto; ++k) scores[k] = wrapping_add(scores[k], t.pool[e.off + k]);
-                    limit = upto;
-                }
-            }
-        };
+        uint32_t uns = 0;
         size_t tok_start = 0;
         for (size_t i = 0; i < n; ++i) {
+            tag_token[i] = -1;
+            for (uint32_t k = 0; k < nt; ++k) tag_cand[i * nt + k] = -1;
             const bool ends = i + 1 == n || boundaries[i] == 1;
             if (!ends) continue;
-            const uint8_t* bytes = utf8 + start[tok_start];
-            const uint32_t len = start[i + 1] - start[tok_start];
+            int32_t cand[kTagMaxSlots];
+            for (int k = 0; k < kTagMaxSlots; ++k) cand[k] = -1;
+            const int32_t tok = tag_token_at(d, utf8 + start[tok_start], start[i + 1] - start[tok_start],
+                                             d.char_rels ? cstates : nullptr, d.type_rels ? tstates : nullptr, uint32_t(i),
+                                             uint32_t(n), cand, &uns, norm);
             tok_start = i + 1;
-            // token lookup
-            if (len == 0 || len > t.max_token_bytes) continue;
-            uint64_t h = kTagHashInit;
-            for (uint32_t k = 0; k < len; ++k) h = tag_hash_step(h, bytes[k]);
-            h = tag_hash_finish(h);
-            uint32_t tid = 0;
-            bool found = false;
-            for (uint32_t sl = uint32_t(h >> 20) & t.tok_mask;; sl = (sl + 1) & t.tok_mask) {
-                const TagTokenEntry& e = t.tok_tab[sl];
-                if (e.hash == 0) break;
-                if (e.hash == h && e.len == len && memcmp(t.tok_bytes.data() + e.str_off, bytes, len) == 0) { tid = e.tid; found = true; break; }
-            }
-            if (!found) continue;
-            const TagTokenInfo& ti = t.tok_info[tid];
-            if (!ti.usable) { if (unserved) ++*unserved; continue; }
-            std::vector<int32_t> scores(t.pool.begin() + ti.bias_off, t.pool.begin() + ti.bias_off + ti.bias_len);
-            const uint32_t n_ckeys = uint32_t(ti.ckeys[0]) + ti.ckeys[1] + ti.ckeys[2] + ti.ckeys[3] + ti.c_rest;
-            const uint32_t n_tkeys = uint32_t(ti.tkeys[0]) + ti.tkeys[1] + ti.tkeys[2] + ti.tkeys[3] + ti.t_rest;
-            if (char_rels && n_ckeys)
-                add_scorer(t.keys.data() + ti.key_off, ti.ckeys, ti.c_rest, t.c_chain, t.c_link, cstates,
-                           uint32_t(hp.char_suffix_link.size()), char_rels, i, scores);
-            if (type_rels && n_tkeys)
-                add_scorer(t.keys.data() + ti.key_off + n_ckeys, ti.tkeys, ti.t_rest, t.t_chain, t.t_link, tstates,
-                           uint32_t(hp.type_suffix_link.size()), type_rels, i, scores);
-            uint32_t off = 0;
-            bool ok = true;
-            std::vector<int32_t> cand(nt, -1);
-            for (uint32_t k = 0; k < ti.n_slots && k < nt; ++k) {
-                const uint32_t nc = ti.cand[k];
-                if (nc >= 2) {
-                    if (off + nc > scores.size()) { ok = false; break; }
-                    uint32_t best = 0;
-                    int32_t mx = INT32_MIN;
-                    for (uint32_t c = 0; c < nc; ++c) if (scores[off + c] > mx) { best = c; mx = scores[off + c]; }
-                    cand[k] = int32_t(best);
-                    off += nc;
-                } else {
-                    cand[k] = nc == 1 ? 0 : -1;
-                }
-            }
-            if (!ok) { if (unserved) ++*unserved; continue; }
-            tag_token[i] = int32_t(tid);
-            for (uint32_t k = 0; k < nt; ++k) tag_cand[i * nt + k] = cand[k];
+            tag_token[i] = tok;
+            for (uint32_t k = 0; k < nt; ++k) tag_cand[i * nt + k] = tok >= 0 ? cand[k] : -1;
         }
+        if (unserved) *unserved = int32_t(uns);
         return long(nt);
     } catch (const Error& e) {
         set_last_error(e.what());

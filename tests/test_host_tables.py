@@ -24,7 +24,8 @@ def emul():
     so = os.path.join(HERE, "native", "libhost_emul.so")
     srcs = [os.path.join(HERE, "native", "host_emul.cpp")] + [os.path.join(CSRC, f) for f in
                                                              ("predictor_build.cpp", "builder.cpp", "model.cpp", "tags_build.cpp")]
-    deps = srcs + [os.path.join(CSRC, f) for f in ("builder.hpp", "keys.hpp", "predictor_build.hpp", "common.hpp", "tags.hpp")]
+    deps = srcs + [os.path.join(CSRC, f) for f in ("builder.hpp", "keys.hpp", "predictor_build.hpp", "common.hpp", "tags.hpp", "tags_token.hpp",
+                                                     "textnorm.hpp")]
     if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in deps):
         # (tags.hpp declares the launch interface next to the tables: cuda_runtime.h for the types only, nothing is linked)
         cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
@@ -36,7 +37,7 @@ def emul():
     L.emul_last_error.restype = C.c_char_p
     L.emul_predict_tags.restype = C.c_long
     L.emul_predict_tags.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
-                                    C.c_void_p, C.c_void_p, C.c_void_p]
+                                    C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     return L
 
 
@@ -185,11 +186,19 @@ def test_builder_survives_mutated_models(tmp_path):
 
 # ---- tag tables (tags_build.cpp: token table, key lists, chain tables) interpreted with the kernels' steps ---------------
 
-def run_tags(L, model_bytes, text, o):
-    """Tag prediction from the product's flat tag tables on the CPU (tests/native/host_emul.cpp: emul_predict_tags) on
-    the oracle's boundaries and the emulated pattern-id states; returns (tag_token, tag_cand[n, n_tags], unserved)."""
-    _, bd = o.predict(text)
-    _, cs, ts, _ = run(L, model_bytes, text, tags=True)
+def _fullwidth(text):
+    import vaporetto_b200 as vb
+    return "".join(chr(vb.lib().vpt_kytea_fullwidth(ord(c))) for c in text)
+
+
+def run_tags(L, model_bytes, text, o, norm=False):
+    """Tag prediction from the product's flat tag tables on the CPU, by the kernels' own per-token code compiled for the
+    host (csrc/tags_token.hpp through tests/native/host_emul.cpp: emul_predict_tags), on the oracle's boundaries and the
+    emulated pattern-id states; returns (tag_token, tag_cand[n, n_tags], unserved).  norm: the CLI's pre-filter -- the
+    scorer sees the full-width image of the text, the tokens are looked up by the image of their ORIGINAL bytes."""
+    seen = _fullwidth(text) if norm else text
+    _, bd = o.predict(seen)
+    _, cs, ts, _ = run(L, model_bytes, seen, tags=True)
     b = text.encode()
     n = len(cs)
     nt = max(o.n_tags, 1)
@@ -200,16 +209,16 @@ def run_tags(L, model_bytes, text, o):
     cand = np.zeros(n * nt, np.int32)
     uns = np.zeros(1, np.int32)
     rc = L.emul_predict_tags(model_bytes, len(model_bytes), b, len(b), bd.ctypes.data, cs.ctypes.data, ts.ctypes.data,
-                             tok.ctypes.data, cand.ctypes.data, uns.ctypes.data)
+                             int(norm), tok.ctypes.data, cand.ctypes.data, uns.ctypes.data)
     assert rc == o.n_tags, L.emul_last_error()
     return tok, cand.reshape(n, nt)[:, :o.n_tags], int(uns[0])
 
 
-def _check_tags(L, mb, texts):
+def _check_tags(L, mb, texts, norm=False):
     o = OraclePredictor(mb, predict_tags=True)
     for text in texts:
-        tok, cand, uns = run_tags(L, mb, text, o)
-        ott, oti = o.predict_tags(text)
+        tok, cand, uns = run_tags(L, mb, text, o, norm=norm)
+        ott, oti = o.predict_tags(_fullwidth(text) if norm else text)
         assert uns == 0
         # (token ids may be numbered differently only if tokens repeat in the model; the candidates must agree)
         assert (tok >= 0).tolist() == (ott >= 0).tolist(), text
@@ -255,3 +264,24 @@ def test_fused_probe_order_on_the_fuzz_case(emul):
         s = bytes(text[int(offs[i]):int(offs[i + 1])]).decode()
         sc, _, _, info = run(emul, mb, s)
         assert sc == o.predict(s)[0].tolist()
+
+
+def test_tag_tables_with_the_fullwidth_prefilter(emul):
+    """norm = 1 (the CLI default): tokens are looked up by the bytes of their KyteaFullwidthFilter image, computed on the fly
+    from the original bytes (ASCII -> three-byte full-width forms: the byte length changes).  Tokens of the model are
+    full-width strings; the text mixes ASCII, half-width punctuation and kana."""
+    rng = np.random.default_rng(99)
+    alpha = list("あいう人aB1x!?｡-ｱ")  # (ｱ is not mapped: only the ten listed non-ASCII sources are)
+    fw = _fullwidth
+    tms = []
+    for t in range(8):
+        tok = fw("".join(rng.choice(alpha, size=rng.integers(1, 4))))
+        cn = [(fw("".join(rng.choice(alpha, size=rng.integers(1, 3)))), [(int(rng.integers(0, 4)), rng.integers(-99, 99, size=2).tolist())])
+              for _ in range(4)]
+        tms.append(dict(token=tok, tags=[["x", "y"]], char_ngrams=cn, type_ngrams=[], bias=[1, 2]))
+    cng = {fw("".join(rng.choice(alpha, size=rng.integers(1, 4)))): rng.integers(-500, 500, size=4).tolist() for _ in range(30)}
+    model = dict(char_ngrams=list(cng.items()), type_ngrams=[(bytes([2]), [5, -5, 7, 1, 0, 2])], dict=[], bias=-3,
+                 char_window=3, type_window=3, tag_models=tms)
+    texts = ["".join(rng.choice(alpha, size=rng.integers(1, 30))) for _ in range(80)]
+    _check_tags(emul, encode_model(model), texts, norm=True)
+    _check_tags(emul, encode_model(model), [fw(t) for t in texts], norm=False)
