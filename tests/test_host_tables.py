@@ -166,12 +166,16 @@ def test_table_layout_variants(emul, budget, monkeypatch):
 
 def test_builder_survives_mutated_models(tmp_path):
     """ASan + UBSan build of the model reader + host predictor builder against mutated model files (random bytes, bit
-    flips, small values in length / window positions): built or rejected with an error, never a crash."""
+    flips, small values in length / window positions): built or rejected with an error, never a crash.  Tag predictors
+    also get their flat tag tables built, and the tag kernels' per-token code (host build) runs over them with random
+    pattern-id states."""
     import struct
     exe = str(tmp_path / "build_fuzz")
     subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined",
-                           "-I" + CSRC, os.path.join(HERE, "native", "build_fuzz.cpp")] +
-                          [os.path.join(CSRC, f) for f in ("model.cpp", "builder.cpp", "predictor_build.cpp")] + ["-o", exe])
+                           "-I" + CSRC, "-I" + os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include"),
+                           os.path.join(HERE, "native", "build_fuzz.cpp")] +
+                          [os.path.join(CSRC, f) for f in ("model.cpp", "builder.cpp", "predictor_build.cpp", "tags_build.cpp")] +
+                          ["-o", exe])
     samples = [open(os.path.join(GOLDEN, fn), "rb").read() for fn in ("model.bin", "tantivy_model.bin")]
     samples += [encode_model(m) for m in (kat.PREDICTOR_TEST_MODEL, kat.CHAR_ADD_SCORES_WITH_TAGS["model"],
                                           kat.CHAR_ADD_SCORES_3["model"], kat.TYPE_ADD_SCORES["model"],
