@@ -275,7 +275,7 @@ def test_tag_tables_with_the_fullwidth_prefilter(emul):
     from the original bytes (ASCII -> three-byte full-width forms: the byte length changes).  Tokens of the model are
     full-width strings; the text mixes ASCII, half-width punctuation and kana."""
     rng = np.random.default_rng(99)
-    alpha = list("あいう人aB1x!?｡-ｱ")  # (ｱ is not mapped: only the ten listed non-ASCII sources are)
+    alpha = list("あいう人aB1x!?｡-ｱé𠀋Ω")  # (ｱ is not mapped: only the ten listed non-ASCII sources are; 2- and 4-byte characters)
     fw = _fullwidth
     tms = []
     for t in range(8):
