@@ -284,7 +284,7 @@ def test_random_models_vs_oracle(cw, tw, maxdict, tags):
                 assert r.type_states[c0:c0 + len(ots)].tolist() == ots.tolist()
 
 
-@pytest.mark.parametrize("cw,tw", [(3, 3), (3, 2), (4, 4), (0, 3)])
+@pytest.mark.parametrize("cw,tw", [(3, 3), (3, 2), (4, 4), (0, 3), (6, 3)])  # (6, 3): general rows through k_tile_fast
 def test_character_types_at_range_edges(cw, tw):
     """Both sides of every edge of CharacterType::get_type's ranges (sentence.rs:50-67), mixed into kana text: the tile
     kernels type BMP characters from a page table, and a page that holds two types needs its own sub-table -- U+4DBF | U+4DC0
