@@ -72,12 +72,12 @@ def expected(o, data: bytes, no_norm: bool = True, wsconst: str = "") -> bytes:
 
 
 def test_fullwidth_map_matches_reference_fixture():
-    """Every code point up to U+FFFF (and a few beyond): the oracle's table and the library's arithmetic form
+    """Every code point: the oracle's table and the library's arithmetic form
     (csrc/textnorm.hpp, the function the kernels apply) against the map extracted from the reference source."""
     fw = fullwidth_map()
     assert len(fw) == 96
     L, O = vb.lib(), oracle_lib()
-    for c in list(range(0, 0x10000)) + [0x10000, 0x1F600, 0x2A6DF, 0x10FFFF]:
+    for c in range(0, 0x110000):
         want = fw.get(c, c)
         assert O.ora_kytea_fullwidth(c) == want, hex(c)
         assert L.vpt_kytea_fullwidth(c) == want, hex(c)
