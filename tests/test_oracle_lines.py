@@ -250,3 +250,41 @@ def test_split_linebreaks_reference_vectors():
     s = vb.Sentence.from_raw("\n")
     s.split_linebreaks()
     assert s.boundaries().size == 0
+
+
+def test_grapheme_classes_at_range_ends():
+    """Both ends of every range of the grapheme property table (and the code points just outside): the oracle's engine
+    against regex's \\X, and the library's per-character state machine (the engine the device kernel runs) against the
+    oracle, in five contexts (kana, doubled, Devanagari consonants, emoji, Hangul jamo).  A full sweep of the code space
+    (every code point, the same contexts) was run once for both: 0 mismatches."""
+    import re
+    from vpt_testlib.oracle import grapheme_lengths
+    src = open(os.path.join(HERE, "..", "oracle", "grapheme_tables.hpp")).read()
+    cps = set()
+    for m in re.finditer(r"\{0x([0-9A-F]+), 0x([0-9A-F]+)", src):
+        lo, hi = int(m.group(1), 16), int(m.group(2), 16)
+        cps.update((lo - 1, lo, hi, hi + 1))
+    ctxs = [lambda ch: "あ" + ch + "あ", lambda ch: ch + ch, lambda ch: "क" + ch + "क",
+            lambda ch: "\U0001f468" + ch + "\U0001f469", lambda ch: "ᄀ" + ch + "ᅡ"]
+
+    def product(text):
+        s = vb.Sentence.from_raw(text)
+        s.boundaries_mut()[:] = 1
+        s.concat_grapheme_clusters()
+        lens, run = [], 1
+        for b in s.boundaries().tolist():
+            if b:
+                lens.append(run)
+                run = 1
+            else:
+                run += 1
+        return lens + [run]
+
+    for c in sorted(cps):
+        if c < 1 or c > 0x10FFFF or 0xD800 <= c <= 0xDFFF:
+            continue
+        for f in ctxs:
+            text = f(chr(c))
+            want = _regex_cluster_lengths(text)
+            assert grapheme_lengths(text) == want, [hex(ord(x)) for x in text]
+            assert product(text) == want, [hex(ord(x)) for x in text]
